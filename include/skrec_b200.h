@@ -1,0 +1,139 @@
+/*
+ * skrec_b200.h -- C ABI of the B200-native full-ranking evaluation path.
+ *
+ * This is the drop-in boundary for scikit-recommender's native evaluation entry point and the
+ * Python loop around it.  Each entry cites the reference interface it replaces (paths relative
+ * to the reference checkout):
+ *
+ *   skr_eval_scores / skr_eval_scores_host
+ *       replace  eval_score_matrix()            skrec/utils/py/cython/pyx_eval_matrix.pyx:22-37
+ *       and      cpp_evaluate_matrix()          skrec/utils/py/cython/include/evaluate.h:57-76
+ *       plus the train-item masking loop        skrec/utils/py/evaluator.py:195-200
+ *   skr_eval_fused / skr_eval_fused_host
+ *       replace one whole pass of RankingEvaluator.evaluate()   skrec/utils/py/evaluator.py:163-214
+ *       for models whose predict() is U_b @ I^T (+ bias)         BPRMF.py:84-88, LightGCN.py:102-107,
+ *                                                                MultVAE.py:138-141, SelfCF.py:235-241
+ *   skr_metrics_from_topk
+ *       replaces the metric functions           skrec/utils/py/cython/include/metric.h:19-118
+ *   skr_set_train_csr / skr_set_test_csr
+ *       replace RankingEvaluator.set_train_data / set_test_data  skrec/utils/py/evaluator.py:140-145
+ *       (STL sets cannot cross a C ABI: `vector<unordered_set<int>>` becomes CSR)
+ *   skr_colsum_f32_seq
+ *       replaces np.mean(all_results, axis=0)   skrec/utils/py/evaluator.py:206-208 (float32, row order)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; 0 = ok, negative = error; nothing throws.
+ *   - the caller owns every buffer it passes; a ctx owns only its device copies of the CSRs and
+ *     its workspace.  One ctx per (device, stream user); calls on one ctx must not overlap.
+ *   - `*_dev` pointers are device memory on the ctx's device; `*_host` are host memory
+ *     (pinned or pageable).  `stream` is a cudaStream_t passed as void* (NULL = legacy default).
+ *   - device entry points are asynchronous on `stream`; `*_host` entry points return after
+ *     their results are in host memory.
+ *   - rows: the CSRs passed to skr_set_*_csr have one row per EVALUATED user, in evaluation
+ *     order (evaluator.py:181-184).  A call covers rows [row0, row0 + n_rows).
+ *   - per-user output layout is the reference's: [n_rows, n_metrics * top_k], metric-major,
+ *     K ascending (evaluate.h:47-51).  metric ids: 1 Precision, 2 Recall, 3 MAP, 4 NDCG, 5 MRR
+ *     (evaluator.py:57).
+ *   - ties: score descending, then item id ascending (the reference's order on ties is an
+ *     artefact of libstdc++'s heap; on tie-free rows both agree bit for bit).
+ *   - `sums_dev` / `sums_host`: double[n_metrics * top_k]; device entry points ADD the column
+ *     sums over the rows of the call into it (zero it before the first batch).
+ */
+#ifndef SKREC_B200_H
+#define SKREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKR_ABI_VERSION 1
+
+#define SKR_OK 0
+#define SKR_ERR_INVALID (-1)     /* bad argument (message in skr_last_error) */
+#define SKR_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define SKR_ERR_NOMEM (-3)       /* device or host allocation failed */
+#define SKR_ERR_UNSUPPORTED (-4) /* shape outside what the chosen kernel supports */
+#define SKR_ERR_STATE (-5)       /* call order (e.g. no test CSR set) */
+
+/* scoring arithmetic of the fused path */
+#define SKR_PREC_AUTO 0   /* 3xTF32 on tensor cores when the shape allows, else FP32 FMA */
+#define SKR_PREC_FP32 1   /* FP32 FMA on CUDA cores (exact products, sequential k order) */
+#define SKR_PREC_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split, 3 products, FP32 accumulate */
+#define SKR_PREC_1XTF32 3 /* single TF32 pass; NOT reference-grade, for measurement only */
+
+typedef struct skr_ctx skr_ctx;
+
+int skr_abi_version(void);
+
+/* Context bound to CUDA device `device`.  Fails (SKR_ERR_CUDA) when no such device exists. */
+int skr_ctx_create(int device, skr_ctx **out);
+int skr_ctx_destroy(skr_ctx *ctx);
+/* Message of the last failure on `ctx` (or of the last failed skr_ctx_create when ctx is NULL). */
+const char *skr_last_error(const skr_ctx *ctx);
+
+/* Train interactions to mask (evaluator.py:140-141).  Host CSR; rows need not be sorted and may
+ * hold duplicates.  indptr == NULL clears masking (user_train_dict=None). */
+int skr_set_train_csr(skr_ctx *ctx, const int64_t *indptr_host, const int32_t *indices_host,
+                      int64_t n_rows, int64_t n_items);
+/* Test interactions (evaluator.py:143-145); duplicates are dropped like the reference's set. */
+int skr_set_test_csr(skr_ctx *ctx, const int64_t *indptr_host, const int32_t *indices_host,
+                     int64_t n_rows, int64_t n_items);
+
+/* Score-matrix-in: mask train items, select top-K, per-user metrics, column sums.
+ * scores_dev: float32 [n_rows, ld], not modified.  Any of the four outputs may be NULL.
+ * topk_idx_dev int32 [n_rows, top_k]; topk_val_dev float32 [n_rows, top_k];
+ * per_user_dev float32 [n_rows, n_metrics*top_k]. */
+int skr_eval_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64_t n_items, int64_t ld,
+                    int64_t row0, const int32_t *metric_ids, int n_metrics, int top_k,
+                    int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev, double *sums_dev,
+                    void *stream);
+
+/* Same with a HOST score matrix and host outputs; the H2D/D2H copies are part of the call.
+ * sums_host is ADDED to as well.  (What a Cython/ctypes binding of eval_score_matrix calls.) */
+int skr_eval_scores_host(skr_ctx *ctx, const float *scores_host, int64_t n_rows, int64_t n_items, int64_t ld,
+                         int64_t row0, const int32_t *metric_ids, int n_metrics, int top_k,
+                         int32_t *topk_idx_host, float *per_user_host, double *sums_host, void *stream);
+
+/* Fused: scores = user_vecs @ item_vecs^T (+ bias) are produced tile by tile on chip and never
+ * written to HBM; masking, top-K, metrics and sums as above.
+ * user_vecs_dev float32 [n_rows, ld_u] (row r = evaluated user row0 + r), item_vecs_dev float32
+ * [n_items, ld_i], bias_dev float32 [n_items] or NULL, d = embedding width. */
+int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u,
+                   const float *item_vecs_dev, int64_t n_items, int64_t ld_i, int d,
+                   const float *bias_dev, int64_t row0, const int32_t *metric_ids, int n_metrics,
+                   int top_k, int precision, int32_t *topk_idx_dev, float *topk_val_dev,
+                   float *per_user_dev, double *sums_dev, void *stream);
+
+/* Same with HOST embedding tables and host outputs (copies inside the call). */
+int skr_eval_fused_host(skr_ctx *ctx, const float *user_vecs_host, int64_t n_rows, int64_t ld_u,
+                        const float *item_vecs_host, int64_t n_items, int64_t ld_i, int d,
+                        const float *bias_host, int64_t row0, const int32_t *metric_ids, int n_metrics,
+                        int top_k, int precision, int32_t *topk_idx_host, float *per_user_host,
+                        double *sums_host, void *stream);
+
+/* Metrics of given rank lists (metric.h:19-118): topk_idx_dev int32 [n_rows, top_k]. */
+int skr_metrics_from_topk(skr_ctx *ctx, const int32_t *topk_idx_dev, int64_t n_rows, int64_t row0,
+                          const int32_t *metric_ids, int n_metrics, int top_k, float *per_user_dev,
+                          double *sums_dev, void *stream);
+
+/* acc[c] = (...((acc[c] + x[0,c]) + x[1,c]) + ...) in float32, rows in order: numpy's
+ * np.sum(axis=0) on a C-ordered float32 array (evaluator.py:208).  acc_dev float32 [n_cols]. */
+int skr_colsum_f32_seq(skr_ctx *ctx, const float *per_user_dev, int64_t n_rows, int64_t n_cols,
+                       float *acc_dev, void *stream);
+
+/* Number of kernels this library has launched on `ctx` since creation (bench.py's gpu_launches). */
+int64_t skr_launch_count(const skr_ctx *ctx);
+
+/* Name of the scoring kernel the last skr_eval_fused* call on ctx used: "tcgen05_3xtf32",
+ * "tcgen05_1xtf32" or "simt_fp32". */
+const char *skr_last_fused_kernel(const skr_ctx *ctx);
+
+/* Tunables (0 = library default): item-range chunks per user tile of the fused path. */
+int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKREC_B200_H */

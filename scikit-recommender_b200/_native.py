@@ -1,0 +1,203 @@
+"""ctypes binding of the C ABI in include/skrec_b200.h (libskrec_b200.so, in-tree).
+
+There is no Python/CPU fallback: if the shared library is missing, or no sm_100 device exists,
+the product path raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libskrec_b200.so")
+
+SKR_OK = 0
+PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "1xtf32": 3}
+
+# every symbol include/skrec_b200.h declares (tests check the library exports all of them)
+SYMBOLS = (
+    "skr_abi_version", "skr_ctx_create", "skr_ctx_destroy", "skr_last_error", "skr_set_train_csr",
+    "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
+    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option",
+)
+
+_lib = None
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("skrec_b200 native error %d: %s" % (code, message))
+        self.code = code
+
+
+def lib():
+    """Load the CUDA extension; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python scikit-recommender_b200/build.py` "
+                          "(there is no CPU fallback for the evaluation path)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.skr_abi_version.restype = _int
+    L.skr_ctx_create.argtypes = [_int, ctypes.POINTER(_vp)]
+    L.skr_ctx_destroy.argtypes = [_vp]
+    L.skr_last_error.argtypes = [_vp]
+    L.skr_last_error.restype = ctypes.c_char_p
+    L.skr_set_train_csr.argtypes = [_vp, _vp, _vp, _i64, _i64]
+    L.skr_set_test_csr.argtypes = [_vp, _vp, _vp, _i64, _i64]
+    L.skr_eval_scores.argtypes = [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]
+    L.skr_eval_scores_host.argtypes = [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp]
+    L.skr_eval_fused.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _i64, _vp, _int, _int, _int,
+                                 _vp, _vp, _vp, _vp, _vp]
+    L.skr_eval_fused_host.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _i64, _vp, _int, _int, _int,
+                                      _vp, _vp, _vp, _vp]
+    L.skr_metrics_from_topk.argtypes = [_vp, _vp, _i64, _i64, _vp, _int, _int, _vp, _vp, _vp]
+    L.skr_colsum_f32_seq.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp]
+    L.skr_launch_count.argtypes = [_vp]
+    L.skr_launch_count.restype = _i64
+    L.skr_last_fused_kernel.argtypes = [_vp]
+    L.skr_last_fused_kernel.restype = ctypes.c_char_p
+    L.skr_set_option.argtypes = [_vp, ctypes.c_char_p, _i64]
+    for name in SYMBOLS:
+        getattr(L, name)
+    if L.skr_abi_version() != 1:
+        raise ImportError("libskrec_b200.so ABI version %d, expected 1" % L.skr_abi_version())
+    _lib = L
+    return L
+
+
+def _np_ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _dev_ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Context(object):
+    """One native context per CUDA device (owns the device CSRs and workspace)."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        h = _vp()
+        rc = self._L.skr_ctx_create(int(device), ctypes.byref(h))
+        if rc != SKR_OK:
+            raise NativeError(rc, (self._L.skr_last_error(None) or b"").decode())
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.skr_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != SKR_OK:
+            raise NativeError(rc, (self._L.skr_last_error(self._h) or b"").decode())
+
+    # -- CSR ------------------------------------------------------------------------------------
+    def set_train_csr(self, indptr, indices, n_items):
+        if indptr is None:
+            self._check(self._L.skr_set_train_csr(self._h, None, None, 0, int(n_items)))
+            return
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        self._check(self._L.skr_set_train_csr(self._h, _np_ptr(ip), _np_ptr(ix), ip.size - 1, int(n_items)))
+
+    def set_test_csr(self, indptr, indices, n_items):
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        self._check(self._L.skr_set_test_csr(self._h, _np_ptr(ip), _np_ptr(ix), ip.size - 1, int(n_items)))
+
+    def set_option(self, name, value):
+        self._check(self._L.skr_set_option(self._h, name.encode(), int(value)))
+
+    @property
+    def launch_count(self):
+        return int(self._L.skr_launch_count(self._h))
+
+    @property
+    def last_fused_kernel(self):
+        return (self._L.skr_last_fused_kernel(self._h) or b"").decode()
+
+    # -- device entry points (torch CUDA tensors) -----------------------------------------------
+    def eval_scores(self, scores, row0, metric_ids, top_k, topk_idx=None, topk_val=None, per_user=None, sums=None,
+                    stream=None):
+        m = np.ascontiguousarray(metric_ids, dtype=np.int32)
+        assert scores.is_cuda and scores.dim() == 2 and scores.stride(1) == 1
+        self._check(self._L.skr_eval_scores(self._h, _dev_ptr(scores), scores.shape[0], scores.shape[1], scores.stride(0),
+                                            int(row0), _np_ptr(m), int(m.size), int(top_k), _dev_ptr(topk_idx),
+                                            _dev_ptr(topk_val), _dev_ptr(per_user), _dev_ptr(sums), _stream_ptr(stream)))
+
+    def eval_fused(self, user_vecs, item_vecs, bias, row0, metric_ids, top_k, precision="auto", topk_idx=None,
+                   topk_val=None, per_user=None, sums=None, stream=None):
+        m = np.ascontiguousarray(metric_ids, dtype=np.int32)
+        assert user_vecs.is_cuda and item_vecs.is_cuda and user_vecs.stride(1) == 1 and item_vecs.stride(1) == 1
+        assert user_vecs.shape[1] == item_vecs.shape[1]
+        self._check(self._L.skr_eval_fused(self._h, _dev_ptr(user_vecs), user_vecs.shape[0], user_vecs.stride(0),
+                                           _dev_ptr(item_vecs), item_vecs.shape[0], item_vecs.stride(0),
+                                           int(user_vecs.shape[1]), _dev_ptr(bias), int(row0), _np_ptr(m), int(m.size),
+                                           int(top_k), PREC[precision], _dev_ptr(topk_idx), _dev_ptr(topk_val),
+                                           _dev_ptr(per_user), _dev_ptr(sums), _stream_ptr(stream)))
+
+    def metrics_from_topk(self, topk_idx, row0, metric_ids, top_k, per_user=None, sums=None, stream=None):
+        m = np.ascontiguousarray(metric_ids, dtype=np.int32)
+        self._check(self._L.skr_metrics_from_topk(self._h, _dev_ptr(topk_idx), topk_idx.shape[0], int(row0), _np_ptr(m),
+                                                  int(m.size), int(top_k), _dev_ptr(per_user), _dev_ptr(sums),
+                                                  _stream_ptr(stream)))
+
+    def colsum_f32_seq(self, per_user, acc, stream=None):
+        self._check(self._L.skr_colsum_f32_seq(self._h, _dev_ptr(per_user), per_user.shape[0], per_user.shape[1],
+                                               _dev_ptr(acc), _stream_ptr(stream)))
+
+    # -- host entry points (numpy arrays; copies inside the call) -------------------------------
+    def eval_scores_host(self, scores, row0, metric_ids, top_k, want_topk=False, want_per_user=True):
+        s = scores
+        assert isinstance(s, np.ndarray) and s.dtype == np.float32 and s.ndim == 2 and s.strides[1] == 4
+        m = np.ascontiguousarray(metric_ids, dtype=np.int32)
+        B = s.shape[0]
+        mk = int(m.size) * int(top_k)
+        idx = np.empty((B, top_k), np.int32) if want_topk else None
+        pu = np.empty((B, mk), np.float32) if want_per_user else None
+        sums = np.zeros(mk, np.float64)
+        self._check(self._L.skr_eval_scores_host(self._h, _np_ptr(s), B, s.shape[1], s.strides[0] // 4, int(row0),
+                                                 _np_ptr(m), int(m.size), int(top_k), _np_ptr(idx), _np_ptr(pu),
+                                                 _np_ptr(sums), None))
+        return pu, idx, sums
+
+    def eval_fused_host(self, user_vecs, item_vecs, bias, row0, metric_ids, top_k, precision="auto", want_topk=False,
+                        want_per_user=False):
+        u, v = user_vecs, item_vecs
+        for a in (u, v):
+            assert isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == 2 and a.strides[1] == 4
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        m = np.ascontiguousarray(metric_ids, dtype=np.int32)
+        B = u.shape[0]
+        mk = int(m.size) * int(top_k)
+        idx = np.empty((B, top_k), np.int32) if want_topk else None
+        pu = np.empty((B, mk), np.float32) if want_per_user else None
+        sums = np.zeros(mk, np.float64)
+        self._check(self._L.skr_eval_fused_host(self._h, _np_ptr(u), B, u.strides[0] // 4, _np_ptr(v), v.shape[0],
+                                                v.strides[0] // 4, int(u.shape[1]), _np_ptr(b), int(row0), _np_ptr(m),
+                                                int(m.size), int(top_k), PREC[precision], _np_ptr(idx), _np_ptr(pu),
+                                                _np_ptr(sums), None))
+        return pu, idx, sums
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if isinstance(stream, int):
+        return ctypes.c_void_p(stream)
+    return ctypes.c_void_p(stream.cuda_stream)

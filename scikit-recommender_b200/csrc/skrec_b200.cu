@@ -1,0 +1,618 @@
+// skrec_b200.cu -- C ABI (include/skrec_b200.h) over the sm_100a kernels.
+//
+// Host side of the hot path: context, CSR normalisation + upload (the device form of
+// RankingEvaluator.set_train_data / set_test_data, evaluator.py:140-145), workspace, kernel
+// selection and launch.  No torch types, no CPU compute fallback: every entry point either
+// launches CUDA kernels or fails with an error code.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/skrec_b200.h"
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "k_fused_simt.cuh"
+#include "k_fused_tc.cuh"
+#include "k_metrics.cuh"
+#include "k_scores.cuh"
+
+using namespace skr;
+
+namespace {
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+std::string g_create_error;
+
+}  // namespace
+
+struct skr_ctx {
+    int device = 0;
+    int n_sm = 148;
+    size_t max_smem = 0;
+    std::string err;
+    // train CSR (sorted, unique) + fused-path mask keys
+    bool has_train = false;
+    int64_t tr_rows = 0, tr_items = 0;
+    int64_t *d_tr_indptr = nullptr;
+    int32_t *d_tr_idx = nullptr;
+    uint32_t *d_mask_keys = nullptr;
+    int64_t *d_mask_tile_ptr = nullptr;
+    // test CSR (sorted, unique)
+    bool has_test = false;
+    int64_t te_rows = 0, te_items = 0;
+    int64_t *d_te_indptr = nullptr;
+    int32_t *d_te_idx = nullptr;
+    // 1/log2(i+2) table (metric.h:78,82), host glibc
+    double *d_disc = nullptr;
+    int disc_n = 0;
+    // workspace, grow-only
+    Buf keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx;
+    int *d_err = nullptr;
+    int64_t launches = 0;
+    const char *last_fused = "none";
+    int64_t opt_chunks = 0;
+    int64_t opt_stages = 0;
+    EncodeTiledFn encode = nullptr;
+};
+
+namespace {
+
+int fail(skr_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define SKR_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SKR_ERR_NOMEM : SKR_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                    \
+    } while (0)
+
+int ensure(skr_ctx *ctx, Buf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return SKR_OK;
+    if (b.p) SKR_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    SKR_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return SKR_OK;
+}
+
+void free_dev(void *p)
+{
+    if (p) cudaFree(p);
+}
+
+// rows -> sorted unique, validated
+int normalise_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indices, int64_t n_rows, int64_t n_items,
+                  std::vector<int64_t> &optr, std::vector<int32_t> &oidx)
+{
+    if (n_rows < 0 || n_items <= 0) return fail(ctx, SKR_ERR_INVALID, "csr: n_rows=%lld n_items=%lld", (long long)n_rows, (long long)n_items);
+    if (indptr[0] < 0) return fail(ctx, SKR_ERR_INVALID, "csr: indptr[0] < 0");
+    optr.assign((size_t)n_rows + 1, 0);
+    oidx.clear();
+    oidx.reserve((size_t)(indptr[n_rows] - indptr[0]));
+    std::vector<int32_t> tmp;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        if (indptr[r + 1] < indptr[r]) return fail(ctx, SKR_ERR_INVALID, "csr: indptr not monotone at row %lld", (long long)r);
+        tmp.assign(indices + indptr[r], indices + indptr[r + 1]);
+        bool sorted = true;
+        for (size_t i = 0; i < tmp.size(); ++i) {
+            if (tmp[i] < 0 || tmp[i] >= n_items)
+                return fail(ctx, SKR_ERR_INVALID, "csr: item %d out of [0,%lld) in row %lld", tmp[i], (long long)n_items, (long long)r);
+            if (i && tmp[i] <= tmp[i - 1]) sorted = false;
+        }
+        if (!sorted) {
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        }
+        oidx.insert(oidx.end(), tmp.begin(), tmp.end());
+        optr[(size_t)r + 1] = (int64_t)oidx.size();
+    }
+    return SKR_OK;
+}
+
+template <typename T>
+int upload(skr_ctx *ctx, T **dst, const std::vector<T> &src)
+{
+    free_dev(*dst);
+    *dst = nullptr;
+    size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    SKR_CUDA(ctx, cudaMalloc((void **)dst, bytes));
+    if (!src.empty()) SKR_CUDA(ctx, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SKR_OK;
+}
+
+int check_metrics(skr_ctx *ctx, const int32_t *metric_ids, int n_metrics, int top_k, MetricIds &m)
+{
+    if (!metric_ids || n_metrics < 1 || n_metrics > 8) return fail(ctx, SKR_ERR_INVALID, "n_metrics=%d not in [1,8]", n_metrics);
+    if (top_k < 1) return fail(ctx, SKR_ERR_INVALID, "top_k=%d", top_k);
+    m.n = n_metrics;
+    for (int i = 0; i < n_metrics; ++i) {
+        if (metric_ids[i] < 1 || metric_ids[i] > 5) return fail(ctx, SKR_ERR_INVALID, "metric id %d not in 1..5", metric_ids[i]);
+        m.id[i] = metric_ids[i];
+    }
+    for (int i = n_metrics; i < 8; ++i) m.id[i] = 0;
+    return SKR_OK;
+}
+
+int ensure_disc(skr_ctx *ctx, int K)
+{
+    if (K <= ctx->disc_n) return SKR_OK;
+    int n = std::max(K, 1024);
+    std::vector<double> h((size_t)n);
+    for (int i = 0; i < n; ++i) h[(size_t)i] = 1.0 / log2((double)(unsigned)(i + 2));  // metric.h:78
+    free_dev(ctx->d_disc);
+    ctx->d_disc = nullptr;
+    SKR_CUDA(ctx, cudaMalloc((void **)&ctx->d_disc, sizeof(double) * (size_t)n));
+    SKR_CUDA(ctx, cudaMemcpy(ctx->d_disc, h.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    ctx->disc_n = n;
+    return SKR_OK;
+}
+
+// keys [n_rows, K] sorted -> outputs.  Shared tail of every evaluation entry point.
+int run_metrics(skr_ctx *ctx, const u64 *keys, const int32_t *idx_in, int64_t n_rows, int64_t row0, const MetricIds &m,
+                int K, int32_t *topk_idx, float *topk_val, float *per_user, double *sums, cudaStream_t st)
+{
+    if (!ctx->has_test) return fail(ctx, SKR_ERR_STATE, "no test CSR set (skr_set_test_csr)");
+    if (row0 < 0 || row0 + n_rows > ctx->te_rows)
+        return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the test CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->te_rows);
+    int rc = ensure_disc(ctx, K);
+    if (rc) return rc;
+    const int MK = m.n * K;
+    float *pu = per_user;
+    if (!pu) {
+        rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float));
+        if (rc) return rc;
+        pu = (float *)ctx->per_user.p;
+    }
+    const size_t smem = (size_t)K4_WARPS * MK * sizeof(float) + (size_t)K4_WARPS * ((K + 31) / 32) * sizeof(uint32_t);
+    if (smem > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((n_rows + K4_WARPS - 1) / K4_WARPS);
+    k_metrics<<<grid, K4_WARPS * 32, smem, st>>>(keys, idx_in, K, n_rows, row0, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc, pu,
+                                                topk_idx, topk_val);
+    ctx->launches++;
+    if (sums) {
+        const int nblk = (int)std::min<int64_t>(n_rows, 2 * ctx->n_sm);
+        rc = ensure(ctx, ctx->partial, (size_t)nblk * MK * sizeof(double));
+        if (rc) return rc;
+        k_colsum_partial<<<nblk, 256, 0, st>>>(pu, n_rows, MK, (double *)ctx->partial.p);
+        k_colsum_final<<<(MK + 127) / 128, 128, 0, st>>>((const double *)ctx->partial.p, nblk, MK, sums);
+        ctx->launches += 2;
+    }
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
+int pick_chunks(const skr_ctx *ctx, int n_rt, int n_ct, int K)
+{
+    int smax = std::min(std::min(n_ct, 1024 / K), 16);
+    if (smax < 1) smax = 1;
+    if (ctx->opt_chunks > 0) return (int)std::min<int64_t>(ctx->opt_chunks, smax);
+    long best_cost = -1;
+    int best = 1;
+    for (int S = 1; S <= smax; ++S) {
+        long rounds = ((long)n_rt * S + ctx->n_sm - 1) / ctx->n_sm;
+        long tiles = (n_ct + S - 1) / S;
+        long cost = rounds * (tiles + 6);  // +6 tiles: CTA start-up, heap warm-up and merge cost per chunk
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = S; }
+    }
+    return best;
+}
+
+int make_tmap(skr_ctx *ctx, CUtensorMap *map, const float *base, int64_t n_rows, int d_pad)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d_pad * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SKR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SKR_OK;
+}
+
+template <int PER>
+void launch_merge(const u64 *part, int S, int K, int64_t n_rows, int64_t row0, const int64_t *tp, const int32_t *ti, u64 *out, cudaStream_t st)
+{
+    k_merge_partials<PER><<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(part, S, K, n_rows, row0, tp, ti, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int skr_abi_version(void) { return SKR_ABI_VERSION; }
+
+const char *skr_last_error(const skr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int skr_ctx_create(int device, skr_ctx **out)
+{
+    if (!out) return fail(nullptr, SKR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(nullptr, SKR_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, SKR_ERR_INVALID, "device %d not in [0,%d)", device, n);
+    skr_ctx *ctx = new (std::nothrow) skr_ctx();
+    if (!ctx) return fail(nullptr, SKR_ERR_NOMEM, "host allocation failed");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, SKR_ERR_CUDA, "device %d: %s", device, cudaGetErrorString(e));
+    }
+    if (prop.major != 10) {
+        delete ctx;
+        return fail(nullptr, SKR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->max_smem = prop.sharedMemPerBlockOptin;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        delete ctx;
+        return fail(nullptr, SKR_ERR_CUDA, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    }
+    ctx->encode = (EncodeTiledFn)fn;
+    if ((e = cudaMalloc((void **)&ctx->d_err, sizeof(int))) != cudaSuccess || (e = cudaMemset(ctx->d_err, 0, sizeof(int))) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, SKR_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return SKR_OK;
+}
+
+int skr_ctx_destroy(skr_ctx *ctx)
+{
+    if (!ctx) return SKR_OK;
+    cudaSetDevice(ctx->device);
+    free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr);
+    free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_err);
+    Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
+                   &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx};
+    for (Buf *b : bufs) free_dev(b->p);
+    delete ctx;
+    return SKR_OK;
+}
+
+int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return SKR_ERR_INVALID;
+    if (!strcmp(name, "chunks")) { ctx->opt_chunks = value; return SKR_OK; }
+    if (!strcmp(name, "stages")) { ctx->opt_stages = value; return SKR_OK; }
+    return fail(ctx, SKR_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int64_t skr_launch_count(const skr_ctx *ctx) { return ctx ? ctx->launches : 0; }
+const char *skr_last_fused_kernel(const skr_ctx *ctx) { return ctx ? ctx->last_fused : "none"; }
+
+int skr_set_train_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indices, int64_t n_rows, int64_t n_items)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!indptr) {
+        ctx->has_train = false;
+        return SKR_OK;
+    }
+    if (n_items >= (1ll << 25)) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_items=%lld >= 2^25 (mask key packing)", (long long)n_items);
+    std::vector<int64_t> optr;
+    std::vector<int32_t> oidx;
+    int rc = normalise_csr(ctx, indptr, indices, n_rows, n_items, optr, oidx);
+    if (rc) return rc;
+    // fused-path mask keys: per 128-row user tile, ascending (item << 7 | row_in_tile)
+    const int64_t n_rt = (n_rows + TM - 1) / TM;
+    std::vector<int64_t> tile_ptr((size_t)n_rt + 1, 0);
+    std::vector<uint32_t> keys(oidx.size());
+    for (int64_t rt = 0; rt < n_rt; ++rt) {
+        const int64_t r0 = rt * TM, r1 = std::min<int64_t>(r0 + TM, n_rows);
+        const int64_t b = optr[(size_t)r0], e = optr[(size_t)r1];
+        tile_ptr[(size_t)rt] = b;
+        for (int64_t r = r0; r < r1; ++r)
+            for (int64_t p = optr[(size_t)r]; p < optr[(size_t)r + 1]; ++p)
+                keys[(size_t)p] = ((uint32_t)oidx[(size_t)p] << 7) | (uint32_t)(r - r0);
+        std::sort(keys.begin() + b, keys.begin() + e);
+    }
+    tile_ptr[(size_t)n_rt] = (int64_t)oidx.size();
+    if ((rc = upload(ctx, &ctx->d_tr_indptr, optr))) return rc;
+    if ((rc = upload(ctx, &ctx->d_tr_idx, oidx))) return rc;
+    if ((rc = upload(ctx, &ctx->d_mask_keys, keys))) return rc;
+    if ((rc = upload(ctx, &ctx->d_mask_tile_ptr, tile_ptr))) return rc;
+    ctx->tr_rows = n_rows;
+    ctx->tr_items = n_items;
+    ctx->has_train = true;
+    return SKR_OK;
+}
+
+int skr_set_test_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indices, int64_t n_rows, int64_t n_items)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!indptr || n_rows <= 0) return fail(ctx, SKR_ERR_INVALID, "test CSR must not be empty (evaluator.py:144)");
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int64_t> optr;
+    std::vector<int32_t> oidx;
+    int rc = normalise_csr(ctx, indptr, indices, n_rows, n_items, optr, oidx);
+    if (rc) return rc;
+    if ((rc = upload(ctx, &ctx->d_te_indptr, optr))) return rc;
+    if ((rc = upload(ctx, &ctx->d_te_idx, oidx))) return rc;
+    ctx->te_rows = n_rows;
+    ctx->te_items = n_items;
+    ctx->has_test = true;
+    return SKR_OK;
+}
+
+int skr_metrics_from_topk(skr_ctx *ctx, const int32_t *topk_idx_dev, int64_t n_rows, int64_t row0, const int32_t *metric_ids,
+                          int n_metrics, int top_k, float *per_user_dev, double *sums_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!topk_idx_dev || n_rows <= 0) return fail(ctx, SKR_ERR_INVALID, "metrics_from_topk: empty input");
+    MetricIds m;
+    int rc = check_metrics(ctx, metric_ids, n_metrics, top_k, m);
+    if (rc) return rc;
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_metrics(ctx, nullptr, topk_idx_dev, n_rows, row0, m, top_k, nullptr, nullptr, per_user_dev, sums_dev, (cudaStream_t)stream);
+}
+
+int skr_colsum_f32_seq(skr_ctx *ctx, const float *per_user_dev, int64_t n_rows, int64_t n_cols, float *acc_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!per_user_dev || !acc_dev || n_rows < 0 || n_cols <= 0) return fail(ctx, SKR_ERR_INVALID, "colsum_f32_seq: bad arguments");
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_colsum_f32_seq<<<(unsigned)((n_cols + 63) / 64), 64, 0, (cudaStream_t)stream>>>(per_user_dev, n_rows, (int)n_cols, acc_dev);
+    ctx->launches++;
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
+int skr_eval_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64_t n_items, int64_t ld, int64_t row0,
+                    const int32_t *metric_ids, int n_metrics, int top_k, int32_t *topk_idx_dev, float *topk_val_dev,
+                    float *per_user_dev, double *sums_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    MetricIds m;
+    int rc = check_metrics(ctx, metric_ids, n_metrics, top_k, m);
+    if (rc) return rc;
+    if (!scores_dev || n_rows <= 0) return fail(ctx, SKR_ERR_INVALID, "eval_scores: empty input");
+    if (top_k > K2_MAX_K) return fail(ctx, SKR_ERR_UNSUPPORTED, "top_k=%d > %d", top_k, K2_MAX_K);
+    if (n_items < top_k) return fail(ctx, SKR_ERR_INVALID, "n_items=%lld < top_k=%d (evaluate.h:45 would read out of bounds)", (long long)n_items, top_k);
+    if (n_items > 0x7fffffffll - K2_CHUNK) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_items=%lld too large", (long long)n_items);
+    if (ld < n_items) return fail(ctx, SKR_ERR_INVALID, "ld=%lld < n_items=%lld", (long long)ld, (long long)n_items);
+    if (ctx->has_train && (row0 < 0 || row0 + n_rows > ctx->tr_rows))
+        return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the train CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->tr_rows);
+    if (ctx->has_train && ctx->tr_items > n_items) return fail(ctx, SKR_ERR_INVALID, "train CSR has %lld items, scores only %lld", (long long)ctx->tr_items, (long long)n_items);
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = ensure(ctx, ctx->keys, (size_t)n_rows * top_k * sizeof(u64));
+    if (rc) return rc;
+    k_topk_scores<<<(unsigned)n_rows, K2_THREADS, 0, st>>>(scores_dev, ld, (int)n_items, row0, ctx->has_train ? ctx->d_tr_indptr : nullptr,
+                                                          ctx->has_train ? ctx->d_tr_idx : nullptr, top_k, (u64 *)ctx->keys.p);
+    ctx->launches++;
+    SKR_CUDA(ctx, cudaGetLastError());
+    return run_metrics(ctx, (const u64 *)ctx->keys.p, nullptr, n_rows, row0, m, top_k, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
+}
+
+int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
+                   int64_t n_items, int64_t ld_i, int d, const float *bias_dev, int64_t row0, const int32_t *metric_ids,
+                   int n_metrics, int top_k, int precision, int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev,
+                   double *sums_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    MetricIds m;
+    int rc = check_metrics(ctx, metric_ids, n_metrics, top_k, m);
+    if (rc) return rc;
+    if (!user_vecs_dev || !item_vecs_dev || n_rows <= 0 || d <= 0) return fail(ctx, SKR_ERR_INVALID, "eval_fused: empty input");
+    if (ld_u < d || ld_i < d) return fail(ctx, SKR_ERR_INVALID, "ld_u=%lld / ld_i=%lld < d=%d", (long long)ld_u, (long long)ld_i, d);
+    if (n_items < top_k) return fail(ctx, SKR_ERR_INVALID, "n_items=%lld < top_k=%d (evaluate.h:45 would read out of bounds)", (long long)n_items, top_k);
+    if (n_items >= (1ll << 25)) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_items=%lld >= 2^25", (long long)n_items);
+    if (top_k > 128) return fail(ctx, SKR_ERR_UNSUPPORTED, "fused path supports top_k <= 128 (got %d)", top_k);
+    if (row0 % TM != 0) return fail(ctx, SKR_ERR_INVALID, "row0=%lld must be a multiple of %d", (long long)row0, TM);
+    if (ctx->has_train && (row0 < 0 || row0 + n_rows > ctx->tr_rows))
+        return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the train CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->tr_rows);
+    if (ctx->has_train && ctx->tr_items > n_items) return fail(ctx, SKR_ERR_INVALID, "train CSR has %lld items, item table only %lld", (long long)ctx->tr_items, (long long)n_items);
+    if (precision < SKR_PREC_AUTO || precision > SKR_PREC_1XTF32) return fail(ctx, SKR_ERR_INVALID, "precision=%d", precision);
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = top_k;
+
+    // ---- kernel choice ----
+    const int nkb = (d + TC_KB - 1) / TC_KB;
+    int stages = 0;
+    for (int s = TC_MAX_STAGES; s >= 2; --s)
+        if (tc_smem_bytes(K, s) <= ctx->max_smem) { stages = s; break; }
+    if (ctx->opt_stages >= 2 && ctx->opt_stages <= stages) stages = (int)ctx->opt_stages;
+    const bool tc_ok = (nkb <= 4) && (stages >= 2);
+    bool use_tc = (precision != SKR_PREC_FP32) && tc_ok;
+    if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32))
+        return fail(ctx, SKR_ERR_UNSUPPORTED, "tcgen05 path needs d <= 128 and shared memory for K=%d heaps (d=%d)", K, d);
+    if (!use_tc) {
+        if ((d & 3) || (ld_u & 3) || (ld_i & 3) || ((uintptr_t)user_vecs_dev & 15) || ((uintptr_t)item_vecs_dev & 15))
+            return fail(ctx, SKR_ERR_UNSUPPORTED, "FP32 path needs d, ld_u, ld_i multiples of 4 and 16-byte aligned tables");
+        if (simt_smem_bytes(K) > ctx->max_smem) return fail(ctx, SKR_ERR_UNSUPPORTED, "top_k=%d does not fit shared memory", K);
+    }
+
+    FusedParams P;
+    P.n_rows = n_rows;
+    P.row0 = row0;
+    P.n_items = (int)n_items;
+    P.d = d;
+    P.K = K;
+    P.n_ct = (int)((n_items + TN - 1) / TN);
+    P.n_rt = (int)((n_rows + TM - 1) / TM);
+    P.S = pick_chunks(ctx, P.n_rt, P.n_ct, K);
+    P.tiles_per_chunk = (P.n_ct + P.S - 1) / P.S;
+    P.S = (P.n_ct + P.tiles_per_chunk - 1) / P.tiles_per_chunk;  // drop empty chunks
+    P.mask_keys = ctx->has_train ? ctx->d_mask_keys : nullptr;
+    P.mask_tile_ptr = ctx->has_train ? ctx->d_mask_tile_ptr : nullptr;
+
+    if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(ctx, ctx->part, (size_t)n_rows * P.S * K * sizeof(u64)))) return rc;
+    if ((rc = ensure(ctx, ctx->keys, (size_t)n_rows * K * sizeof(u64)))) return rc;
+    P.thr_g = (uint32_t *)ctx->thr.p;
+    P.part = (u64 *)ctx->part.p;
+    SKR_CUDA(ctx, cudaMemsetAsync(P.thr_g, 0, (size_t)n_rows * sizeof(uint32_t), st));
+    P.bias = nullptr;
+    if (bias_dev) {
+        const int n_pad = P.n_ct * TN;
+        if ((rc = ensure(ctx, ctx->bias, (size_t)n_pad * sizeof(float)))) return rc;
+        k_pad_bias<<<(n_pad + 255) / 256, 256, 0, st>>>(bias_dev, (int)n_items, n_pad, (float *)ctx->bias.p);
+        ctx->launches++;
+        P.bias = (const float *)ctx->bias.p;
+    }
+    const unsigned grid = (unsigned)(P.n_rt * P.S);
+
+    if (use_tc) {
+        const int d_pad = nkb * TC_KB;
+        const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
+        if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;
+        if ((rc = ensure(ctx, ctx->blo, tbytes))) return rc;
+        const int64_t n_el = n_items * d_pad;
+        k_split_tf32<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p, (float *)ctx->blo.p);
+        ctx->launches++;
+        CUtensorMap mhi, mlo;
+        if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
+        if ((rc = make_tmap(ctx, &mlo, (const float *)ctx->blo.p, n_items, d_pad))) return rc;
+        TcArgs A;
+        A.U = user_vecs_dev;
+        A.ld_u = ld_u;
+        A.nkb = nkb;
+        A.stages = stages;
+        A.passes = (precision == SKR_PREC_1XTF32) ? 1 : 3;
+        A.err_flag = ctx->d_err;
+        const size_t smem = tc_smem_bytes(K, stages);
+        SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fused_tc<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
+        ctx->launches++;
+        ctx->last_fused = (A.passes == 3) ? "tcgen05_3xtf32" : "tcgen05_1xtf32";
+    } else {
+        const size_t smem = simt_smem_bytes(K);
+        SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fused_simt<<<grid, SIMT_THREADS, smem, st>>>(user_vecs_dev, ld_u, item_vecs_dev, ld_i, P);
+        ctx->launches++;
+        ctx->last_fused = "simt_fp32";
+    }
+    SKR_CUDA(ctx, cudaGetLastError());
+
+    // ---- merge the S partial lists per row ----
+    const int n = P.S * K;
+    const int64_t *tp = ctx->has_train ? ctx->d_tr_indptr : nullptr;
+    const int32_t *ti = ctx->has_train ? ctx->d_tr_idx : nullptr;
+    u64 *keys = (u64 *)ctx->keys.p;
+    if (n <= 64) launch_merge<2>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+    else if (n <= 128) launch_merge<4>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+    else if (n <= 256) launch_merge<8>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+    else if (n <= 512) launch_merge<16>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+    else launch_merge<32>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+    ctx->launches++;
+    SKR_CUDA(ctx, cudaGetLastError());
+    return run_metrics(ctx, keys, nullptr, n_rows, row0, m, K, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
+}
+
+// ---- host-buffer variants: the copies are part of the call --------------------------------------
+static int finish_host(skr_ctx *ctx, int64_t n_rows, int MK, int K, int32_t *topk_idx_host, float *per_user_host, double *sums_host,
+                       const int32_t *d_idx, const float *d_pu, const double *d_sums, cudaStream_t st)
+{
+    std::vector<double> tmp((size_t)MK);
+    if (topk_idx_host) SKR_CUDA(ctx, cudaMemcpyAsync(topk_idx_host, d_idx, (size_t)n_rows * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (per_user_host) SKR_CUDA(ctx, cudaMemcpyAsync(per_user_host, d_pu, (size_t)n_rows * MK * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (sums_host) SKR_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_sums, (size_t)MK * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SKR_CUDA(ctx, cudaStreamSynchronize(st));
+    if (sums_host) for (int i = 0; i < MK; ++i) sums_host[i] += tmp[(size_t)i];
+    int flag = 0;
+    SKR_CUDA(ctx, cudaMemcpy(&flag, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return fail(ctx, SKR_ERR_CUDA, "kernel watchdog tripped (code %d)", flag);
+    return SKR_OK;
+}
+
+int skr_eval_scores_host(skr_ctx *ctx, const float *scores_host, int64_t n_rows, int64_t n_items, int64_t ld, int64_t row0,
+                         const int32_t *metric_ids, int n_metrics, int top_k, int32_t *topk_idx_host, float *per_user_host,
+                         double *sums_host, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!scores_host || n_rows <= 0 || n_items <= 0 || ld < n_items) return fail(ctx, SKR_ERR_INVALID, "eval_scores_host: bad arguments");
+    if (n_metrics < 1 || n_metrics > 8 || top_k < 1) return fail(ctx, SKR_ERR_INVALID, "eval_scores_host: bad metric list / top_k");
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int MK = n_metrics * top_k;
+    int rc;
+    if ((rc = ensure(ctx, ctx->stage_a, (size_t)n_rows * n_items * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->sums, (size_t)MK * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->out_idx, (size_t)n_rows * top_k * sizeof(int32_t)))) return rc;
+    SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_a.p, (size_t)n_items * sizeof(float), scores_host, (size_t)ld * sizeof(float),
+                                    (size_t)n_items * sizeof(float), (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    SKR_CUDA(ctx, cudaMemsetAsync(ctx->sums.p, 0, (size_t)MK * sizeof(double), st));
+    rc = skr_eval_scores(ctx, (const float *)ctx->stage_a.p, n_rows, n_items, n_items, row0, metric_ids, n_metrics, top_k,
+                         topk_idx_host ? (int32_t *)ctx->out_idx.p : nullptr, nullptr, (float *)ctx->per_user.p, (double *)ctx->sums.p, stream);
+    if (rc) return rc;
+    return finish_host(ctx, n_rows, MK, top_k, topk_idx_host, per_user_host, sums_host, (const int32_t *)ctx->out_idx.p,
+                       (const float *)ctx->per_user.p, (const double *)ctx->sums.p, st);
+}
+
+int skr_eval_fused_host(skr_ctx *ctx, const float *user_vecs_host, int64_t n_rows, int64_t ld_u, const float *item_vecs_host,
+                        int64_t n_items, int64_t ld_i, int d, const float *bias_host, int64_t row0, const int32_t *metric_ids,
+                        int n_metrics, int top_k, int precision, int32_t *topk_idx_host, float *per_user_host, double *sums_host,
+                        void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!user_vecs_host || !item_vecs_host || n_rows <= 0 || n_items <= 0 || d <= 0 || ld_u < d || ld_i < d)
+        return fail(ctx, SKR_ERR_INVALID, "eval_fused_host: bad arguments");
+    if (n_metrics < 1 || n_metrics > 8 || top_k < 1) return fail(ctx, SKR_ERR_INVALID, "eval_fused_host: bad metric list / top_k");
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int MK = n_metrics * top_k;
+    const int64_t dp = (d + 3) & ~3;  // device copies are packed with a 16-byte aligned row pitch
+    int rc;
+    if ((rc = ensure(ctx, ctx->stage_a, (size_t)n_rows * dp * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->stage_b, (size_t)n_items * dp * sizeof(float)))) return rc;
+    if (bias_host && (rc = ensure(ctx, ctx->stage_c, (size_t)n_items * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->sums, (size_t)MK * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->out_idx, (size_t)n_rows * top_k * sizeof(int32_t)))) return rc;
+    if (dp != d) {
+        SKR_CUDA(ctx, cudaMemsetAsync(ctx->stage_a.p, 0, (size_t)n_rows * dp * sizeof(float), st));
+        SKR_CUDA(ctx, cudaMemsetAsync(ctx->stage_b.p, 0, (size_t)n_items * dp * sizeof(float), st));
+    }
+    SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_a.p, (size_t)dp * sizeof(float), user_vecs_host, (size_t)ld_u * sizeof(float),
+                                    (size_t)d * sizeof(float), (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_b.p, (size_t)dp * sizeof(float), item_vecs_host, (size_t)ld_i * sizeof(float),
+                                    (size_t)d * sizeof(float), (size_t)n_items, cudaMemcpyHostToDevice, st));
+    if (bias_host) SKR_CUDA(ctx, cudaMemcpyAsync(ctx->stage_c.p, bias_host, (size_t)n_items * sizeof(float), cudaMemcpyHostToDevice, st));
+    SKR_CUDA(ctx, cudaMemsetAsync(ctx->sums.p, 0, (size_t)MK * sizeof(double), st));
+    rc = skr_eval_fused(ctx, (const float *)ctx->stage_a.p, n_rows, dp, (const float *)ctx->stage_b.p, n_items, dp, (int)dp,
+                        bias_host ? (const float *)ctx->stage_c.p : nullptr, row0, metric_ids, n_metrics, top_k, precision,
+                        topk_idx_host ? (int32_t *)ctx->out_idx.p : nullptr, nullptr, (float *)ctx->per_user.p, (double *)ctx->sums.p, stream);
+    if (rc) return rc;
+    return finish_host(ctx, n_rows, MK, top_k, topk_idx_host, per_user_host, sums_host, (const int32_t *)ctx->out_idx.p,
+                       (const float *)ctx->per_user.p, (const double *)ctx->sums.p, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,273 @@
+"""Host-side mirror of scikit-recommender's evaluation API over the B200 kernels.
+
+Drop-in for `skrec/utils/py/evaluator.py` of the reference: same class names, constructor
+signature and defaults (evaluator.py:82-86), public attributes (`metrics`, `metrics_num`,
+`max_top`, `top_show`, `num_thread`, `batch_size`, `user_pos_train`, `user_pos_test`; read
+directly by bert4rec_utils.py:31-48), exceptions (evaluator.py:118,121,144,180,193) and result
+strings (evaluator.py:25-43,151-161).  `evaluate()` (evaluator.py:163-214) keeps its contract --
+users = keys of the test dict (or the filtered `test_users`), train items masked, top-K,
+Precision/Recall/MAP/NDCG/MRR@1..max_top averaged over users, columns `top_show` reported -- but
+its body runs on the GPU:
+
+  * fused path: a model that offers `eval_embeddings(users) -> (user_vecs[B,d], item_vecs[I,d],
+    bias[I] | None)` (the operands of its own `predict`: BPRMF.py:84-88, LightGCN.py:102-107,
+    MultVAE.py:138-141, SelfCF.py:235-241) is scored tile by tile on tensor cores; the B x I score
+    matrix is never materialised.
+  * score-matrix path: any other model is asked for `predict(batch_users)` exactly like the
+    reference (evaluator.py:192); the returned block is uploaded and masked/ranked on device.
+
+New arguments are keyword-only with defaults, so reference call sites (base.py:25-29) work
+unchanged.  There is no CPU fallback.
+"""
+__all__ = ["MetricReport", "RankingEvaluator", "EarlyStopping"]
+
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .report import EarlyStopping, MetricReport, colour_join
+
+_metric2id = {"Precision": 1, "Recall": 2, "MAP": 3, "NDCG": 4, "MRR": 5}
+_id2metric = {value: key for key, value in _metric2id.items()}
+
+
+def _dict_to_csr(users, d):
+    """{user: int array} restricted to `users` (in order) -> (indptr int64, indices int32)."""
+    counts = np.fromiter((len(d[u]) if u in d else 0 for u in users), dtype=np.int64, count=len(users))
+    indptr = np.zeros(len(users) + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    if indptr[-1] == 0:
+        return indptr, np.zeros(0, np.int32)
+    indices = np.concatenate([np.asarray(d[u], dtype=np.int32).ravel() for u in users if u in d and len(d[u]) > 0])
+    return indptr, np.ascontiguousarray(indices, dtype=np.int32)
+
+
+class _Plan(object):
+    """Device state for one evaluated-user list: native context + CSRs of exactly those rows."""
+
+    def __init__(self, users, n_items, train, test, device):
+        from . import _native
+        self.users = users
+        self.n_items = n_items
+        self.ctx = _native.Context(device)
+        tp, ti = _dict_to_csr(users, test)
+        self.ctx.set_test_csr(tp, ti, n_items)
+        if train:
+            rp, ri = _dict_to_csr(users, train)
+            self.ctx.set_train_csr(rp, ri, n_items)
+        else:
+            self.ctx.set_train_csr(None, None, n_items)
+
+
+class RankingEvaluator(object):
+    """Evaluator for item ranking task (reference evaluator.py:61-214), GPU-resident.
+
+    Args (reference): user_train_dict, user_test_dict, metric, top_k, batch_size, num_thread.
+        `num_thread` is accepted and stored (bert4rec_utils.py:79 reads it) but unused: the CUDA
+        grid replaces the thread pool.  `batch_size` is the user batch of the `predict` path.
+    Keyword-only additions:
+        device: CUDA device index (default: current torch device).
+        precision: "auto" | "3xtf32" | "fp32" | "1xtf32" -- arithmetic of the fused scoring.
+        mean: "f64" (float64 sums, rounded once to float32) or "numpy_f32" (the reference's
+            float32 row-order accumulation of np.mean, evaluator.py:208, bit for bit;
+            single-process only).
+        shard_users: with torch.distributed initialised, each rank evaluates a contiguous slice
+            of the users and the metric sums are all-reduced (default True).
+        process_group: the group to reduce over (default: WORLD).
+    """
+
+    def __init__(self, user_train_dict: Optional[Dict[int, np.ndarray]],
+                 user_test_dict: Dict[int, np.ndarray],
+                 metric: Union[None, str, Tuple[str], List[str]] = None,
+                 top_k: Union[int, List[int], Tuple[int]] = 50,
+                 batch_size: int = 256, num_thread: int = 8, *,
+                 device: Optional[int] = None, precision: str = "auto", mean: str = "f64",
+                 shard_users: bool = True, process_group=None):
+        super(RankingEvaluator, self).__init__()
+        if metric is None:
+            metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
+        elif isinstance(metric, str):
+            metric = [metric]
+        elif isinstance(metric, (tuple, list)):
+            metric = list(metric)
+        else:
+            raise TypeError("The type of 'metric' (%s) is invalid!" % metric.__class__.__name__)
+
+        for m in metric:
+            assert m in _metric2id, f"'{metric}' is not in ('Precision', 'Recall', 'MAP', 'NDCG', 'MRR')."
+
+        self.user_pos_train = dict()
+        self.user_pos_test = dict()
+        self._plans = OrderedDict()
+        self.set_train_data(user_train_dict)
+        self.set_test_data(user_test_dict)
+
+        self.metrics_num = len(metric)
+        self.metrics = [_metric2id[m] for m in metric]
+        self.num_thread = num_thread
+        self.batch_size = batch_size
+
+        if isinstance(top_k, int):
+            self.max_top = top_k
+            self.top_show = np.arange(top_k) + 1
+        else:
+            self.max_top = max(top_k)
+            self.top_show = np.sort(top_k)
+
+        assert precision in ("auto", "3xtf32", "fp32", "1xtf32"), "precision must be auto|3xtf32|fp32|1xtf32"
+        assert mean in ("f64", "numpy_f32"), "mean must be f64|numpy_f32"
+        self.device = device
+        self.precision = precision
+        self.mean = mean
+        self.shard_users = shard_users
+        self.process_group = process_group
+        self.last_stats = {}
+
+    def set_train_data(self, user_train_dict: Optional[Dict[int, np.ndarray]] = None):
+        self.user_pos_train = user_train_dict if user_train_dict is not None else dict()
+        self._plans = OrderedDict()
+
+    def set_test_data(self, user_test_dict: Dict[int, np.ndarray]):
+        assert len(user_test_dict) > 0, "'user_test_dict' can be empty."
+        self.user_pos_test = user_test_dict
+        self._plans = OrderedDict()
+
+    @property
+    def metrics_list(self) -> List[str]:
+        return [f"{_id2metric[mid]}@{str(k)}" for mid in self.metrics for k in self.top_show]
+
+    @property
+    def metrics_str(self) -> str:
+        """All metric names, coloured and tab-joined (reference evaluator.py:151-161)."""
+        return colour_join(self.metrics_list)
+
+    # ------------------------------------------------------------------------------------------
+    def _device_index(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("RankingEvaluator needs a CUDA device (sm_100a); there is no CPU fallback")
+        return torch.cuda.current_device() if self.device is None else int(self.device)
+
+    def _plan(self, users, n_items, key):
+        plan = self._plans.get(key)
+        if plan is not None and plan.n_items == n_items:
+            self._plans.move_to_end(key)
+            return plan
+        plan = _Plan(users, n_items, self.user_pos_train, self.user_pos_test, self._device_index())
+        self._plans[key] = plan
+        while len(self._plans) > 6:
+            self._plans.popitem(last=False)
+        return plan
+
+    def _shard(self, n):
+        """(rank, world, lo, hi): this rank's contiguous slice of n evaluated users."""
+        from . import dist
+        if not self.shard_users:
+            return 0, 1, 0, n
+        rank, world = dist.rank_world(self.process_group)
+        lo, hi = dist.shard_range(n, rank, world)
+        return rank, world, lo, hi
+
+    def evaluate(self, model, test_users: Optional[Iterable[int]] = None) -> MetricReport:
+        """Evaluate `model` (reference evaluator.py:163-214).
+
+        `model` must have `predict(users) -> float32 ndarray [B, num_items]`; if it also has
+        `eval_embeddings(users)` the fused path is used.
+        """
+        import torch
+        from . import dist
+
+        assert hasattr(model, "predict") or hasattr(model, "eval_embeddings"), "the model must have attribute 'predict'."
+        if test_users is not None:
+            test_users = [u for u in test_users if u in self.user_pos_test]
+            key_all = ("subset", hash(tuple(test_users)), len(test_users))
+        else:
+            test_users = list(self.user_pos_test.keys())
+            key_all = ("all",)
+        assert isinstance(test_users, Iterable), "'test_user' must be iterable."
+
+        rank, world, lo, hi = self._shard(len(test_users))
+        users = test_users[lo:hi] if world > 1 else test_users
+        key = key_all + (rank, world)
+        dev = torch.device("cuda", self._device_index())
+        K, M = self.max_top, self.metrics_num
+        MK = M * K
+        sums = torch.zeros(MK + 1, dtype=torch.float64, device=dev)  # [column sums | user count]
+        per_user = None
+        path = "none"
+
+        if len(users) > 0:
+            with torch.cuda.device(dev):
+                if self.mean == "numpy_f32":
+                    per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev)
+                if hasattr(model, "eval_embeddings"):
+                    path = self._evaluate_fused(model, users, key, dev, sums, per_user)
+                else:
+                    path = self._evaluate_predict(model, users, key, dev, sums, per_user)
+            sums[MK] = float(len(users))
+
+        if self.mean == "numpy_f32":
+            if world > 1:
+                raise RuntimeError("mean='numpy_f32' reproduces a sequential sum and is single-process only")
+            plan = self._plans[key]
+            acc = torch.zeros(MK, dtype=torch.float32, device=dev)
+            plan.ctx.colsum_f32_seq(per_user, acc)
+            final_results = (acc / torch.tensor(float(len(users)), dtype=torch.float32, device=dev)).cpu().numpy()
+        else:
+            if world > 1:
+                dist.allreduce_sums(sums, self.process_group)
+            host = sums.cpu().numpy()
+            final_results = dist.finalize_means(host[:MK], host[MK])
+
+        self.last_stats = {"path": path, "users": len(users), "world": world}
+        final_results = np.reshape(final_results, [self.metrics_num, self.max_top])
+        final_results = final_results[:, self.top_show - 1]
+        final_results = np.reshape(final_results, [-1])
+        return MetricReport(self.metrics_list, final_results)
+
+    # ------------------------------------------------------------------------------------------
+    def _to_dev(self, x, dev):
+        import torch
+        if x is None:
+            return None
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        t = x.detach().to(device=dev, dtype=torch.float32)
+        if t.dim() == 2 and t.stride(1) != 1:
+            t = t.contiguous()
+        if t.dim() == 1:
+            t = t.contiguous()
+        return t
+
+    def _evaluate_fused(self, model, users, key, dev, sums, per_user):
+        user_vecs, item_vecs, bias = model.eval_embeddings(users)
+        uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
+        assert uv.dim() == 2 and iv.dim() == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
+        assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
+        plan = self._plan(users, int(iv.shape[0]), key)
+        MK = self.metrics_num * self.max_top
+        plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision,
+                            per_user=per_user, sums=sums[:MK])
+        return "fused:" + plan.ctx.last_fused_kernel
+
+    def _evaluate_predict(self, model, users, key, dev, sums, per_user):
+        import torch
+        plan = None
+        MK = self.metrics_num * self.max_top
+        for b0 in range(0, len(users), self.batch_size):  # sequential, last batch short (batch_iterator.py:98-106)
+            batch_users = users[b0:b0 + self.batch_size]
+            ranking_score = model.predict(batch_users)  # (B,N)
+            if isinstance(ranking_score, torch.Tensor):
+                s = ranking_score.detach().to(device=dev, dtype=torch.float32)
+            else:
+                assert isinstance(ranking_score, np.ndarray), "'ranking_score' must be an np.ndarray"
+                s = torch.from_numpy(np.ascontiguousarray(ranking_score, dtype=np.float32)).to(dev)
+            if s.stride(1) != 1:
+                s = s.contiguous()
+            if plan is None:
+                plan = self._plan(users, int(s.shape[1]), key)
+            plan.ctx.eval_scores(s, b0, self.metrics, self.max_top,
+                                 per_user=None if per_user is None else per_user[b0:b0 + len(batch_users)],
+                                 sums=sums[:MK])
+        return "scores"
