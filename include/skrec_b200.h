@@ -130,7 +130,13 @@ int64_t skr_launch_count(const skr_ctx *ctx);
  * "tcgen05_1xtf32" or "simt_fp32". */
 const char *skr_last_fused_kernel(const skr_ctx *ctx);
 
-/* Tunables (0 = library default): item-range chunks per user tile of the fused path. */
+/* Device time, in milliseconds, of the scoring kernel launched by a recent skr_eval_fused* call on
+ * ctx: back = 0 is the last call, 1 the one before, ... (CUDA events recorded on the call's stream
+ * around that one launch; waits for it).  The ring holds skr_set_option("event_ring", n) calls. */
+int skr_fused_kernel_ms(skr_ctx *ctx, int back, float *ms_out);
+
+/* Tunables: "chunks" (item-range chunks per user tile of the fused path, 0 = automatic), "stages"
+ * (TMA ring depth, 0 = automatic), "event_ring" (see skr_fused_kernel_ms). */
 int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -66,6 +66,10 @@ def _cython_build(src, modname, dst_dir, tmp, cplus):
     cmd = [sys.executable, "-m", "cython", "-3", src, "-o", gen]
     if cplus:
         cmd.insert(4, "--cplus")
+    else:
+        # plain .py modules: keep Python semantics (annotations stay hints, e.g. an OrderedDict is a
+        # fine `Dict`), so the compiled evaluator behaves exactly like the interpreted one
+        cmd[4:4] = ["-X", "annotation_typing=False"]
     _run(cmd)
     out = os.path.join(dst_dir, modname + _ext_suffix())
     cc = ["g++", "-std=c++11"] if cplus else ["gcc"]

@@ -70,6 +70,8 @@ struct skr_ctx {
     int64_t opt_chunks = 0;
     int64_t opt_stages = 0;
     EncodeTiledFn encode = nullptr;
+    std::vector<cudaEvent_t> ev0, ev1;  // ring of event pairs around the scoring kernel
+    int64_t ev_calls = 0;
 };
 
 namespace {
@@ -288,6 +290,12 @@ int skr_ctx_create(int device, skr_ctx **out)
         delete ctx;
         return fail(nullptr, SKR_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     }
+    ctx->ev0.resize(1);
+    ctx->ev1.resize(1);
+    if ((e = cudaEventCreate(&ctx->ev0[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1[0])) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, SKR_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    }
     *out = ctx;
     return SKR_OK;
 }
@@ -301,6 +309,8 @@ int skr_ctx_destroy(skr_ctx *ctx)
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx};
     for (Buf *b : bufs) free_dev(b->p);
+    for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
     delete ctx;
     return SKR_OK;
 }
@@ -310,7 +320,30 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!ctx || !name) return SKR_ERR_INVALID;
     if (!strcmp(name, "chunks")) { ctx->opt_chunks = value; return SKR_OK; }
     if (!strcmp(name, "stages")) { ctx->opt_stages = value; return SKR_OK; }
+    if (!strcmp(name, "event_ring")) {
+        if (value < 1 || value > 65536) return fail(ctx, SKR_ERR_INVALID, "event_ring=%lld not in [1,65536]", (long long)value);
+        cudaSetDevice(ctx->device);
+        while ((int64_t)ctx->ev0.size() < value) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return fail(ctx, SKR_ERR_CUDA, "cudaEventCreate failed");
+            ctx->ev0.push_back(a);
+            ctx->ev1.push_back(b);
+        }
+        ctx->ev_calls = 0;
+        return SKR_OK;
+    }
     return fail(ctx, SKR_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int skr_fused_kernel_ms(skr_ctx *ctx, int back, float *ms_out)
+{
+    if (!ctx || !ms_out) return SKR_ERR_INVALID;
+    const int64_t n = (int64_t)ctx->ev0.size();
+    if (back < 0 || back >= n || back >= ctx->ev_calls) return fail(ctx, SKR_ERR_STATE, "no timing for call -%d (ring %lld, calls %lld)", back, (long long)n, (long long)ctx->ev_calls);
+    const size_t i = (size_t)((ctx->ev_calls - 1 - back) % n);
+    SKR_CUDA(ctx, cudaEventSynchronize(ctx->ev1[i]));
+    SKR_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0[i], ctx->ev1[i]));
+    return SKR_OK;
 }
 
 int64_t skr_launch_count(const skr_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -509,16 +542,21 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         A.err_flag = ctx->d_err;
         const size_t smem = tc_smem_bytes(K, stages);
         SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[(size_t)(ctx->ev_calls % (int64_t)ctx->ev0.size())], st));
         k_fused_tc<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[(size_t)(ctx->ev_calls % (int64_t)ctx->ev1.size())], st));
         ctx->launches++;
         ctx->last_fused = (A.passes == 3) ? "tcgen05_3xtf32" : "tcgen05_1xtf32";
     } else {
         const size_t smem = simt_smem_bytes(K);
         SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[(size_t)(ctx->ev_calls % (int64_t)ctx->ev0.size())], st));
         k_fused_simt<<<grid, SIMT_THREADS, smem, st>>>(user_vecs_dev, ld_u, item_vecs_dev, ld_i, P);
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[(size_t)(ctx->ev_calls % (int64_t)ctx->ev1.size())], st));
         ctx->launches++;
         ctx->last_fused = "simt_fp32";
     }
+    ctx->ev_calls++;
     SKR_CUDA(ctx, cudaGetLastError());
 
     // ---- merge the S partial lists per row ----
