@@ -81,7 +81,7 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
     const int64_t my_row = row_base + tid;
     const bool owner = tid < TM;
     const bool my_valid = owner && my_row < P.n_rows;
-    if (owner) { scnt[tid] = 0; thr_row[tid] = NINF; }
+    if (owner) { scnt[tid] = 0; thr_row[tid] = my_valid ? NINF : -NINF; }  // rows beyond n_rows collect nothing
 
     // cursor into this user tile's mask keys
     int64_t mcur = 0, mend = 0;

@@ -1,0 +1,30 @@
+"""ncu target: a few launches of the fused scoring kernel on the c2 workload (development aid)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from skrec_b200 import _native, synth  # noqa: E402
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+cfgname = sys.argv[3] if len(sys.argv) > 3 else "c2"
+d = synth.make_config(cfgname, device="cuda")
+cfg = d["config"]
+ctx = _native.Context(0)
+ctx.set_train_csr(d["train_indptr"], d["train_indices"], d["items"])
+ctx.set_test_csr(d["test_indptr"], d["test_indices"], d["items"])
+ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"]).cuda()
+b = None if d["bias"] is None else torch.from_numpy(d["bias"]).cuda()
+ids = [synth.METRIC_IDS[m] for m in cfg["metric"]]
+K = max(cfg["top_k"])
+sums = torch.zeros(len(ids) * K, dtype=torch.float64, device="cuda")
+ms = []
+for _ in range(n):
+    sums.zero_()
+    ctx.eval_fused(ue, ie, b, 0, ids, K, precision=prec, sums=sums)
+    torch.cuda.synchronize()
+    ms.append(ctx.fused_kernel_ms(0))
+print("%s %s kernel ms:" % (cfgname, prec), ["%.3f" % m for m in ms], "NDCG@%d=%.6f" % (K, float(sums[-1]) / d["users"]))
