@@ -230,6 +230,8 @@ def run_ours(args):
     launches = ctx.launch_count - launches0 + args.steps * (3 if world == 1 else 4)  # + zero_, fill, (all-reduce) per step
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = [ctx.fused_kernel_ms(i) for i in range(args.steps)]
+    prepass_ms = [ctx.fused_prepass_ms(i) for i in range(args.steps)]
+    plan = ctx.fused_stats()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -299,6 +301,7 @@ def run_ours(args):
         traffic = json.load(open(tp)).get(ctx.last_fused_kernel)
     roofline = {"bound": "tensor", "kernel": ctx.last_fused_kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "prepass_kernel_ms": float(np.mean(prepass_ms)), "plan": plan,
                 "algorithmic_flops_per_launch": flops, "mma_passes": passes, "tensor_pipe_utilisation_est": passes * achieved / peak,
                 "peak_note": peak_note}
 

@@ -134,9 +134,16 @@ const char *skr_last_fused_kernel(const skr_ctx *ctx);
  * ctx: back = 0 is the last call, 1 the one before, ... (CUDA events recorded on the call's stream
  * around that one launch; waits for it).  The ring holds skr_set_option("event_ring", n) calls. */
 int skr_fused_kernel_ms(skr_ctx *ctx, int back, float *ms_out);
+/* Same for the sampled threshold pre-pass that precedes the main scoring kernel (0 for the FP32 path). */
+int skr_fused_prepass_ms(skr_ctx *ctx, int back, float *ms_out);
+/* Plan and outcome of the last tcgen05 skr_eval_fused* call: out[0..7) = sample tiles, sample stride,
+ * threshold rank r, sub-list capacity, item chunks, TMA stages, rows re-done by the exact kernel.
+ * Synchronises the device. */
+int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out);
 
 /* Tunables: "chunks" (item-range chunks per user tile of the fused path, 0 = automatic), "stages"
- * (TMA ring depth, 0 = automatic), "event_ring" (see skr_fused_kernel_ms). */
+ * (TMA ring depth, 0 = automatic), "sample_tiles" / "rank" (pre-pass size and threshold rank, 0 =
+ * automatic), "event_ring" (see skr_fused_kernel_ms). */
 int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -18,7 +18,7 @@ PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "1xtf32": 3}
 SYMBOLS = (
     "skr_abi_version", "skr_ctx_create", "skr_ctx_destroy", "skr_last_error", "skr_set_train_csr",
     "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
-    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms",
+    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats",
 )
 
 _lib = None
@@ -63,6 +63,8 @@ def lib():
     L.skr_last_fused_kernel.restype = ctypes.c_char_p
     L.skr_set_option.argtypes = [_vp, ctypes.c_char_p, _i64]
     L.skr_fused_kernel_ms.argtypes = [_vp, _int, ctypes.POINTER(ctypes.c_float)]
+    L.skr_fused_prepass_ms.argtypes = [_vp, _int, ctypes.POINTER(ctypes.c_float)]
+    L.skr_fused_stats.argtypes = [_vp, ctypes.POINTER(_i64), _int]
     for name in SYMBOLS:
         getattr(L, name)
     if L.skr_abi_version() != 1:
@@ -135,6 +137,16 @@ class Context(object):
         ms = ctypes.c_float(0.0)
         self._check(self._L.skr_fused_kernel_ms(self._h, int(back), ctypes.byref(ms)))
         return float(ms.value)
+
+    def fused_prepass_ms(self, back=0):
+        ms = ctypes.c_float(0.0)
+        self._check(self._L.skr_fused_prepass_ms(self._h, int(back), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def fused_stats(self):
+        out = (_i64 * 7)()
+        self._check(self._L.skr_fused_stats(self._h, out, 7))
+        return dict(zip(("sample_tiles", "stride", "rank", "cap", "chunks", "stages", "exact_rows"), [int(x) for x in out]))
 
     # -- device entry points (torch CUDA tensors) -----------------------------------------------
     def eval_scores(self, scores, row0, metric_ids, top_k, topk_idx=None, topk_val=None, per_user=None, sums=None,

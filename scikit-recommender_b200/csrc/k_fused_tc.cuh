@@ -1,4 +1,4 @@
-// k_fused_tc.cuh -- fused score + bias + train mask + running top-K on tcgen05 / TMEM (sm_100a).
+// k_fused_tc.cuh -- fused score + bias + train mask + candidate selection on tcgen05 / TMEM (sm_100a).
 //
 // scores = U_tile (128 users) x I_tile^T (128 items) are produced by tcgen05.mma kind::tf32 with
 // FP32 accumulation in TMEM and consumed straight out of TMEM by the epilogue warps: the U x I
@@ -10,16 +10,30 @@
 // tensor core's operand rounding mode does not matter.  (1xTF32 breaks the
 // 1e-5 metric contract, 3xTF32 does not.)
 //
-// Operands: A (users) lives in TMEM for the whole work item -- each epilogue thread loads its
-// user's row from global memory, splits it in registers and tcgen05.st's hi/lo into TMEM lanes
-// (TS-mode MMA; no shared memory for A).  B (items) is pre-split by k_split_tf32 into hi/lo
-// tables and streamed by TMA (SWIZZLE_128B, 128 rows x 32 floats per box) through an mbarrier
-// ring of k-block stages.
+// Selection (round-1 ncu finding: per-row heaps in shared memory made the epilogue, not the MMA,
+// the bottleneck by 20x).  The kernel now runs in two modes over the same pipeline:
+//   SAMPLE  - a strided ~f = 6/K fraction of the item tiles is scored once in 1xTF32; each row keeps
+//             the R largest 32-column group maxima (train items masked) in registers.  The r-th
+//             largest of them is a threshold T0 that, with overwhelming probability, has between K
+//             and a few K catalogue items above it.  It only steers work: results never depend on it.
+//   COLLECT - every item tile is scored in 3xTF32; a max tree over 32 scores and ONE compare against
+//             T0 rejects almost every 32-column group; survivors that are not train items are
+//             appended (rank key = ord(score) << 32 | ~item) to the row's candidate list in HBM.
+// k_select_cands then sorts each row's ~3-5 K candidates; a row whose list is short (< K) or
+// overflowed is re-done exactly by k_row_exact (k_scores.cuh).  No heaps, no thresholds to update,
+// no shared memory per row: K is limited only by the list capacity.
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one lane),
-// warp 2 train-mask bitmap builder, warp 3 idle, warps 4-7 epilogue (thread t <-> TMEM lane t
-// <-> user row t).  Accumulators and bitmaps are double buffered so the epilogue of tile n
-// overlaps the MMAs of tile n+1.
+// Operands: A (users) lives in TMEM for the whole work item -- each epilogue thread of the first
+// warpgroup loads its user's row from global memory, splits it in registers and tcgen05.st's hi/lo
+// into TMEM lanes (TS-mode MMA; no shared memory for A).  B (items) is pre-split by k_split_tf32
+// into hi/lo tables and streamed by TMA (SWIZZLE_128B, 128 rows x 32 floats per box) through an
+// mbarrier ring of k-block stages.
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one lane),
+// warp 2 train-mask bitmap builder, warp 3 idle, warps 4-7 epilogue of columns 0-63, warps 8-11
+// epilogue of columns 64-127 (thread <-> TMEM lane <-> user row; two warps per SM sub-partition so
+// the TMEM-load and compare latencies of one hide behind the other).  Accumulators and bitmaps are
+// double buffered so the epilogue of tile n overlaps the MMAs of tile n+1.
 //
 // TMEM columns: [0, 32*nkb) A_hi, [32*nkb, 64*nkb) A_lo, [256, 384) acc 0, [384, 512) acc 1.
 #pragma once
@@ -28,23 +42,23 @@
 
 namespace skr {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;
+constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_KB = 32;                             // floats per k-block (one 128-byte swizzle row)
 constexpr int TC_TILE_BYTES = TN * TC_KB * 4;         // 16 KB: one operand tile of one k-block
 constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // hi + lo
-constexpr int TC_CAP = 8;                             // staged survivors per row
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_ACC_COL = 256;                       // first accumulator column
+constexpr int TC_R = 32;                              // group maxima kept per row and warpgroup (SAMPLE)
 constexpr long long TC_TIMEOUT_CYCLES = 4000000000ll; // watchdog: ~2 s
 
-__host__ __device__ inline size_t tc_smem_bytes(int K, int stages)
+enum { TC_MODE_COLLECT = 0, TC_MODE_SAMPLE = 1 };
+
+__host__ __device__ inline size_t tc_smem_bytes(int stages)
 {
     return (size_t)1024                          // alignment slack
            + (size_t)stages * TC_STAGE_BYTES
-           + (size_t)K * TM * 8                  // heaps
-           + (size_t)TC_CAP * TM * 8             // staging
            + (size_t)2 * 4 * TM * 4              // two bitmaps
-           + (size_t)TM * 4                      // hcnt
            + 256;                                // barriers + tmem pointer
 }
 
@@ -76,17 +90,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 // Bounded wait: a pipeline bug must not hang the GPU box; it traps with a flag set instead.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err_flag, int code)
+__device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, int *err_flag, int code)
 {
-    if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 512; ++i)
+            if (mbar_try_wait(bar, parity)) return;
         if (clock64() - t0 > TC_TIMEOUT_CYCLES) {
             if (err_flag != nullptr) atomicExch(err_flag, code);
             __threadfence_system();
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err_flag, int code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, err_flag, code);
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
 {
@@ -168,8 +189,29 @@ struct TcArgs {
     int nkb;          // k-blocks of 32 (d padded)
     int stages;
     int passes;       // 3 = 3xTF32, 1 = single TF32 pass
+    int mode;         // TC_MODE_*
     int *err_flag;    // device int, set before a watchdog trap
+    // SAMPLE: item tiles 0, stride, 2*stride, ...; out: samp[row][2][TC_R] group maxima, descending
+    int stride;
+    int n_samp;
+    float *samp;
+    // COLLECT: threshold rank r (1-based) in the merged sample lists; candidate lists
+    int r;
+    int cap;                 // entries per (row, chunk, column half) sub-list
+    u64 *cand;               // [n_rows, S*2, cap]
+    uint32_t *cand_cnt;      // [n_rows, S*2] entries wanted (> cap means overflow)
 };
+
+// descending insertion of x into v[0..TC_R): branch-free compare-exchange chain
+__device__ __forceinline__ void sorted_insert(float (&v)[TC_R], float x)
+{
+#pragma unroll
+    for (int i = 0; i < TC_R; ++i) {
+        const float hi = fmaxf(v[i], x);
+        x = fminf(v[i], x);
+        v[i] = hi;
+    }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, TcArgs A, FusedParams P)
@@ -177,13 +219,10 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *b_tiles = smem;
-    u64 *heap = reinterpret_cast<u64 *>(smem + (size_t)A.stages * TC_STAGE_BYTES);
-    u64 *stage = heap + (size_t)P.K * TM;
-    uint32_t *bitmap = reinterpret_cast<uint32_t *>(stage + TC_CAP * TM);  // [2][4][TM]
-    int *hcnt = reinterpret_cast<int *>(bitmap + 2 * 4 * TM);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(hcnt + TM);
-    uint64_t *full = bars;                        // [TC_MAX_STAGES]
-    uint64_t *empty = bars + TC_MAX_STAGES;       // [TC_MAX_STAGES]
+    uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + (size_t)A.stages * TC_STAGE_BYTES);  // [2][4][TM]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bitmap + 2 * 4 * TM);
+    uint64_t *full = bars;                            // [TC_MAX_STAGES]
+    uint64_t *empty = bars + TC_MAX_STAGES;           // [TC_MAX_STAGES]
     uint64_t *tmem_full = bars + 2 * TC_MAX_STAGES;   // [2]
     uint64_t *tmem_empty = tmem_full + 2;             // [2]
     uint64_t *bm_full = tmem_empty + 2;               // [2]
@@ -193,8 +232,11 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = blockIdx.x / P.n_rt, rt = blockIdx.x % P.n_rt;
-    const int t0 = c * P.tiles_per_chunk;
-    const int t1 = min(t0 + P.tiles_per_chunk, P.n_ct);
+    const bool sample = (A.mode == TC_MODE_SAMPLE);
+    // tiles of this work item: COLLECT t0 + i, SAMPLE i * stride
+    const int t0 = sample ? 0 : c * P.tiles_per_chunk;
+    const int n_tiles = sample ? A.n_samp : (min(t0 + P.tiles_per_chunk, P.n_ct) - t0);
+    const int t_step = sample ? A.stride : 1;
     const int64_t row_base = (int64_t)rt * TM;
     const int nkb = A.nkb;
 
@@ -202,9 +244,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tmem_full + b, 1);
-            mbar_init(tmem_empty + b, TM);
+            mbar_init(tmem_empty + b, TC_EPI_THREADS);
             mbar_init(bm_full + b, 1);
-            mbar_init(bm_empty + b, TM);
+            mbar_init(bm_empty + b, TC_EPI_THREADS);
         }
         mbar_init(a_ready, TM);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -227,7 +269,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         if (lane == 0) {
             const uint32_t tx_bytes = (A.passes == 3) ? TC_STAGE_BYTES : TC_TILE_BYTES;
             int it = 0;
-            for (int t = t0; t < t1; ++t) {
+            for (int i = 0; i < n_tiles; ++i) {
+                const int t = t0 + i * t_step;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % A.stages;
                     const uint32_t ph = (uint32_t)((it / A.stages) & 1);
@@ -247,8 +290,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             const uint32_t a_hi0 = tmem_base;
             const uint32_t a_lo0 = tmem_base + (uint32_t)(nkb * TC_KB);
             int it = 0;
-            for (int t = t0; t < t1; ++t) {
-                const int i = t - t0, b = i & 1;
+            for (int i = 0; i < n_tiles; ++i) {
+                const int b = i & 1;
                 const uint32_t u = (uint32_t)((i >> 1) & 1);
                 mbar_wait(tmem_empty + b, u ^ 1u, A.err_flag, 3);
                 tc_fence_after();
@@ -289,21 +332,22 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             if (lane == 0) mcur = lower_bound_u32(P.mask_keys, __ldg(P.mask_tile_ptr + rt_abs), mend, ((uint32_t)(t0 * TN)) << 7);
             mcur = __shfl_sync(0xffffffffu, mcur, 0);
         }
-        for (int t = t0; t < t1; ++t) {
-            const int i = t - t0, b = i & 1;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int b = i & 1;
             const uint32_t u = (uint32_t)((i >> 1) & 1);
-            const int col0 = t * TN;
+            const int col0 = (t0 + i * t_step) * TN;
             mbar_wait(bm_empty + b, u ^ 1u, A.err_flag, 5);
             uint32_t *bm = bitmap + b * 4 * TM;
             for (int q = lane; q < 4 * TM; q += 32) bm[q] = oob_bits(col0, q / TM, P.n_items);
             __syncwarp();
             if (P.mask_keys != nullptr) {
+                const uint32_t lo = ((uint32_t)col0) << 7;
                 const uint32_t lim = ((uint32_t)(col0 + TN)) << 7;
-                for (;;) {
+                for (;;) {  // keys ascending: skip those before this tile (SAMPLE strides), set those inside
                     const int64_t p = mcur + lane;
                     const uint32_t key = (p < mend) ? __ldg(P.mask_keys + p) : 0xffffffffu;
                     const bool in = key < lim;
-                    if (in) {
+                    if (in && key >= lo) {
                         const int cc = (int)(key >> 7) - col0;
                         atomicOr(&bm[(cc >> 5) * TM + (int)(key & 127u)], 1u << (cc & 31));
                     }
@@ -316,26 +360,39 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             if (lane == 0) mbar_arrive(bm_full + b);
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread <-> user row ======================================================
-        const int r = tid - 128;  // TMEM lane
+        // ===== epilogue: thread <-> user row, warpgroup wg <-> columns [64 wg, 64 wg + 64) ==========
+        const int wg = (warp - 4) >> 2;
+        const int r = (tid - 128) & 127;  // TMEM lane
         const int64_t my_row = row_base + r;
         const bool my_valid = my_row < P.n_rows;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const float NINF = -__int_as_float(0x7f800000);
         const float PINF = __int_as_float(0x7f800000);
 
-        // A: my user's vector -> hi/lo TF32 -> TMEM
-        {
+        if (wg == 0) {  // A: my user's vector -> hi/lo TF32 -> TMEM
             const float *urow = A.U + (my_valid ? my_row : 0) * A.ld_u;
+            const bool vec = ((A.ld_u & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.U) & 15) == 0);
             for (int kb = 0; kb < nkb; ++kb) {
                 uint32_t hi[32], lo[32];
+                float x[32];
+                if (vec && my_valid && kb * TC_KB + 32 <= P.d) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 f = __ldg(reinterpret_cast<const float4 *>(urow + kb * TC_KB) + q);
+                        x[4 * q + 0] = f.x; x[4 * q + 1] = f.y; x[4 * q + 2] = f.z; x[4 * q + 3] = f.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int k = kb * TC_KB + q;
+                        x[q] = (my_valid && k < P.d) ? __ldg(urow + k) : 0.0f;
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
-                    const int k = kb * TC_KB + q;
-                    const float x = (my_valid && k < P.d) ? __ldg(urow + k) : 0.0f;
-                    const uint32_t h = to_tf32(x);
+                    const uint32_t h = to_tf32(x[q]);
                     hi[q] = h;
-                    lo[q] = to_tf32(x - __uint_as_float(h));
+                    lo[q] = to_tf32(x[q] - __uint_as_float(h));
                 }
                 tmem_st32(lane_addr + (uint32_t)(kb * TC_KB), hi);
                 if (A.passes == 3) tmem_st32(lane_addr + (uint32_t)(nkb * TC_KB + kb * TC_KB), lo);
@@ -345,88 +402,107 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             mbar_arrive(a_ready);
         }
 
-        u64 *my_heap = heap + r;
-        u64 *my_stage = stage + r;
-        int hn = 0, sn = 0;
-        float thr = my_valid ? NINF : PINF;  // rows beyond n_rows never collect anything
-        uint32_t published = 0;
-
-        auto drain = [&]() {
-            for (int q = 0; q < sn; ++q) heap_push(my_heap, hn, P.K, my_stage[q * TM]);
-            sn = 0;
-            if (hn == P.K) {
-                const float rs = key_score(my_heap[0]);
-                if (rs > thr) thr = rs;
+        // COLLECT: T0 = r-th largest of the row's two sampled lists (a 2-way merge of sorted lists)
+        float thr = PINF;  // rows beyond n_rows collect nothing
+        u64 *my_list = nullptr;
+        uint32_t cnt = 0;
+        float v[TC_R];  // SAMPLE: largest group maxima so far, descending
+#pragma unroll
+        for (int q = 0; q < TC_R; ++q) v[q] = NINF;
+        if (!sample && my_valid) {
+            const float *la = A.samp + my_row * (2 * TC_R), *lb = la + TC_R;
+            int ia = 0, ib = 0;
+            float t = NINF;
+            for (int q = 0; q < A.r; ++q) {
+                const float xa = (ia < TC_R) ? __ldg(la + ia) : NINF;
+                const float xb = (ib < TC_R) ? __ldg(lb + ib) : NINF;
+                if (xa >= xb) { t = xa; ++ia; } else { t = xb; ++ib; }
             }
-        };
+            thr = t;
+            my_list = A.cand + ((my_row * P.S + c) * 2 + wg) * (int64_t)A.cap;
+        }
 
-        for (int t = t0; t < t1; ++t) {
-            const int i = t - t0, b = i & 1;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int b = i & 1;
             const uint32_t u = (uint32_t)((i >> 1) & 1);
-            const int col0 = t * TN;
-            uint32_t g = 0;
-            if (my_valid) g = __ldcg(P.thr_g + my_row);
+            const int col0 = (t0 + i * t_step) * TN + wg * 64;
             mbar_wait(tmem_full + b, u, A.err_flag, 6);
             tc_fence_after();
             mbar_wait(bm_full + b, u, A.err_flag, 7);
-            if (g != 0) {
-                const float gf = unord_f32(g);
-                if (gf > thr) thr = gf;
-            }
-            const uint32_t *bm = bitmap + b * 4 * TM + r;
-            const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC_COL + b * TN);
+            const uint32_t *bm = bitmap + b * 4 * TM + (wg * 2) * TM + r;
+            const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC_COL + b * TN + wg * 64);
 #pragma unroll 1
-            for (int gq = 0; gq < TN / 32; ++gq) {
-                uint32_t v[32];
-                tmem_ld32(acc_addr + (uint32_t)(gq * 32), v);
-                float bias_v[32];
+            for (int gq = 0; gq < 2; ++gq) {
+                uint32_t raw[32];
+                __syncwarp();
+                tmem_ld32(acc_addr + (uint32_t)(gq * 32), raw);
+                const uint32_t mword = bm[gq * TM];
+                float s[32];
                 if (P.bias != nullptr) {
                     const float4 *b4 = reinterpret_cast<const float4 *>(P.bias + col0 + gq * 32);
+                    float bv[32];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 x = __ldg(b4 + q);
-                        bias_v[4 * q + 0] = x.x; bias_v[4 * q + 1] = x.y; bias_v[4 * q + 2] = x.z; bias_v[4 * q + 3] = x.w;
+                        bv[4 * q + 0] = x.x; bv[4 * q + 1] = x.y; bv[4 * q + 2] = x.z; bv[4 * q + 3] = x.w;
                     }
-                }
-                tmem_wait_ld();
-                float s[32];
-                float mx = NINF;
+                    tmem_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    s[q] = __uint_as_float(v[q]);
-                    if (P.bias != nullptr) s[q] += bias_v[q];
-                    mx = fmaxf(mx, s[q]);
-                }
-                if (mx >= thr) {
-                    const uint32_t mword = bm[gq * TM];
+                    for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]) + bv[q];
+                } else {
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        if (s[q] >= thr && ((mword >> q) & 1u) == 0u) {
-                            if (sn == TC_CAP) drain();
-                            my_stage[sn * TM] = make_key(s[q], (uint32_t)(col0 + gq * 32 + q));
-                            ++sn;
+                    for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]);
+                }
+                if (sample) {
+                    if (mword != 0u) {  // train items (and columns past the catalogue) do not count
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if ((mword >> q) & 1u) s[q] = NINF;
+                    }
+                    float mx = NINF;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) mx = fmaxf(mx, s[q]);
+                    if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
+                } else {
+                    // level-1 maxima over triples, then the group maximum
+                    float m1[11];
+#pragma unroll
+                    for (int q = 0; q < 10; ++q) m1[q] = fmaxf(fmaxf(s[3 * q], s[3 * q + 1]), s[3 * q + 2]);
+                    m1[10] = fmaxf(s[30], s[31]);
+                    float mx = m1[0];
+#pragma unroll
+                    for (int q = 1; q < 11; ++q) mx = fmaxf(mx, m1[q]);
+                    if (mx >= thr) {
+#pragma unroll
+                        for (int q = 0; q < 11; ++q) {
+                            if (m1[q] >= thr) {
+#pragma unroll
+                                for (int e = 3 * q; e < 3 * q + 3 && e < 32; ++e) {
+                                    if (s[e] >= thr && ((mword >> e) & 1u) == 0u) {
+                                        if (cnt < (uint32_t)A.cap) my_list[cnt] = make_key(s[e], (uint32_t)(col0 + gq * 32 + e));
+                                        ++cnt;
+                                    }
+                                }
+                            }
                         }
                     }
                 }
             }
-            // accumulator b is free for the MMA of tile i+2
+            // this thread is done with accumulator b and bitmap b
             tc_fence_before();
             mbar_arrive(tmem_empty + b);
-            drain();
             mbar_arrive(bm_empty + b);
-            if (my_valid && hn == P.K) {
-                const uint32_t o = (uint32_t)(my_heap[0] >> 32);
-                if (o > published) { atomicMax(P.thr_g + my_row, o); published = o; }
-            }
         }
 
-        // partial list out: [row, c, K]; the four epilogue warps write coalesced along K
-        hcnt[r] = hn;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int idx = r; idx < TM * P.K; idx += 128) {
-            const int rr = idx / P.K, ii = idx - rr * P.K;
-            const int64_t row = row_base + rr;
-            if (row < P.n_rows) P.part[(row * P.S + c) * P.K + ii] = (ii < hcnt[rr]) ? heap[ii * TM + rr] : 0ull;
+        if (my_valid) {
+            if (sample) {
+                float *dst = A.samp + (my_row * 2 + wg) * TC_R;
+#pragma unroll
+                for (int q = 0; q < TC_R; ++q) dst[q] = v[q];
+            } else {
+                A.cand_cnt[(my_row * P.S + c) * 2 + wg] = cnt;
+            }
         }
     }
 
@@ -436,6 +512,63 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+}
+
+// ---- candidate lists -> sorted top-K ----------------------------------------------------------------
+// One warp per row: gather the row's n_sub sub-lists into shared memory, sort (warp bitonic, size
+// picked from the row's own candidate count), write the K best keys.  Rows with fewer than K
+// candidates (threshold estimate too high, or fewer than K unmasked items) or with an overflowed
+// sub-list go on the fail list and are re-done exactly by k_row_exact.
+constexpr int SEL_WARPS = 4;
+constexpr int SEL_MAX = 1024;  // candidates a row may carry into the sort
+
+template <int PER>
+__device__ __forceinline__ void sel_sort_write(const u64 *buf, int n, int K, u64 *dst, int lane)
+{
+    u64 v[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int i = e * 32 + lane;
+        v[e] = (i < n) ? buf[i] : 0ull;
+    }
+    warp_bitonic_desc<PER>(v, lane);
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int i = e * 32 + lane;
+        if (i < K) dst[i] = v[e];
+    }
+}
+
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+k_select_cands(const u64 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int K,
+               int64_t n_rows, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count)
+{
+    __shared__ u64 sbuf[SEL_WARPS][SEL_MAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp;
+    if (row >= n_rows) return;
+    u64 *buf = sbuf[warp];
+    const uint32_t *cc = cand_cnt + row * n_sub;
+    int n = 0;
+    bool bad = false;
+    for (int s = 0; s < n_sub; ++s) {
+        const int c = (int)__ldg(cc + s);
+        if (c > cap || n + c > SEL_MAX) { bad = true; break; }
+        const u64 *src = cand + (row * n_sub + s) * (int64_t)cap;
+        for (int i = lane; i < c; i += 32) buf[n + i] = src[i];
+        n += c;
+    }
+    if (bad || n < K) {
+        if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+        return;
+    }
+    __syncwarp();
+    u64 *dst = out_keys + row * (int64_t)K;
+    if (n <= 64) sel_sort_write<2>(buf, n, K, dst, lane);
+    else if (n <= 128) sel_sort_write<4>(buf, n, K, dst, lane);
+    else if (n <= 256) sel_sort_write<8>(buf, n, K, dst, lane);
+    else if (n <= 512) sel_sort_write<16>(buf, n, K, dst, lane);
+    else sel_sort_write<32>(buf, n, K, dst, lane);
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------

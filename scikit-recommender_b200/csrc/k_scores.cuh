@@ -1,20 +1,25 @@
-// k_scores.cuh -- K2: score-matrix-in top-K with train-item masking.
+// k_scores.cuh -- K2: per-row streaming top-K with train-item masking, one CTA per row.
 //
-// Replaces, for a device-resident float32 [B, I] score block, the reference's masking loop
-// (evaluator.py:195-200) and the per-row selection of eval_one_user (evaluate.h:27-45).
-// One CTA streams one row exactly once (HBM-bound: 4*I bytes per user); a running threshold
-// (the K-th key so far) filters the stream, survivors go to a shared-memory buffer that is
-// folded into the sorted top-K by a block bitonic sort whenever it could overflow.
-// Masked (train) items become -inf and stay candidates, like the reference.
+// k_topk_scores: score-matrix-in.  Replaces, for a device-resident float32 [B, I] score block, the
+//   reference's masking loop (evaluator.py:195-200) and the per-row selection of eval_one_user
+//   (evaluate.h:27-45).  HBM-bound: each row is streamed exactly once (4*I bytes per user).
+// k_row_exact:   the same selection over scores computed on the fly in FP32 (u . item_j + bias_j),
+//   for the few rows the fused tensor-core path could not settle from its candidate lists.
+//
+// A running threshold (the K-th key so far) filters the stream, survivors go to a shared-memory
+// buffer that is folded into the sorted top-K by a block bitonic sort of only the power-of-two prefix
+// in use.  Masked (train) items become -inf and stay candidates, like the reference; keys order
+// them by ascending item id.
 #pragma once
 #include "common.cuh"
 
 namespace skr {
 
 constexpr int K2_THREADS = 256;
-constexpr int K2_CHUNK = 1024;  // elements per pass: one float4 per thread
+constexpr int K2_CHUNK = 1024;  // elements per pass: four per thread
 constexpr int K2_P = 2048;      // key slots in shared memory (sorted top-K + survivor buffer)
 constexpr int K2_MAX_K = 512;
+constexpr int K2_MAX_D = 1024;  // k_row_exact keeps the user vector in shared memory
 
 __device__ __forceinline__ float4 ldg_stream_f4(const float *p)
 {
@@ -25,47 +30,79 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float *p)
     return r;
 }
 
-__device__ __forceinline__ void k2_load4(const float *__restrict__ row, int j0, int n_items, bool vec_ok, float (&v)[4])
-{
-    if (vec_ok && j0 + 3 < n_items) {
-        float4 t = ldg_stream_f4(row + j0);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
+// score source: a row of a score matrix
+struct RowLoad {
+    const float *row;
+    bool vec_ok;
+    __device__ __forceinline__ void get4(int j0, int n_items, float (&v)[4]) const
+    {
+        if (vec_ok && j0 + 3 < n_items) {
+            const float4 t = ldg_stream_f4(row + j0);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (j0 + q < n_items) ? __ldg(row + j0 + q) : 0.0f;
+            for (int q = 0; q < 4; ++q) v[q] = (j0 + q < n_items) ? __ldg(row + j0 + q) : 0.0f;
+        }
     }
-}
+};
 
-__global__ void __launch_bounds__(K2_THREADS)
-k_topk_scores(const float *__restrict__ scores, int64_t ld, int n_items, int64_t row0,
-              const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K,
-              u64 *__restrict__ out_keys)
+// score source: FP32 dot products of one user vector (shared memory) with item rows, k ascending
+struct RowDot {
+    const float *u;  // shared memory, d floats
+    const float *V;
+    int64_t ld_v;
+    int d;
+    const float *bias;  // or null
+    bool vec_ok;
+    __device__ __forceinline__ void get4(int j0, int n_items, float (&v)[4]) const
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q;
+            float acc = 0.0f;
+            if (j < n_items) {
+                const float *it = V + (int64_t)j * ld_v;
+                int k = 0;
+                if (vec_ok) {
+                    for (; k + 4 <= d; k += 4) {
+                        const float4 x = __ldg(reinterpret_cast<const float4 *>(it + k));
+                        acc = fmaf(u[k], x.x, acc);
+                        acc = fmaf(u[k + 1], x.y, acc);
+                        acc = fmaf(u[k + 2], x.z, acc);
+                        acc = fmaf(u[k + 3], x.w, acc);
+                    }
+                }
+                for (; k < d; ++k) acc = fmaf(u[k], __ldg(it + k), acc);
+                if (bias != nullptr) acc += __ldg(bias + j);
+            }
+            v[q] = acc;
+        }
+    }
+};
+
+// Whole-block routine: exact top-K keys of one row, sorted, to out[0..K).
+template <class Src>
+__device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int64_t tr_begin, int64_t tr_end,
+                                               const int32_t *__restrict__ tr_idx, int K, u64 *__restrict__ out,
+                                               u64 *keys, uint32_t *bitmap, int *s_cnt)
 {
-    __shared__ u64 keys[K2_P];
-    __shared__ uint32_t bitmap[K2_CHUNK / 32];
-    __shared__ int s_cnt;
-
     const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t r = blockIdx.x;
-    const float *row = scores + r * ld;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-
-    int64_t cur = 0, te = 0;
-    if (tr_indptr != nullptr) { cur = __ldg(tr_indptr + row0 + r); te = __ldg(tr_indptr + row0 + r + 1); }
+    int64_t cur = tr_begin;
+    const int64_t te = tr_end;
     int next_train = (cur < te) ? __ldg(tr_idx + cur) : 0x7fffffff;
 
     int base = 0;  // keys[0..base) hold the sorted best-so-far
     u64 thr_key = 0;
     float thr_f = -__int_as_float(0x7f800000);
-    if (tid == 0) s_cnt = 0;
+    if (tid == 0) *s_cnt = 0;
     __syncthreads();
 
-    float v[4], nxt[4];
-    k2_load4(row, tid * 4, n_items, vec_ok, v);
+    float v[4], nxt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    src.get4(tid * 4, n_items, v);
 
     for (int c0 = 0; c0 < n_items; c0 += K2_CHUNK) {
         const int j0 = c0 + tid * 4;
-        if (c0 + K2_CHUNK < n_items) k2_load4(row, j0 + K2_CHUNK, n_items, vec_ok, nxt);
+        if (c0 + K2_CHUNK < n_items) src.get4(j0 + K2_CHUNK, n_items, nxt);
 
         // train items that fall into this chunk -> bitmap (sorted CSR row, cursor moves forward)
         uint32_t mbits = 0;
@@ -99,13 +136,13 @@ k_topk_scores(const float *__restrict__ scores, int64_t ld, int n_items, int64_t
             if (bal) {
                 int leader = __ffs(bal) - 1;
                 int pos = 0;
-                if (lane == leader) pos = atomicAdd(&s_cnt, __popc(bal));
+                if (lane == leader) pos = atomicAdd(s_cnt, __popc(bal));
                 pos = __shfl_sync(0xffffffffu, pos, leader);
                 if (pass) keys[base + pos + __popc(bal & ((1u << lane) - 1u))] = key;
             }
         }
         __syncthreads();
-        const int cnt = s_cnt;
+        const int cnt = *s_cnt;
         const bool last = (c0 + K2_CHUNK >= n_items);
         if (last || base + cnt + K2_CHUNK > K2_P) {
             const int tot = base + cnt;
@@ -120,13 +157,59 @@ k_topk_scores(const float *__restrict__ scores, int64_t ld, int n_items, int64_t
                 thr_f = key_score(thr_key);
             }
             __syncthreads();
-            if (tid == 0) s_cnt = 0;
+            if (tid == 0) *s_cnt = 0;
             __syncthreads();
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = nxt[q];
     }
-    for (int i = tid; i < K; i += K2_THREADS) out_keys[r * K + i] = keys[i];
+    for (int i = tid; i < K; i += K2_THREADS) out[i] = keys[i];
+}
+
+__global__ void __launch_bounds__(K2_THREADS)
+k_topk_scores(const float *__restrict__ scores, int64_t ld, int n_items, int64_t row0,
+              const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K,
+              u64 *__restrict__ out_keys)
+{
+    __shared__ u64 keys[K2_P];
+    __shared__ uint32_t bitmap[K2_CHUNK / 32];
+    __shared__ int s_cnt;
+    const int64_t r = blockIdx.x;
+    RowLoad src;
+    src.row = scores + r * ld;
+    src.vec_ok = ((reinterpret_cast<uintptr_t>(src.row) & 15) == 0);
+    int64_t tb = 0, te = 0;
+    if (tr_indptr != nullptr) { tb = __ldg(tr_indptr + row0 + r); te = __ldg(tr_indptr + row0 + r + 1); }
+    topk_row_block(src, n_items, tb, te, tr_idx, K, out_keys + r * K, keys, bitmap, &s_cnt);
+}
+
+// rows on the fail list of k_select_cands: exact FP32 scores on the fly, same selection
+__global__ void __launch_bounds__(K2_THREADS)
+k_row_exact(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_count, const float *__restrict__ U, int64_t ld_u,
+            const float *__restrict__ V, int64_t ld_v, int d, const float *__restrict__ bias, int n_items, int64_t row0,
+            const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K, u64 *__restrict__ out_keys)
+{
+    __shared__ u64 keys[K2_P];
+    __shared__ uint32_t bitmap[K2_CHUNK / 32];
+    __shared__ int s_cnt;
+    __shared__ float u_s[K2_MAX_D];
+    const int n_fail = *fail_count;
+    for (int i = blockIdx.x; i < n_fail; i += gridDim.x) {
+        const int64_t r = fail_list[i];
+        __syncthreads();
+        for (int k = threadIdx.x; k < d; k += K2_THREADS) u_s[k] = U[r * ld_u + k];
+        __syncthreads();
+        RowDot src;
+        src.u = u_s;
+        src.V = V;
+        src.ld_v = ld_v;
+        src.d = d;
+        src.bias = bias;
+        src.vec_ok = ((ld_v & 3) == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
+        int64_t tb = 0, te = 0;
+        if (tr_indptr != nullptr) { tb = __ldg(tr_indptr + row0 + r); te = __ldg(tr_indptr + row0 + r + 1); }
+        topk_row_block(src, n_items, tb, te, tr_idx, K, out_keys + r * K, keys, bitmap, &s_cnt);
+    }
 }
 
 }  // namespace skr

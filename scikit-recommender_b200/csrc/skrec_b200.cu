@@ -63,14 +63,17 @@ struct skr_ctx {
     double *d_disc = nullptr;
     int disc_n = 0;
     // workspace, grow-only
-    Buf keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx;
+    Buf keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
     int64_t launches = 0;
     const char *last_fused = "none";
     int64_t opt_chunks = 0;
     int64_t opt_stages = 0;
+    int64_t opt_sample_tiles = 0;
+    int64_t opt_rank = 0;
+    struct Plan { int n_samp, stride, r, cap, S, stages; } last_plan = {0, 0, 0, 0, 0, 0};
     EncodeTiledFn encode = nullptr;
-    std::vector<cudaEvent_t> ev0, ev1;  // ring of event pairs around the scoring kernel
+    std::vector<cudaEvent_t> ev0, ev1, ev2;  // ring: ev2 before the pre-pass, ev0/ev1 around the main scoring kernel
     int64_t ev_calls = 0;
 };
 
@@ -213,9 +216,10 @@ int run_metrics(skr_ctx *ctx, const u64 *keys, const int32_t *idx_in, int64_t n_
     return SKR_OK;
 }
 
-int pick_chunks(const skr_ctx *ctx, int n_rt, int n_ct, int K)
+int pick_chunks(const skr_ctx *ctx, int n_rt, int n_ct, int K, bool lists)
 {
-    int smax = std::min(std::min(n_ct, 1024 / K), 16);
+    // heap path: S*K keys must fit one warp sort; list path: chunks are independent, only balance matters
+    int smax = lists ? std::min(n_ct, 16) : std::min(std::min(n_ct, 1024 / K), 16);
     if (smax < 1) smax = 1;
     if (ctx->opt_chunks > 0) return (int)std::min<int64_t>(ctx->opt_chunks, smax);
     long best_cost = -1;
@@ -292,7 +296,9 @@ int skr_ctx_create(int device, skr_ctx **out)
     }
     ctx->ev0.resize(1);
     ctx->ev1.resize(1);
-    if ((e = cudaEventCreate(&ctx->ev0[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1[0])) != cudaSuccess) {
+    ctx->ev2.resize(1);
+    if ((e = cudaEventCreate(&ctx->ev0[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1[0])) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev2[0])) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, SKR_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
     }
@@ -307,10 +313,12 @@ int skr_ctx_destroy(skr_ctx *ctx)
     free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr);
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_err);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
-                   &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx};
+                   &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
+                   &ctx->fail_list};
     for (Buf *b : bufs) free_dev(b->p);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev2) cudaEventDestroy(e);
     delete ctx;
     return SKR_OK;
 }
@@ -320,14 +328,18 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!ctx || !name) return SKR_ERR_INVALID;
     if (!strcmp(name, "chunks")) { ctx->opt_chunks = value; return SKR_OK; }
     if (!strcmp(name, "stages")) { ctx->opt_stages = value; return SKR_OK; }
+    if (!strcmp(name, "sample_tiles")) { ctx->opt_sample_tiles = value; return SKR_OK; }
+    if (!strcmp(name, "rank")) { ctx->opt_rank = value; return SKR_OK; }
     if (!strcmp(name, "event_ring")) {
         if (value < 1 || value > 65536) return fail(ctx, SKR_ERR_INVALID, "event_ring=%lld not in [1,65536]", (long long)value);
         cudaSetDevice(ctx->device);
         while ((int64_t)ctx->ev0.size() < value) {
-            cudaEvent_t a, b;
-            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return fail(ctx, SKR_ERR_CUDA, "cudaEventCreate failed");
+            cudaEvent_t a, b, c;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess || cudaEventCreate(&c) != cudaSuccess)
+                return fail(ctx, SKR_ERR_CUDA, "cudaEventCreate failed");
             ctx->ev0.push_back(a);
             ctx->ev1.push_back(b);
+            ctx->ev2.push_back(c);
         }
         ctx->ev_calls = 0;
         return SKR_OK;
@@ -343,6 +355,33 @@ int skr_fused_kernel_ms(skr_ctx *ctx, int back, float *ms_out)
     const size_t i = (size_t)((ctx->ev_calls - 1 - back) % n);
     SKR_CUDA(ctx, cudaEventSynchronize(ctx->ev1[i]));
     SKR_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0[i], ctx->ev1[i]));
+    return SKR_OK;
+}
+
+int skr_fused_prepass_ms(skr_ctx *ctx, int back, float *ms_out)
+{
+    if (!ctx || !ms_out) return SKR_ERR_INVALID;
+    const int64_t n = (int64_t)ctx->ev0.size();
+    if (back < 0 || back >= n || back >= ctx->ev_calls) return fail(ctx, SKR_ERR_STATE, "no timing for call -%d", back);
+    const size_t i = (size_t)((ctx->ev_calls - 1 - back) % n);
+    SKR_CUDA(ctx, cudaEventSynchronize(ctx->ev0[i]));
+    SKR_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev2[i], ctx->ev0[i]));
+    return SKR_OK;
+}
+
+int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out)
+{
+    if (!ctx || !out || n_out < 7) return SKR_ERR_INVALID;
+    int n_fail = 0;
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->fail_list.p) SKR_CUDA(ctx, cudaMemcpy(&n_fail, ctx->fail_list.p, sizeof(int), cudaMemcpyDeviceToHost));
+    out[0] = ctx->last_plan.n_samp;
+    out[1] = ctx->last_plan.stride;
+    out[2] = ctx->last_plan.r;
+    out[3] = ctx->last_plan.cap;
+    out[4] = ctx->last_plan.S;
+    out[5] = ctx->last_plan.stages;
+    out[6] = n_fail;
     return SKR_OK;
 }
 
@@ -480,12 +519,12 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
     const int nkb = (d + TC_KB - 1) / TC_KB;
     int stages = 0;
     for (int s = TC_MAX_STAGES; s >= 2; --s)
-        if (tc_smem_bytes(K, s) <= ctx->max_smem) { stages = s; break; }
+        if (tc_smem_bytes(s) <= ctx->max_smem) { stages = s; break; }
     if (ctx->opt_stages >= 2 && ctx->opt_stages <= stages) stages = (int)ctx->opt_stages;
-    const bool tc_ok = (nkb <= 4) && (stages >= 2);
+    const bool tc_ok = (nkb <= 4) && (stages >= 2) && (d <= K2_MAX_D);
     bool use_tc = (precision != SKR_PREC_FP32) && tc_ok;
     if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32))
-        return fail(ctx, SKR_ERR_UNSUPPORTED, "tcgen05 path needs d <= 128 and shared memory for K=%d heaps (d=%d)", K, d);
+        return fail(ctx, SKR_ERR_UNSUPPORTED, "tcgen05 path needs d <= 128 (d=%d)", d);
     if (!use_tc) {
         if ((d & 3) || (ld_u & 3) || (ld_i & 3) || ((uintptr_t)user_vecs_dev & 15) || ((uintptr_t)item_vecs_dev & 15))
             return fail(ctx, SKR_ERR_UNSUPPORTED, "FP32 path needs d, ld_u, ld_i multiples of 4 and 16-byte aligned tables");
@@ -500,18 +539,18 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
     P.K = K;
     P.n_ct = (int)((n_items + TN - 1) / TN);
     P.n_rt = (int)((n_rows + TM - 1) / TM);
-    P.S = pick_chunks(ctx, P.n_rt, P.n_ct, K);
+    P.S = pick_chunks(ctx, P.n_rt, P.n_ct, K, use_tc);
     P.tiles_per_chunk = (P.n_ct + P.S - 1) / P.S;
     P.S = (P.n_ct + P.tiles_per_chunk - 1) / P.tiles_per_chunk;  // drop empty chunks
     P.mask_keys = ctx->has_train ? ctx->d_mask_keys : nullptr;
     P.mask_tile_ptr = ctx->has_train ? ctx->d_mask_tile_ptr : nullptr;
+    P.thr_g = nullptr;
+    P.part = nullptr;
 
-    if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;
-    if ((rc = ensure(ctx, ctx->part, (size_t)n_rows * P.S * K * sizeof(u64)))) return rc;
     if ((rc = ensure(ctx, ctx->keys, (size_t)n_rows * K * sizeof(u64)))) return rc;
-    P.thr_g = (uint32_t *)ctx->thr.p;
-    P.part = (u64 *)ctx->part.p;
-    SKR_CUDA(ctx, cudaMemsetAsync(P.thr_g, 0, (size_t)n_rows * sizeof(uint32_t), st));
+    u64 *keys = (u64 *)ctx->keys.p;
+    const int64_t *tp = ctx->has_train ? ctx->d_tr_indptr : nullptr;
+    const int32_t *ti = ctx->has_train ? ctx->d_tr_idx : nullptr;
     P.bias = nullptr;
     if (bias_dev) {
         const int n_pad = P.n_ct * TN;
@@ -521,8 +560,11 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         P.bias = (const float *)ctx->bias.p;
     }
     const unsigned grid = (unsigned)(P.n_rt * P.S);
+    const size_t ring = ctx->ev0.size();
+    const size_t slot = (size_t)(ctx->ev_calls % (int64_t)ring);
 
     if (use_tc) {
+        // operand prep: item table -> hi/lo TF32 tables, TMA descriptors
         const int d_pad = nkb * TC_KB;
         const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
         if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;
@@ -533,43 +575,93 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         CUtensorMap mhi, mlo;
         if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
         if ((rc = make_tmap(ctx, &mlo, (const float *)ctx->blo.p, n_items, d_pad))) return rc;
+
+        // sampling plan (k_fused_tc.cuh header): fraction f ~ 6/K of the item tiles, threshold = r-th largest
+        // sampled group maximum with r = K f + 4.5 sqrt(K f) + 8 (a ~4-sigma margin against fewer than K survivors)
+        int n_samp = (int)lround(6.0 * P.n_ct / K);
+        n_samp = std::max(1, std::min(n_samp, std::max(1, P.n_ct / 3)));
+        if (ctx->opt_sample_tiles > 0) n_samp = (int)std::min<int64_t>(ctx->opt_sample_tiles, P.n_ct);
+        const int stride = std::max(1, P.n_ct / n_samp);
+        n_samp = (P.n_ct + stride - 1) / stride;
+        const double f_eff = std::min(1.0, (double)n_samp * TN / (double)n_items);
+        const double kf = K * f_eff;
+        int r = (int)ceil(kf + 4.5 * sqrt(kf) + 8.0);
+        r = std::max(1, std::min(r, TC_R));
+        if (ctx->opt_rank > 0) r = (int)std::min<int64_t>(ctx->opt_rank, TC_R);
+        const double expect = r / f_eff;  // candidates per row
+        int cap = next_pow2((int)(2.0 * expect / (2 * P.S)) + 24);
+        cap = std::max(32, std::min(cap, 512));
+        const int n_sub = 2 * P.S;
+
+        if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 2 * TC_R * sizeof(float)))) return rc;
+        if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * cap * sizeof(u64)))) return rc;
+        if ((rc = ensure(ctx, ctx->cand_cnt, (size_t)n_rows * n_sub * sizeof(uint32_t)))) return rc;
+        if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
+        int *fail_count = (int *)ctx->fail_list.p;             // [0] = count, [1..] = rows
+        int32_t *fail_list = (int32_t *)ctx->fail_list.p + 1;
+        SKR_CUDA(ctx, cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+
         TcArgs A;
         A.U = user_vecs_dev;
         A.ld_u = ld_u;
         A.nkb = nkb;
         A.stages = stages;
-        A.passes = (precision == SKR_PREC_1XTF32) ? 1 : 3;
         A.err_flag = ctx->d_err;
-        const size_t smem = tc_smem_bytes(K, stages);
+        A.stride = stride;
+        A.n_samp = n_samp;
+        A.samp = (float *)ctx->samp.p;
+        A.r = r;
+        A.cap = cap;
+        A.cand = (u64 *)ctx->cand.p;
+        A.cand_cnt = (uint32_t *)ctx->cand_cnt.p;
+        const size_t smem = tc_smem_bytes(stages);
         SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[(size_t)(ctx->ev_calls % (int64_t)ctx->ev0.size())], st));
+        // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
+        A.mode = TC_MODE_SAMPLE;
+        A.passes = 1;
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
+        k_fused_tc<<<(unsigned)P.n_rt, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
+        // main pass: every item tile, reference-grade scores, survivors to the candidate lists
+        A.mode = TC_MODE_COLLECT;
+        A.passes = (precision == SKR_PREC_1XTF32) ? 1 : 3;
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
         k_fused_tc<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
-        SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[(size_t)(ctx->ev_calls % (int64_t)ctx->ev1.size())], st));
-        ctx->launches++;
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
+        ctx->launches += 2;
+        SKR_CUDA(ctx, cudaGetLastError());
+        k_select_cands<<<(unsigned)((n_rows + SEL_WARPS - 1) / SEL_WARPS), SEL_WARPS * 32, 0, st>>>(
+            A.cand, A.cand_cnt, n_sub, cap, K, n_rows, keys, fail_list, fail_count);
+        k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, user_vecs_dev, ld_u, item_vecs_dev, ld_i, d,
+                                                                      bias_dev, (int)n_items, row0, tp, ti, K, keys);
+        ctx->launches += 2;
         ctx->last_fused = (A.passes == 3) ? "tcgen05_3xtf32" : "tcgen05_1xtf32";
+        ctx->last_plan = {n_samp, stride, r, cap, P.S, stages};
     } else {
+        if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;
+        if ((rc = ensure(ctx, ctx->part, (size_t)n_rows * P.S * K * sizeof(u64)))) return rc;
+        P.thr_g = (uint32_t *)ctx->thr.p;
+        P.part = (u64 *)ctx->part.p;
+        SKR_CUDA(ctx, cudaMemsetAsync(P.thr_g, 0, (size_t)n_rows * sizeof(uint32_t), st));
         const size_t smem = simt_smem_bytes(K);
         SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[(size_t)(ctx->ev_calls % (int64_t)ctx->ev0.size())], st));
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
         k_fused_simt<<<grid, SIMT_THREADS, smem, st>>>(user_vecs_dev, ld_u, item_vecs_dev, ld_i, P);
-        SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[(size_t)(ctx->ev_calls % (int64_t)ctx->ev1.size())], st));
+        SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches++;
         ctx->last_fused = "simt_fp32";
+        SKR_CUDA(ctx, cudaGetLastError());
+        // merge the S partial lists per row
+        const int n = P.S * K;
+        if (n <= 64) launch_merge<2>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+        else if (n <= 128) launch_merge<4>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+        else if (n <= 256) launch_merge<8>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+        else if (n <= 512) launch_merge<16>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+        else launch_merge<32>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
+        ctx->launches++;
+        ctx->last_plan = {0, 0, 0, 0, P.S, 0};
     }
     ctx->ev_calls++;
-    SKR_CUDA(ctx, cudaGetLastError());
-
-    // ---- merge the S partial lists per row ----
-    const int n = P.S * K;
-    const int64_t *tp = ctx->has_train ? ctx->d_tr_indptr : nullptr;
-    const int32_t *ti = ctx->has_train ? ctx->d_tr_idx : nullptr;
-    u64 *keys = (u64 *)ctx->keys.p;
-    if (n <= 64) launch_merge<2>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-    else if (n <= 128) launch_merge<4>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-    else if (n <= 256) launch_merge<8>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-    else if (n <= 512) launch_merge<16>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-    else launch_merge<32>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-    ctx->launches++;
     SKR_CUDA(ctx, cudaGetLastError());
     return run_metrics(ctx, keys, nullptr, n_rows, row0, m, K, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
 }

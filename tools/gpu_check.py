@@ -131,6 +131,7 @@ def stage_tc_small():
     for U, I, d, K, ue, ie, b, tr, te in _small_cases(np):
         out = _fused(np, torch, ctx, ue, ie, b, tr, te, [1, 2, 4], K, "3xtf32")
         _report(np, oracle, "tc3 U=%d I=%d d=%d K=%d" % (U, I, d, K), out, ue, ie, b, tr, te, [1, 2, 4], K)
+        print("      prepass %.3f ms, plan %s" % (ctx.fused_prepass_ms(0), ctx.fused_stats()), flush=True)
 
 
 def stage_tc_c2():
@@ -142,13 +143,24 @@ def stage_tc_c2():
     te = (d["test_indptr"], d["test_indices"])
     res = {}
     for prec in ("3xtf32", "fp32", "1xtf32"):
-        for chunks in ((0, 1, 2, 5, 8) if prec == "3xtf32" else (0,)):
+        for chunks in ((0, 2, 5, 8, 13) if prec == "3xtf32" else (0,)):
             ctx.set_option("chunks", chunks)
             out = _fused(np, torch, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, prec)
             out = _fused(np, torch, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, prec)
             res[(prec, chunks)] = out
-            print("c2 %s chunks=%d: kernel %.3f ms -> %.1f TFLOP/s algorithmic; NDCG@50 %.6f" % (
-                prec, chunks, out[4], 2.0 * d["users"] * d["items"] * 64 / out[4] / 1e9, out[3][149] / d["users"]), flush=True)
+            print("c2 %s chunks=%d: kernel %.3f ms (+ prepass %.3f) -> %.1f TFLOP/s algorithmic; NDCG@50 %.6f; %s" % (
+                prec, chunks, out[4], ctx.fused_prepass_ms(0), 2.0 * d["users"] * d["items"] * 64 / out[4] / 1e9,
+                out[3][149] / d["users"], ctx.fused_stats() if prec != "fp32" else ""), flush=True)
+    ctx.set_option("chunks", 0)
+    for st, rk in ((16, 0), (64, 0), (0, 16), (0, 32)):
+        ctx.set_option("sample_tiles", st)
+        ctx.set_option("rank", rk)
+        out = _fused(np, torch, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, "3xtf32")
+        out = _fused(np, torch, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, "3xtf32")
+        print("c2 3xtf32 sample_tiles=%d rank=%d: kernel %.3f ms (+ prepass %.3f); NDCG@50 %.6f; %s" % (
+            st, rk, out[4], ctx.fused_prepass_ms(0), out[3][149] / d["users"], ctx.fused_stats()), flush=True)
+    ctx.set_option("sample_tiles", 0)
+    ctx.set_option("rank", 0)
     a, b = res[("3xtf32", 0)], res[("fp32", 0)]
     diff = a[0] != b[0]
     print("c2 tc3 vs simt: idx mismatch %.4f%%, max val gap at mismatches %.3e, max mean-metric diff %.3e" % (

@@ -27,4 +27,5 @@ for _ in range(n):
     ctx.eval_fused(ue, ie, b, 0, ids, K, precision=prec, sums=sums)
     torch.cuda.synchronize()
     ms.append(ctx.fused_kernel_ms(0))
-print("%s %s kernel ms:" % (cfgname, prec), ["%.3f" % m for m in ms], "NDCG@%d=%.6f" % (K, float(sums[-1]) / d["users"]))
+print("%s %s kernel ms:" % (cfgname, prec), ["%.3f" % m for m in ms], "prepass %.3f" % ctx.fused_prepass_ms(0),
+      "NDCG@%d=%.6f" % (K, float(sums[-1]) / d["users"]), ctx.fused_stats())
