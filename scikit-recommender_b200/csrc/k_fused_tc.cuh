@@ -29,8 +29,8 @@
 // into hi/lo tables and streamed by TMA (SWIZZLE_128B, 128 rows x 32 floats per box) through an
 // mbarrier ring of k-block stages.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one lane),
-// warp 2 train-mask bitmap builder, warp 3 idle, warps 4-7 epilogue of columns 0-63, warps 8-11
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer of the even tiles
+// (one lane), warp 2 train-mask bitmap builder, warp 3 MMA issuer of the odd tiles, warps 4-7 epilogue of columns 0-63, warps 8-11
 // epilogue of columns 64-127 (thread <-> TMEM lane <-> user row; two warps per SM sub-partition so
 // the TMEM-load and compare latencies of one hide behind the other).  Accumulators and bitmaps are
 // double buffered so the epilogue of tile n overlaps the MMAs of tile n+1.
@@ -191,15 +191,17 @@ struct TcArgs {
     int passes;       // 3 = 3xTF32, 1 = single TF32 pass
     int mode;         // TC_MODE_*
     int *err_flag;    // device int, set before a watchdog trap
+    int dbg;          // timing experiments only (results invalid): 1 no epilogue work, 2 no MMA, 4 no appends, 8 no TMA
     // SAMPLE: item tiles 0, stride, 2*stride, ...; out: samp[row][2][TC_R] group maxima, descending
     int stride;
     int n_samp;
     float *samp;
-    // COLLECT: threshold rank r (1-based) in the merged sample lists; candidate lists
-    int r;
+    // COLLECT: per-row thresholds (k_sample_thr) and candidate lists
+    const float *thr;        // [n_rows]
     int cap;                 // entries per (row, chunk, column half) sub-list
-    u64 *cand;               // [n_rows, S*2, cap]
-    uint32_t *cand_cnt;      // [n_rows, S*2] entries wanted (> cap means overflow)
+    int sub_stride;          // storage stride in entries: power of two >= cap + 32 (room for one group past cap)
+    uint2 *cand;             // [n_rows, S*2, sub_stride] (score bits, item), base aligned to the stride
+    uint32_t *cand_cnt;      // [n_rows, S*2] entries written (cap + 1 means overflow)
 };
 
 // descending insertion of x into v[0..TC_R): branch-free compare-exchange chain
@@ -244,11 +246,11 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tmem_full + b, 1);
-            mbar_init(tmem_empty + b, TC_EPI_THREADS);
+            mbar_init(tmem_empty + b, TC_EPI_THREADS / 32);
             mbar_init(bm_full + b, 1);
-            mbar_init(bm_empty + b, TC_EPI_THREADS);
+            mbar_init(bm_empty + b, TC_EPI_THREADS / 32);
         }
-        mbar_init(a_ready, TM);
+        mbar_init(a_ready, TM / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -275,6 +277,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     const int s = it % A.stages;
                     const uint32_t ph = (uint32_t)((it / A.stages) & 1);
                     mbar_wait(empty + s, ph ^ 1u, A.err_flag, 1);
+                    if (A.dbg & 8) { mbar_arrive(full + s); continue; }
                     mbar_expect_tx(full + s, tx_bytes);
                     unsigned char *dst = b_tiles + (size_t)s * TC_STAGE_BYTES;
                     tma_load_2d(dst, &tm_bhi, kb * TC_KB, t * TN, full + s);
@@ -282,21 +285,24 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =========================================================================
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers: warp 1 takes the even tiles (accumulator 0), warp 3 the odd ones (accumulator 1).
+        // One thread can issue a tcgen05.mma only every ~80 cycles (measured: MMA-only time = 1434 + 78 n
+        // cycles per tile for n MMAs), which is slower than an M128 N128 K8 MMA executes (64 cycles); two
+        // issuers keep the tensor pipe fed and hide each other's per-tile barrier latencies.
         if (lane == 0) {
+            const int p = (warp == 1) ? 0 : 1;
             mbar_wait(a_ready, 0, A.err_flag, 2);
             tc_fence_after();
             const uint32_t a_hi0 = tmem_base;
             const uint32_t a_lo0 = tmem_base + (uint32_t)(nkb * TC_KB);
-            int it = 0;
-            for (int i = 0; i < n_tiles; ++i) {
-                const int b = i & 1;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + p * TN);
+            for (int i = p; i < n_tiles; i += 2) {
                 const uint32_t u = (uint32_t)((i >> 1) & 1);
-                mbar_wait(tmem_empty + b, u ^ 1u, A.err_flag, 3);
+                mbar_wait(tmem_empty + p, u ^ 1u, A.err_flag, 3);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + b * TN);
                 uint32_t acc = 0;
+                int it = i * nkb;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % A.stages;
                     const uint32_t ph = (uint32_t)((it / A.stages) & 1);
@@ -305,7 +311,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     const uint32_t bhi = smem_u32(b_tiles + (size_t)s * TC_STAGE_BYTES);
                     const uint32_t blo = bhi + TC_TILE_BYTES;
 #pragma unroll
-                    for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 = 32 bytes
+                    for (int k8 = 0; k8 < ((A.dbg & 2) ? 0 : 4); ++k8) {  // UMMA K = 8 tf32 = 32 bytes
                         const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
                         const uint64_t dhi = make_b_desc(bhi + k8 * 32);
                         if (A.passes == 3) {
@@ -320,7 +326,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     }
                     tc_commit(empty + s);  // stage reusable once these MMAs have read it
                 }
-                tc_commit(tmem_full + b);  // accumulator b complete
+                tc_commit(tmem_full + p);  // accumulator p complete
             }
         }
     } else if (warp == 2) {
@@ -332,6 +338,10 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             if (lane == 0) mcur = lower_bound_u32(P.mask_keys, __ldg(P.mask_tile_ptr + rt_abs), mend, ((uint32_t)(t0 * TN)) << 7);
             mcur = __shfl_sync(0xffffffffu, mcur, 0);
         }
+        // the next 32 keys are always in flight / in a register before the tile that needs them:
+        // the global-load latency hides behind the wait for the bitmap buffer
+        uint32_t key = 0xffffffffu;
+        if (P.mask_keys != nullptr) key = (mcur + lane < mend) ? __ldg(P.mask_keys + mcur + lane) : 0xffffffffu;
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
             const uint32_t u = (uint32_t)((i >> 1) & 1);
@@ -344,15 +354,15 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 const uint32_t lo = ((uint32_t)col0) << 7;
                 const uint32_t lim = ((uint32_t)(col0 + TN)) << 7;
                 for (;;) {  // keys ascending: skip those before this tile (SAMPLE strides), set those inside
-                    const int64_t p = mcur + lane;
-                    const uint32_t key = (p < mend) ? __ldg(P.mask_keys + p) : 0xffffffffu;
                     const bool in = key < lim;
                     if (in && key >= lo) {
                         const int cc = (int)(key >> 7) - col0;
                         atomicOr(&bm[(cc >> 5) * TM + (int)(key & 127u)], 1u << (cc & 31));
                     }
                     const int n_in = __popc(__ballot_sync(0xffffffffu, in));
+                    if (n_in == 0) break;
                     mcur += n_in;
+                    key = (mcur + lane < mend) ? __ldg(P.mask_keys + mcur + lane) : 0xffffffffu;
                     if (n_in < 32) break;
                 }
             }
@@ -399,28 +409,24 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(a_ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
         }
 
-        // COLLECT: T0 = r-th largest of the row's two sampled lists (a 2-way merge of sorted lists)
+        // COLLECT: fixed per-row threshold from the sampled pre-pass; survivors go to this thread's sub-list
         float thr = PINF;  // rows beyond n_rows collect nothing
-        u64 *my_list = nullptr;
-        uint32_t cnt = 0;
+        uint2 *wbase = nullptr, *wp = nullptr, *wend = nullptr;
+        bool overflow = false;
         float v[TC_R];  // SAMPLE: largest group maxima so far, descending
 #pragma unroll
         for (int q = 0; q < TC_R; ++q) v[q] = NINF;
         if (!sample && my_valid) {
-            const float *la = A.samp + my_row * (2 * TC_R), *lb = la + TC_R;
-            int ia = 0, ib = 0;
-            float t = NINF;
-            for (int q = 0; q < A.r; ++q) {
-                const float xa = (ia < TC_R) ? __ldg(la + ia) : NINF;
-                const float xb = (ib < TC_R) ? __ldg(lb + ib) : NINF;
-                if (xa >= xb) { t = xa; ++ia; } else { t = xb; ++ib; }
-            }
-            thr = t;
-            my_list = A.cand + ((my_row * P.S + c) * 2 + wg) * (int64_t)A.cap;
+            thr = __ldg(A.thr + my_row);
+            wbase = A.cand + ((my_row * P.S + c) * 2 + wg) * (int64_t)A.sub_stride;
+            wp = wbase;
+            wend = wbase + A.cap;
         }
+        const float QNAN = __int_as_float(0x7fffffff);  // masked score: fails every >=, ignored by fmaxf
 
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
@@ -432,7 +438,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             const uint32_t *bm = bitmap + b * 4 * TM + (wg * 2) * TM + r;
             const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC_COL + b * TN + wg * 64);
 #pragma unroll 1
-            for (int gq = 0; gq < 2; ++gq) {
+            for (int gq = 0; gq < ((A.dbg & 1) ? 0 : 2); ++gq) {
                 uint32_t raw[32];
                 __syncwarp();
                 tmem_ld32(acc_addr + (uint32_t)(gq * 32), raw);
@@ -454,45 +460,51 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 #pragma unroll
                     for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]);
                 }
+                if (mword != 0u) {  // train items (and columns past the catalogue) never count
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if ((mword >> q) & 1u) s[q] = QNAN;
+                }
                 if (sample) {
-                    if (mword != 0u) {  // train items (and columns past the catalogue) do not count
-#pragma unroll
-                        for (int q = 0; q < 32; ++q)
-                            if ((mword >> q) & 1u) s[q] = NINF;
-                    }
-                    float mx = NINF;
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) mx = fmaxf(mx, s[q]);
-                    if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
-                } else {
-                    // level-1 maxima over triples, then the group maximum
                     float m1[11];
 #pragma unroll
                     for (int q = 0; q < 10; ++q) m1[q] = fmaxf(fmaxf(s[3 * q], s[3 * q + 1]), s[3 * q + 2]);
                     m1[10] = fmaxf(s[30], s[31]);
-                    float mx = m1[0];
+                    float mx = fmaxf(fmaxf(m1[0], m1[1]), m1[2]);
+                    mx = fmaxf(mx, fmaxf(fmaxf(m1[3], m1[4]), m1[5]));
+                    mx = fmaxf(mx, fmaxf(fmaxf(m1[6], m1[7]), m1[8]));
+                    mx = fmaxf(mx, fmaxf(m1[9], m1[10]));
+                    if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
+                } else if (!(A.dbg & 4)) {
+                    // straight-line, predicated (no branches, no divergence): one compare per score,
+                    // survivors appended as (score bits, item)
+                    const uint32_t cb = (uint32_t)(col0 + gq * 32);
+                    // address = list base (64-bit) + 32-bit byte offset: one IMAD.WIDE per store
+                    const unsigned long long wb = reinterpret_cast<unsigned long long>(wbase);
+                    uint32_t off = (uint32_t)(reinterpret_cast<unsigned long long>(wp) - wb);
 #pragma unroll
-                    for (int q = 1; q < 11; ++q) mx = fmaxf(mx, m1[q]);
-                    if (mx >= thr) {
-#pragma unroll
-                        for (int q = 0; q < 11; ++q) {
-                            if (m1[q] >= thr) {
-#pragma unroll
-                                for (int e = 3 * q; e < 3 * q + 3 && e < 32; ++e) {
-                                    if (s[e] >= thr && ((mword >> e) & 1u) == 0u) {
-                                        if (cnt < (uint32_t)A.cap) my_list[cnt] = make_key(s[e], (uint32_t)(col0 + gq * 32 + e));
-                                        ++cnt;
-                                    }
-                                }
-                            }
-                        }
+                    for (int q = 0; q < 32; ++q) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+                            "setp.ge.f32 p, %1, %2;\n\t"
+                            "mad.wide.u32 a, %0, 1, %5;\n\t"
+                            "@p st.global.v2.b32 [a], {%3, %4};\n\t"
+                            "@p add.u32 %0, %0, 8;\n\t}"
+                            : "+r"(off)
+                            : "f"(s[q]), "f"(thr), "r"(__float_as_uint(s[q])), "r"(cb + q), "l"(wb)
+                            : "memory");
                     }
+                    wp = reinterpret_cast<uint2 *>(wb + off);
+                    if (wp >= wend) { overflow = (wend != nullptr); wp = wend; }
                 }
             }
             // this thread is done with accumulator b and bitmap b
             tc_fence_before();
-            mbar_arrive(tmem_empty + b);
-            mbar_arrive(bm_empty + b);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tmem_empty + b);
+                mbar_arrive(bm_empty + b);
+            }
         }
 
         if (my_valid) {
@@ -501,7 +513,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 #pragma unroll
                 for (int q = 0; q < TC_R; ++q) dst[q] = v[q];
             } else {
-                A.cand_cnt[(my_row * P.S + c) * 2 + wg] = cnt;
+                A.cand_cnt[(my_row * P.S + c) * 2 + wg] = overflow ? (uint32_t)(A.cap + 1) : (uint32_t)(wp - wbase);
             }
         }
     }
@@ -512,6 +524,25 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+}
+
+// ---- sampled group maxima -> per-row threshold -------------------------------------------------------
+// thr[row] = r-th largest of the row's two descending lists (one per column half) = r-th largest
+// sampled group maximum.  With fewer than r finite entries it is -inf (everything is a candidate).
+__global__ void k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const float *la = samp + row * (2 * TC_R), *lb = la + TC_R;
+    const float NINF = -__int_as_float(0x7f800000);
+    int ia = 0, ib = 0;
+    float t = NINF;
+    for (int q = 0; q < r; ++q) {
+        const float xa = (ia < TC_R) ? la[ia] : NINF;
+        const float xb = (ib < TC_R) ? lb[ib] : NINF;
+        if (xa >= xb) { t = xa; ++ia; } else { t = xb; ++ib; }
+    }
+    thr[row] = t;
 }
 
 // ---- candidate lists -> sorted top-K ----------------------------------------------------------------
@@ -540,7 +571,7 @@ __device__ __forceinline__ void sel_sort_write(const u64 *buf, int n, int K, u64
 }
 
 __global__ void __launch_bounds__(SEL_WARPS * 32)
-k_select_cands(const u64 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int K,
+k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
                int64_t n_rows, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count)
 {
     __shared__ u64 sbuf[SEL_WARPS][SEL_MAX];
@@ -554,8 +585,11 @@ k_select_cands(const u64 *__restrict__ cand, const uint32_t *__restrict__ cand_c
     for (int s = 0; s < n_sub; ++s) {
         const int c = (int)__ldg(cc + s);
         if (c > cap || n + c > SEL_MAX) { bad = true; break; }
-        const u64 *src = cand + (row * n_sub + s) * (int64_t)cap;
-        for (int i = lane; i < c; i += 32) buf[n + i] = src[i];
+        const uint2 *src = cand + (row * n_sub + s) * (int64_t)sub_stride;
+        for (int i = lane; i < c; i += 32) {
+            const uint2 e = src[i];
+            buf[n + i] = make_key(__uint_as_float(e.x), e.y);
+        }
         n += c;
     }
     if (bad || n < K) {

@@ -71,6 +71,7 @@ struct skr_ctx {
     int64_t opt_stages = 0;
     int64_t opt_sample_tiles = 0;
     int64_t opt_rank = 0;
+    int64_t opt_dbg = 0;
     struct Plan { int n_samp, stride, r, cap, S, stages; } last_plan = {0, 0, 0, 0, 0, 0};
     EncodeTiledFn encode = nullptr;
     std::vector<cudaEvent_t> ev0, ev1, ev2;  // ring: ev2 before the pre-pass, ev0/ev1 around the main scoring kernel
@@ -330,6 +331,7 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "stages")) { ctx->opt_stages = value; return SKR_OK; }
     if (!strcmp(name, "sample_tiles")) { ctx->opt_sample_tiles = value; return SKR_OK; }
     if (!strcmp(name, "rank")) { ctx->opt_rank = value; return SKR_OK; }
+    if (!strcmp(name, "dbg")) { ctx->opt_dbg = value; return SKR_OK; }
     if (!strcmp(name, "event_ring")) {
         if (value < 1 || value > 65536) return fail(ctx, SKR_ERR_INVALID, "event_ring=%lld not in [1,65536]", (long long)value);
         cudaSetDevice(ctx->device);
@@ -594,7 +596,9 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         const int n_sub = 2 * P.S;
 
         if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 2 * TC_R * sizeof(float)))) return rc;
-        if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * cap * sizeof(u64)))) return rc;
+        const int sub_stride = next_pow2(cap + 32);
+        if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * sub_stride * sizeof(uint2) + 8192))) return rc;
+        if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(float)))) return rc;
         if ((rc = ensure(ctx, ctx->cand_cnt, (size_t)n_rows * n_sub * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
         int *fail_count = (int *)ctx->fail_list.p;             // [0] = count, [1..] = rows
@@ -607,12 +611,14 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         A.nkb = nkb;
         A.stages = stages;
         A.err_flag = ctx->d_err;
+        A.dbg = (int)ctx->opt_dbg;
         A.stride = stride;
         A.n_samp = n_samp;
         A.samp = (float *)ctx->samp.p;
-        A.r = r;
+        A.thr = (const float *)ctx->thr.p;
         A.cap = cap;
-        A.cand = (u64 *)ctx->cand.p;
+        A.sub_stride = sub_stride;
+        A.cand = (uint2 *)(((uintptr_t)ctx->cand.p + 8191) & ~(uintptr_t)8191);  // stride-aligned (stride <= 8 KB)
         A.cand_cnt = (uint32_t *)ctx->cand_cnt.p;
         const size_t smem = tc_smem_bytes(stages);
         SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -621,16 +627,17 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         A.passes = 1;
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         k_fused_tc<<<(unsigned)P.n_rt, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
+        k_sample_thr<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p);
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         A.mode = TC_MODE_COLLECT;
         A.passes = (precision == SKR_PREC_1XTF32) ? 1 : 3;
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
         k_fused_tc<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
-        ctx->launches += 2;
+        ctx->launches += 3;
         SKR_CUDA(ctx, cudaGetLastError());
         k_select_cands<<<(unsigned)((n_rows + SEL_WARPS - 1) / SEL_WARPS), SEL_WARPS * 32, 0, st>>>(
-            A.cand, A.cand_cnt, n_sub, cap, K, n_rows, keys, fail_list, fail_count);
+            A.cand, A.cand_cnt, n_sub, cap, sub_stride, K, n_rows, keys, fail_list, fail_count);
         k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, user_vecs_dev, ld_u, item_vecs_dev, ld_i, d,
                                                                       bias_dev, (int)n_items, row0, tp, ti, K, keys);
         ctx->launches += 2;
