@@ -32,6 +32,7 @@ struct FusedParams {
     const float *bias;                 // [n_ct*TN] padded, or null
     const uint32_t *mask_keys;         // per user tile, ascending (item << 7 | row_in_tile), or null
     const int64_t *mask_tile_ptr;      // [total user tiles + 1]
+    const uint32_t *mask_tile_off;     // [total user tiles, n_ct + 1] key offsets of each item tile within the user tile
     uint32_t *thr_g;                   // [n_rows] ord(score) thresholds, 0 = none
     u64 *part;                         // [n_rows, S, K] partial lists
 };

@@ -29,9 +29,9 @@
 // into hi/lo tables and streamed by TMA (SWIZZLE_128B, 128 rows x 32 floats per box) through an
 // mbarrier ring of k-block stages.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer of the even tiles
-// (one lane), warp 2 train-mask bitmap builder, warp 3 MMA issuer of the odd tiles, warps 4-7 epilogue of columns 0-63, warps 8-11
-// epilogue of columns 64-127 (thread <-> TMEM lane <-> user row; two warps per SM sub-partition so
+// Warp roles (384 threads): warps 0-3 epilogue of columns 0-63, warps 4-7 epilogue of columns 64-127,
+// warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer of the even tiles (one lane), warp 10
+// train-mask bitmap builder, warp 11 MMA issuer of the odd tiles (thread <-> TMEM lane <-> user row; two warps per SM sub-partition so
 // the TMEM-load and compare latencies of one hide behind the other).  Accumulators and bitmaps are
 // double buffered so the epilogue of tile n overlaps the MMAs of tile n+1.
 //
@@ -47,7 +47,7 @@ constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_KB = 32;                             // floats per k-block (one 128-byte swizzle row)
 constexpr int TC_TILE_BYTES = TN * TC_KB * 4;         // 16 KB: one operand tile of one k-block
 constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // hi + lo
-constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_ACC_COL = 256;                       // first accumulator column
 constexpr int TC_R = 32;                              // group maxima kept per row and warpgroup (SAMPLE)
 constexpr long long TC_TIMEOUT_CYCLES = 4000000000ll; // watchdog: ~2 s
@@ -59,6 +59,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int stages)
     return (size_t)1024                          // alignment slack
            + (size_t)stages * TC_STAGE_BYTES
            + (size_t)2 * 4 * TM * 4              // two bitmaps
+           + (size_t)8 * TC_EPI_THREADS * 16     // score staging: one 32-float row per epilogue thread, [8][256] float4
            + 256;                                // barriers + tmem pointer
 }
 
@@ -222,7 +223,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *b_tiles = smem;
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + (size_t)A.stages * TC_STAGE_BYTES);  // [2][4][TM]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bitmap + 2 * 4 * TM);
+    float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + 2 * 4 * TM);  // [8][TC_EPI_THREADS]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 8 * TC_EPI_THREADS);
     uint64_t *full = bars;                            // [TC_MAX_STAGES]
     uint64_t *empty = bars + TC_MAX_STAGES;           // [TC_MAX_STAGES]
     uint64_t *tmem_full = bars + 2 * TC_MAX_STAGES;   // [2]
@@ -232,7 +234,10 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     uint64_t *a_ready = bm_empty + 2;                 // [1]
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_ready + 1);
 
+    // Epilogue = warps 0-7, helpers = warps 8-11: the warp scheduler favours higher warp ids, and the
+    // latency-critical single-thread roles (TMA producer, MMA issuers) must not queue behind the epilogue.
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int role = warp - 8;  // 0 TMA producer, 1 MMA issuer (even tiles) + TMEM allocator, 2 mask builder, 3 MMA issuer (odd tiles)
     const int c = blockIdx.x / P.n_rt, rt = blockIdx.x % P.n_rt;
     const bool sample = (A.mode == TC_MODE_SAMPLE);
     // tiles of this work item: COLLECT t0 + i, SAMPLE i * stride
@@ -253,11 +258,11 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         mbar_init(a_ready, TM / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0 && lane == 0) {
+    if (role == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo) : "memory");
     }
-    if (warp == 1) {
+    if (role == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -266,7 +271,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
+    if (role == 0) {
         // ===== TMA producer: item k-block tiles (hi, lo) through the stage ring ==================
         if (lane == 0) {
             const uint32_t tx_bytes = (A.passes == 3) ? TC_STAGE_BYTES : TC_TILE_BYTES;
@@ -285,13 +290,13 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 }
             }
         }
-    } else if (warp == 1 || warp == 3) {
+    } else if (role == 1 || role == 3) {
         // ===== MMA issuers: warp 1 takes the even tiles (accumulator 0), warp 3 the odd ones (accumulator 1).
         // One thread can issue a tcgen05.mma only every ~80 cycles (measured: MMA-only time = 1434 + 78 n
         // cycles per tile for n MMAs), which is slower than an M128 N128 K8 MMA executes (64 cycles); two
         // issuers keep the tensor pipe fed and hide each other's per-tile barrier latencies.
         if (lane == 0) {
-            const int p = (warp == 1) ? 0 : 1;
+            const int p = (role == 1) ? 0 : 1;
             mbar_wait(a_ready, 0, A.err_flag, 2);
             tc_fence_after();
             const uint32_t a_hi0 = tmem_base;
@@ -308,14 +313,13 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     const uint32_t ph = (uint32_t)((it / A.stages) & 1);
                     mbar_wait(full + s, ph, A.err_flag, 4);
                     tc_fence_after();
-                    const uint32_t bhi = smem_u32(b_tiles + (size_t)s * TC_STAGE_BYTES);
-                    const uint32_t blo = bhi + TC_TILE_BYTES;
+                    const uint64_t d0 = make_b_desc(smem_u32(b_tiles + (size_t)s * TC_STAGE_BYTES));
 #pragma unroll
                     for (int k8 = 0; k8 < ((A.dbg & 2) ? 0 : 4); ++k8) {  // UMMA K = 8 tf32 = 32 bytes
                         const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
-                        const uint64_t dhi = make_b_desc(bhi + k8 * 32);
+                        const uint64_t dhi = d0 + (uint64_t)(k8 * 2);  // start-address field counts 16-byte units
                         if (A.passes == 3) {
-                            const uint64_t dlo = make_b_desc(blo + k8 * 32);
+                            const uint64_t dlo = dhi + (uint64_t)(TC_TILE_BYTES >> 4);
                             tc_mma_ts(d_tmem, a_lo0 + acol, dhi, TC_IDESC, acc);
                             tc_mma_ts(d_tmem, a_hi0 + acol, dlo, TC_IDESC, 1u);
                             tc_mma_ts(d_tmem, a_hi0 + acol, dhi, TC_IDESC, 1u);
@@ -329,50 +333,57 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 tc_commit(tmem_full + p);  // accumulator p complete
             }
         }
-    } else if (warp == 2) {
+    } else if (role == 2) {
         // ===== train-mask bitmap builder ===========================================================
-        int64_t mcur = 0, mend = 0;
+        // Keys of this user tile are sorted by item; mask_tile_off gives, per item tile, where its keys
+        // start, so nothing is searched or skipped and every load address is known tiles ahead: the
+        // offsets and first 32 keys of tile i+1 are fetched while tile i is being built.
+        const uint32_t *keys = nullptr;
+        const uint32_t *offs = nullptr;
         if (P.mask_keys != nullptr) {
             const int64_t rt_abs = (P.row0 / TM) + rt;
-            mend = __ldg(P.mask_tile_ptr + rt_abs + 1);
-            if (lane == 0) mcur = lower_bound_u32(P.mask_keys, __ldg(P.mask_tile_ptr + rt_abs), mend, ((uint32_t)(t0 * TN)) << 7);
-            mcur = __shfl_sync(0xffffffffu, mcur, 0);
+            keys = P.mask_keys + __ldg(P.mask_tile_ptr + rt_abs);
+            offs = P.mask_tile_off + rt_abs * (int64_t)(P.n_ct + 1);
         }
-        // the next 32 keys are always in flight / in a register before the tile that needs them:
-        // the global-load latency hides behind the wait for the bitmap buffer
-        uint32_t key = 0xffffffffu;
-        if (P.mask_keys != nullptr) key = (mcur + lane < mend) ? __ldg(P.mask_keys + mcur + lane) : 0xffffffffu;
+        uint32_t nb = 0, ne = 0, nkey = 0xffffffffu;  // next tile: key range and first batch
+        if (keys != nullptr && n_tiles > 0) {
+            nb = __ldg(offs + t0);
+            ne = __ldg(offs + t0 + 1);
+            if (nb + lane < ne) nkey = __ldg(keys + nb + lane);
+        }
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
             const uint32_t u = (uint32_t)((i >> 1) & 1);
             const int col0 = (t0 + i * t_step) * TN;
+            const uint32_t kb0 = nb, ke0 = ne;
+            uint32_t key = nkey;
+            if (keys != nullptr && i + 1 < n_tiles) {  // prefetch for tile i + 1
+                const int tn = t0 + (i + 1) * t_step;
+                nb = __ldg(offs + tn);
+                ne = __ldg(offs + tn + 1);
+            }
             mbar_wait(bm_empty + b, u ^ 1u, A.err_flag, 5);
             uint32_t *bm = bitmap + b * 4 * TM;
             for (int q = lane; q < 4 * TM; q += 32) bm[q] = oob_bits(col0, q / TM, P.n_items);
             __syncwarp();
-            if (P.mask_keys != nullptr) {
-                const uint32_t lo = ((uint32_t)col0) << 7;
-                const uint32_t lim = ((uint32_t)(col0 + TN)) << 7;
-                for (;;) {  // keys ascending: skip those before this tile (SAMPLE strides), set those inside
-                    const bool in = key < lim;
-                    if (in && key >= lo) {
+            if (keys != nullptr) {
+                for (uint32_t p = kb0; p < ke0; p += 32) {
+                    if (p != kb0) key = (p + lane < ke0) ? __ldg(keys + p + lane) : 0xffffffffu;
+                    if (p + lane < ke0) {
                         const int cc = (int)(key >> 7) - col0;
                         atomicOr(&bm[(cc >> 5) * TM + (int)(key & 127u)], 1u << (cc & 31));
                     }
-                    const int n_in = __popc(__ballot_sync(0xffffffffu, in));
-                    if (n_in == 0) break;
-                    mcur += n_in;
-                    key = (mcur + lane < mend) ? __ldg(P.mask_keys + mcur + lane) : 0xffffffffu;
-                    if (n_in < 32) break;
                 }
+                nkey = 0xffffffffu;
+                if (i + 1 < n_tiles && nb + lane < ne) nkey = __ldg(keys + nb + lane);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bm_full + b);
         }
-    } else if (warp >= 4) {
+    } else if (role < 0) {
         // ===== epilogue: thread <-> user row, warpgroup wg <-> columns [64 wg, 64 wg + 64) ==========
-        const int wg = (warp - 4) >> 2;
-        const int r = (tid - 128) & 127;  // TMEM lane
+        const int wg = warp >> 2;
+        const int r = tid & 127;  // TMEM lane
         const int64_t my_row = row_base + r;
         const bool my_valid = my_row < P.n_rows;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -416,7 +427,6 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         // COLLECT: fixed per-row threshold from the sampled pre-pass; survivors go to this thread's sub-list
         float thr = PINF;  // rows beyond n_rows collect nothing
         uint2 *wbase = nullptr, *wp = nullptr, *wend = nullptr;
-        bool overflow = false;
         float v[TC_R];  // SAMPLE: largest group maxima so far, descending
 #pragma unroll
         for (int q = 0; q < TC_R; ++q) v[q] = NINF;
@@ -427,6 +437,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             wend = wbase + A.cap;
         }
         const float QNAN = __int_as_float(0x7fffffff);  // masked score: fails every >=, ignored by fmaxf
+        float4 *my_stage = stage_buf + tid;  // element q of my row: float (q & 3) of my_stage[(q >> 2) * TC_EPI_THREADS]
 
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
@@ -460,7 +471,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 #pragma unroll
                     for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]);
                 }
-                if (mword != 0u) {  // train items (and columns past the catalogue) never count
+                if (sample && mword != 0u) {  // train items (and columns past the catalogue) never count
 #pragma unroll
                     for (int q = 0; q < 32; ++q)
                         if ((mword >> q) & 1u) s[q] = QNAN;
@@ -476,26 +487,37 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     mx = fmaxf(mx, fmaxf(m1[9], m1[10]));
                     if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
                 } else if (!(A.dbg & 4)) {
-                    // straight-line, predicated (no branches, no divergence): one compare per score,
-                    // survivors appended as (score bits, item)
-                    const uint32_t cb = (uint32_t)(col0 + gq * 32);
-                    // address = list base (64-bit) + 32-bit byte offset: one IMAD.WIDE per store
-                    const unsigned long long wb = reinterpret_cast<unsigned long long>(wbase);
-                    uint32_t off = (uint32_t)(reinterpret_cast<unsigned long long>(wp) - wb);
+                    // Detection costs two instructions per score on two different pipes and no
+                    // predicates: d = s - T0 (FMA pipe), then a funnel shift (ALU pipe) collects the sign
+                    // bit of d; bit q of `pass` ends up set iff s[q] >= T0 and item q is not masked.
+                    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // four independent chains of 8 for ILP
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
-                            "setp.ge.f32 p, %1, %2;\n\t"
-                            "mad.wide.u32 a, %0, 1, %5;\n\t"
-                            "@p st.global.v2.b32 [a], {%3, %4};\n\t"
-                            "@p add.u32 %0, %0, 8;\n\t}"
-                            : "+r"(off)
-                            : "f"(s[q]), "f"(thr), "r"(__float_as_uint(s[q])), "r"(cb + q), "l"(wb)
-                            : "memory");
+                    for (int q = 0; q < 8; ++q) {
+                        m0 = __funnelshift_l(__float_as_uint(s[q] - thr), m0, 1);
+                        m1 = __funnelshift_l(__float_as_uint(s[q + 8] - thr), m1, 1);
+                        m2 = __funnelshift_l(__float_as_uint(s[q + 16] - thr), m2, 1);
+                        m3 = __funnelshift_l(__float_as_uint(s[q + 24] - thr), m3, 1);
                     }
-                    wp = reinterpret_cast<uint2 *>(wb + off);
-                    if (wp >= wend) { overflow = (wend != nullptr); wp = wend; }
+                    // chain j holds items 8j..8j+7 with item 8j in bit 7: assemble so that item 0 lands in
+                    // bit 31, then reverse
+                    const uint32_t m = (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
+                    uint32_t pass = ~__brev(m) & ~mword;
+                    if (pass != 0u) {
+                        // rare per lane: park my 32 scores in shared memory so they can be indexed,
+                        // then append each survivor as (score bits, item) to my list in HBM
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            my_stage[q * TC_EPI_THREADS] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+                        const uint32_t cb = (uint32_t)(col0 + gq * 32);
+                        const float *row_f = reinterpret_cast<const float *>(my_stage);
+                        do {
+                            const int q = __ffs(pass) - 1;
+                            pass &= pass - 1u;
+                            const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
+                            if (wp < wend) *wp = make_uint2(__float_as_uint(sc), cb + (uint32_t)q);
+                            ++wp;
+                        } while (pass != 0u);
+                    }
                 }
             }
             // this thread is done with accumulator b and bitmap b
@@ -513,7 +535,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 #pragma unroll
                 for (int q = 0; q < TC_R; ++q) dst[q] = v[q];
             } else {
-                A.cand_cnt[(my_row * P.S + c) * 2 + wg] = overflow ? (uint32_t)(A.cap + 1) : (uint32_t)(wp - wbase);
+                A.cand_cnt[(my_row * P.S + c) * 2 + wg] = (uint32_t)(wp - wbase);  // > cap means overflow
             }
         }
     }
@@ -521,7 +543,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1) {
+    if (role == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }

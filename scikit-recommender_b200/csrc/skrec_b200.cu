@@ -54,6 +54,7 @@ struct skr_ctx {
     int32_t *d_tr_idx = nullptr;
     uint32_t *d_mask_keys = nullptr;
     int64_t *d_mask_tile_ptr = nullptr;
+    uint32_t *d_mask_tile_off = nullptr;
     // test CSR (sorted, unique)
     bool has_test = false;
     int64_t te_rows = 0, te_items = 0;
@@ -311,7 +312,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
 {
     if (!ctx) return SKR_OK;
     cudaSetDevice(ctx->device);
-    free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr);
+    free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr); free_dev(ctx->d_mask_tile_off);
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_err);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
@@ -407,6 +408,8 @@ int skr_set_train_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indice
     const int64_t n_rt = (n_rows + TM - 1) / TM;
     std::vector<int64_t> tile_ptr((size_t)n_rt + 1, 0);
     std::vector<uint32_t> keys(oidx.size());
+    const int64_t n_ct = (n_items + TN - 1) / TN;
+    std::vector<uint32_t> tile_off((size_t)n_rt * (size_t)(n_ct + 1), 0);
     for (int64_t rt = 0; rt < n_rt; ++rt) {
         const int64_t r0 = rt * TM, r1 = std::min<int64_t>(r0 + TM, n_rows);
         const int64_t b = optr[(size_t)r0], e = optr[(size_t)r1];
@@ -415,12 +418,21 @@ int skr_set_train_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indice
             for (int64_t p = optr[(size_t)r]; p < optr[(size_t)r + 1]; ++p)
                 keys[(size_t)p] = ((uint32_t)oidx[(size_t)p] << 7) | (uint32_t)(r - r0);
         std::sort(keys.begin() + b, keys.begin() + e);
+        // where each 128-item tile starts inside this user tile's keys
+        uint32_t *off = tile_off.data() + (size_t)rt * (size_t)(n_ct + 1);
+        int64_t p = b;
+        for (int64_t ct = 0; ct <= n_ct; ++ct) {
+            const uint32_t lim = (uint32_t)std::min<int64_t>(ct * TN, n_items) << 7;
+            while (p < e && keys[(size_t)p] < lim) ++p;
+            off[ct] = (uint32_t)(p - b);
+        }
     }
     tile_ptr[(size_t)n_rt] = (int64_t)oidx.size();
     if ((rc = upload(ctx, &ctx->d_tr_indptr, optr))) return rc;
     if ((rc = upload(ctx, &ctx->d_tr_idx, oidx))) return rc;
     if ((rc = upload(ctx, &ctx->d_mask_keys, keys))) return rc;
     if ((rc = upload(ctx, &ctx->d_mask_tile_ptr, tile_ptr))) return rc;
+    if ((rc = upload(ctx, &ctx->d_mask_tile_off, tile_off))) return rc;
     ctx->tr_rows = n_rows;
     ctx->tr_items = n_items;
     ctx->has_train = true;
@@ -511,7 +523,7 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
     if (row0 % TM != 0) return fail(ctx, SKR_ERR_INVALID, "row0=%lld must be a multiple of %d", (long long)row0, TM);
     if (ctx->has_train && (row0 < 0 || row0 + n_rows > ctx->tr_rows))
         return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the train CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->tr_rows);
-    if (ctx->has_train && ctx->tr_items > n_items) return fail(ctx, SKR_ERR_INVALID, "train CSR has %lld items, item table only %lld", (long long)ctx->tr_items, (long long)n_items);
+    if (ctx->has_train && ctx->tr_items != n_items) return fail(ctx, SKR_ERR_INVALID, "train CSR was built for %lld items, item table has %lld", (long long)ctx->tr_items, (long long)n_items);
     if (precision < SKR_PREC_AUTO || precision > SKR_PREC_1XTF32) return fail(ctx, SKR_ERR_INVALID, "precision=%d", precision);
     SKR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -546,6 +558,7 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
     P.S = (P.n_ct + P.tiles_per_chunk - 1) / P.tiles_per_chunk;  // drop empty chunks
     P.mask_keys = ctx->has_train ? ctx->d_mask_keys : nullptr;
     P.mask_tile_ptr = ctx->has_train ? ctx->d_mask_tile_ptr : nullptr;
+    P.mask_tile_off = ctx->has_train ? ctx->d_mask_tile_off : nullptr;
     P.thr_g = nullptr;
     P.part = nullptr;
 
