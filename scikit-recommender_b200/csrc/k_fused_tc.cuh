@@ -567,66 +567,6 @@ __global__ void k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int
     thr[row] = t;
 }
 
-// ---- candidate lists -> sorted top-K ----------------------------------------------------------------
-// One warp per row: gather the row's n_sub sub-lists into shared memory, sort (warp bitonic, size
-// picked from the row's own candidate count), write the K best keys.  Rows with fewer than K
-// candidates (threshold estimate too high, or fewer than K unmasked items) or with an overflowed
-// sub-list go on the fail list and are re-done exactly by k_row_exact.
-constexpr int SEL_WARPS = 4;
-constexpr int SEL_MAX = 1024;  // candidates a row may carry into the sort
-
-template <int PER>
-__device__ __forceinline__ void sel_sort_write(const u64 *buf, int n, int K, u64 *dst, int lane)
-{
-    u64 v[PER];
-#pragma unroll
-    for (int e = 0; e < PER; ++e) {
-        const int i = e * 32 + lane;
-        v[e] = (i < n) ? buf[i] : 0ull;
-    }
-    warp_bitonic_desc<PER>(v, lane);
-#pragma unroll
-    for (int e = 0; e < PER; ++e) {
-        const int i = e * 32 + lane;
-        if (i < K) dst[i] = v[e];
-    }
-}
-
-__global__ void __launch_bounds__(SEL_WARPS * 32)
-k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
-               int64_t n_rows, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count)
-{
-    __shared__ u64 sbuf[SEL_WARPS][SEL_MAX];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp;
-    if (row >= n_rows) return;
-    u64 *buf = sbuf[warp];
-    const uint32_t *cc = cand_cnt + row * n_sub;
-    int n = 0;
-    bool bad = false;
-    for (int s = 0; s < n_sub; ++s) {
-        const int c = (int)__ldg(cc + s);
-        if (c > cap || n + c > SEL_MAX) { bad = true; break; }
-        const uint2 *src = cand + (row * n_sub + s) * (int64_t)sub_stride;
-        for (int i = lane; i < c; i += 32) {
-            const uint2 e = src[i];
-            buf[n + i] = make_key(__uint_as_float(e.x), e.y);
-        }
-        n += c;
-    }
-    if (bad || n < K) {
-        if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
-        return;
-    }
-    __syncwarp();
-    u64 *dst = out_keys + row * (int64_t)K;
-    if (n <= 64) sel_sort_write<2>(buf, n, K, dst, lane);
-    else if (n <= 128) sel_sort_write<4>(buf, n, K, dst, lane);
-    else if (n <= 256) sel_sort_write<8>(buf, n, K, dst, lane);
-    else if (n <= 512) sel_sort_write<16>(buf, n, K, dst, lane);
-    else sel_sort_write<32>(buf, n, K, dst, lane);
-}
-
 // ---- operand preparation ---------------------------------------------------------------------------
 // item table -> hi/lo TF32 tables [n, d_pad] (zero padded in k), one thread per output element
 __global__ void k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad,

@@ -14,102 +14,114 @@ struct MetricIds {
     int id[8];
 };
 
-constexpr int K4_WARPS = 4;
+constexpr int K4_WARPS = 8;
 
-// ---- K4: one warp per user ---------------------------------------------------------------
+// ---- K4: one warp per user, every lane owns rank positions i = lane, lane + 32, ... --------------
 // keys: sorted rank keys [n_rows, K] (or null), idx_in: int32 rank lists [n_rows, K] (or null).
+//
+// The reference's recurrences run i = 0..K-1 with float accumulators.  Restated per position without
+// changing a single rounding:
+//   hits(i)    = number of hits at positions <= i        (small integer, exact in float)
+//   Precision  = hits(i) / (float)(i+1);  Recall = hits(i) / (float)L
+//   MAP        : sum_pre changes only AT hits, by pre = hits/(i+1) = Precision(i): the float adds are
+//                replayed in ascending hit order (a warp-uniform loop over the set bits of the hit
+//                mask, usually a handful); position i keeps the value after the last hit <= i.
+//   NDCG       : DCG changes only at hits (same loop, double add rounded to float); iDCG after i
+//                depends only on min(i+1, L): table idcg[n] built on the host with the same operations.
+//   MRR        = (float)(1.0 / (double)(p+1)) from the first hit p on.
+// Rows are dealt round-robin to warps (row = global warp id + j * total warps).  With acc_out != null
+// every warp also sums its rows' values per column in float64 in shared memory; the block folds its
+// warps in warp order and writes one partial row: deterministic, no atomics.
 __global__ void __launch_bounds__(K4_WARPS * 32)
 k_metrics(const u64 *__restrict__ keys, const int32_t *__restrict__ idx_in, int K, int64_t n_rows,
           int64_t row0, const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx,
-          MetricIds mids, const double *__restrict__ disc, float *__restrict__ per_user,
-          int32_t *__restrict__ topk_idx_out, float *__restrict__ topk_val_out)
+          MetricIds mids, const double *__restrict__ disc, const float *__restrict__ idcg, float *__restrict__ per_user,
+          int32_t *__restrict__ topk_idx_out, float *__restrict__ topk_val_out, double *__restrict__ acc_out)
 {
-    extern __shared__ unsigned char k4_smem[];
+    extern __shared__ double k4_acc[];  // [K4_WARPS][M*K] when acc_out != null
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = mids.n;
-    const int hit_words = (K + 31) >> 5;
-    float *outs = reinterpret_cast<float *>(k4_smem) + (size_t)warp * (size_t)(M * K);
-    uint32_t *hits = reinterpret_cast<uint32_t *>(reinterpret_cast<float *>(k4_smem) + (size_t)K4_WARPS * (size_t)(M * K)) +
-                     warp * hit_words;
-
-    const int64_t row = (int64_t)blockIdx.x * K4_WARPS + warp;
-    if (row >= n_rows) return;
-
-    const int64_t tb = __ldg(te_indptr + row0 + row);
-    const int nt = (int)(__ldg(te_indptr + row0 + row + 1) - tb);
-    const int32_t *truth = te_idx + tb;
-
-    for (int i0 = 0; i0 < K; i0 += 32) {
-        const int i = i0 + lane;
-        bool hit = false;
-        if (i < K) {
-            int32_t item;
-            if (keys != nullptr) {
-                u64 k = keys[row * K + i];
-                item = (k == 0) ? -1 : (int32_t)key_item(k);
-                if (topk_val_out != nullptr) topk_val_out[row * K + i] = (k == 0) ? -__int_as_float(0x7f800000) : key_score(k);
-            } else {
-                item = idx_in[row * K + i];
-            }
-            if (topk_idx_out != nullptr) topk_idx_out[row * K + i] = item;
-            hit = (item >= 0) && sorted_contains(truth, nt, item);
-        }
-        unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) hits[i0 >> 5] = bal;
-    }
-    __syncwarp();
-
-    if (lane < M) {
-        float *o = outs + lane * K;
-        const int L = nt > 1 ? nt : 1;
-        const int id = mids.id[lane];
-        if (id == 1) {  // metric.h:19-30
-            float h = 0.0f;
-            for (int i = 0; i < K; ++i) {
-                if ((hits[i >> 5] >> (i & 31)) & 1u) h += 1.0f;
-                o[i] = h / (float)(i + 1);
-            }
-        } else if (id == 2) {  // metric.h:33-45
-            float h = 0.0f;
-            const float tl = (float)L;
-            for (int i = 0; i < K; ++i) {
-                if ((hits[i >> 5] >> (i & 31)) & 1u) h += 1.0f;
-                o[i] = h / tl;
-            }
-        } else if (id == 3) {  // metric.h:48-66
-            float h = 0.0f, sum_pre = 0.0f;
-            for (int i = 0; i < K; ++i) {
-                if ((hits[i >> 5] >> (i & 31)) & 1u) {
-                    h += 1.0f;
-                    float pre = h / (float)(i + 1);
-                    sum_pre += pre;
-                }
-                float den = (float)(L < i + 1 ? L : i + 1);
-                o[i] = sum_pre / den;
-            }
-        } else if (id == 4) {  // metric.h:69-86
-            float idcg = 0.0f, dcg = 0.0f;
-            for (int i = 0; i < K; ++i) {
-                const double t = disc[i];
-                if ((hits[i >> 5] >> (i & 31)) & 1u) dcg = (float)((double)dcg + t);
-                if (i < L) idcg = (float)((double)idcg + t);
-                o[i] = dcg / idcg;
-            }
-        } else {  // id == 5, metric.h:89-109
-            float rr = 0.0f;
-            bool found = false;
-            for (int i = 0; i < K; ++i) {
-                if (!found && ((hits[i >> 5] >> (i & 31)) & 1u)) {
-                    rr = (float)(1.0 / (double)(i + 1));
-                    found = true;
-                }
-                o[i] = rr;
-            }
-        }
-    }
-    __syncwarp();
     const int MK = M * K;
-    for (int c = lane; c < MK; c += 32) per_user[row * MK + c] = outs[c];
+    double *acc = k4_acc + (size_t)warp * MK;
+    if (acc_out != nullptr)
+        for (int c = lane; c < MK; c += 32) acc[c] = 0.0;
+    const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // lanes <= mine
+
+    const int64_t n_warps = (int64_t)gridDim.x * K4_WARPS;
+    for (int64_t row = (int64_t)blockIdx.x * K4_WARPS + warp; row < n_rows; row += n_warps) {
+        const int64_t tb = __ldg(te_indptr + row0 + row);
+        const int nt = (int)(__ldg(te_indptr + row0 + row + 1) - tb);
+        const int32_t *truth = te_idx + tb;
+        const int L = nt > 1 ? nt : 1;
+        const float Lf = (float)L;
+        int hits_c = 0, first = -1;      // carried across 32-position chunks
+        float sum_pre_c = 0.0f, dcg_c = 0.0f;
+        for (int i0 = 0; i0 < K; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < K;
+            bool hit = false;
+            if (valid) {
+                int32_t item;
+                if (keys != nullptr) {
+                    const u64 k = keys[row * K + i];
+                    item = (k == 0) ? -1 : (int32_t)key_item(k);
+                    if (topk_val_out != nullptr) topk_val_out[row * K + i] = (k == 0) ? -__int_as_float(0x7f800000) : key_score(k);
+                } else {
+                    item = idx_in[row * K + i];
+                }
+                if (topk_idx_out != nullptr) topk_idx_out[row * K + i] = item;
+                hit = (item >= 0) && sorted_contains(truth, nt, item);
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            const float hf = (float)(hits_c + __popc(mask & le_mask));
+            const float prec = hf / (float)(i + 1);
+            float my_sum = sum_pre_c, my_dcg = dcg_c;
+            for (uint32_t m = mask; m != 0u; m &= m - 1u) {  // hits of this chunk, ascending
+                const int b = __ffs(m) - 1;
+                sum_pre_c = sum_pre_c + __shfl_sync(0xffffffffu, prec, b);  // metric.h:57-59
+                dcg_c = (float)((double)dcg_c + __ldg(disc + i0 + b));      // metric.h:78
+                if (lane >= b) { my_sum = sum_pre_c; my_dcg = dcg_c; }
+            }
+            if (first < 0 && mask != 0u) first = i0 + __ffs(mask) - 1;
+            hits_c += __popc(mask);
+            if (valid) {
+                for (int mi = 0; mi < M; ++mi) {
+                    const int id = mids.id[mi];
+                    float val;
+                    if (id == 1) val = prec;                                              // metric.h:19-30
+                    else if (id == 2) val = hf / Lf;                                      // metric.h:33-45
+                    else if (id == 3) val = my_sum / (float)(L < i + 1 ? L : i + 1);      // metric.h:48-66
+                    else if (id == 4) val = my_dcg / __ldg(idcg + (L < i + 1 ? L : i + 1));  // metric.h:69-86
+                    else val = (first >= 0 && i >= first) ? (float)(1.0 / (double)(first + 1)) : 0.0f;  // metric.h:89-109
+                    if (per_user != nullptr) per_user[row * MK + mi * K + i] = val;
+                    if (acc_out != nullptr) acc[mi * K + i] += (double)val;
+                }
+            }
+        }
+    }
+    if (acc_out != nullptr) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < MK; c += K4_WARPS * 32) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < K4_WARPS; ++w) t += k4_acc[(size_t)w * MK + c];
+            acc_out[(size_t)blockIdx.x * MK + c] = t;
+        }
+    }
+}
+
+// sums[c] += sum over blocks of partial[b][c]: one warp per column, fixed order
+__global__ void __launch_bounds__(256)
+k_colsum_fold(const double *__restrict__ partial, int n_blk, int n_cols, double *__restrict__ sums)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + warp;
+    if (c >= n_cols) return;
+    double t = 0.0;
+    for (int b = lane; b < n_blk; b += 32) t += partial[(size_t)b * n_cols + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) sums[c] += t;
 }
 
 // ---- column sums, deterministic two-stage float64 -------------------------------------------

@@ -1,0 +1,160 @@
+// k_select.cuh -- candidate lists of the fused tensor-core pass -> sorted top-K rank keys.
+//
+// A row arrives with n ~ 3-5 K candidates (score bits, item) spread over its sub-lists.  Sorting all
+// of them (round-1 version: a 256-512 element warp bitonic per row, 4 000 instructions per row and the
+// second most expensive kernel of the step) is wasted work: only the K best are wanted.  One warp per
+// row now
+//   1. gathers the sub-lists into shared memory as (ord(score), item),
+//   2. finds a cut T with K <= #{ord >= T} <= 32 PER by a most-significant-digit radix search over
+//      the span [min, max] of the row's own values (8 bits per pass through a 256-bin histogram; the
+//      search stops as soon as the bin holding the K-th value is small enough to be taken whole --
+//      after one pass for almost every row),
+//   3. compacts the survivors into 64-bit rank keys and sorts just those (warp bitonic, PER = 2 or 4).
+// Rows that cannot be settled here -- a sub-list overflowed, fewer than K candidates (threshold
+// estimate too high or fewer than K unmasked items), more candidates than the buffer, or more than
+// 32 PER values tied at the cut -- go on the fail list and are re-done exactly by k_row_exact.
+#pragma once
+#include "common.cuh"
+
+namespace skr {
+
+constexpr int SEL_WARPS = 4;
+constexpr int SEL_MAX = 512;  // candidates a row may carry into the selection
+
+template <int PER>
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
+               int64_t n_rows, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count)
+{
+    constexpr int CAP = 32 * PER;
+    __shared__ uint2 s_ent[SEL_WARPS][SEL_MAX];
+    __shared__ uint32_t s_hist[SEL_WARPS][256];
+    __shared__ u64 s_key[SEL_WARPS][CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp;
+    if (row >= n_rows) return;
+    uint2 *ent = s_ent[warp];
+    uint32_t *hist = s_hist[warp];
+    u64 *skey = s_key[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // ---- 1. sub-list sizes (n_sub <= 32: one per lane), exclusive scan, gather ---------------------
+    const int c_mine = (lane < n_sub) ? (int)__ldg(cand_cnt + row * n_sub + lane) : 0;
+    int incl = c_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int n = __shfl_sync(0xffffffffu, incl, 31);
+    const bool over = __any_sync(0xffffffffu, c_mine > cap);
+    if (over || n > SEL_MAX || n < K) {
+        if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+        return;
+    }
+    const int off_mine = incl - c_mine;
+    uint32_t vmin = 0xffffffffu, vmax = 0u;
+    for (int s = 0; s < n_sub; ++s) {
+        const int cs = __shfl_sync(0xffffffffu, c_mine, s);
+        const int os = __shfl_sync(0xffffffffu, off_mine, s);
+        const uint2 *src = cand + (row * n_sub + s) * (int64_t)sub_stride;
+        for (int i = lane; i < cs; i += 32) {
+            uint2 e = src[i];
+            e.x = ord_f32(__uint_as_float(e.x));
+            vmin = min(vmin, e.x);
+            vmax = max(vmax, e.x);
+            ent[os + i] = e;
+        }
+    }
+    vmin = __reduce_min_sync(0xffffffffu, vmin);
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    __syncwarp();
+
+    // ---- 2. cut: smallest-known T (as offset from vmin) with K <= #{w >= T} <= CAP ------------------
+    uint32_t T = 0;  // n <= CAP: everything is sorted
+    if (n > CAP) {
+        const uint32_t range = vmax - vmin;
+        int width_bits = 32 - __clz(range | 1u);  // values w = ord - vmin lie in [0, 2^width_bits)
+        uint32_t base = 0;                         // current bucket: [base, base + 2^width_bits)
+        int above = 0;                             // values at or beyond the bucket's end (all selected)
+        bool ok = false;
+        for (;;) {
+            const int shift = width_bits > 8 ? width_bits - 8 : 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hist[q * 32 + lane] = 0u;
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const uint32_t w = ent[i].x - vmin;
+                const uint32_t rel = (w - base) >> shift;  // w < base wraps to a huge value
+                if (w >= base && rel < 256u) atomicAdd(&hist[rel], 1u);
+            }
+            __syncwarp();
+            // lane l owns bins 8 l .. 8 l + 7; counts from the top bin down
+            uint32_t h[8];
+            int t_l = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { h[q] = hist[lane * 8 + q]; t_l += (int)h[q]; }
+            int suf = t_l;  // inclusive suffix sum over lanes >= mine
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += t;
+            }
+            const int with_me = above + suf, without_me = with_me - t_l;
+            const bool mine = (with_me >= K) && (without_me < K);
+            const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;  // exactly one lane (n >= K)
+            int j = 0, c_above = without_me, c_with = without_me;
+            if (mine) {
+#pragma unroll
+                for (int q = 7; q >= 0; --q) {
+                    if (c_with < K) { c_above = c_with; c_with += (int)h[q]; j = lane * 8 + q; }
+                }
+            }
+            j = __shfl_sync(0xffffffffu, j, owner);
+            c_above = __shfl_sync(0xffffffffu, c_above, owner);
+            c_with = __shfl_sync(0xffffffffu, c_with, owner);
+            base += (uint32_t)j << shift;
+            if (c_with <= CAP) { ok = true; break; }
+            if (shift == 0) break;  // more than CAP values tied around the K-th: exact path
+            above = c_above;
+            width_bits = shift;
+            __syncwarp();
+        }
+        if (!ok) {
+            if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+            return;
+        }
+        T = base;
+    }
+
+    // ---- 3. compact the survivors into rank keys, sort, write the K best ---------------------------
+#pragma unroll
+    for (int e = 0; e < PER; ++e) skey[e * 32 + lane] = 0ull;
+    __syncwarp();
+    int m = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        uint2 e = make_uint2(0u, 0u);
+        bool take = false;
+        if (i < n) {
+            e = ent[i];
+            take = (e.x - vmin) >= T;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, take);
+        if (take) skey[m + __popc(bal & lt_mask)] = ((u64)e.x << 32) | (u64)(~e.y);
+        m += __popc(bal);
+    }
+    __syncwarp();
+    u64 v[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) v[e] = skey[e * 32 + lane];
+    warp_bitonic_desc<PER>(v, lane);
+    u64 *dst = out_keys + row * (int64_t)K;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int i = e * 32 + lane;
+        if (i < K) dst[i] = v[e];
+    }
+}
+
+}  // namespace skr

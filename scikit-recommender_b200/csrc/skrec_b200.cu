@@ -24,6 +24,7 @@
 #include "k_fused_tc.cuh"
 #include "k_metrics.cuh"
 #include "k_scores.cuh"
+#include "k_select.cuh"
 
 using namespace skr;
 
@@ -62,6 +63,7 @@ struct skr_ctx {
     int32_t *d_te_idx = nullptr;
     // 1/log2(i+2) table (metric.h:78,82), host glibc
     double *d_disc = nullptr;
+    float *d_idcg = nullptr;  // iDCG after n terms (metric.h:82), host-accumulated
     int disc_n = 0;
     // workspace, grow-only
     Buf keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
@@ -175,11 +177,22 @@ int ensure_disc(skr_ctx *ctx, int K)
     if (K <= ctx->disc_n) return SKR_OK;
     int n = std::max(K, 1024);
     std::vector<double> h((size_t)n);
-    for (int i = 0; i < n; ++i) h[(size_t)i] = 1.0 / log2((double)(unsigned)(i + 2));  // metric.h:78
+    std::vector<float> ig((size_t)n + 1);
+    float idcg = 0.0f;
+    ig[0] = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        h[(size_t)i] = 1.0 / log2((double)(unsigned)(i + 2));  // metric.h:78
+        idcg = (float)((double)idcg + h[(size_t)i]);           // metric.h:82, after i + 1 terms
+        ig[(size_t)i + 1] = idcg;
+    }
     free_dev(ctx->d_disc);
+    free_dev(ctx->d_idcg);
     ctx->d_disc = nullptr;
+    ctx->d_idcg = nullptr;
     SKR_CUDA(ctx, cudaMalloc((void **)&ctx->d_disc, sizeof(double) * (size_t)n));
+    SKR_CUDA(ctx, cudaMalloc((void **)&ctx->d_idcg, sizeof(float) * ((size_t)n + 1)));
     SKR_CUDA(ctx, cudaMemcpy(ctx->d_disc, h.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    SKR_CUDA(ctx, cudaMemcpy(ctx->d_idcg, ig.data(), sizeof(float) * ((size_t)n + 1), cudaMemcpyHostToDevice));
     ctx->disc_n = n;
     return SKR_OK;
 }
@@ -194,19 +207,31 @@ int run_metrics(skr_ctx *ctx, const u64 *keys, const int32_t *idx_in, int64_t n_
     int rc = ensure_disc(ctx, K);
     if (rc) return rc;
     const int MK = m.n * K;
+    // column sums ride along in k_metrics (per-warp float64 accumulators in shared memory) when they fit;
+    // otherwise the per-user block is materialised and summed by the two-stage kernels
+    const size_t acc_smem = (size_t)K4_WARPS * MK * sizeof(double);
+    const bool fused_sums = sums != nullptr && acc_smem <= 96 * 1024;
     float *pu = per_user;
-    if (!pu) {
+    if (!pu && sums && !fused_sums) {
         rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float));
         if (rc) return rc;
         pu = (float *)ctx->per_user.p;
     }
-    const size_t smem = (size_t)K4_WARPS * MK * sizeof(float) + (size_t)K4_WARPS * ((K + 31) / 32) * sizeof(uint32_t);
-    if (smem > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((n_rows + K4_WARPS - 1) / K4_WARPS);
-    k_metrics<<<grid, K4_WARPS * 32, smem, st>>>(keys, idx_in, K, n_rows, row0, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc, pu,
-                                                topk_idx, topk_val);
+    const int grid = (int)std::min<int64_t>((n_rows + K4_WARPS - 1) / K4_WARPS, 6 * ctx->n_sm);
+    double *acc = nullptr;
+    if (fused_sums) {
+        rc = ensure(ctx, ctx->partial, (size_t)grid * MK * sizeof(double));
+        if (rc) return rc;
+        acc = (double *)ctx->partial.p;
+        if (acc_smem > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_smem));
+    }
+    k_metrics<<<grid, K4_WARPS * 32, fused_sums ? acc_smem : 0, st>>>(keys, idx_in, K, n_rows, row0, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc,
+                                                                    ctx->d_idcg, pu, topk_idx, topk_val, acc);
     ctx->launches++;
-    if (sums) {
+    if (fused_sums) {
+        k_colsum_fold<<<(MK + 7) / 8, 256, 0, st>>>(acc, grid, MK, sums);
+        ctx->launches++;
+    } else if (sums) {
         const int nblk = (int)std::min<int64_t>(n_rows, 2 * ctx->n_sm);
         rc = ensure(ctx, ctx->partial, (size_t)nblk * MK * sizeof(double));
         if (rc) return rc;
@@ -313,7 +338,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     if (!ctx) return SKR_OK;
     cudaSetDevice(ctx->device);
     free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr); free_dev(ctx->d_mask_tile_off);
-    free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_err);
+    free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
                    &ctx->fail_list};
@@ -649,8 +674,13 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
         SKR_CUDA(ctx, cudaGetLastError());
-        k_select_cands<<<(unsigned)((n_rows + SEL_WARPS - 1) / SEL_WARPS), SEL_WARPS * 32, 0, st>>>(
-            A.cand, A.cand_cnt, n_sub, cap, sub_stride, K, n_rows, keys, fail_list, fail_count);
+        {
+            const unsigned sel_grid = (unsigned)((n_rows + SEL_WARPS - 1) / SEL_WARPS);
+            if (K <= 64)
+                k_select_cands<2><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, sub_stride, K, n_rows, keys, fail_list, fail_count);
+            else
+                k_select_cands<4><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, sub_stride, K, n_rows, keys, fail_list, fail_count);
+        }
         k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, user_vecs_dev, ld_u, item_vecs_dev, ld_i, d,
                                                                       bias_dev, (int)n_items, row0, tp, ti, K, keys);
         ctx->launches += 2;
@@ -715,13 +745,13 @@ int skr_eval_scores_host(skr_ctx *ctx, const float *scores_host, int64_t n_rows,
     int rc;
     if ((rc = ensure(ctx, ctx->stage_a, (size_t)n_rows * n_items * sizeof(float)))) return rc;
     if ((rc = ensure(ctx, ctx->sums, (size_t)MK * sizeof(double)))) return rc;
-    if ((rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float)))) return rc;
+    if (per_user_host && (rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float)))) return rc;
     if ((rc = ensure(ctx, ctx->out_idx, (size_t)n_rows * top_k * sizeof(int32_t)))) return rc;
     SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_a.p, (size_t)n_items * sizeof(float), scores_host, (size_t)ld * sizeof(float),
                                     (size_t)n_items * sizeof(float), (size_t)n_rows, cudaMemcpyHostToDevice, st));
     SKR_CUDA(ctx, cudaMemsetAsync(ctx->sums.p, 0, (size_t)MK * sizeof(double), st));
     rc = skr_eval_scores(ctx, (const float *)ctx->stage_a.p, n_rows, n_items, n_items, row0, metric_ids, n_metrics, top_k,
-                         topk_idx_host ? (int32_t *)ctx->out_idx.p : nullptr, nullptr, (float *)ctx->per_user.p, (double *)ctx->sums.p, stream);
+                         topk_idx_host ? (int32_t *)ctx->out_idx.p : nullptr, nullptr, per_user_host ? (float *)ctx->per_user.p : nullptr, (double *)ctx->sums.p, stream);
     if (rc) return rc;
     return finish_host(ctx, n_rows, MK, top_k, topk_idx_host, per_user_host, sums_host, (const int32_t *)ctx->out_idx.p,
                        (const float *)ctx->per_user.p, (const double *)ctx->sums.p, st);
@@ -745,7 +775,7 @@ int skr_eval_fused_host(skr_ctx *ctx, const float *user_vecs_host, int64_t n_row
     if ((rc = ensure(ctx, ctx->stage_b, (size_t)n_items * dp * sizeof(float)))) return rc;
     if (bias_host && (rc = ensure(ctx, ctx->stage_c, (size_t)n_items * sizeof(float)))) return rc;
     if ((rc = ensure(ctx, ctx->sums, (size_t)MK * sizeof(double)))) return rc;
-    if ((rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float)))) return rc;
+    if (per_user_host && (rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float)))) return rc;
     if ((rc = ensure(ctx, ctx->out_idx, (size_t)n_rows * top_k * sizeof(int32_t)))) return rc;
     if (dp != d) {
         SKR_CUDA(ctx, cudaMemsetAsync(ctx->stage_a.p, 0, (size_t)n_rows * dp * sizeof(float), st));
@@ -759,7 +789,7 @@ int skr_eval_fused_host(skr_ctx *ctx, const float *user_vecs_host, int64_t n_row
     SKR_CUDA(ctx, cudaMemsetAsync(ctx->sums.p, 0, (size_t)MK * sizeof(double), st));
     rc = skr_eval_fused(ctx, (const float *)ctx->stage_a.p, n_rows, dp, (const float *)ctx->stage_b.p, n_items, dp, (int)dp,
                         bias_host ? (const float *)ctx->stage_c.p : nullptr, row0, metric_ids, n_metrics, top_k, precision,
-                        topk_idx_host ? (int32_t *)ctx->out_idx.p : nullptr, nullptr, (float *)ctx->per_user.p, (double *)ctx->sums.p, stream);
+                        topk_idx_host ? (int32_t *)ctx->out_idx.p : nullptr, nullptr, per_user_host ? (float *)ctx->per_user.p : nullptr, (double *)ctx->sums.p, stream);
     if (rc) return rc;
     return finish_host(ctx, n_rows, MK, top_k, topk_idx_host, per_user_host, sums_host, (const int32_t *)ctx->out_idx.p,
                        (const float *)ctx->per_user.p, (const double *)ctx->sums.p, st);
