@@ -140,10 +140,15 @@ int skr_fused_prepass_ms(skr_ctx *ctx, int back, float *ms_out);
  * threshold rank r, sub-list capacity, item chunks, TMA stages, rows re-done by the exact kernel.
  * Synchronises the device. */
 int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out);
+/* Development aid: with skr_set_option("trace_cta", c >= 0) the main tcgen05 pass records, for CTA c,
+ * SM-clock timestamps of its pipeline events per item tile (16 slots per tile, see k_fused_tc.cuh);
+ * this copies up to n_out of them to the host.  Synchronises the device. */
+int skr_fused_trace(skr_ctx *ctx, int64_t *out, int64_t n_out);
 
 /* Tunables: "chunks" (item-range chunks per user tile of the fused path, 0 = automatic), "stages"
- * (TMA ring depth, 0 = automatic), "sample_tiles" / "rank" (pre-pass size and threshold rank, 0 =
- * automatic), "event_ring" (see skr_fused_kernel_ms). */
+ * (ignored: the ring depth is fixed by the kernel instantiation), "sample_tiles" / "rank" (pre-pass size and threshold rank, 0 =
+ * automatic), "event_ring" (see skr_fused_kernel_ms), "trace_cta"
+ * (see skr_fused_trace; -1 = off), "dbg" (timing ablations, results invalid). */
 int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -18,7 +18,7 @@ PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "1xtf32": 3}
 SYMBOLS = (
     "skr_abi_version", "skr_ctx_create", "skr_ctx_destroy", "skr_last_error", "skr_set_train_csr",
     "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
-    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats",
+    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace",
 )
 
 _lib = None
@@ -65,6 +65,7 @@ def lib():
     L.skr_fused_kernel_ms.argtypes = [_vp, _int, ctypes.POINTER(ctypes.c_float)]
     L.skr_fused_prepass_ms.argtypes = [_vp, _int, ctypes.POINTER(ctypes.c_float)]
     L.skr_fused_stats.argtypes = [_vp, ctypes.POINTER(_i64), _int]
+    L.skr_fused_trace.argtypes = [_vp, ctypes.POINTER(_i64), _i64]
     for name in SYMBOLS:
         getattr(L, name)
     if L.skr_abi_version() != 1:
@@ -147,6 +148,13 @@ class Context(object):
         out = (_i64 * 7)()
         self._check(self._L.skr_fused_stats(self._h, out, 7))
         return dict(zip(("sample_tiles", "stride", "rank", "cap", "chunks", "stages", "exact_rows"), [int(x) for x in out]))
+
+    def fused_trace(self, n_tiles):
+        """[n_tiles, 16] SM-clock timestamps of the traced CTA (set_option("trace_cta", c) first)."""
+        import numpy as np
+        out = np.zeros((int(n_tiles), 16), dtype=np.int64)
+        self._check(self._L.skr_fused_trace(self._h, out.ctypes.data_as(ctypes.POINTER(_i64)), out.size))
+        return out
 
     # -- device entry points (torch CUDA tensors) -----------------------------------------------
     def eval_scores(self, scores, row0, metric_ids, top_k, topk_idx=None, topk_val=None, per_user=None, sums=None,

@@ -10,56 +10,66 @@
 // tensor core's operand rounding mode does not matter.  (1xTF32 breaks the
 // 1e-5 metric contract, 3xTF32 does not.)
 //
-// Selection (round-1 ncu finding: per-row heaps in shared memory made the epilogue, not the MMA,
-// the bottleneck by 20x).  The kernel now runs in two modes over the same pipeline:
-//   SAMPLE  - a strided ~f = 6/K fraction of the item tiles is scored once in 1xTF32; each row keeps
-//             the R largest 32-column group maxima (train items masked) in registers.  The r-th
-//             largest of them is a threshold T0 that, with overwhelming probability, has between K
-//             and a few K catalogue items above it.  It only steers work: results never depend on it.
-//   COLLECT - every item tile is scored in 3xTF32; a max tree over 32 scores and ONE compare against
-//             T0 rejects almost every 32-column group; survivors that are not train items are
-//             appended (rank key = ord(score) << 32 | ~item) to the row's candidate list in HBM.
-// k_select_cands then sorts each row's ~3-5 K candidates; a row whose list is short (< K) or
-// overflowed is re-done exactly by k_row_exact (k_scores.cuh).  No heaps, no thresholds to update,
-// no shared memory per row: K is limited only by the list capacity.
+// Selection.  The kernel is one pipeline instantiated in two modes:
+//   SAMPLE  - a strided ~f = 6/K fraction of the item tiles is scored once in 1xTF32; each epilogue
+//             thread keeps the TC_R largest 32-column group maxima (train items masked) of its row and
+//             column quarter in registers.  The r-th largest of the row's 4 TC_R values is a threshold
+//             T0 that, with overwhelming probability, has between K and a few K catalogue items above
+//             it.  It only steers work: results never depend on it.
+//   COLLECT - every item tile is scored in 3xTF32; two instructions per score and no predicates
+//             (d = s - T0 on the FMA pipe, a funnel shift collecting the sign bits on the ALU pipe)
+//             give a 32-bit survivor mask per thread; survivors that are not train items are appended
+//             (score bits, item) to the thread's own candidate sub-list in HBM.
+// k_select_cands (k_select.cuh) then picks and sorts each row's K best out of its ~3-5 K candidates;
+// a row whose lists are short (< K) or overflowed is re-done exactly by k_row_exact (k_scores.cuh).
 //
-// Operands: A (users) lives in TMEM for the whole work item -- each epilogue thread of the first
-// warpgroup loads its user's row from global memory, splits it in registers and tcgen05.st's hi/lo
-// into TMEM lanes (TS-mode MMA; no shared memory for A).  B (items) is pre-split by k_split_tf32
-// into hi/lo tables and streamed by TMA (SWIZZLE_128B, 128 rows x 32 floats per box) through an
-// mbarrier ring of k-block stages.
+// Operands: A (users) lives in TMEM for the whole work item -- epilogue threads load their user's
+// row from global memory, split it in registers and tcgen05.st hi/lo into TMEM lanes (TS-mode MMA; no
+// shared memory for A).  B (items) is pre-split by k_split_tf32 into hi/lo tables and streamed by TMA
+// (SWIZZLE_128B, 128 rows x 32 floats per box) through an mbarrier ring of k-block stages.
 //
-// Warp roles (384 threads): warps 0-3 epilogue of columns 0-63, warps 4-7 epilogue of columns 64-127,
-// warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer of the even tiles (one lane), warp 10
-// train-mask bitmap builder, warp 11 MMA issuer of the odd tiles (thread <-> TMEM lane <-> user row; two warps per SM sub-partition so
-// the TMEM-load and compare latencies of one hide behind the other).  Accumulators and bitmaps are
-// double buffered so the epilogue of tile n overlaps the MMAs of tile n+1.
+// Round-1 measurements that shaped this version (c2, ablation switches A.dbg): the bare pipeline
+// skeleton cost 1270 cycles per tile (a mask builder with exposed global-load latency and four barrier
+// round trips per tile), one thread issued a tcgen05.mma only every ~78 cycles (run-time loop bounds and
+// div/mod by the stage count in the issue loop) and 8 epilogue warps exposed every TMEM-load and
+// barrier latency.  Hence: k-blocks and passes are template parameters (the issue loop is straight-line
+// code), 16 epilogue warps each own one 32-column group of the tile (thread <-> TMEM lane <-> user row;
+// four warps per SM sub-partition hide each other's latencies), the accumulator-ready and mask-ready
+// signals share one barrier per buffer, and the mask builder keeps tile offsets in registers (one
+// coalesced load per 32 tiles) and fetches keys one tile ahead.
 //
-// TMEM columns: [0, 32*nkb) A_hi, [32*nkb, 64*nkb) A_lo, [256, 384) acc 0, [384, 512) acc 1.
+// Warp roles (640 threads): warps 0-15 epilogue (lane quarter = warp & 3, column quarter = warp >> 2),
+// warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer of the even tiles, warp 18 train-mask bitmap
+// builder, warp 19 MMA issuer of the odd tiles.  Accumulators and bitmaps are double buffered so the
+// epilogue of tile n overlaps the MMAs of tile n+1.
+//
+// TMEM columns: [0, 32*NKB) A_hi, [32*NKB, 64*NKB) A_lo, [256, 384) acc 0, [384, 512) acc 1.
 #pragma once
 #include <cuda.h>
 #include "fused_common.cuh"
 
 namespace skr {
 
-constexpr int TC_THREADS = 384;
-constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = TC_EPI_THREADS + 128;
 constexpr int TC_KB = 32;                             // floats per k-block (one 128-byte swizzle row)
 constexpr int TC_TILE_BYTES = TN * TC_KB * 4;         // 16 KB: one operand tile of one k-block
-constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // hi + lo
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_RING_BYTES = 8 * TC_TILE_BYTES;      // 4 stages of hi+lo (3xTF32) or 8 stages of hi (1xTF32)
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_ACC_COL = 256;                       // first accumulator column
-constexpr int TC_R = 32;                              // group maxima kept per row and warpgroup (SAMPLE)
+constexpr int TC_R = 16;                              // group maxima kept per row and column quarter (SAMPLE)
+constexpr int TC_MAX_RANK = 32;                       // largest threshold rank the 4 x TC_R lists support
 constexpr long long TC_TIMEOUT_CYCLES = 4000000000ll; // watchdog: ~2 s
 
 enum { TC_MODE_COLLECT = 0, TC_MODE_SAMPLE = 1 };
 
-__host__ __device__ inline size_t tc_smem_bytes(int stages)
+__host__ __device__ inline size_t tc_smem_bytes()
 {
     return (size_t)1024                          // alignment slack
-           + (size_t)stages * TC_STAGE_BYTES
+           + (size_t)TC_RING_BYTES
            + (size_t)2 * 4 * TM * 4              // two bitmaps
-           + (size_t)8 * TC_EPI_THREADS * 16     // score staging: one 32-float row per epilogue thread, [8][256] float4
+           + (size_t)8 * TC_EPI_THREADS * 16     // score staging: one 32-float row per epilogue thread, [8][512] float4
            + 256;                                // barriers + tmem pointer
 }
 
@@ -187,23 +197,41 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(T
 struct TcArgs {
     const float *U;   // user vectors [n_rows, ld_u]
     int64_t ld_u;
-    int nkb;          // k-blocks of 32 (d padded)
-    int stages;
-    int passes;       // 3 = 3xTF32, 1 = single TF32 pass
-    int mode;         // TC_MODE_*
     int *err_flag;    // device int, set before a watchdog trap
     int dbg;          // timing experiments only (results invalid): 1 no epilogue work, 2 no MMA, 4 no appends, 8 no TMA
-    // SAMPLE: item tiles 0, stride, 2*stride, ...; out: samp[row][2][TC_R] group maxima, descending
+    // SAMPLE: item tiles 0, stride, 2*stride, ...; out: samp[row][4][TC_R] group maxima, descending
     int stride;
     int n_samp;
     float *samp;
     // COLLECT: per-row thresholds (k_sample_thr) and candidate lists
     const float *thr;        // [n_rows]
-    int cap;                 // entries per (row, chunk, column half) sub-list
-    int sub_stride;          // storage stride in entries: power of two >= cap + 32 (room for one group past cap)
-    uint2 *cand;             // [n_rows, S*2, sub_stride] (score bits, item), base aligned to the stride
-    uint32_t *cand_cnt;      // [n_rows, S*2] entries written (cap + 1 means overflow)
+    int cap;                 // entries per (row, chunk, column quarter) sub-list
+    uint2 *cand;             // [n_rows, S*4, cap] (score bits, item)
+    uint32_t *cand_cnt;      // [n_rows, S*4] entries offered (> cap means overflow)
+    // development aid: per-tile clock64 timestamps of one CTA (null = off), [tile][TC_TRACE_SLOTS]
+    long long *trace;
+    int trace_cta;
+    int trace_tiles;
 };
+
+constexpr int TC_TRACE_SLOTS = 16;
+// slots: 0 producer got the stage of kb 0, 1 producer issued the last TMA of the tile, 2 issuer: accumulator free,
+// 3 issuer: first stage full, 4 issuer: tile committed, 5 mask: buffer free, 6 mask: bitmap ready,
+// 7/10 epilogue warp 0/15: tile full, 8/11: accumulator in registers (released), 9/12: tile processed
+__device__ __forceinline__ void tc_trace(const TcArgs &A, int tile, int slot)
+{
+    if (A.trace != nullptr && (int)blockIdx.x == A.trace_cta && tile < A.trace_tiles)
+        A.trace[(size_t)tile * TC_TRACE_SLOTS + slot] = clock64();
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+        ::SKR_W32(r, 0), SKR_W32(r, 8), "r"(taddr)
+        : "memory");
+}
 
 // descending insertion of x into v[0..TC_R): branch-free compare-exchange chain
 __device__ __forceinline__ void sorted_insert(float (&v)[TC_R], float x)
@@ -216,51 +244,52 @@ __device__ __forceinline__ void sorted_insert(float (&v)[TC_R], float x)
     }
 }
 
+template <int NKB, int PASSES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, TcArgs A, FusedParams P)
 {
+    constexpr bool SAMPLE = (MODE == TC_MODE_SAMPLE);
+    constexpr int STAGES = (PASSES == 3) ? 4 : 8;
+    constexpr int STAGE_BYTES = (PASSES == 3) ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
+    static_assert(NKB >= 1 && NKB <= 4 && (PASSES == 1 || PASSES == 3), "tile shape");
+    static_assert(STAGES * STAGE_BYTES == TC_RING_BYTES, "ring size");
+
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *b_tiles = smem;
-    uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + (size_t)A.stages * TC_STAGE_BYTES);  // [2][4][TM]
-    float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + 2 * 4 * TM);  // [8][TC_EPI_THREADS]
+    uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + TC_RING_BYTES);  // [2][4][TM]
+    float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + 2 * 4 * TM);    // [8][TC_EPI_THREADS]
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 8 * TC_EPI_THREADS);
-    uint64_t *full = bars;                            // [TC_MAX_STAGES]
-    uint64_t *empty = bars + TC_MAX_STAGES;           // [TC_MAX_STAGES]
-    uint64_t *tmem_full = bars + 2 * TC_MAX_STAGES;   // [2]
-    uint64_t *tmem_empty = tmem_full + 2;             // [2]
-    uint64_t *bm_full = tmem_empty + 2;               // [2]
-    uint64_t *bm_empty = bm_full + 2;                 // [2]
-    uint64_t *a_ready = bm_empty + 2;                 // [1]
+    uint64_t *full = bars;                            // [TC_MAX_STAGES] TMA landed
+    uint64_t *empty = bars + TC_MAX_STAGES;           // [TC_MAX_STAGES] MMAs that read the stage are done
+    uint64_t *tile_full = bars + 2 * TC_MAX_STAGES;   // [2] accumulator complete (MMA commit) + bitmap built (mask warp)
+    uint64_t *tile_empty = tile_full + 2;             // [2] all 16 epilogue warps are done with accumulator and bitmap
+    uint64_t *a_ready = tile_empty + 2;               // [1] A operand is in TMEM
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_ready + 1);
 
-    // Epilogue = warps 0-7, helpers = warps 8-11: the warp scheduler favours higher warp ids, and the
+    // Epilogue = warps 0-15, helpers = warps 16-19: the warp scheduler favours higher warp ids, and the
     // latency-critical single-thread roles (TMA producer, MMA issuers) must not queue behind the epilogue.
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int role = warp - 8;  // 0 TMA producer, 1 MMA issuer (even tiles) + TMEM allocator, 2 mask builder, 3 MMA issuer (odd tiles)
+    const int role = warp - TC_EPI_WARPS;  // 0 TMA producer, 1 MMA issuer (even tiles) + TMEM allocator, 2 mask builder, 3 MMA issuer (odd tiles)
     const int c = blockIdx.x / P.n_rt, rt = blockIdx.x % P.n_rt;
-    const bool sample = (A.mode == TC_MODE_SAMPLE);
     // tiles of this work item: COLLECT t0 + i, SAMPLE i * stride
-    const int t0 = sample ? 0 : c * P.tiles_per_chunk;
-    const int n_tiles = sample ? A.n_samp : (min(t0 + P.tiles_per_chunk, P.n_ct) - t0);
-    const int t_step = sample ? A.stride : 1;
+    const int t0 = SAMPLE ? 0 : c * P.tiles_per_chunk;
+    const int n_tiles = SAMPLE ? A.n_samp : (min(t0 + P.tiles_per_chunk, P.n_ct) - t0);
+    const int t_step = SAMPLE ? A.stride : 1;
     const int64_t row_base = (int64_t)rt * TM;
-    const int nkb = A.nkb;
 
     if (tid == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(tmem_full + b, 1);
-            mbar_init(tmem_empty + b, TC_EPI_THREADS / 32);
-            mbar_init(bm_full + b, 1);
-            mbar_init(bm_empty + b, TC_EPI_THREADS / 32);
+            mbar_init(tile_full + b, 2);
+            mbar_init(tile_empty + b, TC_EPI_WARPS);
         }
-        mbar_init(a_ready, TM / 32);
+        mbar_init(a_ready, 4 * NKB);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (role == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo) : "memory");
+        if (PASSES == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_blo) : "memory");
     }
     if (role == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
@@ -274,70 +303,79 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     if (role == 0) {
         // ===== TMA producer: item k-block tiles (hi, lo) through the stage ring ==================
         if (lane == 0) {
-            const uint32_t tx_bytes = (A.passes == 3) ? TC_STAGE_BYTES : TC_TILE_BYTES;
-            int it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < n_tiles; ++i) {
                 const int t = t0 + i * t_step;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % A.stages;
-                    const uint32_t ph = (uint32_t)((it / A.stages) & 1);
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
                     mbar_wait(empty + s, ph ^ 1u, A.err_flag, 1);
-                    if (A.dbg & 8) { mbar_arrive(full + s); continue; }
-                    mbar_expect_tx(full + s, tx_bytes);
-                    unsigned char *dst = b_tiles + (size_t)s * TC_STAGE_BYTES;
-                    tma_load_2d(dst, &tm_bhi, kb * TC_KB, t * TN, full + s);
-                    if (A.passes == 3) tma_load_2d(dst + TC_TILE_BYTES, &tm_blo, kb * TC_KB, t * TN, full + s);
+                    if (kb == 0) tc_trace(A, i, 0);
+                    if (A.dbg & 8) {
+                        mbar_arrive(full + s);
+                    } else {
+                        mbar_expect_tx(full + s, STAGE_BYTES);
+                        unsigned char *dst = b_tiles + (size_t)s * STAGE_BYTES;
+                        tma_load_2d(dst, &tm_bhi, kb * TC_KB, t * TN, full + s);
+                        if (PASSES == 3) tma_load_2d(dst + TC_TILE_BYTES, &tm_blo, kb * TC_KB, t * TN, full + s);
+                    }
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
+                tc_trace(A, i, 1);
             }
         }
     } else if (role == 1 || role == 3) {
-        // ===== MMA issuers: warp 1 takes the even tiles (accumulator 0), warp 3 the odd ones (accumulator 1).
-        // One thread can issue a tcgen05.mma only every ~80 cycles (measured: MMA-only time = 1434 + 78 n
-        // cycles per tile for n MMAs), which is slower than an M128 N128 K8 MMA executes (64 cycles); two
-        // issuers keep the tensor pipe fed and hide each other's per-tile barrier latencies.
+        // ===== MMA issuers: warp 17 takes the even tiles (accumulator 0), warp 19 the odd ones (accumulator 1).
+        // Two issuers hide each other's per-tile barrier latencies; the tensor pipe executes in issue order.
         if (lane == 0) {
             const int p = (role == 1) ? 0 : 1;
+            const bool do_mma = !(A.dbg & 2);
             mbar_wait(a_ready, 0, A.err_flag, 2);
             tc_fence_after();
             const uint32_t a_hi0 = tmem_base;
-            const uint32_t a_lo0 = tmem_base + (uint32_t)(nkb * TC_KB);
+            const uint32_t a_lo0 = tmem_base + (uint32_t)(NKB * TC_KB);
             const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + p * TN);
+            const uint64_t desc0 = make_b_desc(smem_u32(b_tiles));
             for (int i = p; i < n_tiles; i += 2) {
-                const uint32_t u = (uint32_t)((i >> 1) & 1);
-                mbar_wait(tmem_empty + p, u ^ 1u, A.err_flag, 3);
+                mbar_wait(tile_empty + p, (uint32_t)(((i >> 1) & 1) ^ 1), A.err_flag, 3);
                 tc_fence_after();
-                uint32_t acc = 0;
-                int it = i * nkb;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % A.stages;
-                    const uint32_t ph = (uint32_t)((it / A.stages) & 1);
+                tc_trace(A, i, 2);
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
+                    const int it = i * NKB + kb;
+                    const int s = it & (STAGES - 1);
+                    const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                     mbar_wait(full + s, ph, A.err_flag, 4);
                     tc_fence_after();
-                    const uint64_t d0 = make_b_desc(smem_u32(b_tiles + (size_t)s * TC_STAGE_BYTES));
+                    if (kb == 0) tc_trace(A, i, 3);
+                    const uint64_t ds = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));  // start-address field counts 16-byte units
+                    if (do_mma) {
 #pragma unroll
-                    for (int k8 = 0; k8 < ((A.dbg & 2) ? 0 : 4); ++k8) {  // UMMA K = 8 tf32 = 32 bytes
-                        const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
-                        const uint64_t dhi = d0 + (uint64_t)(k8 * 2);  // start-address field counts 16-byte units
-                        if (A.passes == 3) {
-                            const uint64_t dlo = dhi + (uint64_t)(TC_TILE_BYTES >> 4);
-                            tc_mma_ts(d_tmem, a_lo0 + acol, dhi, TC_IDESC, acc);
-                            tc_mma_ts(d_tmem, a_hi0 + acol, dlo, TC_IDESC, 1u);
-                            tc_mma_ts(d_tmem, a_hi0 + acol, dhi, TC_IDESC, 1u);
-                        } else {
-                            tc_mma_ts(d_tmem, a_hi0 + acol, dhi, TC_IDESC, acc);
+                        for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 = 32 bytes
+                            const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
+                            const uint64_t dhi = ds + (uint64_t)(k8 * 2);
+                            const uint32_t acc = (kb | k8) ? 1u : 0u;
+                            if (PASSES == 3) {
+                                const uint64_t dlo = dhi + (uint64_t)(TC_TILE_BYTES >> 4);
+                                tc_mma_ts(d_tmem, a_lo0 + acol, dhi, TC_IDESC, acc);
+                                tc_mma_ts(d_tmem, a_hi0 + acol, dlo, TC_IDESC, 1u);
+                                tc_mma_ts(d_tmem, a_hi0 + acol, dhi, TC_IDESC, 1u);
+                            } else {
+                                tc_mma_ts(d_tmem, a_hi0 + acol, dhi, TC_IDESC, acc);
+                            }
                         }
-                        acc = 1u;
                     }
                     tc_commit(empty + s);  // stage reusable once these MMAs have read it
                 }
-                tc_commit(tmem_full + p);  // accumulator p complete
+                tc_commit(tile_full + p);  // accumulator p complete
+                tc_trace(A, i, 4);
             }
         }
     } else if (role == 2) {
         // ===== train-mask bitmap builder ===========================================================
         // Keys of this user tile are sorted by item; mask_tile_off gives, per item tile, where its keys
-        // start, so nothing is searched or skipped and every load address is known tiles ahead: the
-        // offsets and first 32 keys of tile i+1 are fetched while tile i is being built.
+        // start.  Lane l holds the key range of tile (32-tile batch start + l): one coalesced load per
+        // 32 tiles, then shuffles; the first 32 keys of tile i+1 are fetched while tile i is built.
         const uint32_t *keys = nullptr;
         const uint32_t *offs = nullptr;
         if (P.mask_keys != nullptr) {
@@ -345,78 +383,85 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             keys = P.mask_keys + __ldg(P.mask_tile_ptr + rt_abs);
             offs = P.mask_tile_off + rt_abs * (int64_t)(P.n_ct + 1);
         }
-        uint32_t nb = 0, ne = 0, nkey = 0xffffffffu;  // next tile: key range and first batch
-        if (keys != nullptr && n_tiles > 0) {
-            nb = __ldg(offs + t0);
-            ne = __ldg(offs + t0 + 1);
-            if (nb + lane < ne) nkey = __ldg(keys + nb + lane);
-        }
+        uint32_t off_b = 0, off_e = 0, nkey = 0xffffffffu;
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
-            const uint32_t u = (uint32_t)((i >> 1) & 1);
             const int col0 = (t0 + i * t_step) * TN;
-            const uint32_t kb0 = nb, ke0 = ne;
-            uint32_t key = nkey;
-            if (keys != nullptr && i + 1 < n_tiles) {  // prefetch for tile i + 1
-                const int tn = t0 + (i + 1) * t_step;
-                nb = __ldg(offs + tn);
-                ne = __ldg(offs + tn + 1);
-            }
-            mbar_wait(bm_empty + b, u ^ 1u, A.err_flag, 5);
-            uint32_t *bm = bitmap + b * 4 * TM;
-            for (int q = lane; q < 4 * TM; q += 32) bm[q] = oob_bits(col0, q / TM, P.n_items);
-            __syncwarp();
-            if (keys != nullptr) {
-                for (uint32_t p = kb0; p < ke0; p += 32) {
-                    if (p != kb0) key = (p + lane < ke0) ? __ldg(keys + p + lane) : 0xffffffffu;
-                    if (p + lane < ke0) {
-                        const int cc = (int)(key >> 7) - col0;
-                        atomicOr(&bm[(cc >> 5) * TM + (int)(key & 127u)], 1u << (cc & 31));
-                    }
+            if (keys != nullptr && (i & 31) == 0) {
+                const int ti = i + lane;
+                off_b = off_e = 0;
+                if (ti < n_tiles) {
+                    const int t = t0 + ti * t_step;
+                    off_b = __ldg(offs + t);
+                    off_e = __ldg(offs + t + 1);
                 }
-                nkey = 0xffffffffu;
-                if (i + 1 < n_tiles && nb + lane < ne) nkey = __ldg(keys + nb + lane);
+                const uint32_t nb = __shfl_sync(0xffffffffu, off_b, 0), ne = __shfl_sync(0xffffffffu, off_e, 0);
+                nkey = (nb + lane < ne) ? __ldg(keys + nb + lane) : 0xffffffffu;
+            }
+            const uint32_t kb0 = __shfl_sync(0xffffffffu, off_b, i & 31), ke0 = __shfl_sync(0xffffffffu, off_e, i & 31);
+            uint32_t key = nkey;
+            if (keys != nullptr && ((i + 1) & 31) != 0 && i + 1 < n_tiles) {
+                const uint32_t nb = __shfl_sync(0xffffffffu, off_b, (i + 1) & 31), ne = __shfl_sync(0xffffffffu, off_e, (i + 1) & 31);
+                nkey = (nb + lane < ne) ? __ldg(keys + nb + lane) : 0xffffffffu;
+            }
+            mbar_wait(tile_empty + b, (uint32_t)(((i >> 1) & 1) ^ 1), A.err_flag, 5);
+            if (lane == 0) tc_trace(A, i, 5);
+            uint32_t *bm = bitmap + b * 4 * TM;
+            if (col0 + TN <= P.n_items) {
+                uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bm4[q * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+            } else {  // last tile: columns past the catalogue are masked
+                for (int q = lane; q < 4 * TM; q += 32) bm[q] = oob_bits(col0, q / TM, P.n_items);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bm_full + b);
+            for (uint32_t p = kb0; p < ke0; p += 32) {
+                if (p != kb0) key = (p + lane < ke0) ? __ldg(keys + p + lane) : 0xffffffffu;
+                if (p + lane < ke0) {
+                    const int cc = (int)(key >> 7) - col0;
+                    atomicOr(&bm[(cc >> 5) * TM + (int)(key & 127u)], 1u << (cc & 31));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(tile_full + b); tc_trace(A, i, 6); }
         }
-    } else if (role < 0) {
-        // ===== epilogue: thread <-> user row, warpgroup wg <-> columns [64 wg, 64 wg + 64) ==========
-        const int wg = warp >> 2;
-        const int r = tid & 127;  // TMEM lane
+    } else {
+        // ===== epilogue: thread <-> user row (TMEM lane), warp <-> 32 columns of every tile ========
+        const int lq = warp & 3, cq = warp >> 2;
+        const int r = lq * 32 + lane;  // TMEM lane
         const int64_t my_row = row_base + r;
         const bool my_valid = my_row < P.n_rows;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
         const float NINF = -__int_as_float(0x7f800000);
         const float PINF = __int_as_float(0x7f800000);
 
-        if (wg == 0) {  // A: my user's vector -> hi/lo TF32 -> TMEM
+        if (cq < NKB) {  // A: k-block cq of my user's vector -> hi/lo TF32 -> TMEM
+            const int kb = cq;
             const float *urow = A.U + (my_valid ? my_row : 0) * A.ld_u;
             const bool vec = ((A.ld_u & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.U) & 15) == 0);
-            for (int kb = 0; kb < nkb; ++kb) {
-                uint32_t hi[32], lo[32];
-                float x[32];
-                if (vec && my_valid && kb * TC_KB + 32 <= P.d) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 f = __ldg(reinterpret_cast<const float4 *>(urow + kb * TC_KB) + q);
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = kb * TC_KB + h * 16;
+                float x[16];
+                if (vec && my_valid && k0 + 16 <= P.d) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 f = __ldg(reinterpret_cast<const float4 *>(urow + k0) + q);
                         x[4 * q + 0] = f.x; x[4 * q + 1] = f.y; x[4 * q + 2] = f.z; x[4 * q + 3] = f.w;
                     }
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const int k = kb * TC_KB + q;
-                        x[q] = (my_valid && k < P.d) ? __ldg(urow + k) : 0.0f;
-                    }
+                    for (int q = 0; q < 16; ++q) x[q] = (my_valid && k0 + q < P.d) ? __ldg(urow + k0 + q) : 0.0f;
                 }
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const uint32_t h = to_tf32(x[q]);
-                    hi[q] = h;
-                    lo[q] = to_tf32(x[q] - __uint_as_float(h));
+                for (int q = 0; q < 16; ++q) {
+                    const uint32_t hh = to_tf32(x[q]);
+                    hi[q] = hh;
+                    lo[q] = to_tf32(x[q] - __uint_as_float(hh));
                 }
-                tmem_st32(lane_addr + (uint32_t)(kb * TC_KB), hi);
-                if (A.passes == 3) tmem_st32(lane_addr + (uint32_t)(nkb * TC_KB + kb * TC_KB), lo);
+                tmem_st16(lane_addr + (uint32_t)k0, hi);
+                if (PASSES == 3) tmem_st16(lane_addr + (uint32_t)(NKB * TC_KB + k0), lo);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -426,116 +471,114 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 
         // COLLECT: fixed per-row threshold from the sampled pre-pass; survivors go to this thread's sub-list
         float thr = PINF;  // rows beyond n_rows collect nothing
-        uint2 *wbase = nullptr, *wp = nullptr, *wend = nullptr;
+        uint2 *wbase = nullptr;
+        int wn = 0;
         float v[TC_R];  // SAMPLE: largest group maxima so far, descending
 #pragma unroll
         for (int q = 0; q < TC_R; ++q) v[q] = NINF;
-        if (!sample && my_valid) {
+        if (!SAMPLE && my_valid) {
             thr = __ldg(A.thr + my_row);
-            wbase = A.cand + ((my_row * P.S + c) * 2 + wg) * (int64_t)A.sub_stride;
-            wp = wbase;
-            wend = wbase + A.cap;
+            wbase = A.cand + ((my_row * P.S + c) * 4 + cq) * (int64_t)A.cap;
         }
-        const float QNAN = __int_as_float(0x7fffffff);  // masked score: fails every >=, ignored by fmaxf
+        const float QNAN = __int_as_float(0x7fffffff);  // masked score: ignored by fmaxf
         float4 *my_stage = stage_buf + tid;  // element q of my row: float (q & 3) of my_stage[(q >> 2) * TC_EPI_THREADS]
+        const uint32_t *my_bm = bitmap + cq * TM + r;
+        const uint32_t my_acc = lane_addr + (uint32_t)(TC_ACC_COL + cq * 32);
 
         for (int i = 0; i < n_tiles; ++i) {
             const int b = i & 1;
-            const uint32_t u = (uint32_t)((i >> 1) & 1);
-            const int col0 = (t0 + i * t_step) * TN + wg * 64;
-            mbar_wait(tmem_full + b, u, A.err_flag, 6);
+            const int col0 = (t0 + i * t_step) * TN + cq * 32;
+            mbar_wait(tile_full + b, (uint32_t)((i >> 1) & 1), A.err_flag, 6);
             tc_fence_after();
-            mbar_wait(bm_full + b, u, A.err_flag, 7);
-            const uint32_t *bm = bitmap + b * 4 * TM + (wg * 2) * TM + r;
-            const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC_COL + b * TN + wg * 64);
-#pragma unroll 1
-            for (int gq = 0; gq < ((A.dbg & 1) ? 0 : 2); ++gq) {
-                uint32_t raw[32];
-                __syncwarp();
-                tmem_ld32(acc_addr + (uint32_t)(gq * 32), raw);
-                const uint32_t mword = bm[gq * TM];
-                float s[32];
-                if (P.bias != nullptr) {
-                    const float4 *b4 = reinterpret_cast<const float4 *>(P.bias + col0 + gq * 32);
-                    float bv[32];
+            const int tslot = (warp == 0) ? 7 : 10;
+            const bool tr_me = (lane == 0) && (warp == 0 || warp == TC_EPI_WARPS - 1);
+            if (tr_me) tc_trace(A, i, tslot);
+            uint32_t raw[32];
+            uint32_t mword = 0u;
+            if (!(A.dbg & 1)) {
+                tmem_ld32(my_acc + (uint32_t)(b * TN), raw);
+                mword = my_bm[b * 4 * TM];
+                tmem_wait_ld();
+            }
+            // accumulator b and bitmap b are in registers: hand both back before working on them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tile_empty + b);
+            if (tr_me) tc_trace(A, i, tslot + 1);
+            if (A.dbg & 1) continue;
+
+            float s[32];
+            if (P.bias != nullptr) {
+                const float4 *b4 = reinterpret_cast<const float4 *>(P.bias + col0);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 x = __ldg(b4 + q);
-                        bv[4 * q + 0] = x.x; bv[4 * q + 1] = x.y; bv[4 * q + 2] = x.z; bv[4 * q + 3] = x.w;
-                    }
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]) + bv[q];
-                } else {
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]);
+                for (int q = 0; q < 8; ++q) {
+                    const float4 x = __ldg(b4 + q);
+                    s[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + x.x;
+                    s[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + x.y;
+                    s[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + x.z;
+                    s[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + x.w;
                 }
-                if (sample && mword != 0u) {  // train items (and columns past the catalogue) never count
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]);
+            }
+            if (SAMPLE) {
+                if (mword != 0u) {  // train items (and columns past the catalogue) never count
 #pragma unroll
                     for (int q = 0; q < 32; ++q)
                         if ((mword >> q) & 1u) s[q] = QNAN;
                 }
-                if (sample) {
-                    float m1[11];
+                float m1[11];
 #pragma unroll
-                    for (int q = 0; q < 10; ++q) m1[q] = fmaxf(fmaxf(s[3 * q], s[3 * q + 1]), s[3 * q + 2]);
-                    m1[10] = fmaxf(s[30], s[31]);
-                    float mx = fmaxf(fmaxf(m1[0], m1[1]), m1[2]);
-                    mx = fmaxf(mx, fmaxf(fmaxf(m1[3], m1[4]), m1[5]));
-                    mx = fmaxf(mx, fmaxf(fmaxf(m1[6], m1[7]), m1[8]));
-                    mx = fmaxf(mx, fmaxf(m1[9], m1[10]));
-                    if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
-                } else if (!(A.dbg & 4)) {
-                    // Detection costs two instructions per score on two different pipes and no
-                    // predicates: d = s - T0 (FMA pipe), then a funnel shift (ALU pipe) collects the sign
-                    // bit of d; bit q of `pass` ends up set iff s[q] >= T0 and item q is not masked.
-                    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // four independent chains of 8 for ILP
+                for (int q = 0; q < 10; ++q) m1[q] = fmaxf(fmaxf(s[3 * q], s[3 * q + 1]), s[3 * q + 2]);
+                m1[10] = fmaxf(s[30], s[31]);
+                float mx = fmaxf(fmaxf(m1[0], m1[1]), m1[2]);
+                mx = fmaxf(mx, fmaxf(fmaxf(m1[3], m1[4]), m1[5]));
+                mx = fmaxf(mx, fmaxf(fmaxf(m1[6], m1[7]), m1[8]));
+                mx = fmaxf(mx, fmaxf(m1[9], m1[10]));
+                if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
+            } else if (!(A.dbg & 4)) {
+                // Detection costs two instructions per score on two different pipes and no
+                // predicates: d = s - T0 (FMA pipe), then a funnel shift (ALU pipe) collects the sign
+                // bit of d; bit q of `pass` ends up set iff s[q] >= T0 and item q is not masked.
+                uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // four independent chains of 8 for ILP
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        m0 = __funnelshift_l(__float_as_uint(s[q] - thr), m0, 1);
-                        m1 = __funnelshift_l(__float_as_uint(s[q + 8] - thr), m1, 1);
-                        m2 = __funnelshift_l(__float_as_uint(s[q + 16] - thr), m2, 1);
-                        m3 = __funnelshift_l(__float_as_uint(s[q + 24] - thr), m3, 1);
-                    }
-                    // chain j holds items 8j..8j+7 with item 8j in bit 7: assemble so that item 0 lands in
-                    // bit 31, then reverse
-                    const uint32_t m = (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
-                    uint32_t pass = ~__brev(m) & ~mword;
-                    if (pass != 0u) {
-                        // rare per lane: park my 32 scores in shared memory so they can be indexed,
-                        // then append each survivor as (score bits, item) to my list in HBM
+                for (int q = 0; q < 8; ++q) {
+                    m0 = __funnelshift_l(__float_as_uint(s[q] - thr), m0, 1);
+                    m1 = __funnelshift_l(__float_as_uint(s[q + 8] - thr), m1, 1);
+                    m2 = __funnelshift_l(__float_as_uint(s[q + 16] - thr), m2, 1);
+                    m3 = __funnelshift_l(__float_as_uint(s[q + 24] - thr), m3, 1);
+                }
+                // chain j holds items 8j..8j+7 with item 8j in bit 7: assemble so that item 0 lands in
+                // bit 31, then reverse
+                const uint32_t m = (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
+                uint32_t pass = ~__brev(m) & ~mword;
+                if (pass != 0u) {
+                    // rare per lane: park my 32 scores in shared memory so they can be indexed,
+                    // then append each survivor as (score bits, item) to my list in HBM
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            my_stage[q * TC_EPI_THREADS] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
-                        const uint32_t cb = (uint32_t)(col0 + gq * 32);
-                        const float *row_f = reinterpret_cast<const float *>(my_stage);
-                        do {
-                            const int q = __ffs(pass) - 1;
-                            pass &= pass - 1u;
-                            const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
-                            if (wp < wend) *wp = make_uint2(__float_as_uint(sc), cb + (uint32_t)q);
-                            ++wp;
-                        } while (pass != 0u);
-                    }
+                    for (int q = 0; q < 8; ++q)
+                        my_stage[q * TC_EPI_THREADS] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+                    const float *row_f = reinterpret_cast<const float *>(my_stage);
+                    do {
+                        const int q = __ffs(pass) - 1;
+                        pass &= pass - 1u;
+                        const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
+                        if (wn < A.cap) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
+                        ++wn;
+                    } while (pass != 0u);
                 }
             }
-            // this thread is done with accumulator b and bitmap b
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(tmem_empty + b);
-                mbar_arrive(bm_empty + b);
-            }
+            if (tr_me) tc_trace(A, i, tslot + 2);
         }
 
         if (my_valid) {
-            if (sample) {
-                float *dst = A.samp + (my_row * 2 + wg) * TC_R;
+            if (SAMPLE) {
+                float4 *dst = reinterpret_cast<float4 *>(A.samp + (my_row * 4 + cq) * TC_R);
 #pragma unroll
-                for (int q = 0; q < TC_R; ++q) dst[q] = v[q];
+                for (int q = 0; q < TC_R / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             } else {
-                A.cand_cnt[(my_row * P.S + c) * 2 + wg] = (uint32_t)(wp - wbase);  // > cap means overflow
+                A.cand_cnt[(my_row * P.S + c) * 4 + cq] = (uint32_t)wn;  // > cap means overflow
             }
         }
     }
@@ -549,22 +592,28 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 }
 
 // ---- sampled group maxima -> per-row threshold -------------------------------------------------------
-// thr[row] = r-th largest of the row's two descending lists (one per column half) = r-th largest
-// sampled group maximum.  With fewer than r finite entries it is -inf (everything is a candidate).
-__global__ void k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr)
+// thr[row] = r-th largest of the row's 4 x TC_R kept group maxima (one warp per row, two values per lane):
+// the largest T with #{v >= T} >= r, built bit by bit over the monotone integer image of the floats.
+// With fewer than r finite entries it is -inf (everything is a candidate).  A list that was truncated at
+// TC_R can only lower the estimate, i.e. admit more candidates.
+__global__ void __launch_bounds__(256)
+k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr)
 {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= n_rows) return;
-    const float *la = samp + row * (2 * TC_R), *lb = la + TC_R;
-    const float NINF = -__int_as_float(0x7f800000);
-    int ia = 0, ib = 0;
-    float t = NINF;
-    for (int q = 0; q < r; ++q) {
-        const float xa = (ia < TC_R) ? la[ia] : NINF;
-        const float xb = (ib < TC_R) ? lb[ib] : NINF;
-        if (xa >= xb) { t = xa; ++ia; } else { t = xb; ++ib; }
+    const float2 x = __ldg(reinterpret_cast<const float2 *>(samp + row * (4 * TC_R)) + lane);
+    const uint32_t a = ord_f32(x.x), b = ord_f32(x.y);
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, min(a, b)), hi = __reduce_max_sync(0xffffffffu, max(a, b));
+    // bits above the highest bit in which min and max differ are common to every value
+    const int nb = 32 - __clz((lo ^ hi) | 1u);
+    uint32_t T = (nb >= 32) ? 0u : (hi >> nb) << nb;
+    for (int bit = nb - 1; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        const int cnt = __reduce_add_sync(0xffffffffu, (int)(a >= cand) + (int)(b >= cand));
+        if (cnt >= r) T = cand;
     }
-    thr[row] = t;
+    if (lane == 0) thr[row] = unord_f32(T);
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------

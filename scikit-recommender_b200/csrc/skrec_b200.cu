@@ -66,7 +66,7 @@ struct skr_ctx {
     float *d_idcg = nullptr;  // iDCG after n terms (metric.h:82), host-accumulated
     int disc_n = 0;
     // workspace, grow-only
-    Buf keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
+    Buf trace, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
     int64_t launches = 0;
     const char *last_fused = "none";
@@ -75,6 +75,7 @@ struct skr_ctx {
     int64_t opt_sample_tiles = 0;
     int64_t opt_rank = 0;
     int64_t opt_dbg = 0;
+    int64_t opt_trace_cta = -1;  // >= 0: record the tile timeline of that CTA of the main pass (development aid)
     struct Plan { int n_samp, stride, r, cap, S, stages; } last_plan = {0, 0, 0, 0, 0, 0};
     EncodeTiledFn encode = nullptr;
     std::vector<cudaEvent_t> ev0, ev1, ev2;  // ring: ev2 before the pre-pass, ev0/ev1 around the main scoring kernel
@@ -246,7 +247,7 @@ int run_metrics(skr_ctx *ctx, const u64 *keys, const int32_t *idx_in, int64_t n_
 int pick_chunks(const skr_ctx *ctx, int n_rt, int n_ct, int K, bool lists)
 {
     // heap path: S*K keys must fit one warp sort; list path: chunks are independent, only balance matters
-    int smax = lists ? std::min(n_ct, 16) : std::min(std::min(n_ct, 1024 / K), 16);
+    int smax = lists ? std::min(n_ct, 8) : std::min(std::min(n_ct, 1024 / K), 16);  // lists: 4 S sub-lists <= 32
     if (smax < 1) smax = 1;
     if (ctx->opt_chunks > 0) return (int)std::min<int64_t>(ctx->opt_chunks, smax);
     long best_cost = -1;
@@ -270,6 +271,27 @@ int make_tmap(skr_ctx *ctx, CUtensorMap *map, const float *base, int64_t n_rows,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, SKR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SKR_OK;
+}
+
+
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, TcArgs, FusedParams);
+
+template <int NKB>
+TcKernel tc_kernel_for(int passes, int mode)
+{
+    if (mode == TC_MODE_SAMPLE) return k_fused_tc<NKB, 1, TC_MODE_SAMPLE>;
+    return passes == 3 ? k_fused_tc<NKB, 3, TC_MODE_COLLECT> : k_fused_tc<NKB, 1, TC_MODE_COLLECT>;
+}
+
+int launch_tc(skr_ctx *ctx, int nkb, int passes, int mode, unsigned grid, cudaStream_t st, const CUtensorMap &mhi, const CUtensorMap &mlo,
+              const TcArgs &A, const FusedParams &P)
+{
+    TcKernel k = nkb == 1 ? tc_kernel_for<1>(passes, mode) : nkb == 2 ? tc_kernel_for<2>(passes, mode)
+               : nkb == 3 ? tc_kernel_for<3>(passes, mode) : tc_kernel_for<4>(passes, mode);
+    const size_t smem = tc_smem_bytes();
+    SKR_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
     return SKR_OK;
 }
 
@@ -341,7 +363,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
-                   &ctx->fail_list};
+                   &ctx->fail_list, &ctx->trace};
     for (Buf *b : bufs) free_dev(b->p);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
@@ -358,6 +380,7 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "sample_tiles")) { ctx->opt_sample_tiles = value; return SKR_OK; }
     if (!strcmp(name, "rank")) { ctx->opt_rank = value; return SKR_OK; }
     if (!strcmp(name, "dbg")) { ctx->opt_dbg = value; return SKR_OK; }
+    if (!strcmp(name, "trace_cta")) { ctx->opt_trace_cta = value; return SKR_OK; }
     if (!strcmp(name, "event_ring")) {
         if (value < 1 || value > 65536) return fail(ctx, SKR_ERR_INVALID, "event_ring=%lld not in [1,65536]", (long long)value);
         cudaSetDevice(ctx->device);
@@ -410,6 +433,17 @@ int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out)
     out[4] = ctx->last_plan.S;
     out[5] = ctx->last_plan.stages;
     out[6] = n_fail;
+    return SKR_OK;
+}
+
+int skr_fused_trace(skr_ctx *ctx, int64_t *out, int64_t n_out)
+{
+    if (!ctx || !out || n_out < 0) return SKR_ERR_INVALID;
+    if (!ctx->trace.p) return fail(ctx, SKR_ERR_STATE, "no trace recorded (set option trace_cta)");
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SKR_CUDA(ctx, cudaDeviceSynchronize());
+    const size_t n = std::min<size_t>((size_t)n_out * sizeof(int64_t), ctx->trace.cap);
+    SKR_CUDA(ctx, cudaMemcpy(out, ctx->trace.p, n, cudaMemcpyDeviceToHost));
     return SKR_OK;
 }
 
@@ -556,11 +590,7 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
 
     // ---- kernel choice ----
     const int nkb = (d + TC_KB - 1) / TC_KB;
-    int stages = 0;
-    for (int s = TC_MAX_STAGES; s >= 2; --s)
-        if (tc_smem_bytes(s) <= ctx->max_smem) { stages = s; break; }
-    if (ctx->opt_stages >= 2 && ctx->opt_stages <= stages) stages = (int)ctx->opt_stages;
-    const bool tc_ok = (nkb <= 4) && (stages >= 2) && (d <= K2_MAX_D);
+    const bool tc_ok = (nkb <= 4) && (tc_smem_bytes() <= ctx->max_smem);
     bool use_tc = (precision != SKR_PREC_FP32) && tc_ok;
     if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32))
         return fail(ctx, SKR_ERR_UNSUPPORTED, "tcgen05 path needs d <= 128 (d=%d)", d);
@@ -626,16 +656,15 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         const double f_eff = std::min(1.0, (double)n_samp * TN / (double)n_items);
         const double kf = K * f_eff;
         int r = (int)ceil(kf + 4.5 * sqrt(kf) + 8.0);
-        r = std::max(1, std::min(r, TC_R));
-        if (ctx->opt_rank > 0) r = (int)std::min<int64_t>(ctx->opt_rank, TC_R);
+        r = std::max(1, std::min(r, TC_MAX_RANK));
+        if (ctx->opt_rank > 0) r = (int)std::min<int64_t>(ctx->opt_rank, TC_MAX_RANK);
         const double expect = r / f_eff;  // candidates per row
-        int cap = next_pow2((int)(2.0 * expect / (2 * P.S)) + 24);
-        cap = std::max(32, std::min(cap, 512));
-        const int n_sub = 2 * P.S;
+        const int n_sub = 4 * P.S;        // one sub-list per (item chunk, column quarter of the tile)
+        int cap = next_pow2((int)(2.0 * expect / n_sub) + 16);
+        cap = std::max(16, std::min(cap, 512));
 
-        if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 2 * TC_R * sizeof(float)))) return rc;
-        const int sub_stride = next_pow2(cap + 32);
-        if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * sub_stride * sizeof(uint2) + 8192))) return rc;
+        if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 4 * TC_R * sizeof(float)))) return rc;
+        if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * cap * sizeof(uint2)))) return rc;
         if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(float)))) return rc;
         if ((rc = ensure(ctx, ctx->cand_cnt, (size_t)n_rows * n_sub * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
@@ -646,8 +675,6 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         TcArgs A;
         A.U = user_vecs_dev;
         A.ld_u = ld_u;
-        A.nkb = nkb;
-        A.stages = stages;
         A.err_flag = ctx->d_err;
         A.dbg = (int)ctx->opt_dbg;
         A.stride = stride;
@@ -655,37 +682,42 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         A.samp = (float *)ctx->samp.p;
         A.thr = (const float *)ctx->thr.p;
         A.cap = cap;
-        A.sub_stride = sub_stride;
-        A.cand = (uint2 *)(((uintptr_t)ctx->cand.p + 8191) & ~(uintptr_t)8191);  // stride-aligned (stride <= 8 KB)
+        A.cand = (uint2 *)ctx->cand.p;
         A.cand_cnt = (uint32_t *)ctx->cand_cnt.p;
-        const size_t smem = tc_smem_bytes(stages);
-        SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        A.trace = nullptr;
+        A.trace_cta = -1;
+        A.trace_tiles = 0;
+        const int passes = (precision == SKR_PREC_1XTF32) ? 1 : 3;
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
-        A.mode = TC_MODE_SAMPLE;
-        A.passes = 1;
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
-        k_fused_tc<<<(unsigned)P.n_rt, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
-        k_sample_thr<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p);
+        if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)P.n_rt, st, mhi, mlo, A, P))) return rc;
+        k_sample_thr<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p);
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
-        A.mode = TC_MODE_COLLECT;
-        A.passes = (precision == SKR_PREC_1XTF32) ? 1 : 3;
+        if (ctx->opt_trace_cta >= 0) {
+            A.trace_tiles = P.tiles_per_chunk;
+            const size_t tb = (size_t)A.trace_tiles * TC_TRACE_SLOTS * sizeof(long long);
+            if ((rc = ensure(ctx, ctx->trace, tb))) return rc;
+            SKR_CUDA(ctx, cudaMemsetAsync(ctx->trace.p, 0, tb, st));
+            A.trace = (long long *)ctx->trace.p;
+            A.trace_cta = (int)ctx->opt_trace_cta;
+        }
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
-        k_fused_tc<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
+        if ((rc = launch_tc(ctx, nkb, passes, TC_MODE_COLLECT, grid, st, mhi, mlo, A, P))) return rc;
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
         SKR_CUDA(ctx, cudaGetLastError());
         {
             const unsigned sel_grid = (unsigned)((n_rows + SEL_WARPS - 1) / SEL_WARPS);
             if (K <= 64)
-                k_select_cands<2><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, sub_stride, K, n_rows, keys, fail_list, fail_count);
+                k_select_cands<2><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, cap, K, n_rows, keys, fail_list, fail_count);
             else
-                k_select_cands<4><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, sub_stride, K, n_rows, keys, fail_list, fail_count);
+                k_select_cands<4><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, cap, K, n_rows, keys, fail_list, fail_count);
         }
         k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, user_vecs_dev, ld_u, item_vecs_dev, ld_i, d,
                                                                       bias_dev, (int)n_items, row0, tp, ti, K, keys);
         ctx->launches += 2;
-        ctx->last_fused = (A.passes == 3) ? "tcgen05_3xtf32" : "tcgen05_1xtf32";
-        ctx->last_plan = {n_samp, stride, r, cap, P.S, stages};
+        ctx->last_fused = (passes == 3) ? "tcgen05_3xtf32" : "tcgen05_1xtf32";
+        ctx->last_plan = {n_samp, stride, r, cap, P.S, passes == 3 ? 4 : 8};
     } else {
         if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->part, (size_t)n_rows * P.S * K * sizeof(u64)))) return rc;

@@ -11,9 +11,8 @@ ctx.set_test_csr(d["test_indptr"], d["test_indices"], d["items"])
 ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"]).cuda()
 sums = torch.zeros(150, dtype=torch.float64, device="cuda")
 for prec in ("3xtf32", "1xtf32"):
-    for stages in (6, 3, 2):
-        ctx.set_option("stages", stages)
-        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (2, "no MMA"), (3, "no MMA, no epilogue"), (10, "no MMA no TMA"), (9, "no TMA, no epilogue (MMA only)")):
+    for stages in (0,):
+        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (2, "no MMA"), (3, "no MMA, no epilogue"), (9, "no TMA, no epilogue (MMA only)")):
             ctx.set_option("dbg", dbg)
             ms = []
             for _ in range(3):

@@ -143,7 +143,7 @@ def stage_tc_c2():
     te = (d["test_indptr"], d["test_indices"])
     res = {}
     for prec in ("3xtf32", "fp32", "1xtf32"):
-        for chunks in ((0, 2, 5, 8, 13) if prec == "3xtf32" else (0,)):
+        for chunks in ((0, 2, 4, 5, 8) if prec == "3xtf32" else (0,)):
             ctx.set_option("chunks", chunks)
             out = _fused(np, torch, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, prec)
             out = _fused(np, torch, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, prec)
