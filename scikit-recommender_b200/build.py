@@ -24,7 +24,8 @@ def build(force=False, verbose=False):
         if all(os.path.getmtime(s) <= t for s in sources()):
             return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "skrec_b200.cu")]
+    extra = os.environ.get("SKR_NVCC_EXTRA", "").split()  # e.g. -DSKR_TC_TRACE=1 for tools/trace_tiles.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "skrec_b200.cu")]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -127,6 +127,18 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
 }
+// one lane of a converged warp (always the same one for a full mask: tcgen05.commit must come from the
+// thread that issued the MMAs it tracks)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
@@ -161,6 +173,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
         "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : SKR_R32(r, 0), SKR_R32(r, 8), SKR_R32(r, 16), SKR_R32(r, 24)
+        : "r"(taddr)
+        : "memory");
+}
+// load + wait in one statement: the registers are defined only once the data has landed
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
         : SKR_R32(r, 0), SKR_R32(r, 8), SKR_R32(r, 16), SKR_R32(r, 24)
         : "r"(taddr)
         : "memory");
@@ -218,9 +242,12 @@ constexpr int TC_TRACE_SLOTS = 16;
 // slots: 0 producer got the stage of kb 0, 1 producer issued the last TMA of the tile, 2 issuer: accumulator free,
 // 3 issuer: first stage full, 4 issuer: tile committed, 5 mask: buffer free, 6 mask: bitmap ready,
 // 7/10 epilogue warp 0/15: tile full, 8/11: accumulator in registers (released), 9/12: tile processed
+#ifndef SKR_TC_TRACE
+#define SKR_TC_TRACE 0
+#endif
 __device__ __forceinline__ void tc_trace(const TcArgs &A, int tile, int slot)
 {
-    if (A.trace != nullptr && (int)blockIdx.x == A.trace_cta && tile < A.trace_tiles)
+    if (SKR_TC_TRACE && A.trace != nullptr && (int)blockIdx.x == A.trace_cta && tile < A.trace_tiles)
         A.trace[(size_t)tile * TC_TRACE_SLOTS + slot] = clock64();
 }
 
@@ -244,6 +271,77 @@ __device__ __forceinline__ void sorted_insert(float (&v)[TC_R], float x)
     }
 }
 
+// One thread's share of a tile: 32 scores of its row.  SAMPLE: fold the group maximum into the sorted
+// list v.  COLLECT: survivor mask against the row threshold, survivors appended to the sub-list.
+template <bool SAMPLE, bool BIAS>
+__device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const float *__restrict__ bias32, uint32_t mword, float thr, int col0,
+                                           bool my_valid, int cap, bool no_append, float4 *my_stage, uint2 *wbase, int &wn, float (&v)[TC_R])
+{
+    float s[32];
+    if (BIAS) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 x = __ldg(b4 + q);
+            s[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + x.x;
+            s[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + x.y;
+            s[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + x.z;
+            s[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + x.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]);
+    }
+    if (SAMPLE) {
+        if (mword != 0u) {  // train items (and columns past the catalogue) never count
+            const float QNAN = __int_as_float(0x7fffffff);  // ignored by fmaxf
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                if ((mword >> q) & 1u) s[q] = QNAN;
+        }
+        float m1[11];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) m1[q] = fmaxf(fmaxf(s[3 * q], s[3 * q + 1]), s[3 * q + 2]);
+        m1[10] = fmaxf(s[30], s[31]);
+        float mx = fmaxf(fmaxf(m1[0], m1[1]), m1[2]);
+        mx = fmaxf(mx, fmaxf(fmaxf(m1[3], m1[4]), m1[5]));
+        mx = fmaxf(mx, fmaxf(fmaxf(m1[6], m1[7]), m1[8]));
+        mx = fmaxf(mx, fmaxf(m1[9], m1[10]));
+        if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
+    } else if (!no_append) {
+        // Detection costs two instructions per score on two different pipes and no predicates:
+        // d = s - T0 (FMA pipe), then a funnel shift (ALU pipe) collects the sign bit of d; bit q of
+        // `pass` ends up set iff s[q] >= T0 and item q is not masked.
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // four independent chains of 8 for ILP
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            m0 = __funnelshift_l(__float_as_uint(s[q] - thr), m0, 1);
+            m1 = __funnelshift_l(__float_as_uint(s[q + 8] - thr), m1, 1);
+            m2 = __funnelshift_l(__float_as_uint(s[q + 16] - thr), m2, 1);
+            m3 = __funnelshift_l(__float_as_uint(s[q + 24] - thr), m3, 1);
+        }
+        // chain j holds items 8j..8j+7 with item 8j in bit 7: assemble so that item 0 lands in bit 31,
+        // then reverse
+        const uint32_t m = (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
+        uint32_t pass = ~__brev(m) & ~mword;
+        if (pass != 0u) {
+            // rare per lane: park my 32 scores in shared memory so they can be indexed, then append
+            // each survivor as (score bits, item) to my list in HBM
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                my_stage[q * TC_EPI_THREADS] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+            const float *row_f = reinterpret_cast<const float *>(my_stage);
+            do {
+                const int q = __ffs(pass) - 1;
+                pass &= pass - 1u;
+                const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
+                if (wn < cap) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
+                ++wn;
+            } while (pass != 0u);
+        }
+    }
+}
+
 template <int NKB, int PASSES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, TcArgs A, FusedParams P)
@@ -255,7 +353,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     static_assert(STAGES * STAGE_BYTES == TC_RING_BYTES, "ring size");
 
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for SWIZZLE_128B, computed on the shared-window address so that the compiler
+    // keeps every pointer below in the shared address space (LDS/STS, not generic LD/ST)
+    unsigned char *smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     unsigned char *b_tiles = smem;
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + TC_RING_BYTES);  // [2][4][TM]
     float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + 2 * 4 * TM);    // [8][TC_EPI_THREADS]
@@ -302,14 +402,16 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 
     if (role == 0) {
         // ===== TMA producer: item k-block tiles (hi, lo) through the stage ring ==================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int i = 0; i < n_tiles; ++i) {
-                const int t = t0 + i * t_step;
+        // The whole warp stays converged (every operand is warp-uniform and lives in uniform registers);
+        // one elected lane issues the copies.
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int t = t0 + i * t_step;
 #pragma unroll
-                for (int kb = 0; kb < NKB; ++kb) {
-                    mbar_wait(empty + s, ph ^ 1u, A.err_flag, 1);
+            for (int kb = 0; kb < NKB; ++kb) {
+                mbar_wait(empty + s, ph ^ 1u, A.err_flag, 1);
+                if (elect_one()) {
                     if (kb == 0) tc_trace(A, i, 0);
                     if (A.dbg & 8) {
                         mbar_arrive(full + s);
@@ -319,36 +421,40 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                         tma_load_2d(dst, &tm_bhi, kb * TC_KB, t * TN, full + s);
                         if (PASSES == 3) tma_load_2d(dst + TC_TILE_BYTES, &tm_blo, kb * TC_KB, t * TN, full + s);
                     }
-                    if (++s == STAGES) { s = 0; ph ^= 1u; }
+                    if (kb == NKB - 1) tc_trace(A, i, 1);
                 }
-                tc_trace(A, i, 1);
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (role == 1 || role == 3) {
         // ===== MMA issuers: warp 17 takes the even tiles (accumulator 0), warp 19 the odd ones (accumulator 1).
         // Two issuers hide each other's per-tile barrier latencies; the tensor pipe executes in issue order.
-        if (lane == 0) {
-            const int p = (role == 1) ? 0 : 1;
-            const bool do_mma = !(A.dbg & 2);
-            mbar_wait(a_ready, 0, A.err_flag, 2);
+        // Converged warp, one elected lane issues: inside an `if (lane == 0)` region the compiler wraps every
+        // tcgen05.mma in an ELECT / 3 x R2UR / branch loop (~100 cycles per MMA, measured) because it cannot
+        // prove the descriptors uniform; here they are uniform registers and an MMA is a single instruction.
+        const int p = (role == 1) ? 0 : 1;
+        const bool do_mma = !(A.dbg & 2);
+        mbar_wait(a_ready, 0, A.err_flag, 2);
+        tc_fence_after();
+        const uint32_t a_hi0 = tmem_base;
+        const uint32_t a_lo0 = tmem_base + (uint32_t)(NKB * TC_KB);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + p * TN);
+        const uint64_t desc0 = make_b_desc(smem_u32(b_tiles));
+        for (int i = p; i < n_tiles; i += 2) {
+            mbar_wait(tile_empty + p, (uint32_t)(((i >> 1) & 1) ^ 1), A.err_flag, 3);
             tc_fence_after();
-            const uint32_t a_hi0 = tmem_base;
-            const uint32_t a_lo0 = tmem_base + (uint32_t)(NKB * TC_KB);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + p * TN);
-            const uint64_t desc0 = make_b_desc(smem_u32(b_tiles));
-            for (int i = p; i < n_tiles; i += 2) {
-                mbar_wait(tile_empty + p, (uint32_t)(((i >> 1) & 1) ^ 1), A.err_flag, 3);
-                tc_fence_after();
-                tc_trace(A, i, 2);
+            if (elect_one()) tc_trace(A, i, 2);
 #pragma unroll
-                for (int kb = 0; kb < NKB; ++kb) {
-                    const int it = i * NKB + kb;
-                    const int s = it & (STAGES - 1);
-                    const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-                    mbar_wait(full + s, ph, A.err_flag, 4);
-                    tc_fence_after();
+            for (int kb = 0; kb < NKB; ++kb) {
+                const int it = i * NKB + kb;
+                const int s = it & (STAGES - 1);
+                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                mbar_wait(full + s, ph, A.err_flag, 4);
+                tc_fence_after();
+                const uint64_t ds = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));  // start-address field counts 16-byte units
+                if (elect_one()) {
                     if (kb == 0) tc_trace(A, i, 3);
-                    const uint64_t ds = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));  // start-address field counts 16-byte units
                     if (do_mma) {
 #pragma unroll
                         for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 = 32 bytes
@@ -366,9 +472,12 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                         }
                     }
                     tc_commit(empty + s);  // stage reusable once these MMAs have read it
+                    if (kb == NKB - 1) {
+                        tc_commit(tile_full + p);  // accumulator p complete
+                        tc_trace(A, i, 4);
+                    }
                 }
-                tc_commit(tile_full + p);  // accumulator p complete
-                tc_trace(A, i, 4);
+                __syncwarp();
             }
         }
     } else if (role == 2) {
@@ -480,7 +589,6 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             thr = __ldg(A.thr + my_row);
             wbase = A.cand + ((my_row * P.S + c) * 4 + cq) * (int64_t)A.cap;
         }
-        const float QNAN = __int_as_float(0x7fffffff);  // masked score: ignored by fmaxf
         float4 *my_stage = stage_buf + tid;  // element q of my row: float (q & 3) of my_stage[(q >> 2) * TC_EPI_THREADS]
         const uint32_t *my_bm = bitmap + cq * TM + r;
         const uint32_t my_acc = lane_addr + (uint32_t)(TC_ACC_COL + cq * 32);
@@ -496,9 +604,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             uint32_t raw[32];
             uint32_t mword = 0u;
             if (!(A.dbg & 1)) {
-                tmem_ld32(my_acc + (uint32_t)(b * TN), raw);
                 mword = my_bm[b * 4 * TM];
-                tmem_wait_ld();
+                tmem_ld32_wait(my_acc + (uint32_t)(b * TN), raw);
             }
             // accumulator b and bitmap b are in registers: hand both back before working on them
             tc_fence_before();
@@ -507,68 +614,12 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             if (tr_me) tc_trace(A, i, tslot + 1);
             if (A.dbg & 1) continue;
 
-            float s[32];
-            if (P.bias != nullptr) {
-                const float4 *b4 = reinterpret_cast<const float4 *>(P.bias + col0);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 x = __ldg(b4 + q);
-                    s[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + x.x;
-                    s[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + x.y;
-                    s[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + x.z;
-                    s[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + x.w;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) s[q] = __uint_as_float(raw[q]);
-            }
-            if (SAMPLE) {
-                if (mword != 0u) {  // train items (and columns past the catalogue) never count
-#pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        if ((mword >> q) & 1u) s[q] = QNAN;
-                }
-                float m1[11];
-#pragma unroll
-                for (int q = 0; q < 10; ++q) m1[q] = fmaxf(fmaxf(s[3 * q], s[3 * q + 1]), s[3 * q + 2]);
-                m1[10] = fmaxf(s[30], s[31]);
-                float mx = fmaxf(fmaxf(m1[0], m1[1]), m1[2]);
-                mx = fmaxf(mx, fmaxf(fmaxf(m1[3], m1[4]), m1[5]));
-                mx = fmaxf(mx, fmaxf(fmaxf(m1[6], m1[7]), m1[8]));
-                mx = fmaxf(mx, fmaxf(m1[9], m1[10]));
-                if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
-            } else if (!(A.dbg & 4)) {
-                // Detection costs two instructions per score on two different pipes and no
-                // predicates: d = s - T0 (FMA pipe), then a funnel shift (ALU pipe) collects the sign
-                // bit of d; bit q of `pass` ends up set iff s[q] >= T0 and item q is not masked.
-                uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // four independent chains of 8 for ILP
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    m0 = __funnelshift_l(__float_as_uint(s[q] - thr), m0, 1);
-                    m1 = __funnelshift_l(__float_as_uint(s[q + 8] - thr), m1, 1);
-                    m2 = __funnelshift_l(__float_as_uint(s[q + 16] - thr), m2, 1);
-                    m3 = __funnelshift_l(__float_as_uint(s[q + 24] - thr), m3, 1);
-                }
-                // chain j holds items 8j..8j+7 with item 8j in bit 7: assemble so that item 0 lands in
-                // bit 31, then reverse
-                const uint32_t m = (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
-                uint32_t pass = ~__brev(m) & ~mword;
-                if (pass != 0u) {
-                    // rare per lane: park my 32 scores in shared memory so they can be indexed,
-                    // then append each survivor as (score bits, item) to my list in HBM
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        my_stage[q * TC_EPI_THREADS] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
-                    const float *row_f = reinterpret_cast<const float *>(my_stage);
-                    do {
-                        const int q = __ffs(pass) - 1;
-                        pass &= pass - 1u;
-                        const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
-                        if (wn < A.cap) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
-                        ++wn;
-                    } while (pass != 0u);
-                }
-            }
+            // two copies of the per-tile work, so that without a bias the scores are consumed in the very
+            // registers tcgen05.ld wrote (one shared copy costs 32 register moves per tile)
+            if (P.bias != nullptr)
+                tc_process<SAMPLE, true>(raw, P.bias + col0, mword, thr, col0, my_valid, A.cap, (A.dbg & 4) != 0, my_stage, wbase, wn, v);
+            else
+                tc_process<SAMPLE, false>(raw, nullptr, mword, thr, col0, my_valid, A.cap, (A.dbg & 4) != 0, my_stage, wbase, wn, v);
             if (tr_me) tc_trace(A, i, tslot + 2);
         }
 
