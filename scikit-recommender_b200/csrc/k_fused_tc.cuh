@@ -43,7 +43,10 @@
 // builder, warp 19 MMA issuer of the odd tiles.  Accumulators and bitmaps are double buffered so the
 // epilogue of tile n overlaps the MMAs of tile n+1.
 //
-// TMEM columns: [0, 32*NKB) A_hi, [32*NKB, 64*NKB) A_lo, [256, 384) acc 0, [384, 512) acc 1.
+// TMEM columns: [0, 32*NKB) A_hi, [32*NKB, 64*NKB) A_lo (3xTF32 only), then NBUF accumulators of 128 columns
+// at the top: three when A fits 128 columns (d <= 64, or any d <= 128 in one pass), otherwise two.  The third
+// buffer lets the issuers run a tile further ahead of the epilogue, which is what bounds the single-pass
+// modes (their accumulator round trip, not the tensor pipe).
 #pragma once
 #include <cuda.h>
 #include "fused_common.cuh"
@@ -57,7 +60,7 @@ constexpr int TC_KB = 32;                             // floats per k-block (one
 constexpr int TC_TILE_BYTES = TN * TC_KB * 4;         // 16 KB: one operand tile of one k-block
 constexpr int TC_RING_BYTES = 8 * TC_TILE_BYTES;      // 4 stages of hi+lo (3xTF32) or 8 stages of hi (1xTF32)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_ACC_COL = 256;                       // first accumulator column
+constexpr int TC_MAX_BUF = 3;                         // accumulator / bitmap buffers
 constexpr int TC_R = 16;                              // group maxima kept per row and column quarter (SAMPLE)
 constexpr int TC_MAX_RANK = 32;                       // largest threshold rank the 4 x TC_R lists support
 constexpr long long TC_TIMEOUT_CYCLES = 4000000000ll; // watchdog: ~2 s
@@ -68,7 +71,7 @@ __host__ __device__ inline size_t tc_smem_bytes()
 {
     return (size_t)1024                          // alignment slack
            + (size_t)TC_RING_BYTES
-           + (size_t)2 * 4 * TM * 4              // two bitmaps
+           + (size_t)TC_MAX_BUF * 4 * TM * 4     // train-mask bitmaps, one per accumulator buffer
            + (size_t)8 * TC_EPI_THREADS * 16     // score staging: one 32-float row per epilogue thread, [8][512] float4
            + 256;                                // barriers + tmem pointer
 }
@@ -222,7 +225,7 @@ struct TcArgs {
     const float *U;   // user vectors [n_rows, ld_u]
     int64_t ld_u;
     int *err_flag;    // device int, set before a watchdog trap
-    int dbg;          // timing experiments only (results invalid): 1 no epilogue work, 2 no MMA, 4 no appends, 8 no TMA
+    int dbg;          // timing experiments only (results invalid): 1 no epilogue work, 2 no MMA, 4 no appends, 8 no TMA, 16 no bitmaps
     // SAMPLE: item tiles 0, stride, 2*stride, ...; out: samp[row][4][TC_R] group maxima, descending
     int stride;
     int n_samp;
@@ -351,20 +354,23 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     constexpr int STAGE_BYTES = (PASSES == 3) ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
     static_assert(NKB >= 1 && NKB <= 4 && (PASSES == 1 || PASSES == 3), "tile shape");
     static_assert(STAGES * STAGE_BYTES == TC_RING_BYTES, "ring size");
+    constexpr int A_COLS = TC_KB * NKB * (PASSES == 3 ? 2 : 1);
+    constexpr int NBUF = (A_COLS <= 512 - 3 * TN) ? 3 : 2;
+    constexpr int ACC_COL = 512 - NBUF * TN;  // first accumulator column
 
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B, computed on the shared-window address so that the compiler
     // keeps every pointer below in the shared address space (LDS/STS, not generic LD/ST)
     unsigned char *smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     unsigned char *b_tiles = smem;
-    uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + TC_RING_BYTES);  // [2][4][TM]
-    float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + 2 * 4 * TM);    // [8][TC_EPI_THREADS]
+    uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + TC_RING_BYTES);        // [NBUF][4][TM]
+    float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + TC_MAX_BUF * 4 * TM);  // [8][TC_EPI_THREADS]
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 8 * TC_EPI_THREADS);
     uint64_t *full = bars;                            // [TC_MAX_STAGES] TMA landed
     uint64_t *empty = bars + TC_MAX_STAGES;           // [TC_MAX_STAGES] MMAs that read the stage are done
-    uint64_t *tile_full = bars + 2 * TC_MAX_STAGES;   // [2] accumulator complete (MMA commit) + bitmap built (mask warp)
-    uint64_t *tile_empty = tile_full + 2;             // [2] all 16 epilogue warps are done with accumulator and bitmap
-    uint64_t *a_ready = tile_empty + 2;               // [1] A operand is in TMEM
+    uint64_t *tile_full = bars + 2 * TC_MAX_STAGES;   // [NBUF] accumulator complete (MMA commit) + bitmap built (mask warp)
+    uint64_t *tile_empty = tile_full + TC_MAX_BUF;    // [NBUF] all 16 epilogue warps are done with accumulator and bitmap
+    uint64_t *a_ready = tile_empty + TC_MAX_BUF;      // [1] A operand is in TMEM
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(a_ready + 1);
 
     // Epilogue = warps 0-15, helpers = warps 16-19: the warp scheduler favours higher warp ids, and the
@@ -380,7 +386,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 
     if (tid == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < TC_MAX_BUF; ++b) {
             mbar_init(tile_full + b, 2);
             mbar_init(tile_empty + b, TC_EPI_WARPS);
         }
@@ -439,10 +445,11 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         tc_fence_after();
         const uint32_t a_hi0 = tmem_base;
         const uint32_t a_lo0 = tmem_base + (uint32_t)(NKB * TC_KB);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC_COL + p * TN);
         const uint64_t desc0 = make_b_desc(smem_u32(b_tiles));
         for (int i = p; i < n_tiles; i += 2) {
-            mbar_wait(tile_empty + p, (uint32_t)(((i >> 1) & 1) ^ 1), A.err_flag, 3);
+            const int b = i % NBUF;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(ACC_COL + b * TN);
+            mbar_wait(tile_empty + b, (uint32_t)(((i / NBUF) & 1) ^ 1), A.err_flag, 3);
             tc_fence_after();
             if (elect_one()) tc_trace(A, i, 2);
 #pragma unroll
@@ -473,7 +480,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     }
                     tc_commit(empty + s);  // stage reusable once these MMAs have read it
                     if (kb == NKB - 1) {
-                        tc_commit(tile_full + p);  // accumulator p complete
+                        tc_commit(tile_full + b);  // accumulator b complete
                         tc_trace(A, i, 4);
                     }
                 }
@@ -494,7 +501,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         }
         uint32_t off_b = 0, off_e = 0, nkey = 0xffffffffu;
         for (int i = 0; i < n_tiles; ++i) {
-            const int b = i & 1;
+            const int b = i % NBUF;
             const int col0 = (t0 + i * t_step) * TN;
             if (keys != nullptr && (i & 31) == 0) {
                 const int ti = i + lane;
@@ -513,9 +520,14 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 const uint32_t nb = __shfl_sync(0xffffffffu, off_b, (i + 1) & 31), ne = __shfl_sync(0xffffffffu, off_e, (i + 1) & 31);
                 nkey = (nb + lane < ne) ? __ldg(keys + nb + lane) : 0xffffffffu;
             }
-            mbar_wait(tile_empty + b, (uint32_t)(((i >> 1) & 1) ^ 1), A.err_flag, 5);
+            mbar_wait(tile_empty + b, (uint32_t)(((i / NBUF) & 1) ^ 1), A.err_flag, 5);
             if (lane == 0) tc_trace(A, i, 5);
             uint32_t *bm = bitmap + b * 4 * TM;
+            if (A.dbg & 16) {  // timing ablation: no bitmap work at all
+                if (lane == 0) mbar_arrive(tile_full + b);
+                continue;
+            }
+            if (lane == 0) tc_trace(A, i, 13);
             if (col0 + TN <= P.n_items) {
                 uint4 *bm4 = reinterpret_cast<uint4 *>(bm);
 #pragma unroll
@@ -524,6 +536,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 for (int q = lane; q < 4 * TM; q += 32) bm[q] = oob_bits(col0, q / TM, P.n_items);
             }
             __syncwarp();
+            if (lane == 0) tc_trace(A, i, 14);
             for (uint32_t p = kb0; p < ke0; p += 32) {
                 if (p != kb0) key = (p + lane < ke0) ? __ldg(keys + p + lane) : 0xffffffffu;
                 if (p + lane < ke0) {
@@ -532,6 +545,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 }
             }
             __syncwarp();
+            if (lane == 0) tc_trace(A, i, 15);
             if (lane == 0) { mbar_arrive(tile_full + b); tc_trace(A, i, 6); }
         }
     } else {
@@ -591,12 +605,13 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         }
         float4 *my_stage = stage_buf + tid;  // element q of my row: float (q & 3) of my_stage[(q >> 2) * TC_EPI_THREADS]
         const uint32_t *my_bm = bitmap + cq * TM + r;
-        const uint32_t my_acc = lane_addr + (uint32_t)(TC_ACC_COL + cq * 32);
+        const uint32_t my_acc = lane_addr + (uint32_t)(ACC_COL + cq * 32);
 
+        int b = 0;
+        uint32_t bph = 0;  // buffer and its phase for tile i
         for (int i = 0; i < n_tiles; ++i) {
-            const int b = i & 1;
             const int col0 = (t0 + i * t_step) * TN + cq * 32;
-            mbar_wait(tile_full + b, (uint32_t)((i >> 1) & 1), A.err_flag, 6);
+            mbar_wait(tile_full + b, bph, A.err_flag, 6);
             tc_fence_after();
             const int tslot = (warp == 0) ? 7 : 10;
             const bool tr_me = (lane == 0) && (warp == 0 || warp == TC_EPI_WARPS - 1);
@@ -612,6 +627,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(tile_empty + b);
             if (tr_me) tc_trace(A, i, tslot + 1);
+            if (++b == NBUF) { b = 0; bph ^= 1u; }
             if (A.dbg & 1) continue;
 
             // two copies of the per-tile work, so that without a bias the scores are consumed in the very

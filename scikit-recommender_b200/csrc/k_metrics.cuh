@@ -16,8 +16,7 @@ struct MetricIds {
 
 constexpr int K4_WARPS = 8;
 
-// ---- K4: one warp per user, every lane owns rank positions i = lane, lane + 32, ... --------------
-// keys: sorted rank keys [n_rows, K] (or null), idx_in: int32 rank lists [n_rows, K] (or null).
+// ---- per-user metrics, one warp per user, every lane owns rank positions i = lane, lane + 32, ... ---
 //
 // The reference's recurrences run i = 0..K-1 with float accumulators.  Restated per position without
 // changing a single rounding:
@@ -29,39 +28,103 @@ constexpr int K4_WARPS = 8;
 //   NDCG       : DCG changes only at hits (same loop, double add rounded to float); iDCG after i
 //                depends only on min(i+1, L): table idcg[n] built on the host with the same operations.
 //   MRR        = (float)(1.0 / (double)(p+1)) from the first hit p on.
-// Rows are dealt round-robin to warps (row = global warp id + j * total warps).  With acc_out != null
-// every warp also sums its rows' values per column in float64 in shared memory; the block folds its
-// warps in warp order and writes one partial row: deterministic, no atomics.
+struct RowMetrics {
+    // per row
+    const int32_t *truth;
+    int nt, L;
+    float Lf;
+    int hits_c, first;  // carried across 32-position chunks
+    float sum_pre_c, dcg_c;
+
+    __device__ __forceinline__ void begin(const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, int64_t csr_row)
+    {
+        const int64_t tb = __ldg(te_indptr + csr_row);
+        nt = (int)(__ldg(te_indptr + csr_row + 1) - tb);
+        truth = te_idx + tb;
+        L = nt > 1 ? nt : 1;
+        Lf = (float)L;
+        hits_c = 0;
+        first = -1;
+        sum_pre_c = 0.0f;
+        dcg_c = 0.0f;
+    }
+
+    // positions i0 + lane of the rank list; item < 0 = no item.  Writes per_user_row[mi * K + i] and adds
+    // into acc[mi * K + i] (either may be null).  Must be called by the whole warp, chunks in order.
+    __device__ __forceinline__ void chunk(int i0, int lane, int K, int32_t item, const MetricIds &mids, const double *__restrict__ disc,
+                                          const float *__restrict__ idcg, float *__restrict__ per_user_row, double *acc)
+    {
+        const int i = i0 + lane;
+        const bool valid = i < K;
+        const bool hit = valid && (item >= 0) && sorted_contains(truth, nt, item);
+        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // lanes <= mine
+        const float hf = (float)(hits_c + __popc(mask & le_mask));
+        const float prec = hf / (float)(i + 1);
+        float my_sum = sum_pre_c, my_dcg = dcg_c;
+        for (uint32_t m = mask; m != 0u; m &= m - 1u) {  // hits of this chunk, ascending
+            const int b = __ffs(m) - 1;
+            sum_pre_c = sum_pre_c + __shfl_sync(0xffffffffu, prec, b);  // metric.h:57-59
+            dcg_c = (float)((double)dcg_c + __ldg(disc + i0 + b));      // metric.h:78
+            if (lane >= b) { my_sum = sum_pre_c; my_dcg = dcg_c; }
+        }
+        if (first < 0 && mask != 0u) first = i0 + __ffs(mask) - 1;
+        hits_c += __popc(mask);
+        if (valid) {
+            const int M = mids.n;
+            for (int mi = 0; mi < M; ++mi) {
+                const int id = mids.id[mi];
+                float val;
+                if (id == 1) val = prec;                                                 // metric.h:19-30
+                else if (id == 2) val = hf / Lf;                                         // metric.h:33-45
+                else if (id == 3) val = my_sum / (float)(L < i + 1 ? L : i + 1);         // metric.h:48-66
+                else if (id == 4) val = my_dcg / __ldg(idcg + (L < i + 1 ? L : i + 1));  // metric.h:69-86
+                else val = (first >= 0 && i >= first) ? (float)(1.0 / (double)(first + 1)) : 0.0f;  // metric.h:89-109
+                if (per_user_row != nullptr) per_user_row[mi * K + i] = val;
+                if (acc != nullptr) acc[mi * K + i] += (double)val;
+            }
+        }
+    }
+};
+
+// block-level tail of the fused column sums: every warp kept float64 sums of its rows per column in
+// shared memory [n_warps][MK]; fold them in warp order into one partial row (deterministic, no atomics)
+__device__ __forceinline__ void fold_block_sums(const double *acc_all, int n_warps, int MK, double *__restrict__ out_row)
+{
+    __syncthreads();
+    for (int c = threadIdx.x; c < MK; c += blockDim.x) {
+        double t = 0.0;
+        for (int w = 0; w < n_warps; ++w) t += acc_all[(size_t)w * MK + c];
+        out_row[c] = t;
+    }
+}
+
+// ---- K4: metrics from sorted rank keys [n_rows, K] or int32 rank lists [n_rows, K] ---------------------
+// Rows are dealt round-robin to warps.  row_list / row_count (both or neither): evaluate only rows
+// row_list[0 .. *row_count) (the rows the exact kernel re-did).  acc_out: [gridDim.x][M*K] partial sums.
 __global__ void __launch_bounds__(K4_WARPS * 32)
 k_metrics(const u64 *__restrict__ keys, const int32_t *__restrict__ idx_in, int K, int64_t n_rows,
-          int64_t row0, const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx,
+          int64_t row0, const int32_t *__restrict__ row_list, const int *__restrict__ row_count,
+          const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx,
           MetricIds mids, const double *__restrict__ disc, const float *__restrict__ idcg, float *__restrict__ per_user,
           int32_t *__restrict__ topk_idx_out, float *__restrict__ topk_val_out, double *__restrict__ acc_out)
 {
     extern __shared__ double k4_acc[];  // [K4_WARPS][M*K] when acc_out != null
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int M = mids.n;
-    const int MK = M * K;
-    double *acc = k4_acc + (size_t)warp * MK;
-    if (acc_out != nullptr)
+    const int MK = mids.n * K;
+    double *acc = (acc_out != nullptr) ? k4_acc + (size_t)warp * MK : nullptr;
+    if (acc != nullptr)
         for (int c = lane; c < MK; c += 32) acc[c] = 0.0;
-    const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // lanes <= mine
-
+    const int64_t n_list = (row_list != nullptr) ? (int64_t)*row_count : n_rows;
     const int64_t n_warps = (int64_t)gridDim.x * K4_WARPS;
-    for (int64_t row = (int64_t)blockIdx.x * K4_WARPS + warp; row < n_rows; row += n_warps) {
-        const int64_t tb = __ldg(te_indptr + row0 + row);
-        const int nt = (int)(__ldg(te_indptr + row0 + row + 1) - tb);
-        const int32_t *truth = te_idx + tb;
-        const int L = nt > 1 ? nt : 1;
-        const float Lf = (float)L;
-        int hits_c = 0, first = -1;      // carried across 32-position chunks
-        float sum_pre_c = 0.0f, dcg_c = 0.0f;
+    for (int64_t j = (int64_t)blockIdx.x * K4_WARPS + warp; j < n_list; j += n_warps) {
+        const int64_t row = (row_list != nullptr) ? (int64_t)row_list[j] : j;
+        RowMetrics rm;
+        rm.begin(te_indptr, te_idx, row0 + row);
         for (int i0 = 0; i0 < K; i0 += 32) {
             const int i = i0 + lane;
-            const bool valid = i < K;
-            bool hit = false;
-            if (valid) {
-                int32_t item;
+            int32_t item = -1;
+            if (i < K) {
                 if (keys != nullptr) {
                     const u64 k = keys[row * K + i];
                     item = (k == 0) ? -1 : (int32_t)key_item(k);
@@ -70,61 +133,34 @@ k_metrics(const u64 *__restrict__ keys, const int32_t *__restrict__ idx_in, int 
                     item = idx_in[row * K + i];
                 }
                 if (topk_idx_out != nullptr) topk_idx_out[row * K + i] = item;
-                hit = (item >= 0) && sorted_contains(truth, nt, item);
             }
-            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            const float hf = (float)(hits_c + __popc(mask & le_mask));
-            const float prec = hf / (float)(i + 1);
-            float my_sum = sum_pre_c, my_dcg = dcg_c;
-            for (uint32_t m = mask; m != 0u; m &= m - 1u) {  // hits of this chunk, ascending
-                const int b = __ffs(m) - 1;
-                sum_pre_c = sum_pre_c + __shfl_sync(0xffffffffu, prec, b);  // metric.h:57-59
-                dcg_c = (float)((double)dcg_c + __ldg(disc + i0 + b));      // metric.h:78
-                if (lane >= b) { my_sum = sum_pre_c; my_dcg = dcg_c; }
-            }
-            if (first < 0 && mask != 0u) first = i0 + __ffs(mask) - 1;
-            hits_c += __popc(mask);
-            if (valid) {
-                for (int mi = 0; mi < M; ++mi) {
-                    const int id = mids.id[mi];
-                    float val;
-                    if (id == 1) val = prec;                                              // metric.h:19-30
-                    else if (id == 2) val = hf / Lf;                                      // metric.h:33-45
-                    else if (id == 3) val = my_sum / (float)(L < i + 1 ? L : i + 1);      // metric.h:48-66
-                    else if (id == 4) val = my_dcg / __ldg(idcg + (L < i + 1 ? L : i + 1));  // metric.h:69-86
-                    else val = (first >= 0 && i >= first) ? (float)(1.0 / (double)(first + 1)) : 0.0f;  // metric.h:89-109
-                    if (per_user != nullptr) per_user[row * MK + mi * K + i] = val;
-                    if (acc_out != nullptr) acc[mi * K + i] += (double)val;
-                }
-            }
+            rm.chunk(i0, lane, K, item, mids, disc, idcg, per_user != nullptr ? per_user + row * MK : nullptr, acc);
         }
     }
-    if (acc_out != nullptr) {
-        __syncthreads();
-        for (int c = threadIdx.x; c < MK; c += K4_WARPS * 32) {
-            double t = 0.0;
-#pragma unroll
-            for (int w = 0; w < K4_WARPS; ++w) t += k4_acc[(size_t)w * MK + c];
-            acc_out[(size_t)blockIdx.x * MK + c] = t;
-        }
-    }
+    if (acc_out != nullptr) fold_block_sums(k4_acc, K4_WARPS, MK, acc_out + (size_t)blockIdx.x * MK);
 }
 
-// sums[c] += sum over blocks of partial[b][c]: one warp per column, fixed order
+// sums[c] += sum over blocks of partial[b][c]: one block per column, fixed reduction tree
 __global__ void __launch_bounds__(256)
 k_colsum_fold(const double *__restrict__ partial, int n_blk, int n_cols, double *__restrict__ sums)
 {
+    __shared__ double s_t[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 8 + warp;
-    if (c >= n_cols) return;
+    const int c = blockIdx.x;
     double t = 0.0;
-    for (int b = lane; b < n_blk; b += 32) t += partial[(size_t)b * n_cols + c];
+    for (int b = threadIdx.x; b < n_blk; b += 256) t += partial[(size_t)b * n_cols + c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) sums[c] += t;
+    if (lane == 0) s_t[warp] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += s_t[w];
+        sums[c] += a;
+    }
 }
 
-// ---- column sums, deterministic two-stage float64 -------------------------------------------
 __global__ void k_colsum_partial(const float *__restrict__ per_user, int64_t n_rows, int n_cols,
                                  double *__restrict__ partial)
 {

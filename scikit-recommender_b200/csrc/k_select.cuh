@@ -10,11 +10,15 @@
 //      search stops as soon as the bin holding the K-th value is small enough to be taken whole --
 //      after one pass for almost every row),
 //   3. compacts the survivors into 64-bit rank keys and sorts just those (warp bitonic, PER = 2 or 4).
+//   4. with the sorted keys still in registers (element e of lane l is rank e*32 + l) runs the metric
+//      recurrences of k_metrics.cuh on them and adds the row into the warp's float64 column sums -- the
+//      rank keys of a settled row never travel to HBM unless the caller asked for the top-K lists.
 // Rows that cannot be settled here -- a sub-list overflowed, fewer than K candidates (threshold
 // estimate too high or fewer than K unmasked items), more candidates than the buffer, or more than
 // 32 PER values tied at the cut -- go on the fail list and are re-done exactly by k_row_exact.
 #pragma once
 #include "common.cuh"
+#include "k_metrics.cuh"
 
 namespace skr {
 
@@ -24,137 +28,160 @@ constexpr int SEL_MAX = 512;  // candidates a row may carry into the selection
 template <int PER>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
-               int64_t n_rows, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count)
+               int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count,
+               const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
+               const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
+               float *__restrict__ topk_val_out, double *__restrict__ acc_out)
 {
     constexpr int CAP = 32 * PER;
     __shared__ uint2 s_ent[SEL_WARPS][SEL_MAX];
     __shared__ uint32_t s_hist[SEL_WARPS][256];
     __shared__ u64 s_key[SEL_WARPS][CAP];
+    extern __shared__ double sel_acc[];  // [SEL_WARPS][M*K] when acc_out != null
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp;
-    if (row >= n_rows) return;
     uint2 *ent = s_ent[warp];
     uint32_t *hist = s_hist[warp];
     u64 *skey = s_key[warp];
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const int MK = mids.n * K;
+    double *acc = (acc_out != nullptr) ? sel_acc + (size_t)warp * MK : nullptr;
+    if (acc != nullptr)
+        for (int c = lane; c < MK; c += 32) acc[c] = 0.0;
 
-    // ---- 1. sub-list sizes (n_sub <= 32: one per lane), exclusive scan, gather ---------------------
-    const int c_mine = (lane < n_sub) ? (int)__ldg(cand_cnt + row * n_sub + lane) : 0;
-    int incl = c_mine;
+    const int64_t n_warps = (int64_t)gridDim.x * SEL_WARPS;
+    for (int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp; row < n_rows; row += n_warps) {
+        __syncwarp();
+        // ---- 1. sub-list sizes (n_sub <= 32: one per lane), exclusive scan, gather -----------------
+        const int c_mine = (lane < n_sub) ? (int)__ldg(cand_cnt + row * n_sub + lane) : 0;
+        int incl = c_mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int n = __shfl_sync(0xffffffffu, incl, 31);
-    const bool over = __any_sync(0xffffffffu, c_mine > cap);
-    if (over || n > SEL_MAX || n < K) {
-        if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
-        return;
-    }
-    const int off_mine = incl - c_mine;
-    uint32_t vmin = 0xffffffffu, vmax = 0u;
-    for (int s = 0; s < n_sub; ++s) {
-        const int cs = __shfl_sync(0xffffffffu, c_mine, s);
-        const int os = __shfl_sync(0xffffffffu, off_mine, s);
-        const uint2 *src = cand + (row * n_sub + s) * (int64_t)sub_stride;
-        for (int i = lane; i < cs; i += 32) {
-            uint2 e = src[i];
-            e.x = ord_f32(__uint_as_float(e.x));
-            vmin = min(vmin, e.x);
-            vmax = max(vmax, e.x);
-            ent[os + i] = e;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-    }
-    vmin = __reduce_min_sync(0xffffffffu, vmin);
-    vmax = __reduce_max_sync(0xffffffffu, vmax);
-    __syncwarp();
+        const int n = __shfl_sync(0xffffffffu, incl, 31);
+        const bool over = __any_sync(0xffffffffu, c_mine > cap);
+        if (over || n > SEL_MAX || n < K) {
+            if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+            continue;
+        }
+        const int off_mine = incl - c_mine;
+        uint32_t vmin = 0xffffffffu, vmax = 0u;
+        for (int s = 0; s < n_sub; ++s) {
+            const int cs = __shfl_sync(0xffffffffu, c_mine, s);
+            const int os = __shfl_sync(0xffffffffu, off_mine, s);
+            const uint2 *src = cand + (row * n_sub + s) * (int64_t)sub_stride;
+            for (int i = lane; i < cs; i += 32) {
+                uint2 e = src[i];
+                e.x = ord_f32(__uint_as_float(e.x));
+                vmin = min(vmin, e.x);
+                vmax = max(vmax, e.x);
+                ent[os + i] = e;
+            }
+        }
+        vmin = __reduce_min_sync(0xffffffffu, vmin);
+        vmax = __reduce_max_sync(0xffffffffu, vmax);
+        __syncwarp();
 
-    // ---- 2. cut: smallest-known T (as offset from vmin) with K <= #{w >= T} <= CAP ------------------
-    uint32_t T = 0;  // n <= CAP: everything is sorted
-    if (n > CAP) {
-        const uint32_t range = vmax - vmin;
-        int width_bits = 32 - __clz(range | 1u);  // values w = ord - vmin lie in [0, 2^width_bits)
-        uint32_t base = 0;                         // current bucket: [base, base + 2^width_bits)
-        int above = 0;                             // values at or beyond the bucket's end (all selected)
-        bool ok = false;
-        for (;;) {
-            const int shift = width_bits > 8 ? width_bits - 8 : 0;
+        // ---- 2. cut: smallest-known T (as offset from vmin) with K <= #{w >= T} <= CAP --------------
+        uint32_t T = 0;  // n <= CAP: everything is sorted
+        bool ok = true;
+        if (n > CAP) {
+            const uint32_t range = vmax - vmin;
+            int width_bits = 32 - __clz(range | 1u);  // values w = ord - vmin lie in [0, 2^width_bits)
+            uint32_t base = 0;                         // current bucket: [base, base + 2^width_bits)
+            int above = 0;                             // values at or beyond the bucket's end (all selected)
+            ok = false;
+            for (;;) {
+                const int shift = width_bits > 8 ? width_bits - 8 : 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) hist[q * 32 + lane] = 0u;
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) {
-                const uint32_t w = ent[i].x - vmin;
-                const uint32_t rel = (w - base) >> shift;  // w < base wraps to a huge value
-                if (w >= base && rel < 256u) atomicAdd(&hist[rel], 1u);
-            }
-            __syncwarp();
-            // lane l owns bins 8 l .. 8 l + 7; counts from the top bin down
-            uint32_t h[8];
-            int t_l = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { h[q] = hist[lane * 8 + q]; t_l += (int)h[q]; }
-            int suf = t_l;  // inclusive suffix sum over lanes >= mine
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_down_sync(0xffffffffu, suf, o);
-                if (lane + o < 32) suf += t;
-            }
-            const int with_me = above + suf, without_me = with_me - t_l;
-            const bool mine = (with_me >= K) && (without_me < K);
-            const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;  // exactly one lane (n >= K)
-            int j = 0, c_above = without_me, c_with = without_me;
-            if (mine) {
-#pragma unroll
-                for (int q = 7; q >= 0; --q) {
-                    if (c_with < K) { c_above = c_with; c_with += (int)h[q]; j = lane * 8 + q; }
+                for (int q = 0; q < 8; ++q) hist[q * 32 + lane] = 0u;
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    const uint32_t w = ent[i].x - vmin;
+                    const uint32_t rel = (w - base) >> shift;  // w < base wraps to a huge value
+                    if (w >= base && rel < 256u) atomicAdd(&hist[rel], 1u);
                 }
+                __syncwarp();
+                // lane l owns bins 8 l .. 8 l + 7; counts from the top bin down
+                uint32_t h[8];
+                int t_l = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { h[q] = hist[lane * 8 + q]; t_l += (int)h[q]; }
+                int suf = t_l;  // inclusive suffix sum over lanes >= mine
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (lane + o < 32) suf += t;
+                }
+                const int with_me = above + suf, without_me = with_me - t_l;
+                const bool mine = (with_me >= K) && (without_me < K);
+                const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;  // exactly one lane (n >= K)
+                int j = 0, c_above = without_me, c_with = without_me;
+                if (mine) {
+#pragma unroll
+                    for (int q = 7; q >= 0; --q) {
+                        if (c_with < K) { c_above = c_with; c_with += (int)h[q]; j = lane * 8 + q; }
+                    }
+                }
+                j = __shfl_sync(0xffffffffu, j, owner);
+                c_above = __shfl_sync(0xffffffffu, c_above, owner);
+                c_with = __shfl_sync(0xffffffffu, c_with, owner);
+                base += (uint32_t)j << shift;
+                if (c_with <= CAP) { ok = true; break; }
+                if (shift == 0) break;  // more than CAP values tied around the K-th: exact path
+                above = c_above;
+                width_bits = shift;
+                __syncwarp();
             }
-            j = __shfl_sync(0xffffffffu, j, owner);
-            c_above = __shfl_sync(0xffffffffu, c_above, owner);
-            c_with = __shfl_sync(0xffffffffu, c_with, owner);
-            base += (uint32_t)j << shift;
-            if (c_with <= CAP) { ok = true; break; }
-            if (shift == 0) break;  // more than CAP values tied around the K-th: exact path
-            above = c_above;
-            width_bits = shift;
-            __syncwarp();
+            T = base;
         }
         if (!ok) {
             if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
-            return;
+            continue;
         }
-        T = base;
-    }
 
-    // ---- 3. compact the survivors into rank keys, sort, write the K best ---------------------------
+        // ---- 3. compact the survivors into rank keys, sort ------------------------------------------
 #pragma unroll
-    for (int e = 0; e < PER; ++e) skey[e * 32 + lane] = 0ull;
-    __syncwarp();
-    int m = 0;
-    for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        uint2 e = make_uint2(0u, 0u);
-        bool take = false;
-        if (i < n) {
-            e = ent[i];
-            take = (e.x - vmin) >= T;
+        for (int e = 0; e < PER; ++e) skey[e * 32 + lane] = 0ull;
+        __syncwarp();
+        int m = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            uint2 e = make_uint2(0u, 0u);
+            bool take = false;
+            if (i < n) {
+                e = ent[i];
+                take = (e.x - vmin) >= T;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, take);
+            if (take) skey[m + __popc(bal & lt_mask)] = ((u64)e.x << 32) | (u64)(~e.y);
+            m += __popc(bal);
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, take);
-        if (take) skey[m + __popc(bal & lt_mask)] = ((u64)e.x << 32) | (u64)(~e.y);
-        m += __popc(bal);
-    }
-    __syncwarp();
-    u64 v[PER];
+        __syncwarp();
+        u64 v[PER];
 #pragma unroll
-    for (int e = 0; e < PER; ++e) v[e] = skey[e * 32 + lane];
-    warp_bitonic_desc<PER>(v, lane);
-    u64 *dst = out_keys + row * (int64_t)K;
+        for (int e = 0; e < PER; ++e) v[e] = skey[e * 32 + lane];
+        warp_bitonic_desc<PER>(v, lane);
+
+        // ---- 4. outputs: top-K lists on request, metrics straight from the registers ------------------
+        RowMetrics rm;
+        rm.begin(te_indptr, te_idx, row0 + row);
 #pragma unroll
-    for (int e = 0; e < PER; ++e) {
-        const int i = e * 32 + lane;
-        if (i < K) dst[i] = v[e];
+        for (int e = 0; e < PER; ++e) {
+            const int i = e * 32 + lane;
+            if (e * 32 < K) {
+                if (i < K) {
+                    if (out_keys != nullptr) out_keys[row * (int64_t)K + i] = v[e];
+                    if (topk_idx_out != nullptr) topk_idx_out[row * (int64_t)K + i] = (int32_t)key_item(v[e]);
+                    if (topk_val_out != nullptr) topk_val_out[row * (int64_t)K + i] = key_score(v[e]);
+                }
+                rm.chunk(e * 32, lane, K, (int32_t)key_item(v[e]), mids, disc, idcg,
+                         per_user != nullptr ? per_user + row * (int64_t)MK : nullptr, acc);
+            }
+        }
     }
+    if (acc_out != nullptr) fold_block_sums(sel_acc, SEL_WARPS, MK, acc_out + (size_t)blockIdx.x * MK);
 }
 
 }  // namespace skr

@@ -226,16 +226,80 @@ int run_metrics(skr_ctx *ctx, const u64 *keys, const int32_t *idx_in, int64_t n_
         acc = (double *)ctx->partial.p;
         if (acc_smem > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_smem));
     }
-    k_metrics<<<grid, K4_WARPS * 32, fused_sums ? acc_smem : 0, st>>>(keys, idx_in, K, n_rows, row0, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc,
-                                                                    ctx->d_idcg, pu, topk_idx, topk_val, acc);
+    k_metrics<<<grid, K4_WARPS * 32, fused_sums ? acc_smem : 0, st>>>(keys, idx_in, K, n_rows, row0, nullptr, nullptr, ctx->d_te_indptr, ctx->d_te_idx,
+                                                                    m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc);
     ctx->launches++;
     if (fused_sums) {
-        k_colsum_fold<<<(MK + 7) / 8, 256, 0, st>>>(acc, grid, MK, sums);
+        k_colsum_fold<<<MK, 256, 0, st>>>(acc, grid, MK, sums);
         ctx->launches++;
     } else if (sums) {
         const int nblk = (int)std::min<int64_t>(n_rows, 2 * ctx->n_sm);
         rc = ensure(ctx, ctx->partial, (size_t)nblk * MK * sizeof(double));
         if (rc) return rc;
+        k_colsum_partial<<<nblk, 256, 0, st>>>(pu, n_rows, MK, (double *)ctx->partial.p);
+        k_colsum_final<<<(MK + 127) / 128, 128, 0, st>>>((const double *)ctx->partial.p, nblk, MK, sums);
+        ctx->launches += 2;
+    }
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
+// Tail of the tensor-core path: candidate lists -> (select + sort + metrics in one kernel), the rows that
+// kernel could not settle -> exact re-scoring -> metrics of just those rows, then the column sums.
+struct ExactArgs {
+    const float *U; int64_t ld_u; const float *V; int64_t ld_v; int d; const float *bias; int n_items;
+    const int64_t *tr_indptr; const int32_t *tr_idx;
+};
+
+int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
+                       const MetricIds &m, int K, const ExactArgs &E, int32_t *fail_list, int *fail_count, int32_t *topk_idx,
+                       float *topk_val, float *per_user, double *sums, cudaStream_t st)
+{
+    if (!ctx->has_test) return fail(ctx, SKR_ERR_STATE, "no test CSR set (skr_set_test_csr)");
+    if (row0 < 0 || row0 + n_rows > ctx->te_rows)
+        return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the test CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->te_rows);
+    int rc = ensure_disc(ctx, K);
+    if (rc) return rc;
+    const int MK = m.n * K;
+    const size_t acc_sel = (size_t)SEL_WARPS * MK * sizeof(double), acc_k4 = (size_t)K4_WARPS * MK * sizeof(double);
+    const bool fused_sums = sums != nullptr && acc_k4 <= 96 * 1024;
+    float *pu = per_user;
+    if (!pu && sums && !fused_sums) {
+        if ((rc = ensure(ctx, ctx->per_user, (size_t)n_rows * MK * sizeof(float)))) return rc;
+        pu = (float *)ctx->per_user.p;
+    }
+    if ((rc = ensure(ctx, ctx->keys, (size_t)n_rows * K * sizeof(u64)))) return rc;  // written only for re-done rows
+    u64 *keys = (u64 *)ctx->keys.p;
+    const int g_sel = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
+    const int g_fix = (int)std::min<int64_t>((n_rows + K4_WARPS - 1) / K4_WARPS, ctx->n_sm);
+    double *acc = nullptr;
+    if (fused_sums) {
+        if ((rc = ensure(ctx, ctx->partial, (size_t)(g_sel + g_fix) * MK * sizeof(double)))) return rc;
+        acc = (double *)ctx->partial.p;
+        if (acc_k4 > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_k4));
+    }
+    const size_t dyn_sel = fused_sums ? acc_sel : 0;
+    if (K <= 64) {
+        if (dyn_sel > 16 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_select_cands<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel));
+        k_select_cands<2><<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count,
+                                                                 ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc);
+    } else {
+        if (dyn_sel > 16 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_select_cands<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel));
+        k_select_cands<4><<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count,
+                                                                 ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc);
+    }
+    k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
+                                                                  E.tr_indptr, E.tr_idx, K, keys);
+    k_metrics<<<g_fix, K4_WARPS * 32, fused_sums ? acc_k4 : 0, st>>>(keys, nullptr, K, n_rows, row0, fail_list, fail_count, ctx->d_te_indptr,
+                                                                     ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val,
+                                                                     acc ? acc + (size_t)g_sel * MK : nullptr);
+    ctx->launches += 3;
+    if (fused_sums) {
+        k_colsum_fold<<<MK, 256, 0, st>>>(acc, g_sel + g_fix, MK, sums);
+        ctx->launches++;
+    } else if (sums) {
+        const int nblk = (int)std::min<int64_t>(n_rows, 2 * ctx->n_sm);
+        if ((rc = ensure(ctx, ctx->partial, (size_t)nblk * MK * sizeof(double)))) return rc;
         k_colsum_partial<<<nblk, 256, 0, st>>>(pu, n_rows, MK, (double *)ctx->partial.p);
         k_colsum_final<<<(MK + 127) / 128, 128, 0, st>>>((const double *)ctx->partial.p, nblk, MK, sums);
         ctx->launches += 2;
@@ -706,18 +770,12 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
         SKR_CUDA(ctx, cudaGetLastError());
-        {
-            const unsigned sel_grid = (unsigned)((n_rows + SEL_WARPS - 1) / SEL_WARPS);
-            if (K <= 64)
-                k_select_cands<2><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, cap, K, n_rows, keys, fail_list, fail_count);
-            else
-                k_select_cands<4><<<sel_grid, SEL_WARPS * 32, 0, st>>>(A.cand, A.cand_cnt, n_sub, cap, cap, K, n_rows, keys, fail_list, fail_count);
-        }
-        k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, user_vecs_dev, ld_u, item_vecs_dev, ld_i, d,
-                                                                      bias_dev, (int)n_items, row0, tp, ti, K, keys);
-        ctx->launches += 2;
         ctx->last_fused = (passes == 3) ? "tcgen05_3xtf32" : "tcgen05_1xtf32";
         ctx->last_plan = {n_samp, stride, r, cap, P.S, passes == 3 ? 4 : 8};
+        ctx->ev_calls++;
+        const ExactArgs E = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (int)n_items, tp, ti};
+        return run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
+                                  per_user_dev, sums_dev, st);
     } else {
         if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->part, (size_t)n_rows * P.S * K * sizeof(u64)))) return rc;

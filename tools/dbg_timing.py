@@ -12,7 +12,7 @@ ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"])
 sums = torch.zeros(150, dtype=torch.float64, device="cuda")
 for prec in ("3xtf32", "1xtf32"):
     for stages in (0,):
-        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (2, "no MMA"), (3, "no MMA, no epilogue"), (9, "no TMA, no epilogue (MMA only)")):
+        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (2, "no MMA"), (3, "no MMA, no epilogue"), (19, "no MMA, no epilogue, no bitmaps"), (16, "no bitmaps"), (9, "no TMA, no epilogue (MMA only)")):
             ctx.set_option("dbg", dbg)
             ms = []
             for _ in range(3):

@@ -47,6 +47,8 @@ steady = tr[10:tiles - 2]
 for s, n in enumerate(names):
     dt = np.diff(steady[:, s])
     print("%-10s per-tile period: mean %.0f  min %d  max %d" % (n, dt.mean(), dt.min(), dt.max()))
+print("mask builder: free->start %.0f | zero %.0f | keys %.0f | arrive %.0f" % ((steady[:, 13] - steady[:, 5]).mean(), (steady[:, 14] - steady[:, 13]).mean(),
+      (steady[:, 15] - steady[:, 14]).mean(), (steady[:, 6] - steady[:, 15]).mean()))
 print("issFree->issCommit %.0f | issCommit->e0Full %.0f | e0Full->e0Rel %.0f | e0Rel->e0Done %.0f | e15Full->e15Rel %.0f | e15Rel->issFree(+2) %.0f | mskFree->mskRdy %.0f | mskRdy->e0Full %.0f" % (
     (steady[:, 4] - steady[:, 2]).mean(), (steady[:, 7] - steady[:, 4]).mean(), (steady[:, 8] - steady[:, 7]).mean(),
     (steady[:, 9] - steady[:, 8]).mean(), (steady[:, 11] - steady[:, 10]).mean(),
