@@ -11,7 +11,8 @@ namespace skr {
 
 struct MetricIds {
     int n;
-    int id[8];
+    uint32_t packed;  // metric id of column block mi in bits [4 mi, 4 mi + 4): a register, not an indexed array
+    __host__ __device__ __forceinline__ int id(int mi) const { return (int)((packed >> (4 * mi)) & 15u); }
 };
 
 constexpr int K4_WARPS = 8;
@@ -73,7 +74,7 @@ struct RowMetrics {
         if (valid) {
             const int M = mids.n;
             for (int mi = 0; mi < M; ++mi) {
-                const int id = mids.id[mi];
+                const int id = mids.id(mi);
                 float val;
                 if (id == 1) val = prec;                                                 // metric.h:19-30
                 else if (id == 2) val = hf / Lf;                                         // metric.h:33-45

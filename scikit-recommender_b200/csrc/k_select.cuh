@@ -159,10 +159,41 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             m += __popc(bal);
         }
         __syncwarp();
+        // Sort.  Fast path: the survivors' scores span less than 2^(32 - BITS) float steps above the cut, so
+        // (steps above the cut + 1) << BITS | slot is a 32-bit key with the same order as long as no two
+        // survivors have equal scores; the 64-bit rank keys are fetched back by slot afterwards.  Rows with
+        // a wider span or with tied scores take the 64-bit network (item id decides ties).
+        constexpr int BITS = (PER <= 2) ? 6 : 7;
+        static_assert((1 << BITS) >= CAP, "slot bits");
+        const uint32_t cut = vmin + T;
         u64 v[PER];
+        bool fast = (vmax - cut) < ((1u << (32 - BITS)) - 2u);
+        if (fast) {
+            uint32_t v32[PER];
 #pragma unroll
-        for (int e = 0; e < PER; ++e) v[e] = skey[e * 32 + lane];
-        warp_bitonic_desc<PER>(v, lane);
+            for (int e = 0; e < PER; ++e) {
+                const int i = e * 32 + lane;
+                const u64 k = skey[i];
+                v32[e] = (k != 0ull) ? ((((uint32_t)(k >> 32) - cut + 1u) << BITS) | (uint32_t)i) : 0u;
+            }
+            warp_bitonic_desc32<PER>(v32, lane);
+            bool tie = false;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) {
+                const uint32_t mine = v32[e] >> BITS;
+                uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+                const uint32_t wrap = (e + 1 < PER) ? __shfl_sync(0xffffffffu, v32[(e + 1 < PER) ? e + 1 : e] >> BITS, 0) : 0u;
+                if (lane == 31) next = wrap;
+                tie |= (mine != 0u) && (mine == next);
+                v[e] = (v32[e] != 0u) ? skey[v32[e] & (uint32_t)(CAP - 1)] : 0ull;
+            }
+            fast = !__any_sync(0xffffffffu, tie);
+        }
+        if (!fast) {
+#pragma unroll
+            for (int e = 0; e < PER; ++e) v[e] = skey[e * 32 + lane];
+            warp_bitonic_desc<PER>(v, lane);
+        }
 
         // ---- 4. outputs: top-K lists on request, metrics straight from the registers ------------------
         RowMetrics rm;

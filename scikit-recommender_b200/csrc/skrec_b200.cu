@@ -165,11 +165,11 @@ int check_metrics(skr_ctx *ctx, const int32_t *metric_ids, int n_metrics, int to
     if (!metric_ids || n_metrics < 1 || n_metrics > 8) return fail(ctx, SKR_ERR_INVALID, "n_metrics=%d not in [1,8]", n_metrics);
     if (top_k < 1) return fail(ctx, SKR_ERR_INVALID, "top_k=%d", top_k);
     m.n = n_metrics;
+    m.packed = 0u;
     for (int i = 0; i < n_metrics; ++i) {
         if (metric_ids[i] < 1 || metric_ids[i] > 5) return fail(ctx, SKR_ERR_INVALID, "metric id %d not in 1..5", metric_ids[i]);
-        m.id[i] = metric_ids[i];
+        m.packed |= (uint32_t)metric_ids[i] << (4 * i);
     }
-    for (int i = n_metrics; i < 8; ++i) m.id[i] = 0;
     return SKR_OK;
 }
 

@@ -131,6 +131,7 @@ class RankingEvaluator(object):
     def set_test_data(self, user_test_dict: Dict[int, np.ndarray]):
         assert len(user_test_dict) > 0, "'user_test_dict' can be empty."
         self.user_pos_test = user_test_dict
+        self._all_users = list(user_test_dict.keys())  # evaluation order of evaluate(model) (evaluator.py:184)
         self._plans = OrderedDict()
 
     @property
@@ -183,7 +184,10 @@ class RankingEvaluator(object):
             test_users = [u for u in test_users if u in self.user_pos_test]
             key_all = ("subset", hash(tuple(test_users)), len(test_users))
         else:
-            test_users = list(self.user_pos_test.keys())
+            if len(self._all_users) != len(self.user_pos_test):  # the dict was mutated behind our back
+                self._all_users = list(self.user_pos_test.keys())
+                self._plans = OrderedDict()
+            test_users = self._all_users
             key_all = ("all",)
         assert isinstance(test_users, Iterable), "'test_user' must be iterable."
 
@@ -193,19 +197,17 @@ class RankingEvaluator(object):
         dev = torch.device("cuda", self._device_index())
         K, M = self.max_top, self.metrics_num
         MK = M * K
-        sums = torch.zeros(MK + 1, dtype=torch.float64, device=dev)  # [column sums | user count]
         per_user = None
         path = "none"
+        col_sums = np.zeros(MK, dtype=np.float64)  # this rank's float64 column sums
+        want_pu = self.mean == "numpy_f32"
 
         if len(users) > 0:
             with torch.cuda.device(dev):
-                if self.mean == "numpy_f32":
-                    per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev)
                 if hasattr(model, "eval_embeddings"):
-                    path = self._evaluate_fused(model, users, key, dev, sums, per_user)
+                    path, col_sums, per_user = self._evaluate_fused(model, users, key, dev, want_pu)
                 else:
-                    path = self._evaluate_predict(model, users, key, dev, sums, per_user)
-            sums[MK] = float(len(users))
+                    path, col_sums, per_user = self._evaluate_predict(model, users, key, dev, want_pu)
 
         if self.mean == "numpy_f32":
             if world > 1:
@@ -215,10 +217,13 @@ class RankingEvaluator(object):
             plan.ctx.colsum_f32_seq(per_user, acc)
             final_results = (acc / torch.tensor(float(len(users)), dtype=torch.float32, device=dev)).cpu().numpy()
         else:
+            n_users = float(len(users))
             if world > 1:
-                dist.allreduce_sums(sums, self.process_group)
-            host = sums.cpu().numpy()
-            final_results = dist.finalize_means(host[:MK], host[MK])
+                packed = torch.from_numpy(np.concatenate([col_sums, [n_users]])).to(dev)  # [column sums | user count]
+                dist.allreduce_sums(packed, self.process_group)
+                host = packed.cpu().numpy()
+                col_sums, n_users = host[:MK], host[MK]
+            final_results = dist.finalize_means(col_sums, n_users)
 
         self.last_stats = {"path": path, "users": len(users), "world": world}
         final_results = np.reshape(final_results, [self.metrics_num, self.max_top])
@@ -240,21 +245,53 @@ class RankingEvaluator(object):
             t = t.contiguous()
         return t
 
-    def _evaluate_fused(self, model, users, key, dev, sums, per_user):
+    @staticmethod
+    def _host_f32(x):
+        """numpy float32 view of a host array / CPU tensor with unit inner stride (no copy when possible)."""
+        import torch
+        if x is None:
+            return None
+        if isinstance(x, torch.Tensor):
+            x = x.detach()
+            if x.dtype != torch.float32:
+                x = x.float()
+            x = x.numpy()
+        x = np.asarray(x, dtype=np.float32)
+        if x.ndim >= 1 and x.strides[-1] != 4:
+            x = np.ascontiguousarray(x)
+        return x
+
+    def _evaluate_fused(self, model, users, key, dev, want_pu):
+        """-> (path, float64 column sums [M*K] on the host, per-user block on the device or None)"""
+        import torch
         user_vecs, item_vecs, bias = model.eval_embeddings(users)
+        MK = self.metrics_num * self.max_top
+        on_host = not (isinstance(user_vecs, torch.Tensor) and user_vecs.is_cuda) and \
+            not (isinstance(item_vecs, torch.Tensor) and item_vecs.is_cuda)
+        if on_host and not want_pu:
+            # host tables (numpy / CPU tensors, pinned or not): one native call does H2D, the whole
+            # pipeline and the D2H of the sums, with a single synchronisation at the end
+            uv, iv, b = self._host_f32(user_vecs), self._host_f32(item_vecs), self._host_f32(bias)
+            assert uv.ndim == 2 and iv.ndim == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
+            assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
+            plan = self._plan(users, int(iv.shape[0]), key)
+            _, _, sums = plan.ctx.eval_fused_host(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision)
+            return "fused:" + plan.ctx.last_fused_kernel, sums, None
         uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
         assert uv.dim() == 2 and iv.dim() == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
         assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
         plan = self._plan(users, int(iv.shape[0]), key)
-        MK = self.metrics_num * self.max_top
-        plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision,
-                            per_user=per_user, sums=sums[:MK])
-        return "fused:" + plan.ctx.last_fused_kernel
+        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
+        per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
+        plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision, per_user=per_user, sums=sums)
+        return "fused:" + plan.ctx.last_fused_kernel, sums.cpu().numpy(), per_user
 
-    def _evaluate_predict(self, model, users, key, dev, sums, per_user):
+    def _evaluate_predict(self, model, users, key, dev, want_pu):
         import torch
         plan = None
         MK = self.metrics_num * self.max_top
+        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
+        per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
         for b0 in range(0, len(users), self.batch_size):  # sequential, last batch short (batch_iterator.py:98-106)
             batch_users = users[b0:b0 + self.batch_size]
             ranking_score = model.predict(batch_users)  # (B,N)
@@ -269,5 +306,5 @@ class RankingEvaluator(object):
                 plan = self._plan(users, int(s.shape[1]), key)
             plan.ctx.eval_scores(s, b0, self.metrics, self.max_top,
                                  per_user=None if per_user is None else per_user[b0:b0 + len(batch_users)],
-                                 sums=sums[:MK])
-        return "scores"
+                                 sums=sums)
+        return "scores", sums.cpu().numpy(), per_user
