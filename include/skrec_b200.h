@@ -106,6 +106,25 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
                    int top_k, int precision, int32_t *topk_idx_dev, float *topk_val_dev,
                    float *per_user_dev, double *sums_dev, void *stream);
 
+/* Item-sharded evaluation (catalogue beyond one HBM): the reference has no counterpart -- its
+ * `predict` always returns all columns (base.py:73).  Step 1, on every rank: the rows' sorted top-K over the
+ * item rows [item_offset, item_offset + n_items) this rank holds, as 64-bit rank keys
+ * (ord(score) << 32 | ~global_item, larger = ranked earlier) in keys_out_dev [n_rows, top_k].  The train CSR
+ * of ctx must be the column partition of that shard with shard-local item ids. */
+int skr_topk_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u,
+                   const float *item_vecs_dev, int64_t n_items, int64_t ld_i, int d,
+                   const float *bias_dev, int64_t row0, int64_t item_offset, int top_k, int precision,
+                   uint64_t *keys_out_dev, void *stream);
+
+/* Step 2, after the ranks exchanged their lists (NCCL all-gather): keys_all_dev is [n_shards, n_rows_total,
+ * top_k]; merges the n_shards lists of rows [row_begin, row_begin + n_rows) -- exact, the shards are
+ * disjoint -- and evaluates them against test CSR rows row0 .. row0 + n_rows like skr_eval_scores.  Needs
+ * n_shards * top_k <= 1024. */
+int skr_eval_merged_topk(skr_ctx *ctx, const uint64_t *keys_all_dev, int n_shards, int64_t n_rows_total,
+                         int64_t row_begin, int64_t n_rows, int64_t row0, const int32_t *metric_ids,
+                         int n_metrics, int top_k, int32_t *topk_idx_dev, float *topk_val_dev,
+                         float *per_user_dev, double *sums_dev, void *stream);
+
 /* Same with HOST embedding tables and host outputs (copies inside the call). */
 int skr_eval_fused_host(skr_ctx *ctx, const float *user_vecs_host, int64_t n_rows, int64_t ld_u,
                         const float *item_vecs_host, int64_t n_items, int64_t ld_i, int d,

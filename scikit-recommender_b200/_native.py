@@ -18,7 +18,7 @@ PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "1xtf32": 3}
 SYMBOLS = (
     "skr_abi_version", "skr_ctx_create", "skr_ctx_destroy", "skr_last_error", "skr_set_train_csr",
     "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
-    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace",
+    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace", "skr_topk_fused", "skr_eval_merged_topk",
 )
 
 _lib = None
@@ -55,6 +55,8 @@ def lib():
                                  _vp, _vp, _vp, _vp, _vp]
     L.skr_eval_fused_host.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _i64, _vp, _int, _int, _int,
                                       _vp, _vp, _vp, _vp]
+    L.skr_topk_fused.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _i64, _i64, _int, _int, _vp, _vp]
+    L.skr_eval_merged_topk.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]
     L.skr_metrics_from_topk.argtypes = [_vp, _vp, _i64, _i64, _vp, _int, _int, _vp, _vp, _vp]
     L.skr_colsum_f32_seq.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp]
     L.skr_launch_count.argtypes = [_vp]
@@ -175,6 +177,25 @@ class Context(object):
                                            int(user_vecs.shape[1]), _dev_ptr(bias), int(row0), _np_ptr(m), int(m.size),
                                            int(top_k), PREC[precision], _dev_ptr(topk_idx), _dev_ptr(topk_val),
                                            _dev_ptr(per_user), _dev_ptr(sums), _stream_ptr(stream)))
+
+    def topk_fused(self, user_vecs, item_vecs, bias, row0, item_offset, top_k, keys_out, precision="auto", stream=None):
+        """Sorted top-K rank keys (int64 view of uint64) of the rows over this rank's item shard -> keys_out [n, K]."""
+        assert user_vecs.is_cuda and item_vecs.is_cuda and keys_out.is_cuda and keys_out.is_contiguous()
+        assert keys_out.shape == (user_vecs.shape[0], int(top_k)) and keys_out.element_size() == 8
+        self._check(self._L.skr_topk_fused(self._h, _dev_ptr(user_vecs), user_vecs.shape[0], user_vecs.stride(0),
+                                           _dev_ptr(item_vecs), item_vecs.shape[0], item_vecs.stride(0),
+                                           int(user_vecs.shape[1]), _dev_ptr(bias), int(row0), int(item_offset), int(top_k),
+                                           PREC[precision], _dev_ptr(keys_out), _stream_ptr(stream)))
+
+    def eval_merged_topk(self, keys_all, row_begin, n_rows, row0, metric_ids, top_k, topk_idx=None, topk_val=None,
+                         per_user=None, sums=None, stream=None):
+        """keys_all: [n_shards, n_rows_total, K] gathered per-shard lists; merge + metrics of a row slice."""
+        m = np.ascontiguousarray(metric_ids, dtype=np.int32)
+        assert keys_all.is_cuda and keys_all.is_contiguous() and keys_all.dim() == 3 and keys_all.shape[2] == int(top_k)
+        self._check(self._L.skr_eval_merged_topk(self._h, _dev_ptr(keys_all), int(keys_all.shape[0]), int(keys_all.shape[1]),
+                                                 int(row_begin), int(n_rows), int(row0), _np_ptr(m), int(m.size), int(top_k),
+                                                 _dev_ptr(topk_idx), _dev_ptr(topk_val), _dev_ptr(per_user), _dev_ptr(sums),
+                                                 _stream_ptr(stream)))
 
     def metrics_from_topk(self, topk_idx, row0, metric_ids, top_k, per_user=None, sums=None, stream=None):
         m = np.ascontiguousarray(metric_ids, dtype=np.int32)

@@ -206,20 +206,23 @@ __global__ void k_colsum_f32_seq(const float *__restrict__ per_user, int64_t n_r
 // candidates the reference ranks last (evaluator.py:195-200).
 template <int PER>
 __global__ void __launch_bounds__(128)
-k_merge_partials(const u64 *__restrict__ part, int S, int K, int64_t n_rows, int64_t row0,
+k_merge_partials(const u64 *__restrict__ part, int S, int K, int64_t n_rows, int64_t row0, int64_t stride_row, int64_t stride_s,
                  const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx,
                  u64 *__restrict__ out_keys)
 {
+    // list s of row r starts at part[r * stride_row + s * stride_s]: [rows][S][K] for the chunk lists of one
+    // GPU, [S][rows][K] for per-shard lists gathered from S GPUs
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + warp;
     if (row >= n_rows) return;
     const int n = S * K;
-    const u64 *src = part + row * (int64_t)n;
+    const u64 *src = part + row * stride_row;
     u64 v[PER];
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
-        int i = e * 32 + lane;
-        v[e] = (i < n) ? src[i] : 0ull;
+        const int i = e * 32 + lane;
+        const int s = i / K;
+        v[e] = (i < n) ? src[(int64_t)s * stride_s + (i - s * K)] : 0ull;
     }
     warp_bitonic_desc<PER>(v, lane);
     u64 *dst = out_keys + row * (int64_t)K;
@@ -238,6 +241,13 @@ k_merge_partials(const u64 *__restrict__ part, int S, int K, int64_t n_rows, int
         for (int64_t p = tb + lane; p < te && n_valid + (p - tb) < K; p += 32)
             dst[n_valid + (p - tb)] = make_key(ninf, (uint32_t)__ldg(tr_idx + p));
     }
+}
+
+// item ids of rank keys: shard-local -> global (key = ord << 32 | ~item, so item + off is key - off)
+__global__ void k_offset_keys(u64 *__restrict__ keys, int64_t n, uint32_t item_offset)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keys[i] != 0ull) keys[i] -= (u64)item_offset;
 }
 
 }  // namespace skr

@@ -196,8 +196,9 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         }
 
         // ---- 4. outputs: top-K lists on request, metrics straight from the registers ------------------
+        const bool do_metrics = te_indptr != nullptr;  // null: keys only (per-shard lists of item-sharded evaluation)
         RowMetrics rm;
-        rm.begin(te_indptr, te_idx, row0 + row);
+        if (do_metrics) rm.begin(te_indptr, te_idx, row0 + row);
 #pragma unroll
         for (int e = 0; e < PER; ++e) {
             const int i = e * 32 + lane;
@@ -207,8 +208,9 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                     if (topk_idx_out != nullptr) topk_idx_out[row * (int64_t)K + i] = (int32_t)key_item(v[e]);
                     if (topk_val_out != nullptr) topk_val_out[row * (int64_t)K + i] = key_score(v[e]);
                 }
-                rm.chunk(e * 32, lane, K, (int32_t)key_item(v[e]), mids, disc, idcg,
-                         per_user != nullptr ? per_user + row * (int64_t)MK : nullptr, acc);
+                if (do_metrics)
+                    rm.chunk(e * 32, lane, K, (int32_t)key_item(v[e]), mids, disc, idcg,
+                             per_user != nullptr ? per_user + row * (int64_t)MK : nullptr, acc);
             }
         }
     }

@@ -253,8 +253,22 @@ struct ExactArgs {
 
 int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
                        const MetricIds &m, int K, const ExactArgs &E, int32_t *fail_list, int *fail_count, int32_t *topk_idx,
-                       float *topk_val, float *per_user, double *sums, cudaStream_t st)
+                       float *topk_val, float *per_user, double *sums, u64 *keys_only, cudaStream_t st)
 {
+    if (keys_only != nullptr) {  // per-shard lists: sorted keys out, no metrics
+        const int g = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
+        if (K <= 64)
+            k_select_cands<2><<<g, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr,
+                                                            nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        else
+            k_select_cands<4><<<g, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr,
+                                                            nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
+                                                                      E.tr_indptr, E.tr_idx, K, keys_only);
+        ctx->launches += 2;
+        SKR_CUDA(ctx, cudaGetLastError());
+        return SKR_OK;
+    }
     if (!ctx->has_test) return fail(ctx, SKR_ERR_STATE, "no test CSR set (skr_set_test_csr)");
     if (row0 < 0 || row0 + n_rows > ctx->te_rows)
         return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the test CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->te_rows);
@@ -360,9 +374,26 @@ int launch_tc(skr_ctx *ctx, int nkb, int passes, int mode, unsigned grid, cudaSt
 }
 
 template <int PER>
-void launch_merge(const u64 *part, int S, int K, int64_t n_rows, int64_t row0, const int64_t *tp, const int32_t *ti, u64 *out, cudaStream_t st)
+void launch_merge(const u64 *part, int S, int K, int64_t n_rows, int64_t row0, int64_t stride_row, int64_t stride_s, const int64_t *tp,
+                  const int32_t *ti, u64 *out, cudaStream_t st)
 {
-    k_merge_partials<PER><<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(part, S, K, n_rows, row0, tp, ti, out);
+    k_merge_partials<PER><<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(part, S, K, n_rows, row0, stride_row, stride_s, tp, ti, out);
+}
+
+// S lists of K keys per row -> sorted top-K keys
+int merge_lists(skr_ctx *ctx, const u64 *part, int S, int K, int64_t n_rows, int64_t row0, int64_t stride_row, int64_t stride_s,
+                const int64_t *tp, const int32_t *ti, u64 *out, cudaStream_t st)
+{
+    const int n = S * K;
+    if (n > 1024) return fail(ctx, SKR_ERR_UNSUPPORTED, "merge of %d lists x %d keys exceeds 1024 keys per row", S, K);
+    if (n <= 64) launch_merge<2>(part, S, K, n_rows, row0, stride_row, stride_s, tp, ti, out, st);
+    else if (n <= 128) launch_merge<4>(part, S, K, n_rows, row0, stride_row, stride_s, tp, ti, out, st);
+    else if (n <= 256) launch_merge<8>(part, S, K, n_rows, row0, stride_row, stride_s, tp, ti, out, st);
+    else if (n <= 512) launch_merge<16>(part, S, K, n_rows, row0, stride_row, stride_s, tp, ti, out, st);
+    else launch_merge<32>(part, S, K, n_rows, row0, stride_row, stride_s, tp, ti, out, st);
+    ctx->launches++;
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
 }
 
 }  // namespace
@@ -629,15 +660,14 @@ int skr_eval_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64
     return run_metrics(ctx, (const u64 *)ctx->keys.p, nullptr, n_rows, row0, m, top_k, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
 }
 
-int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
-                   int64_t n_items, int64_t ld_i, int d, const float *bias_dev, int64_t row0, const int32_t *metric_ids,
-                   int n_metrics, int top_k, int precision, int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev,
-                   double *sums_dev, void *stream)
+// The fused pipeline.  keys_only == null: metrics of the rows (skr_eval_fused).  keys_only != null: the rows'
+// sorted top-K rank keys over this item table with item ids shifted by item_offset, no metrics (skr_topk_fused).
+static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
+                          int64_t n_items, int64_t ld_i, int d, const float *bias_dev, int64_t row0, const MetricIds &m, int top_k,
+                          int precision, int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev, double *sums_dev,
+                          u64 *keys_only, int64_t item_offset, void *stream)
 {
-    if (!ctx) return SKR_ERR_INVALID;
-    MetricIds m;
-    int rc = check_metrics(ctx, metric_ids, n_metrics, top_k, m);
-    if (rc) return rc;
+    int rc;
     if (!user_vecs_dev || !item_vecs_dev || n_rows <= 0 || d <= 0) return fail(ctx, SKR_ERR_INVALID, "eval_fused: empty input");
     if (ld_u < d || ld_i < d) return fail(ctx, SKR_ERR_INVALID, "ld_u=%lld / ld_i=%lld < d=%d", (long long)ld_u, (long long)ld_i, d);
     if (n_items < top_k) return fail(ctx, SKR_ERR_INVALID, "n_items=%lld < top_k=%d (evaluate.h:45 would read out of bounds)", (long long)n_items, top_k);
@@ -774,8 +804,9 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         ctx->last_plan = {n_samp, stride, r, cap, P.S, passes == 3 ? 4 : 8};
         ctx->ev_calls++;
         const ExactArgs E = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (int)n_items, tp, ti};
-        return run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
-                                  per_user_dev, sums_dev, st);
+        rc = run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
+                                per_user_dev, sums_dev, keys_only, st);
+        if (rc || keys_only == nullptr) return rc;
     } else {
         if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->part, (size_t)n_rows * P.S * K * sizeof(u64)))) return rc;
@@ -792,18 +823,67 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
         ctx->last_fused = "simt_fp32";
         SKR_CUDA(ctx, cudaGetLastError());
         // merge the S partial lists per row
-        const int n = P.S * K;
-        if (n <= 64) launch_merge<2>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-        else if (n <= 128) launch_merge<4>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-        else if (n <= 256) launch_merge<8>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-        else if (n <= 512) launch_merge<16>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-        else launch_merge<32>(P.part, P.S, K, n_rows, row0, tp, ti, keys, st);
-        ctx->launches++;
+        if ((rc = merge_lists(ctx, P.part, P.S, K, n_rows, row0, (int64_t)P.S * K, K, tp, ti, keys_only ? keys_only : keys, st))) return rc;
         ctx->last_plan = {0, 0, 0, 0, P.S, 0};
+        ctx->ev_calls++;
+        SKR_CUDA(ctx, cudaGetLastError());
+        if (keys_only == nullptr) return run_metrics(ctx, keys, nullptr, n_rows, row0, m, K, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
     }
-    ctx->ev_calls++;
+    // keys only: shard-local item ids -> global
+    if (item_offset != 0) {
+        const int64_t nk = n_rows * K;
+        k_offset_keys<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>(keys_only, nk, (uint32_t)item_offset);
+        ctx->launches++;
+    }
     SKR_CUDA(ctx, cudaGetLastError());
-    return run_metrics(ctx, keys, nullptr, n_rows, row0, m, K, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
+    return SKR_OK;
+}
+
+int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
+                   int64_t n_items, int64_t ld_i, int d, const float *bias_dev, int64_t row0, const int32_t *metric_ids,
+                   int n_metrics, int top_k, int precision, int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev,
+                   double *sums_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    MetricIds m;
+    int rc = check_metrics(ctx, metric_ids, n_metrics, top_k, m);
+    if (rc) return rc;
+    return fused_pipeline(ctx, user_vecs_dev, n_rows, ld_u, item_vecs_dev, n_items, ld_i, d, bias_dev, row0, m, top_k, precision, topk_idx_dev,
+                          topk_val_dev, per_user_dev, sums_dev, nullptr, 0, stream);
+}
+
+int skr_topk_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev, int64_t n_items,
+                   int64_t ld_i, int d, const float *bias_dev, int64_t row0, int64_t item_offset, int top_k, int precision,
+                   uint64_t *keys_out_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!keys_out_dev) return fail(ctx, SKR_ERR_INVALID, "topk_fused: keys_out is NULL");
+    if (item_offset < 0 || item_offset + n_items > 0xffffffffll) return fail(ctx, SKR_ERR_INVALID, "item_offset=%lld", (long long)item_offset);
+    MetricIds m;
+    m.n = 0;
+    m.packed = 0u;
+    return fused_pipeline(ctx, user_vecs_dev, n_rows, ld_u, item_vecs_dev, n_items, ld_i, d, bias_dev, row0, m, top_k, precision, nullptr, nullptr,
+                          nullptr, nullptr, (u64 *)keys_out_dev, item_offset, stream);
+}
+
+int skr_eval_merged_topk(skr_ctx *ctx, const uint64_t *keys_all_dev, int n_shards, int64_t n_rows_total, int64_t row_begin, int64_t n_rows,
+                         int64_t row0, const int32_t *metric_ids, int n_metrics, int top_k, int32_t *topk_idx_dev, float *topk_val_dev,
+                         float *per_user_dev, double *sums_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    MetricIds m;
+    int rc = check_metrics(ctx, metric_ids, n_metrics, top_k, m);
+    if (rc) return rc;
+    if (!keys_all_dev || n_shards < 1 || n_rows <= 0 || row_begin < 0 || row_begin + n_rows > n_rows_total)
+        return fail(ctx, SKR_ERR_INVALID, "eval_merged_topk: bad arguments");
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = ensure(ctx, ctx->keys, (size_t)n_rows * top_k * sizeof(u64)))) return rc;
+    // lists gathered from the shards: [n_shards][n_rows_total][K]; merge rows [row_begin, row_begin + n_rows)
+    const u64 *src = (const u64 *)keys_all_dev + row_begin * (int64_t)top_k;
+    if ((rc = merge_lists(ctx, src, n_shards, top_k, n_rows, row0, top_k, n_rows_total * (int64_t)top_k, nullptr, nullptr, (u64 *)ctx->keys.p, st)))
+        return rc;
+    return run_metrics(ctx, (const u64 *)ctx->keys.p, nullptr, n_rows, row0, m, top_k, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
 }
 
 // ---- host-buffer variants: the copies are part of the call --------------------------------------

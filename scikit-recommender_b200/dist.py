@@ -38,6 +38,21 @@ def allreduce_sums(sums, group=None):
     return sums
 
 
+def allgather_keys(keys, group=None):
+    """Item-sharded evaluation: every rank contributes its [n, K] per-shard rank keys (int64 view of
+    uint64) and receives all of them as [world, n, K], shard order = rank order (NCCL all-gather over
+    NVLink on GPUs, gloo on CPU tensors in the tests)."""
+    import torch
+    import torch.distributed as td
+    world = td.get_world_size(group)
+    out = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+    try:
+        td.all_gather_into_tensor(out, keys.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):  # backends without the fused form
+        td.all_gather([out[r] for r in range(world)], keys.contiguous(), group=group)
+    return out
+
+
 def finalize_means(col_sums, n_users):
     """float64 column sums / user count, rounded once to float32 (what MetricReport carries)."""
     n = float(n_users)

@@ -32,32 +32,46 @@ _metric2id = {"Precision": 1, "Recall": 2, "MAP": 3, "NDCG": 4, "MRR": 5}
 _id2metric = {value: key for key, value in _metric2id.items()}
 
 
-def _dict_to_csr(users, d):
-    """{user: int array} restricted to `users` (in order) -> (indptr int64, indices int32)."""
+def _dict_to_csr(users, d, col_range=None):
+    """{user: int array} restricted to `users` (in order) -> (indptr int64, indices int32).
+    col_range=(lo, hi): keep only items in [lo, hi) and renumber them from 0 (an item shard's column
+    partition of the interactions)."""
     counts = np.fromiter((len(d[u]) if u in d else 0 for u in users), dtype=np.int64, count=len(users))
     indptr = np.zeros(len(users) + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     if indptr[-1] == 0:
         return indptr, np.zeros(0, np.int32)
     indices = np.concatenate([np.asarray(d[u], dtype=np.int32).ravel() for u in users if u in d and len(d[u]) > 0])
+    if col_range is not None:
+        lo, hi = col_range
+        keep = (indices >= lo) & (indices < hi)
+        rows = np.repeat(np.arange(len(users), dtype=np.int64), counts)
+        kept = np.bincount(rows[keep], minlength=len(users)).astype(np.int64)
+        indptr = np.zeros(len(users) + 1, dtype=np.int64)
+        np.cumsum(kept, out=indptr[1:])
+        indices = indices[keep] - np.int32(lo)
     return indptr, np.ascontiguousarray(indices, dtype=np.int32)
 
 
 class _Plan(object):
     """Device state for one evaluated-user list: native context + CSRs of exactly those rows."""
 
-    def __init__(self, users, n_items, train, test, device):
+    def __init__(self, users, n_items, train, test, device, item_range=None):
+        """item_range=(lo, hi): this rank scores only item rows [lo, hi) (item-sharded evaluation): the
+        train CSR becomes that column partition with shard-local ids; the test CSR keeps global ids."""
         from . import _native
         self.users = users
         self.n_items = n_items
+        self.item_range = item_range
         self.ctx = _native.Context(device)
         tp, ti = _dict_to_csr(users, test)
         self.ctx.set_test_csr(tp, ti, n_items)
+        n_local = n_items if item_range is None else item_range[1] - item_range[0]
         if train:
-            rp, ri = _dict_to_csr(users, train)
-            self.ctx.set_train_csr(rp, ri, n_items)
+            rp, ri = _dict_to_csr(users, train, item_range)
+            self.ctx.set_train_csr(rp, ri, n_local)
         else:
-            self.ctx.set_train_csr(None, None, n_items)
+            self.ctx.set_train_csr(None, None, n_local)
 
 
 class RankingEvaluator(object):
@@ -74,6 +88,11 @@ class RankingEvaluator(object):
             single-process only).
         shard_users: with torch.distributed initialised, each rank evaluates a contiguous slice
             of the users and the metric sums are all-reduced (default True).
+        shard: "users" (default; the item table is replicated) or "items" (catalogue beyond one HBM:
+            every rank holds a contiguous range of item rows, computes every user's top-K over its
+            range, the per-rank lists are all-gathered and merged, then the sums all-reduced).  With
+            "items" the model's `eval_embeddings` may take `item_shard=(rank, world)` and return just
+            its rows plus the catalogue size, `(user_vecs, item_rows, bias_rows | None, n_items)`.
         process_group: the group to reduce over (default: WORLD).
     """
 
@@ -83,7 +102,7 @@ class RankingEvaluator(object):
                  top_k: Union[int, List[int], Tuple[int]] = 50,
                  batch_size: int = 256, num_thread: int = 8, *,
                  device: Optional[int] = None, precision: str = "auto", mean: str = "f64",
-                 shard_users: bool = True, process_group=None):
+                 shard_users: bool = True, shard: str = "users", process_group=None):
         super(RankingEvaluator, self).__init__()
         if metric is None:
             metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
@@ -117,6 +136,8 @@ class RankingEvaluator(object):
 
         assert precision in ("auto", "3xtf32", "fp32", "1xtf32"), "precision must be auto|3xtf32|fp32|1xtf32"
         assert mean in ("f64", "numpy_f32"), "mean must be f64|numpy_f32"
+        assert shard in ("users", "items"), "shard must be users|items"
+        self.shard = shard
         self.device = device
         self.precision = precision
         self.mean = mean
@@ -150,12 +171,12 @@ class RankingEvaluator(object):
             raise RuntimeError("RankingEvaluator needs a CUDA device (sm_100a); there is no CPU fallback")
         return torch.cuda.current_device() if self.device is None else int(self.device)
 
-    def _plan(self, users, n_items, key):
+    def _plan(self, users, n_items, key, item_range=None):
         plan = self._plans.get(key)
-        if plan is not None and plan.n_items == n_items:
+        if plan is not None and plan.n_items == n_items and plan.item_range == item_range:
             self._plans.move_to_end(key)
             return plan
-        plan = _Plan(users, n_items, self.user_pos_train, self.user_pos_test, self._device_index())
+        plan = _Plan(users, n_items, self.user_pos_train, self.user_pos_test, self._device_index(), item_range)
         self._plans[key] = plan
         while len(self._plans) > 6:
             self._plans.popitem(last=False)
@@ -192,19 +213,27 @@ class RankingEvaluator(object):
         assert isinstance(test_users, Iterable), "'test_user' must be iterable."
 
         rank, world, lo, hi = self._shard(len(test_users))
+        item_sharded = self.shard == "items" and world > 1
+        if item_sharded:
+            assert hasattr(model, "eval_embeddings"), "shard='items' needs a model with eval_embeddings"
+            assert self.mean == "f64", "shard='items' supports mean='f64' only"
+            lo, hi = 0, len(test_users)  # every rank sees every user; the items are what is split
         users = test_users[lo:hi] if world > 1 else test_users
-        key = key_all + (rank, world)
+        key = key_all + (rank, world, self.shard)
         dev = torch.device("cuda", self._device_index())
         K, M = self.max_top, self.metrics_num
         MK = M * K
         per_user = None
         path = "none"
+        n_mine = 0
         col_sums = np.zeros(MK, dtype=np.float64)  # this rank's float64 column sums
         want_pu = self.mean == "numpy_f32"
 
         if len(users) > 0:
             with torch.cuda.device(dev):
-                if hasattr(model, "eval_embeddings"):
+                if item_sharded:
+                    path, col_sums, n_mine = self._evaluate_item_sharded(model, users, key, dev, rank, world)
+                elif hasattr(model, "eval_embeddings"):
                     path, col_sums, per_user = self._evaluate_fused(model, users, key, dev, want_pu)
                 else:
                     path, col_sums, per_user = self._evaluate_predict(model, users, key, dev, want_pu)
@@ -217,7 +246,7 @@ class RankingEvaluator(object):
             plan.ctx.colsum_f32_seq(per_user, acc)
             final_results = (acc / torch.tensor(float(len(users)), dtype=torch.float32, device=dev)).cpu().numpy()
         else:
-            n_users = float(len(users))
+            n_users = float(n_mine) if item_sharded else float(len(users))
             if world > 1:
                 packed = torch.from_numpy(np.concatenate([col_sums, [n_users]])).to(dev)  # [column sums | user count]
                 dist.allreduce_sums(packed, self.process_group)
@@ -285,6 +314,46 @@ class RankingEvaluator(object):
         per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
         plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision, per_user=per_user, sums=sums)
         return "fused:" + plan.ctx.last_fused_kernel, sums.cpu().numpy(), per_user
+
+    def _evaluate_item_sharded(self, model, users, key, dev, rank, world, chunk_rows=1 << 18):
+        """Item-sharded evaluation.  Per user chunk: local top-K over this rank's item rows
+        (fused kernels) -> all-gather of the [n, K] rank keys -> this rank merges and evaluates its slice
+        of the chunk's users.  -> (path, float64 column sums of my slices, number of users in them)"""
+        import inspect
+        import torch
+        from . import dist
+        try:
+            takes_shard = "item_shard" in inspect.signature(model.eval_embeddings).parameters
+        except (TypeError, ValueError):
+            takes_shard = False
+        if takes_shard:
+            user_vecs, item_rows, bias_rows, n_items = model.eval_embeddings(users, item_shard=(rank, world))
+            ilo, ihi = dist.shard_range(int(n_items), rank, world)
+        else:
+            user_vecs, item_vecs, bias = model.eval_embeddings(users)
+            n_items = int(item_vecs.shape[0])
+            ilo, ihi = dist.shard_range(n_items, rank, world)
+            item_rows = item_vecs[ilo:ihi]
+            bias_rows = None if bias is None else bias[ilo:ihi]
+        uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_rows, dev), self._to_dev(bias_rows, dev)
+        assert iv.shape[0] == ihi - ilo, "eval_embeddings(item_shard=...) must return exactly this rank's item rows"
+        assert uv.shape[0] == len(users) and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
+        K, MK = self.max_top, self.metrics_num * self.max_top
+        assert world * K <= 1024, "shard='items': world_size * max(top_k) must not exceed 1024"
+        plan = self._plan(users, int(n_items), key, (ilo, ihi))
+        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
+        n_mine = 0
+        chunk_rows = max(128, (int(chunk_rows) // 128) * 128)  # row offsets of the fused kernels are multiples of 128
+        for c0 in range(0, len(users), chunk_rows):
+            n = min(chunk_rows, len(users) - c0)
+            keys = torch.empty((n, K), dtype=torch.int64, device=dev)
+            plan.ctx.topk_fused(uv[c0:c0 + n], iv, b, c0, ilo, K, keys, precision=self.precision)
+            keys_all = dist.allgather_keys(keys, self.process_group)  # [world, n, K]
+            lo, hi = dist.shard_range(n, rank, world)
+            if hi > lo:
+                plan.ctx.eval_merged_topk(keys_all, lo, hi - lo, c0 + lo, self.metrics, K, sums=sums)
+                n_mine += hi - lo
+        return "items:" + plan.ctx.last_fused_kernel, sums.cpu().numpy(), n_mine
 
     def _evaluate_predict(self, model, users, key, dev, want_pu):
         import torch

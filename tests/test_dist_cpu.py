@@ -69,3 +69,59 @@ def test_two_rank_gloo_equals_single_process(tmp_path):
     got = np.load(out)
     assert np.max(np.abs(got - single)) <= 1e-7
     assert np.max(np.abs(got - oracle.mean_f32(per))) < 1e-5
+
+
+# ---- item-sharded evaluation, host logic (gloo, world_size 2): gather layout + column partition -------
+def _pack_keys(scores, items):
+    """rank keys as the kernels build them: ord(score) << 32 | ~item (int64 view)"""
+    b = scores.astype(np.float32).view(np.uint32).astype(np.uint64)
+    ordv = np.where(b & np.uint64(0x80000000), (~b) & np.uint64(0xffffffff), b | np.uint64(0x80000000))
+    return ((ordv << np.uint64(32)) | ((~items.astype(np.uint64)) & np.uint64(0xffffffff))).view(np.int64)
+
+
+def _items_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    s, indptr, indices, metric, K = _workload()
+    U, I = s.shape
+    lo, hi = dist.shard_range(I, rank, world)
+    # this rank's exact top-K over its item range (descending score; scores are tie-free)
+    order = np.argsort(-s[:, lo:hi], axis=1, kind="stable")[:, :K]
+    keys = _pack_keys(np.take_along_axis(s[:, lo:hi], order, 1), order + lo)
+    gathered = dist.allgather_keys(torch.from_numpy(keys)).numpy()
+    if rank == 0:
+        np.save(out_path, gathered)
+    td.destroy_process_group()
+
+
+def test_two_rank_gloo_item_shard_gather_and_merge(tmp_path):
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = str(tmp_path / "keys.npy")
+    mp.spawn(_items_worker, args=(2, port, out), nprocs=2, join=True)
+    s, indptr, indices, metric, K = _workload()
+    g = np.load(out).view(np.uint64)  # [world, U, K], shard order = rank order
+    assert g.shape == (2, s.shape[0], K)
+    merged = np.sort(np.concatenate([g[0], g[1]], axis=1), axis=1)[:, ::-1][:, :K]  # larger key = ranked earlier
+    items = (~merged).astype(np.uint32).astype(np.int64)
+    expect = np.argsort(-s, axis=1, kind="stable")[:, :K]
+    assert np.array_equal(items, expect)
+    for r in range(2):
+        lo, hi = dist.shard_range(s.shape[1], r, 2)
+        it = (~g[r]).astype(np.uint32)
+        assert it.min() >= lo and it.max() < hi
+
+
+def test_column_partition_of_interactions():
+    import importlib
+    ev = importlib.import_module("skrec_b200.evaluator")
+    d = {3: np.array([5, 1, 9, 7], np.int32), 4: np.array([], np.int32), 8: np.array([2, 8], np.int32)}
+    users = [8, 3, 4, 99]
+    ptr, idx = ev._dict_to_csr(users, d)
+    assert ptr.tolist() == [0, 2, 6, 6, 6] and idx.tolist() == [2, 8, 5, 1, 9, 7]
+    ptr, idx = ev._dict_to_csr(users, d, (5, 9))
+    assert ptr.tolist() == [0, 1, 3, 3, 3] and idx.tolist() == [3, 0, 2]
+    ptr, idx = ev._dict_to_csr(users, d, (100, 200))
+    assert ptr.tolist() == [0, 0, 0, 0, 0] and idx.size == 0

@@ -450,3 +450,105 @@ def test_c2_item_permutation_invariance(torch_cuda, ctx, c2_data):
     assert np.max(np.abs(a[3] - b[3]) / U) <= TOL_METRIC
     same = (perm[a[0]] == b[0])
     assert same.mean() > 0.995
+
+
+# ---- item-sharded evaluation: per-shard lists + merge == unsharded --------------------------
+def _col_partition(tr, lo, hi):
+    """Column partition [lo, hi) of a CSR with shard-local ids."""
+    indptr, indices = tr
+    keep = (indices >= lo) & (indices < hi)
+    rows = np.repeat(np.arange(indptr.size - 1), np.diff(indptr))
+    cnt = np.bincount(rows[keep], minlength=indptr.size - 1)
+    ptr = np.zeros(indptr.size, np.int64)
+    np.cumsum(cnt, out=ptr[1:])
+    return ptr, (indices[keep] - lo).astype(np.int32)
+
+
+@pytest.mark.parametrize("precision", ["3xtf32", "fp32"])
+@pytest.mark.parametrize("n_shards", [2, 3])
+def test_item_sharded_lists_merge_to_the_unsharded_result(torch_cuda, precision, n_shards):
+    from skrec_b200 import _native, dist
+    torch = torch_cuda
+    U, I, d, K = 389, 4000, 64, 50
+    ue, ie, b, tr, te = _fused_case(77, U, I, d, True, 80)
+    metric = [1, 2, 3, 4, 5]
+    ref_ctx = _native.Context(0)
+    ref = _run_fused(torch, ref_ctx, ue, ie, b, tr, te, metric, K, precision)
+    ued, ied, bd = torch.from_numpy(ue).cuda(), torch.from_numpy(ie).cuda(), torch.from_numpy(b).cuda()
+    keys_all = torch.empty((n_shards, U, K), dtype=torch.int64, device="cuda")
+    for s in range(n_shards):
+        lo, hi = dist.shard_range(I, s, n_shards)
+        c = _native.Context(0)
+        ptr, idx = _col_partition(tr, lo, hi)
+        c.set_train_csr(ptr, idx, hi - lo)
+        c.topk_fused(ued, ied[lo:hi], bd[lo:hi], 0, lo, K, keys_all[s], precision=precision)
+        torch.cuda.synchronize()
+        c.close()
+    # every per-shard list holds global ids of its own range, ranked by descending key
+    ka = keys_all.cpu().numpy().view(np.uint64)
+    for s in range(n_shards):
+        lo, hi = dist.shard_range(I, s, n_shards)
+        items = (~ka[s]).astype(np.uint32)
+        assert items.min() >= lo and items.max() < hi
+        assert np.all(ka[s][:, :-1] > ka[s][:, 1:])
+    MK = len(metric) * K
+    idx = torch.empty((U, K), dtype=torch.int32, device="cuda")
+    val = torch.empty((U, K), dtype=torch.float32, device="cuda")
+    per = torch.empty((U, MK), dtype=torch.float32, device="cuda")
+    sums = torch.zeros(MK, dtype=torch.float64, device="cuda")
+    ref_ctx.set_test_csr(te[0], te[1], I)
+    # merged in two row slices, like two ranks would
+    cut = 200
+    ref_ctx.eval_merged_topk(keys_all, 0, cut, 0, metric, K, topk_idx=idx[:cut], topk_val=val[:cut], per_user=per[:cut], sums=sums)
+    ref_ctx.eval_merged_topk(keys_all, cut, U - cut, cut, metric, K, topk_idx=idx[cut:], topk_val=val[cut:], per_user=per[cut:], sums=sums)
+    torch.cuda.synchronize()
+    got = (idx.cpu().numpy(), val.cpu().numpy(), per.cpu().numpy(), sums.cpu().numpy())
+    # sharding changes neither a score nor an order: bit-identical to the unsharded run, and right vs the oracle
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    assert np.max(np.abs(got[3] - ref[3])) < 1e-9
+    _check_fused(*got, ue, ie, b, tr, te, metric, K)
+    ref_ctx.close()
+
+
+def _items_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as td
+    from skrec_b200 import RankingEvaluator, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    data = synth.make(users=1500, items=6000, d=64, nnz_train=60000, nnz_test=12000, seed=11, bias=True)
+    model = synth.EmbeddingModel(data["user_emb"], data["item_emb"], data["bias"])
+    out = {}
+    for shard in ("users", "items"):
+        ev = RankingEvaluator(data["train"], data["test"], metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], top_k=[10, 50],
+                              device=rank, shard=shard)
+        rep = ev.evaluate(model)
+        out[shard] = np.array(list(rep.values()), np.float32)
+        out[shard + "_path"] = ev.last_stats["path"]
+    if rank == 0:
+        np.savez(out_path, users=out["users"], items=out["items"], path=out["items_path"])
+    td.destroy_process_group()
+
+
+def test_item_sharded_evaluator_two_gpus_nccl(torch_cuda, tmp_path):
+    """Two ranks, NCCL: shard='items' (all-gather + merge) == shard='users' (all-reduce only) == oracle."""
+    import socket
+    import torch.multiprocessing as mp
+    from skrec_b200 import synth
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = str(tmp_path / "rep.npz")
+    mp.spawn(_items_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    assert str(got["path"]).startswith("items:tcgen05")
+    assert np.max(np.abs(got["users"] - got["items"])) <= 1e-7
+    data = synth.make(users=1500, items=6000, d=64, nnz_train=60000, nnz_test=12000, seed=11, bias=True)
+    plain = synth.PredictOnlyModel(data["user_emb"], data["item_emb"], data["bias"])
+    per, _ = oracle.evaluate_dicts(plain.predict, data["train"], data["test"], [1, 2, 3, 4, 5], 50)
+    expect = oracle.mean_f32(per).reshape(5, 50)[:, np.array([10, 50]) - 1].ravel()
+    assert np.max(np.abs(got["items"] - expect)) <= TOL_METRIC
