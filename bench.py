@@ -204,13 +204,25 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     t_load0 = time.time()
-    warm_until = time.time() + 1.0
-    n_warm = 0
-    while n_warm < max(args.warmup, 3) or time.time() < warm_until:  # >= W steps and >= 1 s so clocks ramp
+    # >= W steps and about 1 s of load so the clocks ramp.  The count must be the same on every rank (each step
+    # holds an all-reduce), so it is fixed up front from the step time rank 0 measures, not decided by a clock.
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
         step()
-        n_warm += 1
-        if n_warm % 16 == 0:
+    torch.cuda.synchronize()
+    t_probe = time.time()
+    for _ in range(20):
+        step()
+    torch.cuda.synchronize()
+    extra = torch.tensor([int(min(5000, max(0.0, 1.0 / max((time.time() - t_probe) / 20, 1e-5))))], dtype=torch.int64, device=dev)
+    if world > 1:
+        td.broadcast(extra, 0)
+    n_extra = int(extra.item())
+    for i in range(n_extra):
+        step()
+        if i % 16 == 15:
             torch.cuda.synchronize()
+    n_warm += 20 + n_extra
     torch.cuda.synchronize()
     if world > 1:
         td.barrier()

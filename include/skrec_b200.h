@@ -106,6 +106,20 @@ int skr_eval_fused(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int
                    int top_k, int precision, int32_t *topk_idx_dev, float *topk_val_dev,
                    float *per_user_dev, double *sums_dev, void *stream);
 
+/* Top-k of every row of a score block without masks or metrics: the GPU form of the reference's
+ * pyx_arg_top_k / pyx_top_k (skrec/utils/py/cython/pyx_sort.pyx:104-187, sort.h:136-170).  Indices (and/or
+ * values) sorted by score desc, ties by lower index; either output may be NULL.  top_k <= 512. */
+int skr_topk_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64_t n_items, int64_t ld,
+                    int top_k, int32_t *topk_idx_dev, float *topk_val_dev, void *stream);
+int skr_topk_scores_host(skr_ctx *ctx, const float *scores_host, int64_t n_rows, int64_t n_items, int64_t ld,
+                         int top_k, int32_t *topk_idx_host, float *topk_val_host, void *stream);
+
+/* Grouped evaluation (base.py:66-71 evaluate_group runs one full evaluation per user group): after ONE
+ * evaluation that kept the per-user block [*, n_cols] on the device, sums_dev[c] += sum of the rows
+ * row_list_dev[0 .. n_list) -- float64, deterministic. */
+int skr_colsum_rows(skr_ctx *ctx, const float *per_user_dev, int64_t n_cols, const int32_t *row_list_dev,
+                    int64_t n_list, double *sums_dev, void *stream);
+
 /* Item-sharded evaluation (catalogue beyond one HBM): the reference has no counterpart -- its
  * `predict` always returns all columns (base.py:73).  Step 1, on every rank: the rows' sorted top-K over the
  * item rows [item_offset, item_offset + n_items) this rank holds, as 64-bit rank keys

@@ -184,6 +184,18 @@ def ref_eval_score_matrix(score_matrix, test_items, metric, top_k, thread_num):
     return eval_score_matrix(score_matrix, test_items, metric, top_k, thread_num)
 
 
+def ref_module(name):
+    """a compiled reference Cython module by name ("pyx_sort", "pyx_eval_matrix", "pyx_utils"), or None"""
+    if not ref_python_available():
+        return None
+    _ref_import()
+    import importlib
+    try:
+        return importlib.import_module("refpkg.cython." + name)
+    except ImportError:
+        return None
+
+
 def RefRankingEvaluator(*args, **kwargs):
     """the reference's RankingEvaluator (evaluator.py:61-214), unmodified, compiled by Cython."""
     _ref_import()

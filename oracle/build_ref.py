@@ -6,7 +6,7 @@ Two products, both git-ignored but shipped to the GPU box by gpurun:
   oracle/_ref/                     the UNMODIFIED reference, compiled from the sources where
                                    they lie under /root/reference -- binaries only:
       libref_eval.so               oracle/ref_shim.cpp + reference evaluate.h/metric.h/thread_pool.h
-      refpkg/cython/pyx_*.so       Cython builds of skrec/utils/py/cython/pyx_{utils,eval_matrix}.pyx
+      refpkg/cython/pyx_*.so       Cython builds of skrec/utils/py/cython/pyx_{utils,eval_matrix,sort}.pyx
       refpkg/{evaluator,batch_iterator}.so
                                    Cython builds of skrec/utils/py/{evaluator,batch_iterator}.py
                                    (so the reference's own RankingEvaluator.evaluate runs on the GPU
@@ -83,7 +83,7 @@ def build_ref(force=False):
     if not os.path.isdir(REF_CY):
         return None  # GPU box: use what travelled
     stamp = os.path.join(OUT_REF, ".built")
-    srcs = [os.path.join(REF_CY, f) for f in ("pyx_utils.pyx", "pyx_eval_matrix.pyx")] + \
+    srcs = [os.path.join(REF_CY, f) for f in ("pyx_utils.pyx", "pyx_eval_matrix.pyx", "pyx_sort.pyx")] + \
            [os.path.join(REF_CY, "include", f) for f in ("evaluate.h", "metric.h", "thread_pool.h")] + \
            [os.path.join(REF_PY, f) for f in ("evaluator.py", "batch_iterator.py")] + \
            [os.path.join(HERE, "ref_shim.cpp"), os.path.abspath(__file__)]
@@ -101,6 +101,7 @@ def build_ref(force=False):
     # 2. reference Cython modules and the reference evaluator, as extension modules
     _cython_build(os.path.join(REF_CY, "pyx_utils.pyx"), "pyx_utils", cy, tmp, True)
     _cython_build(os.path.join(REF_CY, "pyx_eval_matrix.pyx"), "pyx_eval_matrix", cy, tmp, True)
+    _cython_build(os.path.join(REF_CY, "pyx_sort.pyx"), "pyx_sort", cy, tmp, True)  # pins skrec_b200.sort
     _cython_build(os.path.join(REF_PY, "batch_iterator.py"), "batch_iterator", pkg, tmp, False)
     _cython_build(os.path.join(REF_PY, "evaluator.py"), "evaluator", pkg, tmp, False)
     shutil.rmtree(tmp, ignore_errors=True)

@@ -18,7 +18,7 @@ PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "1xtf32": 3}
 SYMBOLS = (
     "skr_abi_version", "skr_ctx_create", "skr_ctx_destroy", "skr_last_error", "skr_set_train_csr",
     "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
-    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace", "skr_topk_fused", "skr_eval_merged_topk",
+    "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace", "skr_topk_fused", "skr_eval_merged_topk", "skr_topk_scores", "skr_topk_scores_host", "skr_colsum_rows",
 )
 
 _lib = None
@@ -57,6 +57,9 @@ def lib():
                                       _vp, _vp, _vp, _vp]
     L.skr_topk_fused.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _vp, _i64, _i64, _int, _int, _vp, _vp]
     L.skr_eval_merged_topk.argtypes = [_vp, _vp, _int, _i64, _i64, _i64, _i64, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp]
+    L.skr_topk_scores.argtypes = [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]
+    L.skr_topk_scores_host.argtypes = [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp]
+    L.skr_colsum_rows.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _vp]
     L.skr_metrics_from_topk.argtypes = [_vp, _vp, _i64, _i64, _vp, _int, _int, _vp, _vp, _vp]
     L.skr_colsum_f32_seq.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp]
     L.skr_launch_count.argtypes = [_vp]
@@ -196,6 +199,27 @@ class Context(object):
                                                  int(row_begin), int(n_rows), int(row0), _np_ptr(m), int(m.size), int(top_k),
                                                  _dev_ptr(topk_idx), _dev_ptr(topk_val), _dev_ptr(per_user), _dev_ptr(sums),
                                                  _stream_ptr(stream)))
+
+    def topk_scores_host(self, scores, top_k, want_idx=True, want_val=False):
+        """Top-k of every row of a host float32 [B, N] block -> (idx int32 [B, k] | None, val float32 [B, k] | None)."""
+        s = scores
+        assert isinstance(s, np.ndarray) and s.dtype == np.float32 and s.ndim == 2 and s.strides[1] == 4
+        idx = np.empty((s.shape[0], int(top_k)), np.int32) if want_idx else None
+        val = np.empty((s.shape[0], int(top_k)), np.float32) if want_val else None
+        self._check(self._L.skr_topk_scores_host(self._h, _np_ptr(s), s.shape[0], s.shape[1], s.strides[0] // 4, int(top_k),
+                                                 _np_ptr(idx), _np_ptr(val), None))
+        return idx, val
+
+    def topk_scores(self, scores, top_k, topk_idx=None, topk_val=None, stream=None):
+        assert scores.is_cuda and scores.dim() == 2 and scores.stride(1) == 1
+        self._check(self._L.skr_topk_scores(self._h, _dev_ptr(scores), scores.shape[0], scores.shape[1], scores.stride(0),
+                                            int(top_k), _dev_ptr(topk_idx), _dev_ptr(topk_val), _stream_ptr(stream)))
+
+    def colsum_rows(self, per_user, row_list, sums, stream=None):
+        """sums[c] += sum over rows row_list (int32 device tensor) of per_user[:, c] in float64."""
+        assert per_user.is_cuda and per_user.is_contiguous() and row_list.is_cuda and sums.is_cuda
+        self._check(self._L.skr_colsum_rows(self._h, _dev_ptr(per_user), per_user.shape[1], _dev_ptr(row_list),
+                                            int(row_list.numel()), _dev_ptr(sums), _stream_ptr(stream)))
 
     def metrics_from_topk(self, topk_idx, row0, metric_ids, top_k, per_user=None, sums=None, stream=None):
         m = np.ascontiguousarray(metric_ids, dtype=np.int32)

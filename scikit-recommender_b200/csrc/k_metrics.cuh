@@ -162,14 +162,28 @@ k_colsum_fold(const double *__restrict__ partial, int n_blk, int n_cols, double 
     }
 }
 
+// row_list != null: sum rows row_list[0..n_rows) of per_user instead of rows 0..n_rows (grouped evaluation)
 __global__ void k_colsum_partial(const float *__restrict__ per_user, int64_t n_rows, int n_cols,
-                                 double *__restrict__ partial)
+                                 double *__restrict__ partial, const int32_t *__restrict__ row_list = nullptr)
 {
     for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
         double acc = 0.0;
-        for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) acc += (double)per_user[r * n_cols + c];
+        for (int64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+            const int64_t row = (row_list != nullptr) ? (int64_t)row_list[r] : r;
+            acc += (double)per_user[row * n_cols + c];
+        }
         partial[(size_t)blockIdx.x * n_cols + c] = acc;
     }
+}
+
+// sorted rank keys -> item ids / scores (the pyx_sort-style top-k entry points)
+__global__ void k_unpack_keys(const u64 *__restrict__ keys, int64_t n, int32_t *__restrict__ idx, float *__restrict__ val)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 k = keys[i];
+    if (idx != nullptr) idx[i] = (k == 0) ? -1 : (int32_t)key_item(k);
+    if (val != nullptr) val[i] = (k == 0) ? -__int_as_float(0x7f800000) : key_score(k);
 }
 
 __global__ void k_colsum_final(const double *__restrict__ partial, int n_blk, int n_cols, double *__restrict__ sums)

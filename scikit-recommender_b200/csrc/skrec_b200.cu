@@ -633,6 +633,67 @@ int skr_colsum_f32_seq(skr_ctx *ctx, const float *per_user_dev, int64_t n_rows, 
     return SKR_OK;
 }
 
+int skr_colsum_rows(skr_ctx *ctx, const float *per_user_dev, int64_t n_cols, const int32_t *row_list_dev, int64_t n_list, double *sums_dev,
+                    void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!per_user_dev || !sums_dev || n_cols <= 0 || n_list < 0 || (n_list > 0 && !row_list_dev))
+        return fail(ctx, SKR_ERR_INVALID, "colsum_rows: bad arguments");
+    if (n_list == 0) return SKR_OK;
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (int)std::min<int64_t>(n_list, 2 * ctx->n_sm);
+    int rc = ensure(ctx, ctx->partial, (size_t)nblk * n_cols * sizeof(double));
+    if (rc) return rc;
+    k_colsum_partial<<<nblk, 256, 0, st>>>(per_user_dev, n_list, (int)n_cols, (double *)ctx->partial.p, row_list_dev);
+    k_colsum_fold<<<(unsigned)n_cols, 256, 0, st>>>((const double *)ctx->partial.p, nblk, (int)n_cols, sums_dev);
+    ctx->launches += 2;
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
+int skr_topk_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64_t n_items, int64_t ld, int top_k, int32_t *topk_idx_dev,
+                    float *topk_val_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!scores_dev || n_rows <= 0 || (!topk_idx_dev && !topk_val_dev)) return fail(ctx, SKR_ERR_INVALID, "topk_scores: empty input / no output");
+    if (top_k < 1 || top_k > K2_MAX_K) return fail(ctx, SKR_ERR_UNSUPPORTED, "top_k=%d not in [1,%d]", top_k, K2_MAX_K);
+    if (n_items < top_k) return fail(ctx, SKR_ERR_INVALID, "n_items=%lld < top_k=%d", (long long)n_items, top_k);
+    if (n_items > 0x7fffffffll - K2_CHUNK) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_items=%lld too large", (long long)n_items);
+    if (ld < n_items) return fail(ctx, SKR_ERR_INVALID, "ld=%lld < n_items=%lld", (long long)ld, (long long)n_items);
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure(ctx, ctx->keys, (size_t)n_rows * top_k * sizeof(u64));
+    if (rc) return rc;
+    k_topk_scores<<<(unsigned)n_rows, K2_THREADS, 0, st>>>(scores_dev, ld, (int)n_items, 0, nullptr, nullptr, top_k, (u64 *)ctx->keys.p);
+    const int64_t nk = n_rows * top_k;
+    k_unpack_keys<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>((const u64 *)ctx->keys.p, nk, topk_idx_dev, topk_val_dev);
+    ctx->launches += 2;
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
+int skr_topk_scores_host(skr_ctx *ctx, const float *scores_host, int64_t n_rows, int64_t n_items, int64_t ld, int top_k,
+                         int32_t *topk_idx_host, float *topk_val_host, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (!scores_host || n_rows <= 0 || n_items <= 0 || ld < n_items || top_k < 1) return fail(ctx, SKR_ERR_INVALID, "topk_scores_host: bad arguments");
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure(ctx, ctx->stage_a, (size_t)n_rows * n_items * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->out_idx, (size_t)n_rows * top_k * sizeof(int32_t)))) return rc;
+    if ((rc = ensure(ctx, ctx->stage_c, (size_t)n_rows * top_k * sizeof(float)))) return rc;
+    SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_a.p, (size_t)n_items * sizeof(float), scores_host, (size_t)ld * sizeof(float),
+                                    (size_t)n_items * sizeof(float), (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    rc = skr_topk_scores(ctx, (const float *)ctx->stage_a.p, n_rows, n_items, n_items, top_k, (int32_t *)ctx->out_idx.p, (float *)ctx->stage_c.p, stream);
+    if (rc) return rc;
+    if (topk_idx_host) SKR_CUDA(ctx, cudaMemcpyAsync(topk_idx_host, ctx->out_idx.p, (size_t)n_rows * top_k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (topk_val_host) SKR_CUDA(ctx, cudaMemcpyAsync(topk_val_host, ctx->stage_c.p, (size_t)n_rows * top_k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SKR_CUDA(ctx, cudaStreamSynchronize(st));
+    return SKR_OK;
+}
+
 int skr_eval_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64_t n_items, int64_t ld, int64_t row0,
                     const int32_t *metric_ids, int n_metrics, int top_k, int32_t *topk_idx_dev, float *topk_val_dev,
                     float *per_user_dev, double *sums_dev, void *stream)

@@ -53,6 +53,62 @@ def _dict_to_csr(users, d, col_range=None):
     return indptr, np.ascontiguousarray(indices, dtype=np.int32)
 
 
+class _LazyRows(object):
+    """Read-only {user: items} view of a CSR (what code that pokes at `user_pos_train` / `user_pos_test`
+    expects) without materialising a dict of arrays."""
+
+    def __init__(self, indptr, indices, keys=None):
+        self.indptr, self.indices = indptr, indices
+        self._keys = keys  # None: every row
+
+    def __len__(self):
+        return int(self.indptr.size - 1) if self._keys is None else int(self._keys.size)
+
+    def __contains__(self, u):
+        u = int(u)
+        return 0 <= u < self.indptr.size - 1 and (self._keys is None or self.indptr[u + 1] > self.indptr[u])
+
+    def __getitem__(self, u):
+        if u not in self:
+            raise KeyError(u)
+        return self.indices[self.indptr[u]:self.indptr[u + 1]]
+
+    def keys(self):
+        return (range(self.indptr.size - 1) if self._keys is None else self._keys.tolist())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def items(self):
+        return ((u, self[u]) for u in self.keys())
+
+
+def _csr_rows(indptr, indices, rows, col_range=None):
+    """rows of a CSR, in the given order -> (indptr int64, indices int32), vectorised"""
+    rows = np.asarray(rows, dtype=np.int64)
+    cnt = indptr[rows + 1] - indptr[rows]
+    optr = np.zeros(rows.size + 1, dtype=np.int64)
+    np.cumsum(cnt, out=optr[1:])
+    if optr[-1] == 0:
+        return optr, np.zeros(0, np.int32)
+    src = np.repeat(indptr[rows] - optr[:-1], cnt) + np.arange(optr[-1], dtype=np.int64)
+    oidx = indices[src]
+    if col_range is not None:
+        lo, hi = col_range
+        keep = (oidx >= lo) & (oidx < hi)
+        kept = np.bincount(np.repeat(np.arange(rows.size, dtype=np.int64), cnt)[keep], minlength=rows.size).astype(np.int64)
+        optr = np.zeros(rows.size + 1, dtype=np.int64)
+        np.cumsum(kept, out=optr[1:])
+        oidx = oidx[keep] - np.int32(lo)
+    return optr, np.ascontiguousarray(oidx, dtype=np.int32)
+
+
+def _rows_to_csr(users, d, col_range=None):
+    if isinstance(d, _LazyRows):
+        return _csr_rows(d.indptr, d.indices, users, col_range)
+    return _dict_to_csr(users, d, col_range)
+
+
 class _Plan(object):
     """Device state for one evaluated-user list: native context + CSRs of exactly those rows."""
 
@@ -64,11 +120,11 @@ class _Plan(object):
         self.n_items = n_items
         self.item_range = item_range
         self.ctx = _native.Context(device)
-        tp, ti = _dict_to_csr(users, test)
+        tp, ti = _rows_to_csr(users, test)
         self.ctx.set_test_csr(tp, ti, n_items)
         n_local = n_items if item_range is None else item_range[1] - item_range[0]
-        if train:
-            rp, ri = _dict_to_csr(users, train, item_range)
+        if train is not None and len(train) > 0:
+            rp, ri = _rows_to_csr(users, train, item_range)
             self.ctx.set_train_csr(rp, ri, n_local)
         else:
             self.ctx.set_train_csr(None, None, n_local)
@@ -144,6 +200,30 @@ class RankingEvaluator(object):
         self.shard_users = shard_users
         self.process_group = process_group
         self.last_stats = {}
+
+    @classmethod
+    def from_csr(cls, train_csr, test_csr, **kwargs):
+        """Build the evaluator straight from interaction matrices, bypassing dict-of-arrays.
+
+        `train_csr` / `test_csr`: scipy.sparse CSR matrices [num_users, num_items] (what
+        `ImplicitFeedback.to_csr_matrix()` gives, dataset.py:131-156) or `(indptr, indices)` pairs;
+        `train_csr` may be None.  Evaluated users = rows with at least one test item, ascending -- the
+        order `to_user_dict()` produces (dataset.py:153-155).  At 10^6 users the reference's dicts of
+        small arrays dominate set-up time; here nothing is built per user in Python."""
+        def split(m):
+            if m is None:
+                return None
+            if hasattr(m, "indptr") and hasattr(m, "indices"):
+                return np.asarray(m.indptr, dtype=np.int64), np.asarray(m.indices, dtype=np.int32)
+            ip, ix = m
+            return np.asarray(ip, dtype=np.int64), np.asarray(ix, dtype=np.int32)
+        tr, te = split(train_csr), split(test_csr)
+        users = np.flatnonzero(np.diff(te[0]) > 0)
+        assert users.size > 0, "'test_csr' can be empty."
+        self = cls(None, _LazyRows(te[0], te[1], users), **kwargs)
+        self.user_pos_train = _LazyRows(tr[0], tr[1], None) if tr is not None else dict()
+        self._csr = (tr, te)
+        return self
 
     def set_train_data(self, user_train_dict: Optional[Dict[int, np.ndarray]] = None):
         self.user_pos_train = user_train_dict if user_train_dict is not None else dict()
@@ -259,6 +339,45 @@ class RankingEvaluator(object):
         final_results = final_results[:, self.top_show - 1]
         final_results = np.reshape(final_results, [-1])
         return MetricReport(self.metrics_list, final_results)
+
+    def evaluate_groups(self, model, groups) -> List[MetricReport]:
+        """One evaluation for several user groups (reference: `evaluate_group`, base.py:66-71, runs
+        `evaluate(group.users)` once per group -- 4 extra full passes for the activity groups of
+        dataset.py:707-765).  `groups`: iterables of user ids.  The union of the groups' test users is
+        evaluated once with the per-user metric block kept on the device; each group's report is the
+        float64 mean of its users' rows.  Same numbers as `[evaluate(model, g) for g in groups]`."""
+        import torch
+        groups = [[u for u in g if u in self.user_pos_test] for g in groups]
+        union, pos = [], {}
+        for g in groups:
+            for u in g:
+                if u not in pos:
+                    pos[u] = len(union)
+                    union.append(u)
+        K, M = self.max_top, self.metrics_num
+        MK = M * K
+        if not union:
+            return [MetricReport(self.metrics_list, np.zeros(M * len(self.top_show), np.float32)) for _ in groups]
+        dev = torch.device("cuda", self._device_index())
+        key = ("subset", hash(tuple(union)), len(union), 0, 1, "groups")
+        with torch.cuda.device(dev):
+            if hasattr(model, "eval_embeddings"):
+                _, _, per_user = self._evaluate_fused(model, union, key, dev, True)
+            else:
+                _, _, per_user = self._evaluate_predict(model, union, key, dev, True)
+            plan = self._plans[key]
+            sums = torch.zeros((len(groups), MK), dtype=torch.float64, device=dev)
+            for gi, g in enumerate(groups):
+                if g:
+                    rows = torch.from_numpy(np.fromiter((pos[u] for u in g), dtype=np.int32, count=len(g))).to(dev)
+                    plan.ctx.colsum_rows(per_user, rows, sums[gi])
+            host = sums.cpu().numpy()
+        from . import dist
+        out = []
+        for gi, g in enumerate(groups):
+            res = dist.finalize_means(host[gi], len(g)).reshape(M, K)[:, self.top_show - 1].reshape(-1)
+            out.append(MetricReport(self.metrics_list, res))
+        return out
 
     # ------------------------------------------------------------------------------------------
     def _to_dev(self, x, dev):

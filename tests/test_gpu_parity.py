@@ -552,3 +552,95 @@ def test_item_sharded_evaluator_two_gpus_nccl(torch_cuda, tmp_path):
     per, _ = oracle.evaluate_dicts(plain.predict, data["train"], data["test"], [1, 2, 3, 4, 5], 50)
     expect = oracle.mean_f32(per).reshape(5, 50)[:, np.array([10, 50]) - 1].ravel()
     assert np.max(np.abs(got["items"] - expect)) <= TOL_METRIC
+
+
+# ---- rows next to the path: pyx_sort-style top-k, adapters, grouped evaluation, CSR ingestion ---
+def test_top_k_and_arg_top_k_like_pyx_sort(torch_cuda):
+    from skrec_b200 import arg_top_k, top_k
+    g = np.random.default_rng(3)
+    a = _tie_free(g, 37, 3001)
+    exp_idx = np.argsort(-a, axis=1, kind="stable")[:, :20]
+    assert np.array_equal(arg_top_k(a, 20, 4), exp_idx)
+    assert np.array_equal(top_k(a, 20), np.take_along_axis(a, exp_idx, 1))
+    v = a[5]
+    assert np.array_equal(arg_top_k(v, 7), exp_idx[5, :7]) and top_k(v, 7).shape == (7,)
+    ties = np.array([[1, 5, 5, 2, 5, 0]], np.int32)
+    assert arg_top_k(ties, 4).tolist() == [[1, 2, 4, 3]]  # equal values: lower index first
+    assert top_k(ties, 4).tolist() == [[5, 5, 5, 2]] and top_k(ties, 4).dtype == np.int32
+    ref = oracle.ref_module("pyx_sort")  # the compiled reference (pyx_sort.pyx:151-187) agrees on tie-free input
+    if ref is not None:
+        assert np.array_equal(ref.pyx_arg_top_k(a, 20, 4), arg_top_k(a, 20, 4))
+        assert np.array_equal(ref.pyx_top_k(a, 20, 4), top_k(a, 20, 4))
+    with pytest.raises(TypeError):
+        arg_top_k(a.astype(np.float64), 3)
+    with pytest.raises(ValueError):
+        arg_top_k(np.zeros((2, 2, 2), np.float32), 1)
+
+
+def test_adapters_through_the_evaluator(torch_cuda):
+    from skrec_b200 import RankingEvaluator, adapters, synth
+    data = synth.make(users=400, items=2500, d=32, nnz_train=9000, nnz_test=2500, seed=21, bias=True)
+    metric, top_k = ["Precision", "Recall", "MAP", "NDCG", "MRR"], [5, 20]
+    ids = [synth.METRIC_IDS[m] for m in metric]
+    cols = np.array(top_k) - 1
+
+    def expect(score_fn):
+        per, _ = oracle.evaluate_dicts(score_fn, data["train"], data["test"], ids, max(top_k))
+        return oracle.mean_f32(per).reshape(len(ids), max(top_k))[:, cols].ravel()
+
+    ue, ie, b = data["user_emb"], data["item_emb"], data["bias"]
+    half = ue.shape[1] // 2
+    cases = {
+        "dot": (adapters.dot_product(ue, ie, b), lambda us: ue[us] @ ie.T + b),
+        "two_tower": (adapters.two_tower_sum(ue[:, :half], ie[:, :half], ue[:, half:], ie[:, half:]), lambda us: ue[us] @ ie.T),
+        "cml": (adapters.neg_euclidean(ue, ie), lambda us: -np.linalg.norm(ue[us][:, None, :].astype(np.float64) - ie[None].astype(np.float64), axis=-1).astype(np.float32)),
+    }
+    for name, (scorer, fn) in cases.items():
+        for dev_tables in (False, True):
+            if dev_tables:
+                scorer.user_table, scorer.item_table = scorer.user_table.cuda(), scorer.item_table.cuda()
+                scorer.bias = None if scorer.bias is None else scorer.bias.cuda()
+            ev = RankingEvaluator(data["train"], data["test"], metric=metric, top_k=top_k, device=0)
+            got = np.array(list(ev.evaluate(scorer).values()), np.float32)
+            assert ev.last_stats["path"].startswith("fused:"), name
+            assert np.max(np.abs(got - expect(fn))) <= TOL_METRIC, (name, dev_tables)
+
+
+def test_evaluate_groups_equals_one_evaluation_per_group(torch_cuda):
+    from skrec_b200 import RankingEvaluator, adapters, synth
+    data = synth.make(users=600, items=3000, d=64, nnz_train=15000, nnz_test=4000, seed=31, bias=False)
+    users = list(data["test"].keys())
+    deg = np.array([len(data["train"].get(u, ())) for u in users])
+    order = np.argsort(deg, kind="stable")
+    groups = [[users[i] for i in part] for part in np.array_split(order, 4)] + [[10 ** 9], users[:5] + users[:5]]
+    for model in (adapters.dot_product(data["user_emb"], data["item_emb"]), synth.PredictOnlyModel(data["user_emb"], data["item_emb"], None)):
+        ev = RankingEvaluator(data["train"], data["test"], metric=["Recall", "NDCG"], top_k=[10, 20], device=0, batch_size=128)
+        reports = ev.evaluate_groups(model, groups)
+        assert len(reports) == len(groups)
+        for g, rep in zip(groups, reports):
+            one = ev.evaluate(model, test_users=g)
+            a, b_ = np.array(list(rep.values())), np.array(list(one.values()))
+            assert rep.metrics_str == one.metrics_str
+            if len([u for u in g if u in data["test"]]) == 0:
+                continue
+            assert np.max(np.abs(a - b_)) <= 2e-7
+
+
+def test_from_csr_equals_dict_construction(torch_cuda):
+    import scipy.sparse as sp
+    from skrec_b200 import RankingEvaluator, adapters, synth
+    data = synth.make(users=500, items=2000, d=64, nnz_train=12000, nnz_test=3000, seed=41, bias=True)
+
+    def to_csr(d):
+        rows = np.concatenate([np.full(len(v), u) for u, v in d.items()])
+        cols = np.concatenate(list(d.values()))
+        return sp.csr_matrix((np.ones(rows.size, np.float32), (rows, cols)), shape=(data["users"], data["items"]))
+    model = adapters.dot_product(data["user_emb"], data["item_emb"], data["bias"])
+    kw = dict(metric=["Precision", "NDCG", "MRR"], top_k=[10, 50], device=0)
+    a = RankingEvaluator(data["train"], data["test"], **kw).evaluate(model)
+    b = RankingEvaluator.from_csr(to_csr(data["train"]), to_csr(data["test"]), **kw).evaluate(model)
+    assert np.array_equal(np.array(list(a.values())), np.array(list(b.values())))
+    sub = list(data["test"].keys())[5:200:3]
+    a = RankingEvaluator(data["train"], data["test"], **kw).evaluate(model, test_users=sub)
+    b = RankingEvaluator.from_csr(to_csr(data["train"]), to_csr(data["test"]), **kw).evaluate(model, test_users=sub)
+    assert np.array_equal(np.array(list(a.values())), np.array(list(b.values())))

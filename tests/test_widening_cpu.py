@@ -1,0 +1,99 @@
+"""Host logic of the rows next to the hot path: score-provider adapters (algebra against the
+reference models' scoring expressions), CSR ingestion helpers, the lazy {user: items} view.  No GPU."""
+import numpy as np
+import pytest
+import torch
+
+from skrec_b200 import adapters
+from skrec_b200 import evaluator as ev
+
+
+def _g(seed=0):
+    return np.random.default_rng(seed)
+
+
+def test_dot_product_and_bias_match_bprmf_expression():
+    g = _g()
+    U, I, b = g.standard_normal((7, 8)).astype(np.float32), g.standard_normal((11, 8)).astype(np.float32), g.standard_normal(11).astype(np.float32)
+    sc = adapters.dot_product(U, I, b)
+    users = [3, 0, 6]
+    uv, iv, bias = sc.eval_embeddings(users)
+    assert torch.equal(uv, torch.from_numpy(U[users])) and iv.shape == (11, 8)
+    want = U[users] @ I.T + b  # BPRMF.py:84-88
+    assert np.allclose(sc.predict(users), want, atol=1e-6)
+    assert np.allclose((uv @ iv.T + bias).numpy(), want, atol=1e-6)
+
+
+def test_two_tower_sum_equals_selfcf_expression():
+    g = _g(1)
+    u_on, u_tg = g.standard_normal((5, 4)).astype(np.float32), g.standard_normal((5, 4)).astype(np.float32)
+    i_on, i_tg = g.standard_normal((9, 4)).astype(np.float32), g.standard_normal((9, 4)).astype(np.float32)
+    sc = adapters.two_tower_sum(u_on, i_tg, u_tg, i_on)
+    want = u_on @ i_tg.T + u_tg @ i_on.T  # SelfCF.py:235-241
+    assert np.allclose(sc.predict(list(range(5))), want, atol=1e-5)
+    assert sc.eval_embeddings([1, 2])[0].shape == (2, 8)
+
+
+def test_neg_euclidean_is_rank_equivalent_to_cml_expression():
+    g = _g(2)
+    U, I = g.standard_normal((6, 5)).astype(np.float32), g.standard_normal((40, 5)).astype(np.float32)
+    sc = adapters.neg_euclidean(U, I)
+    got = sc.predict(list(range(6)))
+    want = -np.linalg.norm(U[:, None, :] - I[None, :, :], axis=-1)  # CML.py:152
+    assert np.array_equal(np.argsort(-got, axis=1, kind="stable"), np.argsort(-want, axis=1, kind="stable"))
+
+
+def test_decoder_layer_and_item_scores_and_user_index():
+    g = _g(3)
+    H, W, c = g.standard_normal((4, 6)).astype(np.float32), g.standard_normal((10, 6)).astype(np.float32), g.standard_normal(10).astype(np.float32)
+    sc = adapters.decoder_layer(H, W, c, user_index={42: 0, 7: 1, 9: 2, 1: 3})
+    assert np.allclose(sc.predict([9, 42]), H[[2, 0]] @ W.T + c, atol=1e-6)  # MultVAE.py:138-141
+    pop = adapters.item_scores(np.arange(10, dtype=np.float32), num_users=3)
+    assert np.array_equal(pop.predict([0, 2]), np.tile(np.arange(10, dtype=np.float32), (2, 1)))  # Pop.py:41-44
+
+
+def test_item_shard_protocol_slices_rows():
+    from skrec_b200 import dist
+    g = _g(4)
+    U, I, b = g.standard_normal((3, 4)).astype(np.float32), g.standard_normal((10, 4)).astype(np.float32), g.standard_normal(10).astype(np.float32)
+    sc = adapters.dot_product(U, I, b)
+    uv, rows, bias, n = sc.eval_embeddings([0, 1, 2], item_shard=(1, 3))
+    lo, hi = dist.shard_range(10, 1, 3)
+    assert n == 10 and torch.equal(rows, torch.from_numpy(I[lo:hi])) and torch.equal(bias, torch.from_numpy(b[lo:hi]))
+
+
+def test_csr_rows_and_lazy_view():
+    indptr = np.array([0, 2, 2, 5, 6], np.int64)
+    indices = np.array([4, 1, 7, 3, 9, 0], np.int32)
+    p, i = ev._csr_rows(indptr, indices, [2, 0, 3])
+    assert p.tolist() == [0, 3, 5, 6] and i.tolist() == [7, 3, 9, 4, 1, 0]
+    p, i = ev._csr_rows(indptr, indices, [2, 0, 3], (3, 8))
+    assert p.tolist() == [0, 2, 3, 3] and i.tolist() == [4, 0, 1]
+    p, i = ev._csr_rows(indptr, indices, [1])
+    assert p.tolist() == [0, 0] and i.size == 0
+    lazy = ev._LazyRows(indptr, indices, np.array([0, 2, 3]))
+    assert len(lazy) == 3 and 1 not in lazy and 2 in lazy and 17 not in lazy
+    assert lazy[2].tolist() == [7, 3, 9] and list(lazy.keys()) == [0, 2, 3]
+    with pytest.raises(KeyError):
+        lazy[1]
+    every = ev._LazyRows(indptr, indices)
+    assert len(every) == 4 and 1 in every and every[1].size == 0
+
+
+def test_from_csr_builds_the_same_evaluator_state_without_a_gpu():
+    import scipy.sparse as sp
+    g = _g(5)
+    tr = sp.random(30, 50, density=0.1, random_state=1, format="csr")
+    te = sp.random(30, 50, density=0.05, random_state=2, format="csr")
+    e = ev.RankingEvaluator.from_csr(tr, te, metric=["NDCG", "Recall"], top_k=[5, 10])
+    users = np.flatnonzero(np.diff(te.indptr) > 0).tolist()
+    assert e._all_users == users and e.max_top == 10 and e.metrics == [4, 2]
+    assert e.metrics_list == ["NDCG@5", "NDCG@10", "Recall@5", "Recall@10"]
+    u = users[0]
+    assert np.array_equal(e.user_pos_test[u], te.indices[te.indptr[u]:te.indptr[u + 1]])
+    assert np.array_equal(e.user_pos_train[u], tr.indices[tr.indptr[u]:tr.indptr[u + 1]])
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        if not torch.cuda.is_available():
+            e.evaluate(adapters.dot_product(np.zeros((30, 4), np.float32), np.zeros((50, 4), np.float32)))
+        else:
+            raise RuntimeError("gpu present")
