@@ -172,12 +172,10 @@ def run_ours(args):
         td.init_process_group("nccl", device_id=dev)
 
     cfg = dict(synth.CONFIGS[args.config])
-    cfg["seed"] = cfg["seed"] + 1000 * rank if world > 1 else cfg["seed"]  # each rank: its own user slice
+    if world > 1:  # each rank: its own user slice of one replicated catalogue
+        cfg["item_seed"] = cfg["seed"] + 7
+        cfg["seed"] = cfg["seed"] + 1000 * rank
     data = synth.make(device=dev, **cfg)
-    if world > 1:  # the item table (and bias) is replicated: rank 0's
-        it = torch.from_numpy(data["item_emb"]).to(dev)
-        td.broadcast(it, 0)
-        data["item_emb"] = it.cpu().numpy()
     U, I, d = data["users"], data["items"], data["d"]
     K = max(cfg["top_k"])
     ids = [synth.METRIC_IDS[m] for m in cfg["metric"]]

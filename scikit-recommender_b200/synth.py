@@ -91,17 +91,20 @@ def _draw_distinct(g, cdf, need, n_items):
     return indptr, out
 
 
-def make(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_pool=200, device=None, **_unused):
+def make(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_pool=200, device=None, item_seed=None, **_unused):
     """Generate one workload.  Returns a dict: user_emb [U,d] f32, item_emb [I,d] f32, bias [I] f32 or
     None, train/test OrderedDict {user: int32 array} (keys ascending), and the CSR forms
-    train_indptr/train_indices/test_indptr/test_indices (rows = users 0..U-1)."""
+    train_indptr/train_indices/test_indptr/test_indices (rows = users 0..U-1).
+    item_seed: draw the item table (and bias) from their own generator -- ranks of a user-sharded run pass
+    the same item_seed and different `seed`s: one replicated catalogue, different user slices."""
     import torch
 
     g = np.random.default_rng(seed)
     U, I = int(users), int(items)
     user_emb = (g.standard_normal((U, d)) * 0.1).astype(np.float32)
-    item_emb = (g.standard_normal((I, d)) * 0.1).astype(np.float32)
-    b = (g.standard_normal(I) * 0.01).astype(np.float32) if bias else None
+    gi = g if item_seed is None else np.random.default_rng(item_seed)
+    item_emb = (gi.standard_normal((I, d)) * 0.1).astype(np.float32)
+    b = (gi.standard_normal(I) * 0.01).astype(np.float32) if bias else None
 
     deg_train = _degrees(g, U, nnz_train, 1, max(1, I // 4))
     deg_test = _degrees(g, U, nnz_test, 1, max(1, I // 8))
