@@ -298,7 +298,7 @@ def run_ours(args):
     k_ms = float(np.mean(kernel_ms))
     flops = 2.0 * U * I * d
     achieved = flops / (k_ms * 1e-3) / 1e12
-    passes = {"tcgen05_3xtf32": 3, "tcgen05_1xtf32": 1}.get(ctx.last_fused_kernel, 1)
+    passes = {"tcgen05_3xtf32": 3, "tcgen05_1xtf32": 1, "tcgen05_tf32r": 1}.get(ctx.last_fused_kernel, 1)
     if ctx.last_fused_kernel.startswith("tcgen05"):
         peak = pk["bf16"] / 2.0
         peak_note = "TF32 dense = 1/2 of the %s cuBLAS bf16 burst peak (%.1f TFLOP/s) in MEASURED_PEAKS.json" % (pk["src"], pk["bf16"])
@@ -334,7 +334,8 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32x3 (fp32-grade)" if passes == 3 else ("tf32" if ctx.last_fused_kernel.startswith("tcgen05") else "f32"),
+            "dtype": "tf32x3 (fp32-grade)" if passes == 3 else ("tf32 candidates + f32 re-scoring (fp32-exact)" if ctx.last_fused_kernel == "tcgen05_tf32r"
+                                                                else ("tf32" if ctx.last_fused_kernel.startswith("tcgen05") else "f32")),
             "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.config, cfg["name"]), "users_per_gpu": U, "items": I, "d": d, "train_nnz": int(data["train_indptr"][-1]),
                        "top_k": cfg["top_k"], "metrics": cfg["metric"], "parallelism": "user-sharded x%d, item table replicated, metric-sum all-reduce" % world,
@@ -354,7 +355,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3a", "c3b"])
-    ap.add_argument("--precision", default="3xtf32", choices=["auto", "3xtf32", "fp32", "1xtf32"])
+    ap.add_argument("--precision", default="3xtf32", choices=["auto", "3xtf32", "fp32", "1xtf32", "tf32r"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.steps = max(1, args.steps)

@@ -62,6 +62,8 @@ extern "C" {
 #define SKR_PREC_FP32 1   /* FP32 FMA on CUDA cores (exact products, sequential k order) */
 #define SKR_PREC_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split, 3 products, FP32 accumulate */
 #define SKR_PREC_1XTF32 3 /* single TF32 pass; NOT reference-grade, for measurement only */
+#define SKR_PREC_TF32R 4  /* single TF32 pass to find candidates inside a rigorous error band, then exact FP32
+                           * re-scoring of the survivors: results equal SKR_PREC_FP32 bit for bit */
 
 typedef struct skr_ctx skr_ctx;
 

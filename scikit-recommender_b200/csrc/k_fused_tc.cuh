@@ -663,8 +663,21 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 // the largest T with #{v >= T} >= r, built bit by bit over the monotone integer image of the floats.
 // With fewer than r finite entries it is -inf (everything is a candidate).  A list that was truncated at
 // TC_R can only lower the estimate, i.e. admit more candidates.
+//
+// precision "tf32r" (eps2_out != null): the main pass scores in ONE TF32 pass and k_select_cands re-scores
+// the survivors exactly, so the threshold is lowered by 2 eps, eps bounding |s_tf32 - s_fp32| for every item
+// of the row:
+//   operands rounded to TF32 (rna): |hi(x) - x| <= 2^-11 |x|, so each product is off by <= (2^-10 + 2^-22) |u_k i_k|;
+//   FP32 accumulation in the tensor core, order and rounding mode unspecified: <= d 2^-22 sum |u_k i_k| (a
+//   very loose bound: every one of <= d additions may lose a full ulp of the running sum, twice);
+//   the exact kernels' own FMA chain: <= d 2^-24 sum |u_k i_k|; the two bias additions: 2^-23 |score|;
+//   sum |u_k i_k| <= ||u|| max_j ||i_j|| (Cauchy-Schwarz), |score| <= that + max |b|.
+// eps = 1.25 [(2^-10 + (1.25 d + 2) 2^-22) ||u|| N_max + 2^-22 B_max]: the 1.25 covers the FP32 evaluation of
+// the norms and leaves slack (tests assert the observed error stays below eps / 2).  eps_coef carries the
+// bracket's first factor, stats = {N_max^2, B_max} from k_item_stats.
 __global__ void __launch_bounds__(256)
-k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr)
+k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
+             int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
@@ -680,7 +693,47 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
         const int cnt = __reduce_add_sync(0xffffffffu, (int)(a >= cand) + (int)(b >= cand));
         if (cnt >= r) T = cand;
     }
-    if (lane == 0) thr[row] = unord_f32(T);
+    float t0 = unord_f32(T);
+    if (eps2_out != nullptr) {
+        float ss = 0.0f;
+        for (int k = lane; k < d; k += 32) {
+            const float v = __ldg(U + row * ld_u + k);
+            ss = fmaf(v, v, ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float eps = 1.25f * (eps_coef * sqrtf(ss) * sqrtf(__ldg(stats)) + 2.384185791015625e-07f * __ldg(stats + 1));
+        float e2 = 2.0f * eps;
+        const float INF = __int_as_float(0x7f800000);
+        if (!(e2 < INF)) e2 = INF;  // overflow / NaN operands: collect everything, the exact kernel settles the row
+        t0 = (e2 < INF) ? __fsub_rd(t0, e2) : -INF;
+        if (lane == 0) eps2_out[row] = e2;
+    }
+    if (lane == 0) thr[row] = t0;
+}
+
+// max_j ||item_j||^2 and max_j |bias_j| (non-negative floats order like their bit patterns: atomicMax on uint)
+__global__ void __launch_bounds__(256)
+k_item_stats(const float *__restrict__ V, int64_t ld_v, int64_t n_items, int d, const float *__restrict__ bias, uint32_t *__restrict__ stats)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float best = 0.0f, bb = 0.0f;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n_items; row += (int64_t)gridDim.x * 8) {
+        float ss = 0.0f;
+        for (int k = lane; k < d; k += 32) {
+            const float v = __ldg(V + row * ld_v + k);
+            ss = fmaf(v, v, ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        best = fmaxf(best, ss);
+        if (bias != nullptr && lane == 0) bb = fmaxf(bb, fabsf(__ldg(bias + row)));
+    }
+    if (lane == 0) {
+        if (!(best == best)) best = __int_as_float(0x7f800000);
+        atomicMax(stats, __float_as_uint(best));
+        if (bias != nullptr) atomicMax(stats + 1, __float_as_uint(bb == bb ? bb : __int_as_float(0x7f800000)));
+    }
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------

@@ -13,6 +13,13 @@
 //   4. with the sorted keys still in registers (element e of lane l is rank e*32 + l) runs the metric
 //      recurrences of k_metrics.cuh on them and adds the row into the warp's float64 column sums -- the
 //      rank keys of a settled row never travel to HBM unless the caller asked for the top-K lists.
+// RESCORE (precision "tf32r"): the candidates' scores came from ONE TF32 pass and carry an error of at most
+// eps per score (bound derived in k_fused_tc.cuh at k_sample_thr).  The cut then only says where to look:
+// with >= K candidates scoring >= cut in TF32, the true K-th best exact score is >= cut - eps, so every
+// member of the true top-K has a TF32 score >= cut - 2 eps.  All candidates down to that bound (complete as
+// long as the bound is not below the collection threshold, else the row is re-done exactly) are re-scored
+// with the FP32 FMA chain of the exact kernels (k ascending, then the bias), and only those exact scores
+// decide membership, order, ties and the reported values: results equal precision="fp32" bit for bit.
 // Rows that cannot be settled here -- a sub-list overflowed, fewer than K candidates (threshold
 // estimate too high or fewer than K unmasked items), more candidates than the buffer, or more than
 // 32 PER values tied at the cut -- go on the fail list and are re-done exactly by k_row_exact.
@@ -24,16 +31,28 @@ namespace skr {
 
 constexpr int SEL_WARPS = 4;
 constexpr int SEL_MAX = 512;  // candidates a row may carry into the selection
+constexpr int SEL_MAX_D = 128;  // RESCORE keeps the user vector in shared memory (the tensor-core path has d <= 128)
 
-template <int PER>
+struct RescoreArgs {
+    const float *U; int64_t ld_u;   // user vectors of the call's rows
+    const float *V; int64_t ld_v;   // item vectors
+    int d;
+    const float *bias;              // or null
+    const float *thr_c;             // [n_rows] threshold the main pass collected with
+    const float *eps2;              // [n_rows] 2 eps of the row
+};
+
+template <int PER, bool RESCORE>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
                int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count,
                const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
                const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
-               float *__restrict__ topk_val_out, double *__restrict__ acc_out)
+               float *__restrict__ topk_val_out, double *__restrict__ acc_out, RescoreArgs R)
 {
     constexpr int CAP = 32 * PER;
+    constexpr int CAPS = RESCORE ? CAP / 2 : CAP;  // size at which the search for the cut stops
+    __shared__ float s_u[RESCORE ? SEL_WARPS : 1][RESCORE ? SEL_MAX_D : 1];
     __shared__ uint2 s_ent[SEL_WARPS][SEL_MAX];
     __shared__ uint32_t s_hist[SEL_WARPS][256];
     __shared__ u64 s_key[SEL_WARPS][CAP];
@@ -86,7 +105,7 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         // ---- 2. cut: smallest-known T (as offset from vmin) with K <= #{w >= T} <= CAP --------------
         uint32_t T = 0;  // n <= CAP: everything is sorted
         bool ok = true;
-        if (n > CAP) {
+        if (RESCORE || n > CAP) {  // RESCORE always needs a cut with >= K candidates above it
             const uint32_t range = vmax - vmin;
             int width_bits = 32 - __clz(range | 1u);  // values w = ord - vmin lie in [0, 2^width_bits)
             uint32_t base = 0;                         // current bucket: [base, base + 2^width_bits)
@@ -128,7 +147,7 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                 c_above = __shfl_sync(0xffffffffu, c_above, owner);
                 c_with = __shfl_sync(0xffffffffu, c_with, owner);
                 base += (uint32_t)j << shift;
-                if (c_with <= CAP) { ok = true; break; }
+                if (c_with <= CAPS) { ok = true; break; }
                 if (shift == 0) break;  // more than CAP values tied around the K-th: exact path
                 above = c_above;
                 width_bits = shift;
@@ -142,6 +161,18 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         }
 
         // ---- 3. compact the survivors into rank keys, sort ------------------------------------------
+        uint32_t cut = vmin + T;
+        if (RESCORE && ok) {
+            // every candidate down to cut - 2 eps must be looked at; complete only if the main pass collected that far
+            const float lb = __fsub_rd(unord_f32(cut), __ldg(R.eps2 + row));
+            ok = lb >= __ldg(R.thr_c + row);
+            const uint32_t ol = ord_f32(lb);
+            T = (ol > vmin) ? ol - vmin : 0u;
+            if (!ok) {
+                if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                continue;
+            }
+        }
 #pragma unroll
         for (int e = 0; e < PER; ++e) skey[e * 32 + lane] = 0ull;
         __syncwarp();
@@ -155,17 +186,52 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                 take = (e.x - vmin) >= T;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, take);
-            if (take) skey[m + __popc(bal & lt_mask)] = ((u64)e.x << 32) | (u64)(~e.y);
+            const int pos = m + __popc(bal & lt_mask);
+            if (take && pos < CAP) skey[pos] = ((u64)e.x << 32) | (u64)(~e.y);
             m += __popc(bal);
+        }
+        if (RESCORE) {
+            if (m > CAP) {  // too many candidates inside the error band
+                if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                continue;
+            }
+            // exact scores of the survivors: the FMA chain of RowDot::get4 (k_scores.cuh), operation for operation
+            float *u = s_u[warp];
+            for (int k = lane; k < R.d; k += 32) u[k] = __ldg(R.U + row * R.ld_u + k);
+            __syncwarp();
+            const bool vec_ok = ((R.ld_v & 3) == 0) && ((reinterpret_cast<uintptr_t>(R.V) & 15) == 0);
+            uint32_t omin = 0xffffffffu, omax = 0u;
+            for (int i = lane; i < m; i += 32) {
+                const uint32_t item = ~(uint32_t)skey[i];
+                const float *it = R.V + (int64_t)item * R.ld_v;
+                float a = 0.0f;
+                int k = 0;
+                if (vec_ok) {
+                    for (; k + 4 <= R.d; k += 4) {
+                        const float4 x = __ldg(reinterpret_cast<const float4 *>(it + k));
+                        a = fmaf(u[k], x.x, a);
+                        a = fmaf(u[k + 1], x.y, a);
+                        a = fmaf(u[k + 2], x.z, a);
+                        a = fmaf(u[k + 3], x.w, a);
+                    }
+                }
+                for (; k < R.d; ++k) a = fmaf(u[k], __ldg(it + k), a);
+                if (R.bias != nullptr) a += __ldg(R.bias + item);
+                const u64 key = make_key(a, item);
+                skey[i] = key;
+                omin = min(omin, (uint32_t)(key >> 32));
+                omax = max(omax, (uint32_t)(key >> 32));
+            }
+            cut = __reduce_min_sync(0xffffffffu, omin);
+            vmax = __reduce_max_sync(0xffffffffu, omax);
         }
         __syncwarp();
         // Sort.  Fast path: the survivors' scores span less than 2^(32 - BITS) float steps above the cut, so
         // (steps above the cut + 1) << BITS | slot is a 32-bit key with the same order as long as no two
         // survivors have equal scores; the 64-bit rank keys are fetched back by slot afterwards.  Rows with
         // a wider span or with tied scores take the 64-bit network (item id decides ties).
-        constexpr int BITS = (PER <= 2) ? 6 : 7;
+        constexpr int BITS = (PER <= 2) ? 6 : (PER <= 4 ? 7 : 8);
         static_assert((1 << BITS) >= CAP, "slot bits");
-        const uint32_t cut = vmin + T;
         u64 v[PER];
         bool fast = (vmax - cut) < ((1u << (32 - BITS)) - 2u);
         if (fast) {

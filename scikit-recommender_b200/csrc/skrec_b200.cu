@@ -66,7 +66,7 @@ struct skr_ctx {
     float *d_idcg = nullptr;  // iDCG after n terms (metric.h:82), host-accumulated
     int disc_n = 0;
     // workspace, grow-only
-    Buf trace, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
+    Buf trace, stats, eps2, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
     int64_t launches = 0;
     const char *last_fused = "none";
@@ -253,16 +253,18 @@ struct ExactArgs {
 
 int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
                        const MetricIds &m, int K, const ExactArgs &E, int32_t *fail_list, int *fail_count, int32_t *topk_idx,
-                       float *topk_val, float *per_user, double *sums, u64 *keys_only, cudaStream_t st)
+                       float *topk_val, float *per_user, double *sums, u64 *keys_only, const RescoreArgs &RA, cudaStream_t st)
 {
+    const bool rescore = RA.U != nullptr;
+    // kernel instantiation: the sort capacity is 64 / 128 keys (K <= 64 / 128); re-scoring doubles it (error band)
+    typedef void (*SelKernel)(const uint2 *, const uint32_t *, int, int, int, int, int64_t, int64_t, u64 *, int32_t *, int *, const int64_t *,
+                              const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs);
+    SelKernel sel = rescore ? (K <= 64 ? (SelKernel)k_select_cands<4, true> : (SelKernel)k_select_cands<8, true>)
+                            : (K <= 64 ? (SelKernel)k_select_cands<2, false> : (SelKernel)k_select_cands<4, false>);
     if (keys_only != nullptr) {  // per-shard lists: sorted keys out, no metrics
         const int g = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
-        if (K <= 64)
-            k_select_cands<2><<<g, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr,
-                                                            nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
-        else
-            k_select_cands<4><<<g, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr,
-                                                            nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        sel<<<g, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m, nullptr,
+                                          nullptr, nullptr, nullptr, nullptr, nullptr, RA);
         k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
                                                                       E.tr_indptr, E.tr_idx, K, keys_only);
         ctx->launches += 2;
@@ -293,15 +295,9 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
         if (acc_k4 > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_k4));
     }
     const size_t dyn_sel = fused_sums ? acc_sel : 0;
-    if (K <= 64) {
-        if (dyn_sel > 16 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_select_cands<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel));
-        k_select_cands<2><<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count,
-                                                                 ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc);
-    } else {
-        if (dyn_sel > 16 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_select_cands<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel));
-        k_select_cands<4><<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count,
-                                                                 ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc);
-    }
+    if (dyn_sel > 8 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel));
+    sel<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
+                                                ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA);
     k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
                                                                   E.tr_indptr, E.tr_idx, K, keys);
     k_metrics<<<g_fix, K4_WARPS * 32, fused_sums ? acc_k4 : 0, st>>>(keys, nullptr, K, n_rows, row0, fail_list, fail_count, ctx->d_te_indptr,
@@ -458,7 +454,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
-                   &ctx->fail_list, &ctx->trace};
+                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2};
     for (Buf *b : bufs) free_dev(b->p);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
@@ -738,7 +734,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
     if (ctx->has_train && (row0 < 0 || row0 + n_rows > ctx->tr_rows))
         return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the train CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->tr_rows);
     if (ctx->has_train && ctx->tr_items != n_items) return fail(ctx, SKR_ERR_INVALID, "train CSR was built for %lld items, item table has %lld", (long long)ctx->tr_items, (long long)n_items);
-    if (precision < SKR_PREC_AUTO || precision > SKR_PREC_1XTF32) return fail(ctx, SKR_ERR_INVALID, "precision=%d", precision);
+    if (precision < SKR_PREC_AUTO || precision > SKR_PREC_TF32R) return fail(ctx, SKR_ERR_INVALID, "precision=%d", precision);
     SKR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int K = top_k;
@@ -747,7 +743,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
     const int nkb = (d + TC_KB - 1) / TC_KB;
     const bool tc_ok = (nkb <= 4) && (tc_smem_bytes() <= ctx->max_smem);
     bool use_tc = (precision != SKR_PREC_FP32) && tc_ok;
-    if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32))
+    if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32 || precision == SKR_PREC_TF32R))
         return fail(ctx, SKR_ERR_UNSUPPORTED, "tcgen05 path needs d <= 128 (d=%d)", d);
     if (!use_tc) {
         if ((d & 3) || (ld_u & 3) || (ld_i & 3) || ((uintptr_t)user_vecs_dev & 15) || ((uintptr_t)item_vecs_dev & 15))
@@ -842,11 +838,23 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.trace = nullptr;
         A.trace_cta = -1;
         A.trace_tiles = 0;
-        const int passes = (precision == SKR_PREC_1XTF32) ? 1 : 3;
+        const bool rescore = (precision == SKR_PREC_TF32R);
+        const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
+        float eps_coef = 0.0f;
+        if (rescore) {
+            if ((rc = ensure(ctx, ctx->stats, 2 * sizeof(float)))) return rc;
+            if ((rc = ensure(ctx, ctx->eps2, (size_t)n_rows * sizeof(float)))) return rc;
+            SKR_CUDA(ctx, cudaMemsetAsync(ctx->stats.p, 0, 2 * sizeof(float), st));
+            k_item_stats<<<(unsigned)std::min<int64_t>((n_items + 7) / 8, 4 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, bias_dev,
+                                                                                                   (uint32_t *)ctx->stats.p);
+            ctx->launches++;
+            eps_coef = (float)(ldexp(1.0, -10) + (1.25 * d + 2.0) * ldexp(1.0, -22));
+        }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)P.n_rt, st, mhi, mlo, A, P))) return rc;
-        k_sample_thr<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p);
+        k_sample_thr<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
+                                                                   (const float *)ctx->stats.p, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr);
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
             A.trace_tiles = P.tiles_per_chunk;
@@ -861,12 +869,14 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
         SKR_CUDA(ctx, cudaGetLastError());
-        ctx->last_fused = (passes == 3) ? "tcgen05_3xtf32" : "tcgen05_1xtf32";
+        ctx->last_fused = (passes == 3) ? "tcgen05_3xtf32" : (rescore ? "tcgen05_tf32r" : "tcgen05_1xtf32");
         ctx->last_plan = {n_samp, stride, r, cap, P.S, passes == 3 ? 4 : 8};
         ctx->ev_calls++;
         const ExactArgs E = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (int)n_items, tp, ti};
+        RescoreArgs RA = {nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr};
+        if (rescore) RA = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (const float *)ctx->thr.p, (const float *)ctx->eps2.p};
         rc = run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
-                                per_user_dev, sums_dev, keys_only, st);
+                                per_user_dev, sums_dev, keys_only, RA, st);
         if (rc || keys_only == nullptr) return rc;
     } else {
         if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;

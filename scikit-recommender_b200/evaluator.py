@@ -138,7 +138,9 @@ class RankingEvaluator(object):
         grid replaces the thread pool.  `batch_size` is the user batch of the `predict` path.
     Keyword-only additions:
         device: CUDA device index (default: current torch device).
-        precision: "auto" | "3xtf32" | "fp32" | "1xtf32" -- arithmetic of the fused scoring.
+        precision: "auto" | "3xtf32" | "fp32" | "tf32r" | "1xtf32" -- arithmetic of the fused scoring
+            ("tf32r": one TF32 pass finds candidates inside a rigorous error band, the survivors are
+            re-scored in exact FP32; same results as "fp32").
         mean: "f64" (float64 sums, rounded once to float32) or "numpy_f32" (the reference's
             float32 row-order accumulation of np.mean, evaluator.py:208, bit for bit;
             single-process only).
@@ -190,7 +192,7 @@ class RankingEvaluator(object):
             self.max_top = max(top_k)
             self.top_show = np.sort(top_k)
 
-        assert precision in ("auto", "3xtf32", "fp32", "1xtf32"), "precision must be auto|3xtf32|fp32|1xtf32"
+        assert precision in ("auto", "3xtf32", "fp32", "1xtf32", "tf32r"), "precision must be auto|3xtf32|fp32|1xtf32|tf32r"
         assert mean in ("f64", "numpy_f32"), "mean must be f64|numpy_f32"
         assert shard in ("users", "items"), "shard must be users|items"
         self.shard = shard

@@ -644,3 +644,70 @@ def test_from_csr_equals_dict_construction(torch_cuda):
     a = RankingEvaluator(data["train"], data["test"], **kw).evaluate(model, test_users=sub)
     b = RankingEvaluator.from_csr(to_csr(data["train"]), to_csr(data["test"]), **kw).evaluate(model, test_users=sub)
     assert np.array_equal(np.array(list(a.values())), np.array(list(b.values())))
+
+
+# ---- precision "tf32r": one TF32 pass + exact re-scoring == the FP32 path, bit for bit -----------------------
+@pytest.mark.parametrize("U,I,d,bias,K,max_train", FUSED_SHAPES + [(700, 9000, 64, True, 50, 60)])
+def test_fused_tf32r_equals_fp32_path_bit_for_bit(torch_cuda, ctx, U, I, d, bias, K, max_train):
+    ue, ie, b, tr, te = _fused_case(U + I + 1, U, I, d, bias, max_train)
+    metric = [1, 2, 3, 4, 5]
+    got = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "tf32r")
+    assert ctx.last_fused_kernel == "tcgen05_tf32r"
+    ref = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "fp32")
+    assert ctx.last_fused_kernel == "simt_fp32"
+    assert np.array_equal(got[0], ref[0])      # same items in the same order
+    assert np.array_equal(got[1], ref[1])      # same float32 scores (the exact FMA chain, not the TF32 value)
+    assert np.array_equal(got[2], ref[2])      # same per-user metric vectors
+    assert np.max(np.abs(got[3] - ref[3])) < 1e-9
+    _check_fused(*got, ue, ie, b, tr, te, metric, K)
+
+
+def test_tf32_error_stays_inside_the_band_tf32r_assumes(torch_cuda, ctx):
+    """|s_tf32 - s_fp32| of the kernels against eps of k_sample_thr (k_fused_tc.cuh): the bound must hold with slack."""
+    g = np.random.default_rng(5)
+    for d, scale in ((32, 0.1), (64, 1.0), (128, 3.0)):
+        U = I = 128
+        ue = (g.standard_normal((U, d)) * scale).astype(np.float32)
+        ie = (g.standard_normal((I, d)) * scale).astype(np.float32)
+        te = _rand_csr(g, U, I, 5, min_n=1)
+        out1 = _run_fused(torch_cuda, ctx, ue, ie, None, None, te, [1], 128, "1xtf32")   # K = I: the lists are whole score rows
+        out2 = _run_fused(torch_cuda, ctx, ue, ie, None, None, te, [1], 128, "fp32")
+        s1 = np.zeros((U, I), np.float32)
+        s2 = np.zeros((U, I), np.float32)
+        np.put_along_axis(s1, out1[0].astype(np.int64), out1[1], 1)
+        np.put_along_axis(s2, out2[0].astype(np.int64), out2[1], 1)
+        err = np.abs(s1.astype(np.float64) - s2.astype(np.float64)).max(axis=1)
+        coef = 2.0 ** -10 + (1.25 * d + 2.0) * 2.0 ** -22
+        eps = 1.25 * coef * np.linalg.norm(ue.astype(np.float64), axis=1) * np.linalg.norm(ie.astype(np.float64), axis=1).max()
+        assert np.all(err <= 0.5 * eps), (d, float((err / eps).max()))
+        assert err.max() > 0  # the single pass really is inexact: the band is needed
+
+
+def test_tf32r_ties_and_degenerate_rows_fall_back_exactly(torch_cuda, ctx):
+    """Many equal scores (popularity-style integer scores) and rows with fewer unmasked items than K."""
+    g = np.random.default_rng(6)
+    U, I, d, K = 200, 1500, 64, 20
+    ue = np.zeros((U, d), np.float32)
+    ue[:, 0] = 1.0
+    ie = np.zeros((I, d), np.float32)
+    ie[:, 0] = g.integers(0, 12, size=I).astype(np.float32)  # heavy ties
+    tr = _rand_csr(g, U, I, 30)
+    te = _rand_csr(g, U, I, 10, min_n=1)
+    got = _run_fused(torch_cuda, ctx, ue, ie, None, tr, te, [1, 2, 4], K, "tf32r")
+    ref = _run_fused(torch_cuda, ctx, ue, ie, None, tr, te, [1, 2, 4], K, "fp32")
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2])
+    S = oracle.scores(ue, ie, None)
+    oracle.mask_rows(S, tr[0], tr[1])
+    eper, etop = oracle.eval_scores(S, te[0], te[1], [1, 2, 4], K, return_topk=True)
+    assert np.array_equal(got[0], etop) and np.array_equal(got[2], eper)  # lower item id first among equals
+
+
+def test_c2_full_size_tf32r_equals_fp32_path(torch_cuda, ctx, c2_data):
+    d = c2_data
+    tr = (d["train_indptr"], d["train_indices"])
+    te = (d["test_indptr"], d["test_indices"])
+    a = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, "tf32r")
+    stats = ctx.fused_stats()
+    b = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, "fp32")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert stats["exact_rows"] < 0.01 * d["users"]  # the fast path settles (almost) every row

@@ -142,7 +142,7 @@ def stage_tc_c2():
     tr = (d["train_indptr"], d["train_indices"])
     te = (d["test_indptr"], d["test_indices"])
     res = {}
-    for prec in ("3xtf32", "fp32", "1xtf32"):
+    for prec in ("3xtf32", "fp32", "1xtf32", "tf32r"):
         for chunks in ((0, 2, 4, 5, 8) if prec == "3xtf32" else (0,)):
             ctx.set_option("chunks", chunks)
             out = _fused(np, torch, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, prec)
@@ -161,6 +161,9 @@ def stage_tc_c2():
             st, rk, out[4], ctx.fused_prepass_ms(0), out[3][149] / d["users"], ctx.fused_stats()), flush=True)
     ctx.set_option("sample_tiles", 0)
     ctx.set_option("rank", 0)
+    a, b = res[("tf32r", 0)], res[("fp32", 0)]
+    print("c2 tf32r vs simt fp32: idx equal %s, val equal %s, per-user equal %s, max sum diff %.3e" % (
+        np.array_equal(a[0], b[0]), np.array_equal(a[1], b[1]), np.array_equal(a[2], b[2]), float(np.max(np.abs(a[3] - b[3])))), flush=True)
     a, b = res[("3xtf32", 0)], res[("fp32", 0)]
     diff = a[0] != b[0]
     print("c2 tc3 vs simt: idx mismatch %.4f%%, max val gap at mismatches %.3e, max mean-metric diff %.3e" % (
