@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3a", "c3b"])
-    ap.add_argument("--precision", default="3xtf32", choices=["auto", "3xtf32", "fp32", "1xtf32", "tf32r"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "3xtf32", "fp32", "1xtf32", "tf32r"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.steps = max(1, args.steps)

@@ -58,7 +58,7 @@ extern "C" {
 #define SKR_ERR_STATE (-5)       /* call order (e.g. no test CSR set) */
 
 /* scoring arithmetic of the fused path */
-#define SKR_PREC_AUTO 0   /* 3xTF32 on tensor cores when the shape allows, else FP32 FMA */
+#define SKR_PREC_AUTO 0   /* tensor cores when the shape allows (3xTF32, or TF32R for large catalogues), else FP32 FMA */
 #define SKR_PREC_FP32 1   /* FP32 FMA on CUDA cores (exact products, sequential k order) */
 #define SKR_PREC_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split, 3 products, FP32 accumulate */
 #define SKR_PREC_1XTF32 3 /* single TF32 pass; NOT reference-grade, for measurement only */

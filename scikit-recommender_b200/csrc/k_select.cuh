@@ -30,7 +30,9 @@
 namespace skr {
 
 constexpr int SEL_WARPS = 4;
-constexpr int SEL_MAX = 512;  // candidates a row may carry into the selection
+// candidates a row may carry into the selection: ~4 K are expected (r / f of the sampling plan), so the
+// buffer follows the sort capacity (K <= 64: 512, K <= 128: 1024)
+__host__ __device__ constexpr int sel_max(int per, bool rescore) { return (rescore ? per / 2 : per) * 256; }
 constexpr int SEL_MAX_D = 128;  // RESCORE keeps the user vector in shared memory (the tensor-core path has d <= 128)
 
 struct RescoreArgs {
@@ -42,8 +44,75 @@ struct RescoreArgs {
     const float *eps2;              // [n_rows] 2 eps of the row
 };
 
+struct SelOut {
+    u64 *out_keys; int32_t *topk_idx; float *topk_val; float *per_user;
+    const int64_t *te_indptr; const int32_t *te_idx; const double *disc; const float *idcg;
+};
+
+// skey[0 .. 32 PER): rank keys of the survivors (0 = empty) -> sorted; emits the K best and their metrics.
+// cut / vmax: smallest / largest ord(score) among them.
+template <int PER>
+__device__ __forceinline__ void sel_sort_emit(const u64 *skey, uint32_t cut, uint32_t vmax, int lane, int K, int64_t row, int64_t row0,
+                                              const MetricIds &mids, const SelOut &O, double *acc)
+{
+    // Sort.  Fast path: the survivors' scores span less than 2^(32 - BITS) float steps above the cut, so
+    // (steps above the cut + 1) << BITS | slot is a 32-bit key with the same order as long as no two
+    // survivors have equal scores; the 64-bit rank keys are fetched back by slot afterwards.  Rows with
+    // a wider span or with tied scores take the 64-bit network (item id decides ties).
+    constexpr int CAP = 32 * PER;
+    constexpr int BITS = (PER <= 2) ? 6 : (PER <= 4 ? 7 : 8);
+    static_assert((1 << BITS) >= CAP, "slot bits");
+    u64 v[PER];
+    bool fast = (vmax - cut) < ((1u << (32 - BITS)) - 2u);
+    if (fast) {
+        uint32_t v32[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = e * 32 + lane;
+            const u64 k = skey[i];
+            v32[e] = (k != 0ull) ? ((((uint32_t)(k >> 32) - cut + 1u) << BITS) | (uint32_t)i) : 0u;
+        }
+        warp_bitonic_desc32<PER>(v32, lane);
+        bool tie = false;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const uint32_t mine = v32[e] >> BITS;
+            uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+            const uint32_t wrap = (e + 1 < PER) ? __shfl_sync(0xffffffffu, v32[(e + 1 < PER) ? e + 1 : e] >> BITS, 0) : 0u;
+            if (lane == 31) next = wrap;
+            tie |= (mine != 0u) && (mine == next);
+            v[e] = (v32[e] != 0u) ? skey[v32[e] & (uint32_t)(CAP - 1)] : 0ull;
+        }
+        fast = !__any_sync(0xffffffffu, tie);
+    }
+    if (!fast) {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) v[e] = skey[e * 32 + lane];
+        warp_bitonic_desc<PER>(v, lane);
+    }
+
+// outputs: top-K lists on request, metrics straight from the registers
+    const bool do_metrics = O.te_indptr != nullptr;  // null: keys only (per-shard lists of item-sharded evaluation)
+    RowMetrics rm;
+    if (do_metrics) rm.begin(O.te_indptr, O.te_idx, row0 + row);
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int i = e * 32 + lane;
+        if (e * 32 < K) {
+            if (i < K) {
+                if (O.out_keys != nullptr) O.out_keys[row * (int64_t)K + i] = v[e];
+                if (O.topk_idx != nullptr) O.topk_idx[row * (int64_t)K + i] = (int32_t)key_item(v[e]);
+                if (O.topk_val != nullptr) O.topk_val[row * (int64_t)K + i] = key_score(v[e]);
+            }
+            if (do_metrics)
+                rm.chunk(e * 32, lane, K, (int32_t)key_item(v[e]), mids, O.disc, O.idcg,
+                         O.per_user != nullptr ? O.per_user + row * (int64_t)(mids.n * K) : nullptr, acc);
+        }
+    }
+}
+
 template <int PER, bool RESCORE>
-__global__ void __launch_bounds__(SEL_WARPS * 32)
+__global__ void __launch_bounds__(SEL_WARPS * 32, RESCORE ? 6 : 8)  // (64 registers make the re-scoring variant spill: measured 1.6x slower)
 k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
                int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count,
                const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
@@ -52,7 +121,8 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
 {
     constexpr int CAP = 32 * PER;
     constexpr int CAPS = RESCORE ? CAP / 2 : CAP;  // size at which the search for the cut stops
-    __shared__ float s_u[RESCORE ? SEL_WARPS : 1][RESCORE ? SEL_MAX_D : 1];
+    constexpr int SEL_MAX = sel_max(PER, RESCORE);
+    __shared__ __align__(16) float s_u[RESCORE ? SEL_WARPS : 1][RESCORE ? SEL_MAX_D : 4];
     __shared__ uint2 s_ent[SEL_WARPS][SEL_MAX];
     __shared__ uint32_t s_hist[SEL_WARPS][256];
     __shared__ u64 s_key[SEL_WARPS][CAP];
@@ -201,84 +271,49 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             __syncwarp();
             const bool vec_ok = ((R.ld_v & 3) == 0) && ((reinterpret_cast<uintptr_t>(R.V) & 15) == 0);
             uint32_t omin = 0xffffffffu, omax = 0u;
-            for (int i = lane; i < m; i += 32) {
-                const uint32_t item = ~(uint32_t)skey[i];
-                const float *it = R.V + (int64_t)item * R.ld_v;
-                float a = 0.0f;
+            for (int i0 = 0; i0 < m; i0 += 64) {  // two candidates per lane in flight: two independent FMA chains
+                const int ia = i0 + lane, ib = ia + 32;
+                const bool va = ia < m, vb = ib < m;
+                const uint32_t item_a = va ? ~(uint32_t)skey[ia] : 0u, item_b = vb ? ~(uint32_t)skey[ib] : 0u;
+                const float *pa = R.V + (int64_t)item_a * R.ld_v, *pb = R.V + (int64_t)item_b * R.ld_v;
+                float a = 0.0f, b = 0.0f;
                 int k = 0;
                 if (vec_ok) {
                     for (; k + 4 <= R.d; k += 4) {
-                        const float4 x = __ldg(reinterpret_cast<const float4 *>(it + k));
-                        a = fmaf(u[k], x.x, a);
-                        a = fmaf(u[k + 1], x.y, a);
-                        a = fmaf(u[k + 2], x.z, a);
-                        a = fmaf(u[k + 3], x.w, a);
+                        const float4 x = __ldg(reinterpret_cast<const float4 *>(pa + k));
+                        const float4 y = __ldg(reinterpret_cast<const float4 *>(pb + k));
+                        const float4 w = *reinterpret_cast<const float4 *>(u + k);
+                        a = fmaf(w.x, x.x, a); b = fmaf(w.x, y.x, b);
+                        a = fmaf(w.y, x.y, a); b = fmaf(w.y, y.y, b);
+                        a = fmaf(w.z, x.z, a); b = fmaf(w.z, y.z, b);
+                        a = fmaf(w.w, x.w, a); b = fmaf(w.w, y.w, b);
                     }
                 }
-                for (; k < R.d; ++k) a = fmaf(u[k], __ldg(it + k), a);
-                if (R.bias != nullptr) a += __ldg(R.bias + item);
-                const u64 key = make_key(a, item);
-                skey[i] = key;
-                omin = min(omin, (uint32_t)(key >> 32));
-                omax = max(omax, (uint32_t)(key >> 32));
+                for (; k < R.d; ++k) { a = fmaf(u[k], __ldg(pa + k), a); b = fmaf(u[k], __ldg(pb + k), b); }
+                if (R.bias != nullptr) { a += __ldg(R.bias + item_a); b += __ldg(R.bias + item_b); }
+                if (va) {
+                    const u64 key = make_key(a, item_a);
+                    skey[ia] = key;
+                    omin = min(omin, (uint32_t)(key >> 32));
+                    omax = max(omax, (uint32_t)(key >> 32));
+                }
+                if (vb) {
+                    const u64 key = make_key(b, item_b);
+                    skey[ib] = key;
+                    omin = min(omin, (uint32_t)(key >> 32));
+                    omax = max(omax, (uint32_t)(key >> 32));
+                }
             }
             cut = __reduce_min_sync(0xffffffffu, omin);
             vmax = __reduce_max_sync(0xffffffffu, omax);
         }
         __syncwarp();
-        // Sort.  Fast path: the survivors' scores span less than 2^(32 - BITS) float steps above the cut, so
-        // (steps above the cut + 1) << BITS | slot is a 32-bit key with the same order as long as no two
-        // survivors have equal scores; the 64-bit rank keys are fetched back by slot afterwards.  Rows with
-        // a wider span or with tied scores take the 64-bit network (item id decides ties).
-        constexpr int BITS = (PER <= 2) ? 6 : (PER <= 4 ? 7 : 8);
-        static_assert((1 << BITS) >= CAP, "slot bits");
-        u64 v[PER];
-        bool fast = (vmax - cut) < ((1u << (32 - BITS)) - 2u);
-        if (fast) {
-            uint32_t v32[PER];
-#pragma unroll
-            for (int e = 0; e < PER; ++e) {
-                const int i = e * 32 + lane;
-                const u64 k = skey[i];
-                v32[e] = (k != 0ull) ? ((((uint32_t)(k >> 32) - cut + 1u) << BITS) | (uint32_t)i) : 0u;
-            }
-            warp_bitonic_desc32<PER>(v32, lane);
-            bool tie = false;
-#pragma unroll
-            for (int e = 0; e < PER; ++e) {
-                const uint32_t mine = v32[e] >> BITS;
-                uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
-                const uint32_t wrap = (e + 1 < PER) ? __shfl_sync(0xffffffffu, v32[(e + 1 < PER) ? e + 1 : e] >> BITS, 0) : 0u;
-                if (lane == 31) next = wrap;
-                tie |= (mine != 0u) && (mine == next);
-                v[e] = (v32[e] != 0u) ? skey[v32[e] & (uint32_t)(CAP - 1)] : 0ull;
-            }
-            fast = !__any_sync(0xffffffffu, tie);
-        }
-        if (!fast) {
-#pragma unroll
-            for (int e = 0; e < PER; ++e) v[e] = skey[e * 32 + lane];
-            warp_bitonic_desc<PER>(v, lane);
-        }
-
-        // ---- 4. outputs: top-K lists on request, metrics straight from the registers ------------------
-        const bool do_metrics = te_indptr != nullptr;  // null: keys only (per-shard lists of item-sharded evaluation)
-        RowMetrics rm;
-        if (do_metrics) rm.begin(te_indptr, te_idx, row0 + row);
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int i = e * 32 + lane;
-            if (e * 32 < K) {
-                if (i < K) {
-                    if (out_keys != nullptr) out_keys[row * (int64_t)K + i] = v[e];
-                    if (topk_idx_out != nullptr) topk_idx_out[row * (int64_t)K + i] = (int32_t)key_item(v[e]);
-                    if (topk_val_out != nullptr) topk_val_out[row * (int64_t)K + i] = key_score(v[e]);
-                }
-                if (do_metrics)
-                    rm.chunk(e * 32, lane, K, (int32_t)key_item(v[e]), mids, disc, idcg,
-                             per_user != nullptr ? per_user + row * (int64_t)MK : nullptr, acc);
-            }
-        }
+        // ---- 4. sort, outputs, metrics.  After re-scoring the survivors usually fit the smaller network. -------
+        const SelOut O = {out_keys, topk_idx_out, topk_val_out, per_user, te_indptr, te_idx, disc, idcg};
+        if (RESCORE && PER >= 4 && m <= 16 * PER && K <= 16 * PER)
+            sel_sort_emit<PER / 2>(skey, cut, vmax, lane, K, row, row0, mids, O, acc);
+        else
+            sel_sort_emit<PER>(skey, cut, vmax, lane, K, row, row0, mids, O, acc);
     }
     if (acc_out != nullptr) fold_block_sums(sel_acc, SEL_WARPS, MK, acc_out + (size_t)blockIdx.x * MK);
 }

@@ -838,6 +838,9 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.trace = nullptr;
         A.trace_cta = -1;
         A.trace_tiles = 0;
+        // AUTO: re-scoring costs a fixed ~60 candidate rows per user, the two extra MMA passes of 3xTF32 grow with
+        // the catalogue: measured break-even between c2 (I d = 2.6 M, 3xTF32 5 % faster) and c3b (5.9 M, tf32r 11 % faster)
+        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 4.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
         const bool rescore = (precision == SKR_PREC_TF32R);
         const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
         float eps_coef = 0.0f;
