@@ -295,7 +295,12 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
         if (acc_k4 > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_k4));
     }
     const size_t dyn_sel = fused_sums ? acc_sel : 0;
-    if (dyn_sel > 8 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel));
+    if (dyn_sel > 0) {  // static (candidate buffers) + dynamic (column sums) may pass 48 KB: opt in for what is left next to the static part
+        cudaFuncAttributes fa;
+        SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, sel));
+        if (fa.sharedSizeBytes + dyn_sel > ctx->max_smem) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_metrics * top_k = %d does not fit shared memory", MK);
+        SKR_CUDA(ctx, cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
+    }
     sel<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
                                                 ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA);
     k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,

@@ -711,3 +711,70 @@ def test_c2_full_size_tf32r_equals_fp32_path(torch_cuda, ctx, c2_data):
     b = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, "fp32")
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert stats["exact_rows"] < 0.01 * d["users"]  # the fast path settles (almost) every row
+
+
+# ---- randomized shape sweep: every fused precision against the oracle on ragged / awkward shapes -------------
+def _sweep_cases():
+    g = np.random.default_rng(2026)
+    cases = []
+    for _ in range(14):
+        U = int(g.choice([1, 2, 31, 127, 128, 129, 255, 300, 513]))
+        I = int(g.choice([130, 200, 257, 1000, 2049, 4100]))
+        d = int(g.choice([1, 3, 4, 17, 32, 50, 64, 100, 128]))
+        K = int(g.choice([1, 2, 5, 10, 50, 64, 65, 100, 128]))
+        cases.append((U, I, d, min(K, I // 2), bool(g.integers(2)), int(g.choice([0, 1, 5, 40])), int(g.integers(1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("U,I,d,K,bias,max_train,seed", _sweep_cases())
+def test_fused_precisions_on_awkward_shapes(torch_cuda, ctx, U, I, d, K, bias, max_train, seed):
+    g = np.random.default_rng(seed)
+    ue = (g.standard_normal((U, d)) * 0.3).astype(np.float32)
+    ie = (g.standard_normal((I, d)) * 0.3).astype(np.float32)
+    b = (g.standard_normal(I) * 0.05).astype(np.float32) if bias else None
+    tr = _rand_csr(g, U, I, max_train) if max_train > 0 else None
+    te = _rand_csr(g, U, I, 8, min_n=0)  # users without test items: all metrics 0, still counted by the caller
+    metric = [int(x) for x in g.permutation(5)[: int(g.integers(1, 6))] + 1]
+    precisions = ["3xtf32", "tf32r"] + (["fp32"] if d % 4 == 0 else [])
+    outs = {}
+    for prec in precisions:
+        outs[prec] = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, prec)
+        # scores here reach |s| ~ 0.09 sqrt(d) * 4: the score tolerance scales with their magnitude
+        _check_fused(*outs[prec], ue, ie, b, tr, te, metric, K, tol_score=TOL_SCORE * max(1.0, 0.5 * d ** 0.5))
+    if "fp32" in outs:
+        assert np.array_equal(outs["tf32r"][0], outs["fp32"][0]) and np.array_equal(outs["tf32r"][2], outs["fp32"][2])
+
+
+def test_fused_special_values_and_limits(torch_cuda, ctx):
+    """Zero vectors (every score ties at 0), huge and tiny magnitudes, -0.0; errors for shapes the path cannot take."""
+    from skrec_b200 import _native
+    g = np.random.default_rng(9)
+    U, I, d, K = 140, 900, 64, 10
+    ue = (g.standard_normal((U, d))).astype(np.float32)
+    ie = (g.standard_normal((I, d))).astype(np.float32)
+    ue[:5] = 0.0                      # all-tie rows: ids 0..K-1 in order (minus train items)
+    ue[5:10] *= 1e18                  # large scores (|s| ~ 1e19), still finite
+    ue[10:15] *= 1e-18                # tiny scores
+    ie[::7] = -0.0
+    tr = _rand_csr(g, U, I, 20)
+    te = _rand_csr(g, U, I, 6, min_n=1)
+    for prec in ("3xtf32", "tf32r", "fp32"):
+        idx, val, per, sums = _run_fused(torch_cuda, ctx, ue, ie, None, tr, te, [1, 2, 3, 4, 5], K, prec)
+        S = oracle.scores(ue, ie, None)
+        oracle.mask_rows(S, tr[0], tr[1])
+        eper, etop = oracle.eval_scores(S, te[0], te[1], [1, 2, 3, 4, 5], K, return_topk=True)
+        assert np.array_equal(idx[:5], etop[:5]), prec       # exact ties: lower item id first
+        assert np.array_equal(per[:5], eper[:5]), prec
+        rel = np.abs(np.take_along_axis(S, idx.astype(np.int64), 1) - np.take_along_axis(S, etop.astype(np.int64), 1))
+        scale = np.abs(np.take_along_axis(S, etop.astype(np.int64), 1)) + 1e-30
+        assert np.max(rel / scale) < 1e-5, prec               # any rank difference is a near-tie relative to the score scale
+        assert np.all(np.isfinite(sums))
+    u, i = torch_cuda.zeros((4, 200), device="cuda"), torch_cuda.zeros((50, 200), device="cuda")
+    ctx.set_train_csr(None, None, 50)
+    ctx.set_test_csr(np.array([0, 1, 2, 3, 4], np.int64), np.array([0, 1, 2, 3], np.int32), 50)
+    with pytest.raises(_native.NativeError):   # d > 128 has no tensor-core instantiation: explicit, not a silent fallback
+        ctx.eval_fused(u, i, None, 0, [1], 5, precision="3xtf32", sums=torch_cuda.zeros(5, dtype=torch_cuda.float64, device="cuda"))
+    ctx.eval_fused(u, i, None, 0, [1], 5, precision="auto", sums=torch_cuda.zeros(5, dtype=torch_cuda.float64, device="cuda"))
+    assert ctx.last_fused_kernel == "simt_fp32"
+    with pytest.raises(_native.NativeError):   # n_items < top_k (evaluate.h:45 would read out of bounds)
+        ctx.eval_fused(u, i, None, 0, [1], 51, sums=torch_cuda.zeros(51, dtype=torch_cuda.float64, device="cuda"))
