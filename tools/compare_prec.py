@@ -1,5 +1,5 @@
 """Whole-evaluate device time of the fused path per precision on several shapes (development aid).
-    python tools/compare_prec.py [shape ...]   shapes: c2 c3a c3b big128 (16384 x 262144, d=128, K=100)"""
+    python tools/compare_prec.py [shape ...]   shapes: c2 c3a c3b big128 (16384 x 262144, d=128, K=100) c4slice (8192 x 1M, d=128)"""
 import os
 import sys
 
@@ -10,7 +10,10 @@ import torch  # noqa: E402
 from skrec_b200 import _native, synth  # noqa: E402
 
 SHAPES = {"big128": dict(users=16384, items=262144, d=128, bias=True, nnz_train=16384 * 50, nnz_test=16384 * 10, top_k=[10, 20, 50, 100],
-                         metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], seed=77, name="16K x 262K, d=128")}
+                         metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], seed=77, name="16K x 262K, d=128"),
+          # one GPU's share of c4 (1M x 1M, d=128, bias, 50 train / 10 test items per user, K up to 100): 8,192 of its 125,000 users
+          "c4slice": dict(users=8192, items=1_000_000, d=128, bias=True, nnz_train=8192 * 50, nnz_test=8192 * 10, top_k=[10, 20, 50, 100],
+                          metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], seed=2025, name="c4 slice: 8,192 users x 1M items, d=128")}
 for name in (sys.argv[1:] or ["c2", "c3b", "big128"]):
     cfg = dict(SHAPES[name]) if name in SHAPES else dict(synth.CONFIGS[name])
     d = synth.make(device="cuda", **cfg)
