@@ -60,8 +60,10 @@ struct RowMetrics {
         const bool hit = valid && (item >= 0) && sorted_contains(truth, nt, item);
         const uint32_t mask = __ballot_sync(0xffffffffu, hit);
         const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // lanes <= mine
+        // 0 / x is exactly +0: skipping those divisions keeps every bit and avoids the IEEE division's slow path,
+        // which the compiler's fast-path check sends every zero numerator through (most positions have no hit yet)
         const float hf = (float)(hits_c + __popc(mask & le_mask));
-        const float prec = hf / (float)(i + 1);
+        const float prec = (hf == 0.0f) ? 0.0f : hf / (float)(i + 1);
         float my_sum = sum_pre_c, my_dcg = dcg_c;
         for (uint32_t m = mask; m != 0u; m &= m - 1u) {  // hits of this chunk, ascending
             const int b = __ffs(m) - 1;
@@ -77,9 +79,9 @@ struct RowMetrics {
                 const int id = mids.id(mi);
                 float val;
                 if (id == 1) val = prec;                                                 // metric.h:19-30
-                else if (id == 2) val = hf / Lf;                                         // metric.h:33-45
-                else if (id == 3) val = my_sum / (float)(L < i + 1 ? L : i + 1);         // metric.h:48-66
-                else if (id == 4) val = my_dcg / __ldg(idcg + (L < i + 1 ? L : i + 1));  // metric.h:69-86
+                else if (id == 2) val = (hf == 0.0f) ? 0.0f : hf / Lf;                                            // metric.h:33-45
+                else if (id == 3) val = (my_sum == 0.0f) ? 0.0f : my_sum / (float)(L < i + 1 ? L : i + 1);        // metric.h:48-66
+                else if (id == 4) val = (my_dcg == 0.0f) ? 0.0f : my_dcg / __ldg(idcg + (L < i + 1 ? L : i + 1)); // metric.h:69-86
                 else val = (first >= 0 && i >= first) ? (float)(1.0 / (double)(first + 1)) : 0.0f;  // metric.h:89-109
                 if (per_user_row != nullptr) per_user_row[mi * K + i] = val;
                 if (acc != nullptr) acc[mi * K + i] += (double)val;

@@ -125,6 +125,7 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
     __shared__ __align__(16) float s_u[RESCORE ? SEL_WARPS : 1][RESCORE ? SEL_MAX_D : 4];
     __shared__ uint2 s_ent[SEL_WARPS][SEL_MAX];
     __shared__ uint32_t s_hist[SEL_WARPS][256];
+    __shared__ int s_off[SEL_WARPS][33];
     __shared__ u64 s_key[SEL_WARPS][CAP];
     extern __shared__ double sel_acc[];  // [SEL_WARPS][M*K] when acc_out != null
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,19 +155,24 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
             continue;
         }
-        const int off_mine = incl - c_mine;
+        // flat gather: candidate j of the row lives in sub-list s(j) = last s with off[s] <= j (binary search over the
+        // <= 32 offsets in shared memory); every lane has useful work in every step, unlike a loop over sub-lists
+        // whose ~17 entries leave half a warp idle (measured: the old gather was a third of the kernel's instructions)
+        s_off[warp][lane] = (lane < n_sub) ? incl - c_mine : 0x7fffffff;
+        __syncwarp();
+        const int *off = s_off[warp];
         uint32_t vmin = 0xffffffffu, vmax = 0u;
-        for (int s = 0; s < n_sub; ++s) {
-            const int cs = __shfl_sync(0xffffffffu, c_mine, s);
-            const int os = __shfl_sync(0xffffffffu, off_mine, s);
-            const uint2 *src = cand + (row * n_sub + s) * (int64_t)sub_stride;
-            for (int i = lane; i < cs; i += 32) {
-                uint2 e = src[i];
-                e.x = ord_f32(__uint_as_float(e.x));
-                vmin = min(vmin, e.x);
-                vmax = max(vmax, e.x);
-                ent[os + i] = e;
-            }
+        const uint2 *row_src = cand + row * n_sub * (int64_t)sub_stride;
+        for (int j = lane; j < n; j += 32) {
+            int s = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (off[s + step] <= j) s += step;
+            uint2 e = row_src[(int64_t)s * sub_stride + (j - off[s])];
+            e.x = ord_f32(__uint_as_float(e.x));
+            vmin = min(vmin, e.x);
+            vmax = max(vmax, e.x);
+            ent[j] = e;
         }
         vmin = __reduce_min_sync(0xffffffffu, vmin);
         vmax = __reduce_max_sync(0xffffffffu, vmax);
