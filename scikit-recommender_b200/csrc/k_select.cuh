@@ -42,6 +42,11 @@ struct RescoreArgs {
     const float *bias;              // or null
     const float *thr_c;             // [n_rows] threshold the main pass collected with
     const float *eps2;              // [n_rows] 2 eps of the row
+    // out: exact rank keys of the re-scored survivors, unsorted, and how many (0 = the row is on the fail list);
+    // sorting and metrics run in k_sort_metrics -- one kernel doing both needs 128 registers and runs at 25 %
+    // occupancy on a latency-bound job (measured 260 us at c2 against ~150 us for the pair)
+    u64 *rs_keys;                   // [n_rows, 32 PER]
+    int *rs_cnt;                    // [n_rows]
 };
 
 struct SelOut {
@@ -112,7 +117,7 @@ __device__ __forceinline__ void sel_sort_emit(const u64 *skey, uint32_t cut, uin
 }
 
 template <int PER, bool RESCORE>
-__global__ void __launch_bounds__(SEL_WARPS * 32, RESCORE ? 6 : 8)  // (64 registers make the re-scoring variant spill: measured 1.6x slower)
+__global__ void __launch_bounds__(SEL_WARPS * 32, 8)
 k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
                int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count,
                const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
@@ -152,7 +157,10 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         const int n = __shfl_sync(0xffffffffu, incl, 31);
         const bool over = __any_sync(0xffffffffu, c_mine > cap);
         if (over || n > SEL_MAX || n < K) {
-            if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+            if (lane == 0) {
+                fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                if (RESCORE) R.rs_cnt[row] = 0;
+            }
             continue;
         }
         // flat gather: candidate j of the row lives in sub-list s(j) = last s with off[s] <= j (binary search over the
@@ -232,7 +240,10 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             T = base;
         }
         if (!ok) {
-            if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+            if (lane == 0) {
+                fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                if (RESCORE) R.rs_cnt[row] = 0;
+            }
             continue;
         }
 
@@ -245,7 +256,10 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             const uint32_t ol = ord_f32(lb);
             T = (ol > vmin) ? ol - vmin : 0u;
             if (!ok) {
-                if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                if (lane == 0) {
+                    fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                    R.rs_cnt[row] = 0;
+                }
                 continue;
             }
         }
@@ -268,10 +282,15 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         }
         if (RESCORE) {
             if (m > CAP) {  // too many candidates inside the error band
-                if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                if (lane == 0) {
+                    fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                    R.rs_cnt[row] = 0;
+                }
                 continue;
             }
-            // exact scores of the survivors: the FMA chain of RowDot::get4 (k_scores.cuh), operation for operation
+            // exact scores of the survivors: the FMA chain of RowDot::get4 (k_scores.cuh), operation for operation.
+            // (Staging the item rows through shared memory with coalesced 128-byte segments was tried and measured
+            // 7 % slower than letting every lane walk its own row: the gather is latency, not L1-tag, bound.)
             float *u = s_u[warp];
             for (int k = lane; k < R.d; k += 32) u[k] = __ldg(R.U + row * R.ld_u + k);
             __syncwarp();
@@ -310,16 +329,64 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                     omax = max(omax, (uint32_t)(key >> 32));
                 }
             }
-            cut = __reduce_min_sync(0xffffffffu, omin);
-            vmax = __reduce_max_sync(0xffffffffu, omax);
+            // hand the exact keys to k_sort_metrics
+            __syncwarp();
+            u64 *dst = R.rs_keys + row * (int64_t)CAP;
+            for (int i = lane; i < m; i += 32) dst[i] = skey[i];
+            if (lane == 0) R.rs_cnt[row] = m;
+            continue;
         }
         __syncwarp();
-        // ---- 4. sort, outputs, metrics.  After re-scoring the survivors usually fit the smaller network. -------
+        // ---- 4. sort, outputs, metrics -----------------------------------------------------------------------
         const SelOut O = {out_keys, topk_idx_out, topk_val_out, per_user, te_indptr, te_idx, disc, idcg};
-        if (RESCORE && PER >= 4 && m <= 16 * PER && K <= 16 * PER)
-            sel_sort_emit<PER / 2>(skey, cut, vmax, lane, K, row, row0, mids, O, acc);
+        sel_sort_emit<PER>(skey, cut, vmax, lane, K, row, row0, mids, O, acc);
+    }
+    if (acc_out != nullptr) fold_block_sums(sel_acc, SEL_WARPS, MK, acc_out + (size_t)blockIdx.x * MK);
+}
+
+// ---- second half of the re-scoring path: exact keys of the survivors -> sorted top-K -> metrics -----------------
+// keys [n_rows, 32 PER] unsorted with cnt[row] valid entries (0: the row is on the fail list and is handled by
+// k_row_exact + k_metrics).  One warp per row, rows dealt round-robin.
+template <int PER>
+__global__ void __launch_bounds__(SEL_WARPS * 32, 8)
+k_sort_metrics(const u64 *__restrict__ rs_keys, const int *__restrict__ rs_cnt, int K, int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys,
+               const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
+               const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
+               float *__restrict__ topk_val_out, double *__restrict__ acc_out)
+{
+    constexpr int CAP = 32 * PER;
+    __shared__ u64 s_key[SEL_WARPS][CAP];
+    extern __shared__ double sel_acc[];  // [SEL_WARPS][M*K] when acc_out != null
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    u64 *skey = s_key[warp];
+    const int MK = mids.n * K;
+    double *acc = (acc_out != nullptr) ? sel_acc + (size_t)warp * MK : nullptr;
+    if (acc != nullptr)
+        for (int c = lane; c < MK; c += 32) acc[c] = 0.0;
+    const SelOut O = {out_keys, topk_idx_out, topk_val_out, per_user, te_indptr, te_idx, disc, idcg};
+    const int64_t n_warps = (int64_t)gridDim.x * SEL_WARPS;
+    for (int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp; row < n_rows; row += n_warps) {
+        const int m = __ldg(rs_cnt + row);
+        if (m == 0) continue;
+        __syncwarp();
+        uint32_t omin = 0xffffffffu, omax = 0u;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int i = e * 32 + lane;
+            const u64 k = (i < m) ? rs_keys[row * (int64_t)CAP + i] : 0ull;
+            skey[i] = k;
+            if (i < m) {
+                omin = min(omin, (uint32_t)(k >> 32));
+                omax = max(omax, (uint32_t)(k >> 32));
+            }
+        }
+        omin = __reduce_min_sync(0xffffffffu, omin);
+        omax = __reduce_max_sync(0xffffffffu, omax);
+        __syncwarp();
+        if (PER >= 4 && m <= 16 * PER && K <= 16 * PER)  // the survivors usually fit the smaller network
+            sel_sort_emit<(PER >= 4 ? PER / 2 : PER)>(skey, omin, omax, lane, K, row, row0, mids, O, acc);
         else
-            sel_sort_emit<PER>(skey, cut, vmax, lane, K, row, row0, mids, O, acc);
+            sel_sort_emit<PER>(skey, omin, omax, lane, K, row, row0, mids, O, acc);
     }
     if (acc_out != nullptr) fold_block_sums(sel_acc, SEL_WARPS, MK, acc_out + (size_t)blockIdx.x * MK);
 }

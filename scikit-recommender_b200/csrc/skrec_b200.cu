@@ -66,7 +66,7 @@ struct skr_ctx {
     float *d_idcg = nullptr;  // iDCG after n terms (metric.h:82), host-accumulated
     int disc_n = 0;
     // workspace, grow-only
-    Buf trace, stats, eps2, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
+    Buf trace, stats, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
     int64_t launches = 0;
     const char *last_fused = "none";
@@ -253,18 +253,35 @@ struct ExactArgs {
 
 int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
                        const MetricIds &m, int K, const ExactArgs &E, int32_t *fail_list, int *fail_count, int32_t *topk_idx,
-                       float *topk_val, float *per_user, double *sums, u64 *keys_only, const RescoreArgs &RA, cudaStream_t st)
+                       float *topk_val, float *per_user, double *sums, u64 *keys_only, RescoreArgs RA, cudaStream_t st)
 {
     const bool rescore = RA.U != nullptr;
-    // kernel instantiation: the sort capacity is 64 / 128 keys (K <= 64 / 128); re-scoring doubles it (error band)
+    // kernel instantiations: the sort capacity is 64 / 128 keys (K <= 64 / 128); re-scoring doubles it (error band) and
+    // splits the job in two kernels: candidates -> exact keys of the survivors, then sort + metrics
     typedef void (*SelKernel)(const uint2 *, const uint32_t *, int, int, int, int, int64_t, int64_t, u64 *, int32_t *, int *, const int64_t *,
                               const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs);
+    typedef void (*SortKernel)(const u64 *, const int *, int, int64_t, int64_t, u64 *, const int64_t *, const int32_t *, MetricIds, const double *,
+                               const float *, float *, int32_t *, float *, double *);
+    const int per = rescore ? (K <= 64 ? 4 : 8) : (K <= 64 ? 2 : 4);
     SelKernel sel = rescore ? (K <= 64 ? (SelKernel)k_select_cands<4, true> : (SelKernel)k_select_cands<8, true>)
                             : (K <= 64 ? (SelKernel)k_select_cands<2, false> : (SelKernel)k_select_cands<4, false>);
+    SortKernel srt = (K <= 64) ? (SortKernel)k_sort_metrics<4> : (SortKernel)k_sort_metrics<8>;
+    int rc;
+    if (rescore) {
+        if ((rc = ensure(ctx, ctx->rs_keys, (size_t)n_rows * 32 * per * sizeof(u64)))) return rc;
+        if ((rc = ensure(ctx, ctx->rs_cnt, (size_t)n_rows * sizeof(int)))) return rc;
+        RA.rs_keys = (u64 *)ctx->rs_keys.p;
+        RA.rs_cnt = (int *)ctx->rs_cnt.p;
+    }
+    const int g_sel = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
     if (keys_only != nullptr) {  // per-shard lists: sorted keys out, no metrics
-        const int g = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
-        sel<<<g, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m, nullptr,
-                                          nullptr, nullptr, nullptr, nullptr, nullptr, RA);
+        sel<<<g_sel, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m,
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA);
+        if (rescore) {
+            srt<<<g_sel, SEL_WARPS * 32, 0, st>>>(RA.rs_keys, RA.rs_cnt, K, n_rows, row0, keys_only, nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr,
+                                                  nullptr, nullptr);
+            ctx->launches++;
+        }
         k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
                                                                       E.tr_indptr, E.tr_idx, K, keys_only);
         ctx->launches += 2;
@@ -274,8 +291,7 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     if (!ctx->has_test) return fail(ctx, SKR_ERR_STATE, "no test CSR set (skr_set_test_csr)");
     if (row0 < 0 || row0 + n_rows > ctx->te_rows)
         return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the test CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->te_rows);
-    int rc = ensure_disc(ctx, K);
-    if (rc) return rc;
+    if ((rc = ensure_disc(ctx, K))) return rc;
     const int MK = m.n * K;
     const size_t acc_sel = (size_t)SEL_WARPS * MK * sizeof(double), acc_k4 = (size_t)K4_WARPS * MK * sizeof(double);
     const bool fused_sums = sums != nullptr && acc_k4 <= 96 * 1024;
@@ -286,7 +302,6 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     }
     if ((rc = ensure(ctx, ctx->keys, (size_t)n_rows * K * sizeof(u64)))) return rc;  // written only for re-done rows
     u64 *keys = (u64 *)ctx->keys.p;
-    const int g_sel = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
     const int g_fix = (int)std::min<int64_t>((n_rows + K4_WARPS - 1) / K4_WARPS, ctx->n_sm);
     double *acc = nullptr;
     if (fused_sums) {
@@ -294,15 +309,25 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
         acc = (double *)ctx->partial.p;
         if (acc_k4 > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_k4));
     }
+    // the kernel that holds the column sums: static (buffers) + dynamic (sums) may pass 48 KB, opt in for what is left
     const size_t dyn_sel = fused_sums ? acc_sel : 0;
-    if (dyn_sel > 0) {  // static (candidate buffers) + dynamic (column sums) may pass 48 KB: opt in for what is left next to the static part
+    if (dyn_sel > 0) {
         cudaFuncAttributes fa;
-        SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, sel));
+        if (rescore) SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, srt)); else SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, sel));
         if (fa.sharedSizeBytes + dyn_sel > ctx->max_smem) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_metrics * top_k = %d does not fit shared memory", MK);
-        SKR_CUDA(ctx, cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
+        if (rescore) SKR_CUDA(ctx, cudaFuncSetAttribute(srt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
+        else SKR_CUDA(ctx, cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
     }
-    sel<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
-                                                ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA);
+    if (rescore) {
+        sel<<<g_sel, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, nullptr, nullptr, m, nullptr,
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA);
+        srt<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(RA.rs_keys, RA.rs_cnt, K, n_rows, row0, nullptr, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc,
+                                                    ctx->d_idcg, pu, topk_idx, topk_val, acc);
+        ctx->launches++;
+    } else {
+        sel<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
+                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA);
+    }
     k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
                                                                   E.tr_indptr, E.tr_idx, K, keys);
     k_metrics<<<g_fix, K4_WARPS * 32, fused_sums ? acc_k4 : 0, st>>>(keys, nullptr, K, n_rows, row0, fail_list, fail_count, ctx->d_te_indptr,
@@ -459,7 +484,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
-                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2};
+                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt};
     for (Buf *b : bufs) free_dev(b->p);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
@@ -881,8 +906,8 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         ctx->last_plan = {n_samp, stride, r, cap, P.S, passes == 3 ? 4 : 8};
         ctx->ev_calls++;
         const ExactArgs E = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (int)n_items, tp, ti};
-        RescoreArgs RA = {nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr};
-        if (rescore) RA = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (const float *)ctx->thr.p, (const float *)ctx->eps2.p};
+        RescoreArgs RA = {nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (rescore) RA = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (const float *)ctx->thr.p, (const float *)ctx->eps2.p, nullptr, nullptr};
         rc = run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
                                 per_user_dev, sums_dev, keys_only, RA, st);
         if (rc || keys_only == nullptr) return rc;
