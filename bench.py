@@ -194,8 +194,8 @@ def run_ours(args):
     def step():
         sums.zero_()
         ctx.eval_fused(ue, ie, bias, 0, ids, K, precision=args.precision, sums=sums[:MK])
-        sums[MK] = float(U)
-        if world > 1:
+        if world > 1:  # [column sums | user count] is what the ranks exchange
+            sums[MK] = float(U)
             td.all_reduce(sums)
 
     sampler = ClockSampler(local)
@@ -237,7 +237,7 @@ def run_ours(args):
     if world > 1:
         td.barrier()
     torch.cuda.synchronize()
-    launches = ctx.launch_count - launches0 + args.steps * (3 if world == 1 else 4)  # + zero_, fill, (all-reduce) per step
+    launches = ctx.launch_count - launches0 + args.steps * (2 if world == 1 else 4)  # + L2 flush, sums.zero_ (, count fill, all-reduce) per step
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = [ctx.fused_kernel_ms(i) for i in range(args.steps)]
     prepass_ms = [ctx.fused_prepass_ms(i) for i in range(args.steps)]
@@ -248,7 +248,7 @@ def run_ours(args):
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * U / (ms_per_step * 1e-3)
-    means = (sums[:MK] / sums[MK]).cpu().numpy().reshape(len(ids), K)[:, np.array(cfg["top_k"]) - 1].ravel()
+    means = (sums[:MK] / float(world * U)).cpu().numpy().reshape(len(ids), K)[:, np.array(cfg["top_k"]) - 1].ravel()
 
     # ---- end to end through the public API, host (pinned) tables ---------------------------------
     ue_h = torch.from_numpy(data["user_emb"]).pin_memory()

@@ -738,10 +738,16 @@ k_item_stats(const float *__restrict__ V, int64_t ld_v, int64_t n_items, int d, 
 
 // ---- operand preparation ---------------------------------------------------------------------------
 // item table -> hi/lo TF32 tables [n, d_pad] (zero padded in k), one thread per output element
+// (also resets the two words the later kernels count into -- fail-list length and, for tf32r, the item statistics --
+// which saves two memset nodes per evaluate)
 __global__ void k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad,
-                             float *__restrict__ hi, float *__restrict__ lo)
+                             float *__restrict__ hi, float *__restrict__ lo, int *__restrict__ zero_a, uint32_t *__restrict__ zero_b2)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) {
+        if (zero_a != nullptr) *zero_a = 0;
+        if (zero_b2 != nullptr) { zero_b2[0] = 0u; zero_b2[1] = 0u; }
+    }
     if (idx >= n * d_pad) return;
     const int64_t r = idx / d_pad;
     const int k = (int)(idx - r * d_pad);

@@ -821,7 +821,10 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;
         if ((rc = ensure(ctx, ctx->blo, tbytes))) return rc;
         const int64_t n_el = n_items * d_pad;
-        k_split_tf32<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p, (float *)ctx->blo.p);
+        if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
+        if ((rc = ensure(ctx, ctx->stats, 2 * sizeof(float)))) return rc;
+        k_split_tf32<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p, (float *)ctx->blo.p,
+                                                                     (int *)ctx->fail_list.p, (uint32_t *)ctx->stats.p);
         ctx->launches++;
         CUtensorMap mhi, mlo;
         if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
@@ -851,7 +854,6 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
         int *fail_count = (int *)ctx->fail_list.p;             // [0] = count, [1..] = rows
         int32_t *fail_list = (int32_t *)ctx->fail_list.p + 1;
-        SKR_CUDA(ctx, cudaMemsetAsync(fail_count, 0, sizeof(int), st));
 
         TcArgs A;
         A.U = user_vecs_dev;
@@ -877,7 +879,6 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         if (rescore) {
             if ((rc = ensure(ctx, ctx->stats, 2 * sizeof(float)))) return rc;
             if ((rc = ensure(ctx, ctx->eps2, (size_t)n_rows * sizeof(float)))) return rc;
-            SKR_CUDA(ctx, cudaMemsetAsync(ctx->stats.p, 0, 2 * sizeof(float), st));
             k_item_stats<<<(unsigned)std::min<int64_t>((n_items + 7) / 8, 4 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, bias_dev,
                                                                                                    (uint32_t *)ctx->stats.p);
             ctx->launches++;

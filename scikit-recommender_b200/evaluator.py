@@ -411,11 +411,41 @@ class RankingEvaluator(object):
             x = np.ascontiguousarray(x)
         return x
 
+    def _fused_can_take(self, d):
+        """Shapes the fused kernels cover: top-K <= 128; d <= 128 on tensor cores, else FP32 FMA with d % 4 == 0."""
+        if self.max_top > 128:
+            return False
+        if self.precision in ("3xtf32", "tf32r", "1xtf32"):
+            return True  # an explicit tensor-core request fails loudly in the library if the shape is out of range
+        return d <= 128 or (d % 4 == 0 and d <= 1024)
+
+    def _evaluate_by_blocks(self, uv, iv, b, users, key, dev, want_pu):
+        """Shapes outside the fused kernels (top-K > 128, odd wide d): score blocks of `batch_size` users on the
+        device (`U_b @ I^T + b`, FP32 -- the one place a library GEMM is used) and feed them to the
+        score-matrix kernels, like the `predict` path but without the host round trip."""
+        import torch
+        MK = self.metrics_num * self.max_top
+        plan = self._plan(users, int(iv.shape[0]), key)
+        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
+        per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
+        step = max(1, min(int(self.batch_size), 4096))
+        for b0 in range(0, len(users), step):
+            s = torch.matmul(uv[b0:b0 + step].float(), iv.float().T)
+            if b is not None:
+                s = s + b
+            plan.ctx.eval_scores(s.contiguous(), b0, self.metrics, self.max_top,
+                                 per_user=None if per_user is None else per_user[b0:b0 + s.shape[0]], sums=sums)
+        return "scores:device_blocks", sums.cpu().numpy(), per_user
+
     def _evaluate_fused(self, model, users, key, dev, want_pu):
         """-> (path, float64 column sums [M*K] on the host, per-user block on the device or None)"""
         import torch
         user_vecs, item_vecs, bias = model.eval_embeddings(users)
         MK = self.metrics_num * self.max_top
+        if not self._fused_can_take(int(item_vecs.shape[1])):
+            uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
+            assert uv.shape[0] == len(users) and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
+            return self._evaluate_by_blocks(uv, iv, b, users, key, dev, want_pu)
         on_host = not (isinstance(user_vecs, torch.Tensor) and user_vecs.is_cuda) and \
             not (isinstance(item_vecs, torch.Tensor) and item_vecs.is_cuda)
         if on_host and not want_pu:

@@ -778,3 +778,20 @@ def test_fused_special_values_and_limits(torch_cuda, ctx):
     assert ctx.last_fused_kernel == "simt_fp32"
     with pytest.raises(_native.NativeError):   # n_items < top_k (evaluate.h:45 would read out of bounds)
         ctx.eval_fused(u, i, None, 0, [1], 51, sums=torch_cuda.zeros(51, dtype=torch_cuda.float64, device="cuda"))
+
+
+def test_evaluator_routes_shapes_outside_the_fused_kernels(torch_cuda):
+    """top-K > 128 or a wide d that is not a multiple of 4: device score blocks + score-matrix kernels, same numbers."""
+    from skrec_b200 import RankingEvaluator, adapters, synth
+    for d, top_k in ((64, [10, 200]), (130, [5, 20])):
+        data = synth.make(users=300, items=1500, d=d, nnz_train=6000, nnz_test=1500, seed=51 + d, bias=True)
+        metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
+        ids = [synth.METRIC_IDS[m] for m in metric]
+        model = adapters.dot_product(data["user_emb"], data["item_emb"], data["bias"])
+        ev = RankingEvaluator(data["train"], data["test"], metric=metric, top_k=top_k, device=0, batch_size=128)
+        got = np.array(list(ev.evaluate(model).values()), np.float32)
+        assert ev.last_stats["path"] == "scores:device_blocks"
+        per, _ = oracle.evaluate_dicts(synth.PredictOnlyModel(data["user_emb"], data["item_emb"], data["bias"]).predict,
+                                       data["train"], data["test"], ids, max(top_k))
+        expect = oracle.mean_f32(per).reshape(len(ids), max(top_k))[:, np.array(top_k) - 1].ravel()
+        assert np.max(np.abs(got - expect)) <= TOL_METRIC
