@@ -235,6 +235,10 @@ struct TcArgs {
     int cap;                 // entries per (row, chunk, column quarter) sub-list
     uint2 *cand;             // [n_rows, S*4, cap] (score bits, item)
     uint32_t *cand_cnt;      // [n_rows, S*4] entries offered (> cap means overflow)
+    // COLLECT work list: CTA b scores item tiles [t0, t0 + n) of user tile rt into sub-list slot `slot` of its rows;
+    // built on the host with unequal chunk counts per user tile and ordered largest first, so that the hardware's
+    // in-order block scheduler packs the SMs evenly (LPT) instead of leaving a quarter of them idle in the last wave
+    const int4 *work;        // {rt, t0, n, slot}
     // development aid: per-tile clock64 timestamps of one CTA (null = off), [tile][TC_TRACE_SLOTS]
     long long *trace;
     int trace_cta;
@@ -377,10 +381,10 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     // latency-critical single-thread roles (TMA producer, MMA issuers) must not queue behind the epilogue.
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = warp - TC_EPI_WARPS;  // 0 TMA producer, 1 MMA issuer (even tiles) + TMEM allocator, 2 mask builder, 3 MMA issuer (odd tiles)
-    const int c = blockIdx.x / P.n_rt, rt = blockIdx.x % P.n_rt;
-    // tiles of this work item: COLLECT t0 + i, SAMPLE i * stride
-    const int t0 = SAMPLE ? 0 : c * P.tiles_per_chunk;
-    const int n_tiles = SAMPLE ? A.n_samp : (min(t0 + P.tiles_per_chunk, P.n_ct) - t0);
+    // tiles of this work item: COLLECT t0 + i (work list), SAMPLE i * stride
+    int4 wk = make_int4((int)blockIdx.x, 0, A.n_samp, 0);
+    if (!SAMPLE) wk = __ldg(A.work + blockIdx.x);
+    const int rt = wk.x, t0 = wk.y, n_tiles = wk.z, c = wk.w;
     const int t_step = SAMPLE ? A.stride : 1;
     const int64_t row_base = (int64_t)rt * TM;
 

@@ -80,15 +80,25 @@ struct RowDot {
     }
 };
 
-// Whole-block routine: exact top-K keys of one row, sorted, to out[0..K).
+// Whole-block routine: exact top-K keys of one row over the items [j_begin, j_end) (j_begin a multiple of
+// K2_CHUNK; 0 .. n_items for the whole row), sorted, to out[0..K) (0 = empty slot when the range holds fewer).
 template <class Src>
 __device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int64_t tr_begin, int64_t tr_end,
                                                const int32_t *__restrict__ tr_idx, int K, u64 *__restrict__ out,
-                                               u64 *keys, uint32_t *bitmap, int *s_cnt)
+                                               u64 *keys, uint32_t *bitmap, int *s_cnt, int j_begin = 0, int j_end = 0x7fffffff)
 {
     const int tid = threadIdx.x, lane = tid & 31;
+    const int n_end = min(n_items, j_end);
     int64_t cur = tr_begin;
     const int64_t te = tr_end;
+    if (j_begin > 0) {  // train items below the range are not ours: first index with item >= j_begin
+        int64_t lo = tr_begin, hi = tr_end;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(tr_idx + mid) < j_begin) lo = mid + 1; else hi = mid;
+        }
+        cur = lo;
+    }
     int next_train = (cur < te) ? __ldg(tr_idx + cur) : 0x7fffffff;
 
     int base = 0;  // keys[0..base) hold the sorted best-so-far
@@ -98,11 +108,11 @@ __device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int6
     __syncthreads();
 
     float v[4], nxt[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    src.get4(tid * 4, n_items, v);
+    src.get4(j_begin + tid * 4, n_end, v);
 
-    for (int c0 = 0; c0 < n_items; c0 += K2_CHUNK) {
+    for (int c0 = j_begin; c0 < n_end; c0 += K2_CHUNK) {
         const int j0 = c0 + tid * 4;
-        if (c0 + K2_CHUNK < n_items) src.get4(j0 + K2_CHUNK, n_items, nxt);
+        if (c0 + K2_CHUNK < n_end) src.get4(j0 + K2_CHUNK, n_end, nxt);
 
         // train items that fall into this chunk -> bitmap (sorted CSR row, cursor moves forward)
         uint32_t mbits = 0;
@@ -126,7 +136,7 @@ __device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int6
         for (int q = 0; q < 4; ++q) {
             float s = v[q];
             if ((mbits >> q) & 1u) s = -__int_as_float(0x7f800000);
-            bool pass = (j0 + q < n_items) && !(s < thr_f);
+            bool pass = (j0 + q < n_end) && !(s < thr_f);
             u64 key = 0;
             if (pass) {
                 key = make_key(s, (uint32_t)(j0 + q));
@@ -143,7 +153,10 @@ __device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int6
         }
         __syncthreads();
         const int cnt = *s_cnt;
-        const bool last = (c0 + K2_CHUNK >= n_items);
+        // every thread must have read the count before anyone appends survivors of the next chunk: a late reader
+        // would see a larger count, could decide to sort on its own and meet barriers the others never reach
+        __syncthreads();
+        const bool last = (c0 + K2_CHUNK >= n_end);
         if (last || base + cnt + K2_CHUNK > K2_P) {
             const int tot = base + cnt;
             int n_sort = next_pow2(tot);
@@ -163,7 +176,7 @@ __device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int6
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[q] = nxt[q];
     }
-    for (int i = tid; i < K; i += K2_THREADS) out[i] = keys[i];
+    for (int i = tid; i < K; i += K2_THREADS) out[i] = (i < base) ? keys[i] : 0ull;
 }
 
 __global__ void __launch_bounds__(K2_THREADS)
@@ -183,18 +196,30 @@ k_topk_scores(const float *__restrict__ scores, int64_t ld, int n_items, int64_t
     topk_row_block(src, n_items, tb, te, tr_idx, K, out_keys + r * K, keys, bitmap, &s_cnt);
 }
 
-// rows on the fail list of k_select_cands: exact FP32 scores on the fly, same selection
+// Rows on the fail list of k_select_cands: exact FP32 scores on the fly, same selection.  A work item is
+// (failed row, one of n_seg item ranges): a handful of failed rows then spreads over the whole GPU instead of
+// occupying one CTA each for the time it takes to walk the catalogue (0.6 ms per row at 92 K items).  The n_seg
+// partial lists of a row are merged by k_merge_fail.
 __global__ void __launch_bounds__(K2_THREADS)
 k_row_exact(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_count, const float *__restrict__ U, int64_t ld_u,
             const float *__restrict__ V, int64_t ld_v, int d, const float *__restrict__ bias, int n_items, int64_t row0,
-            const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K, u64 *__restrict__ out_keys)
+            const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K, int n_seg, int seg_items,
+            int max_seg_rows, u64 *__restrict__ part, u64 *__restrict__ out_keys)
 {
     __shared__ u64 keys[K2_P];
     __shared__ uint32_t bitmap[K2_CHUNK / 32];
     __shared__ int s_cnt;
     __shared__ float u_s[K2_MAX_D];
     const int n_fail = *fail_count;
-    for (int i = blockIdx.x; i < n_fail; i += gridDim.x) {
+    // grid (x, n_seg): block (x, g) walks segment g of the failed rows x, x + gridDim.x, ...  The first max_seg_rows
+    // failed rows are cut in segments (room in `part`); any beyond are walked whole by the g == 0 blocks, straight
+    // into out_keys (that many failures means the thresholds were useless and the time is lost anyway).
+    const int n_segd = min(n_fail, max_seg_rows);
+    const int g = blockIdx.y;
+    const int n_mine = n_segd + ((g == 0) ? (n_fail - n_segd) : 0);
+    for (int i = blockIdx.x; i < n_mine; i += gridDim.x) {
+        const bool whole = i >= n_segd;
+        const int64_t w = (int64_t)i * n_seg + g;
         const int64_t r = fail_list[i];
         __syncthreads();
         for (int k = threadIdx.x; k < d; k += K2_THREADS) u_s[k] = U[r * ld_u + k];
@@ -208,7 +233,36 @@ k_row_exact(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_
         src.vec_ok = ((ld_v & 3) == 0) && ((reinterpret_cast<uintptr_t>(V) & 15) == 0);
         int64_t tb = 0, te = 0;
         if (tr_indptr != nullptr) { tb = __ldg(tr_indptr + row0 + r); te = __ldg(tr_indptr + row0 + r + 1); }
-        topk_row_block(src, n_items, tb, te, tr_idx, K, out_keys + r * K, keys, bitmap, &s_cnt);
+        u64 *dst = whole ? out_keys + r * K : part + w * (int64_t)K;
+        const int j_begin = whole ? 0 : g * seg_items, j_end = whole ? 0x7fffffff : (g + 1) * seg_items;
+        topk_row_block(src, n_items, tb, te, tr_idx, K, dst, keys, bitmap, &s_cnt, j_begin, j_end);
+    }
+}
+
+// n_seg partial lists of every failed row -> its sorted top-K in out_keys[row]
+template <int PER>
+__global__ void __launch_bounds__(128)
+k_merge_fail(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_count, const u64 *__restrict__ part, int n_seg, int K,
+             int max_seg_rows, u64 *__restrict__ out_keys)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_fail = min(*fail_count, max_seg_rows);
+    const int n = n_seg * K;
+    for (int i = blockIdx.x * 4 + warp; i < n_fail; i += gridDim.x * 4) {
+        const u64 *src = part + (int64_t)i * n;
+        u64 v[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int j = e * 32 + lane;
+            v[e] = (j < n) ? src[j] : 0ull;
+        }
+        warp_bitonic_desc<PER>(v, lane);
+        u64 *dst = out_keys + (int64_t)fail_list[i] * K;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int j = e * 32 + lane;
+            if (j < K) dst[j] = v[e];
+        }
     }
 }
 

@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -66,7 +67,7 @@ struct skr_ctx {
     float *d_idcg = nullptr;  // iDCG after n terms (metric.h:82), host-accumulated
     int disc_n = 0;
     // workspace, grow-only
-    Buf trace, stats, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
+    Buf trace, work, stats, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
     int64_t launches = 0;
     const char *last_fused = "none";
@@ -75,8 +76,14 @@ struct skr_ctx {
     int64_t opt_sample_tiles = 0;
     int64_t opt_rank = 0;
     int64_t opt_dbg = 0;
+    int64_t opt_exact_seg_rows = -1;  // development: how many failed rows are cut in segments (-1 = default)
+    bool debug_sync = false;  // SKR_DEBUG_SYNC=1: synchronise and check after every kernel, naming the one that failed
     int64_t opt_trace_cta = -1;  // >= 0: record the tile timeline of that CTA of the main pass (development aid)
     struct Plan { int n_samp, stride, r, cap, S, stages; } last_plan = {0, 0, 0, 0, 0, 0};
+    // cached COLLECT work list (see plan_work)
+    int work_key[4] = {-1, -1, -1, -1};
+    int work_ctas = 0, work_slots = 0, work_min_slots = 0, work_max_tiles = 0;
+    bool work_mixed = false;
     EncodeTiledFn encode = nullptr;
     std::vector<cudaEvent_t> ev0, ev1, ev2;  // ring: ev2 before the pre-pass, ev0/ev1 around the main scoring kernel
     int64_t ev_calls = 0;
@@ -94,6 +101,15 @@ int fail(skr_ctx *ctx, int code, const char *fmt, ...)
     if (ctx) ctx->err = buf; else g_create_error = buf;
     return code;
 }
+
+#define SKR_AFTER(ctx, st, name)                                                                     \
+    do {                                                                                             \
+        if ((ctx)->debug_sync) {                                                                     \
+            cudaError_t e__ = cudaStreamSynchronize(st);                                             \
+            if (e__ == cudaSuccess) e__ = cudaGetLastError();                                        \
+            if (e__ != cudaSuccess) return fail(ctx, SKR_ERR_CUDA, "after %s: %s", name, cudaGetErrorString(e__)); \
+        }                                                                                            \
+    } while (0)
 
 #define SKR_CUDA(ctx, call)                                                                          \
     do {                                                                                             \
@@ -251,6 +267,34 @@ struct ExactArgs {
     const int64_t *tr_indptr; const int32_t *tr_idx;
 };
 
+// exact re-scoring of the rows on the fail list: (row, item segment) work items, then a merge per row
+int run_row_exact(skr_ctx *ctx, const ExactArgs &E, int32_t *fail_list, int *fail_count, int64_t n_rows, int64_t row0, int K, u64 *keys_out,
+                  cudaStream_t st)
+{
+    int n_seg = std::max(1, std::min(16, 1024 / K));
+    int seg_items = (int)(((int64_t)E.n_items + n_seg - 1) / n_seg);
+    seg_items = ((seg_items + K2_CHUNK - 1) / K2_CHUNK) * K2_CHUNK;  // ranges start on chunk boundaries (vector loads)
+    n_seg = (E.n_items + seg_items - 1) / seg_items;
+    // room for the partial lists of as many failed rows as are plausible; beyond that the rows are walked whole
+    const int64_t max_fail = std::min<int64_t>(n_rows, ctx->opt_exact_seg_rows >= 0 ? ctx->opt_exact_seg_rows : 2048);
+    int rc = ensure(ctx, ctx->part, (size_t)max_fail * n_seg * K * sizeof(u64));
+    if (rc) return rc;
+    k_row_exact<<<dim3((unsigned)std::max(1, 4 * ctx->n_sm / n_seg), (unsigned)n_seg), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
+                                                                  E.tr_indptr, E.tr_idx, K, n_seg, seg_items, (int)max_fail, (u64 *)ctx->part.p, keys_out);
+    SKR_AFTER(ctx, st, "k_row_exact");
+    const int n = n_seg * K;
+    const unsigned g = (unsigned)ctx->n_sm;
+    if (n <= 64) k_merge_fail<2><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
+    else if (n <= 128) k_merge_fail<4><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
+    else if (n <= 256) k_merge_fail<8><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
+    else if (n <= 512) k_merge_fail<16><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
+    else k_merge_fail<32><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
+    ctx->launches += 2;
+    SKR_AFTER(ctx, st, "k_merge_fail");
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
 int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
                        const MetricIds &m, int K, const ExactArgs &E, int32_t *fail_list, int *fail_count, int32_t *topk_idx,
                        float *topk_val, float *per_user, double *sums, u64 *keys_only, RescoreArgs RA, cudaStream_t st)
@@ -282,9 +326,8 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
                                                   nullptr, nullptr);
             ctx->launches++;
         }
-        k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
-                                                                      E.tr_indptr, E.tr_idx, K, keys_only);
-        ctx->launches += 2;
+        if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys_only, st))) return rc;
+        ctx->launches += 1;
         SKR_CUDA(ctx, cudaGetLastError());
         return SKR_OK;
     }
@@ -328,12 +371,12 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
         sel<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
                                                     ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA);
     }
-    k_row_exact<<<(unsigned)(2 * ctx->n_sm), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
-                                                                  E.tr_indptr, E.tr_idx, K, keys);
+    SKR_AFTER(ctx, st, "k_select_cands / k_sort_metrics");
+    if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys, st))) return rc;
     k_metrics<<<g_fix, K4_WARPS * 32, fused_sums ? acc_k4 : 0, st>>>(keys, nullptr, K, n_rows, row0, fail_list, fail_count, ctx->d_te_indptr,
                                                                      ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val,
                                                                      acc ? acc + (size_t)g_sel * MK : nullptr);
-    ctx->launches += 3;
+    ctx->launches += 2;
     if (fused_sums) {
         k_colsum_fold<<<MK, 256, 0, st>>>(acc, g_sel + g_fix, MK, sums);
         ctx->launches++;
@@ -346,6 +389,72 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     }
     SKR_CUDA(ctx, cudaGetLastError());
     return SKR_OK;
+}
+
+// ---- work list of the tensor-core main pass ---------------------------------------------------------------
+// A work item = (user tile, contiguous range of item tiles).  With the same number of chunks for every user tile
+// the CTA count is rarely a multiple of the SM count (c2: 702 CTAs = 4.74 waves, the last wave a quarter empty).
+// Here user tiles may get s or s + 1 chunks so that the total is k * n_sm, and the list is ordered largest chunk
+// first: the block scheduler hands CTAs out in index order to whichever SM frees up, i.e. it runs the
+// longest-processing-time-first heuristic for us.  The makespan of every candidate (k waves, or the plain
+// uniform splits) is simulated with a fixed per-CTA overhead and the cheapest wins.
+struct WorkPlan {
+    std::vector<int4> items;
+    int slots = 1, min_slots = 1, max_tiles = 0;
+    bool mixed = false;
+    long makespan = 0;
+};
+
+static long lpt_makespan(const std::vector<int4> &items, int n_sm, int overhead)
+{
+    std::vector<long> load((size_t)n_sm, 0);  // items are already sorted by decreasing size
+    for (const int4 &w : items) {
+        size_t best = 0;
+        for (size_t j = 1; j < load.size(); ++j)
+            if (load[j] < load[best]) best = j;
+        load[best] += w.z + overhead;
+    }
+    return *std::max_element(load.begin(), load.end());
+}
+
+static WorkPlan make_work(int n_rt, int n_ct, int s_lo, int n_plus, int n_sm)
+{
+    // n_plus user tiles get s_lo + 1 chunks, the others s_lo
+    WorkPlan wp;
+    wp.slots = s_lo + (n_plus > 0 ? 1 : 0);
+    wp.min_slots = (n_plus >= n_rt) ? s_lo + 1 : s_lo;
+    wp.mixed = n_plus > 0 && n_plus < n_rt;
+    for (int rt = 0; rt < n_rt; ++rt) {
+        const int s = s_lo + (rt < n_plus ? 1 : 0);
+        for (int c = 0; c < s; ++c) {
+            const int t0 = (int)((long)n_ct * c / s), t1 = (int)((long)n_ct * (c + 1) / s);
+            if (t1 > t0) wp.items.push_back(make_int4(rt, t0, t1 - t0, c));
+        }
+    }
+    std::stable_sort(wp.items.begin(), wp.items.end(), [](const int4 &a, const int4 &b) { return a.z > b.z; });
+    for (const int4 &w : wp.items) wp.max_tiles = std::max(wp.max_tiles, w.z);
+    wp.makespan = lpt_makespan(wp.items, n_sm, 6);
+    return wp;
+}
+
+static WorkPlan plan_work(const skr_ctx *ctx, int n_rt, int n_ct)
+{
+    const int smax = std::min(n_ct, 8);  // 4 sub-lists per chunk, at most 32 per row
+    if (ctx->opt_chunks > 0) return make_work(n_rt, n_ct, (int)std::min<int64_t>(ctx->opt_chunks, smax), 0, ctx->n_sm);
+    WorkPlan best = make_work(n_rt, n_ct, 1, 0, ctx->n_sm);
+    for (int s = 2; s <= smax; ++s) {
+        WorkPlan w = make_work(n_rt, n_ct, s, 0, ctx->n_sm);
+        if (w.makespan < best.makespan) best = w;
+    }
+    for (int k = 1; k <= 16; ++k) {  // k full waves
+        const long C = (long)k * ctx->n_sm;
+        const int s_lo = (int)(C / n_rt), n_plus = (int)(C - (long)s_lo * n_rt);
+        if (s_lo < 1 || n_plus == 0) continue;
+        if (s_lo + 1 > smax) break;
+        WorkPlan w = make_work(n_rt, n_ct, s_lo, n_plus, ctx->n_sm);
+        if (w.makespan < best.makespan) best = w;
+    }
+    return best;
 }
 
 int pick_chunks(const skr_ctx *ctx, int n_rt, int n_ct, int K, bool lists)
@@ -464,6 +573,8 @@ int skr_ctx_create(int device, skr_ctx **out)
         delete ctx;
         return fail(nullptr, SKR_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
     }
+    const char *dbg_env = getenv("SKR_DEBUG_SYNC");
+    ctx->debug_sync = dbg_env != nullptr && dbg_env[0] == '1';
     ctx->ev0.resize(1);
     ctx->ev1.resize(1);
     ctx->ev2.resize(1);
@@ -484,7 +595,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
-                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt};
+                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt, &ctx->work};
     for (Buf *b : bufs) free_dev(b->p);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
@@ -501,6 +612,7 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "sample_tiles")) { ctx->opt_sample_tiles = value; return SKR_OK; }
     if (!strcmp(name, "rank")) { ctx->opt_rank = value; return SKR_OK; }
     if (!strcmp(name, "dbg")) { ctx->opt_dbg = value; return SKR_OK; }
+    if (!strcmp(name, "exact_seg_rows")) { ctx->opt_exact_seg_rows = value; return SKR_OK; }
     if (!strcmp(name, "trace_cta")) { ctx->opt_trace_cta = value; return SKR_OK; }
     if (!strcmp(name, "event_ring")) {
         if (value < 1 || value > 65536) return fail(ctx, SKR_ERR_INVALID, "event_ring=%lld not in [1,65536]", (long long)value);
@@ -843,8 +955,21 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         r = std::max(1, std::min(r, TC_MAX_RANK));
         if (ctx->opt_rank > 0) r = (int)std::min<int64_t>(ctx->opt_rank, TC_MAX_RANK);
         const double expect = r / f_eff;  // candidates per row
+        // work list of the main pass (cached: it depends only on the tile counts)
+        if (ctx->work_key[0] != P.n_rt || ctx->work_key[1] != P.n_ct || ctx->work_key[2] != (int)ctx->opt_chunks) {
+            const WorkPlan wp = plan_work(ctx, P.n_rt, P.n_ct);
+            if ((rc = ensure(ctx, ctx->work, wp.items.size() * sizeof(int4)))) return rc;
+            SKR_CUDA(ctx, cudaMemcpyAsync(ctx->work.p, wp.items.data(), wp.items.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+            SKR_CUDA(ctx, cudaStreamSynchronize(st));  // the host vector goes away; happens once per shape
+            ctx->work_key[0] = P.n_rt; ctx->work_key[1] = P.n_ct; ctx->work_key[2] = (int)ctx->opt_chunks;
+            ctx->work_ctas = (int)wp.items.size(); ctx->work_slots = wp.slots; ctx->work_min_slots = wp.min_slots;
+            ctx->work_max_tiles = wp.max_tiles; ctx->work_mixed = wp.mixed;
+        }
+        P.S = ctx->work_slots;
+        const unsigned grid_tc = (unsigned)ctx->work_ctas;
         const int n_sub = 4 * P.S;        // one sub-list per (item chunk, column quarter of the tile)
-        int cap = next_pow2((int)(2.0 * expect / n_sub) + 16);
+        // capacity of a sub-list: twice the expected share of the user tiles with the fewest chunks
+        int cap = next_pow2((int)(2.0 * expect / (4 * ctx->work_min_slots)) + 16);
         cap = std::max(16, std::min(cap, 512));
 
         if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 4 * TC_R * sizeof(float)))) return rc;
@@ -867,6 +992,9 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.cap = cap;
         A.cand = (uint2 *)ctx->cand.p;
         A.cand_cnt = (uint32_t *)ctx->cand_cnt.p;
+        A.work = (const int4 *)ctx->work.p;
+        if (ctx->work_mixed)  // user tiles with fewer chunks leave their last sub-lists untouched: they must read as empty
+            SKR_CUDA(ctx, cudaMemsetAsync(ctx->cand_cnt.p, 0, (size_t)n_rows * n_sub * sizeof(uint32_t), st));
         A.trace = nullptr;
         A.trace_cta = -1;
         A.trace_tiles = 0;
@@ -887,11 +1015,12 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)P.n_rt, st, mhi, mlo, A, P))) return rc;
+        SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
         k_sample_thr<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
                                                                    (const float *)ctx->stats.p, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr);
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
-            A.trace_tiles = P.tiles_per_chunk;
+            A.trace_tiles = ctx->work_max_tiles;
             const size_t tb = (size_t)A.trace_tiles * TC_TRACE_SLOTS * sizeof(long long);
             if ((rc = ensure(ctx, ctx->trace, tb))) return rc;
             SKR_CUDA(ctx, cudaMemsetAsync(ctx->trace.p, 0, tb, st));
@@ -899,7 +1028,9 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
             A.trace_cta = (int)ctx->opt_trace_cta;
         }
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
-        if ((rc = launch_tc(ctx, nkb, passes, TC_MODE_COLLECT, grid, st, mhi, mlo, A, P))) return rc;
+        SKR_AFTER(ctx, st, "k_sample_thr");
+        if ((rc = launch_tc(ctx, nkb, passes, TC_MODE_COLLECT, grid_tc, st, mhi, mlo, A, P))) return rc;
+        SKR_AFTER(ctx, st, "k_fused_tc COLLECT");
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
         SKR_CUDA(ctx, cudaGetLastError());
