@@ -276,7 +276,7 @@ int run_row_exact(skr_ctx *ctx, const ExactArgs &E, int32_t *fail_list, int *fai
     seg_items = ((seg_items + K2_CHUNK - 1) / K2_CHUNK) * K2_CHUNK;  // ranges start on chunk boundaries (vector loads)
     n_seg = (E.n_items + seg_items - 1) / seg_items;
     // room for the partial lists of as many failed rows as are plausible; beyond that the rows are walked whole
-    const int64_t max_fail = std::min<int64_t>(n_rows, ctx->opt_exact_seg_rows >= 0 ? ctx->opt_exact_seg_rows : 2048);
+    const int64_t max_fail = std::min<int64_t>(n_rows, ctx->opt_exact_seg_rows >= 0 ? ctx->opt_exact_seg_rows : 256);
     int rc = ensure(ctx, ctx->part, (size_t)max_fail * n_seg * K * sizeof(u64));
     if (rc) return rc;
     k_row_exact<<<dim3((unsigned)std::max(1, 4 * ctx->n_sm / n_seg), (unsigned)n_seg), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,

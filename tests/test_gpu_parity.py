@@ -795,3 +795,37 @@ def test_evaluator_routes_shapes_outside_the_fused_kernels(torch_cuda):
                                        data["train"], data["test"], ids, max(top_k))
         expect = oracle.mean_f32(per).reshape(len(ids), max(top_k))[:, np.array(top_k) - 1].ravel()
         assert np.max(np.abs(got - expect)) <= TOL_METRIC
+
+
+@pytest.mark.parametrize("U,I,seg_rows", [(700, 20000, -1), (700, 20000, 0), (3000, 5000, 100)])
+def test_exact_fallback_when_thresholds_are_useless(torch_cuda, U, I, seg_rows):
+    """rank = 1 makes the sampled threshold the largest sampled score: most rows collect fewer than K candidates and
+    go through the exact fallback -- segmented (few rows), whole-row (many rows) or both.  Results stay exact.
+    (This shape also reproduced a barrier race in the streaming selection that the default plan never triggered.)"""
+    from skrec_b200 import _native, synth
+    torch = torch_cuda
+    d = synth.make(users=U, items=I, d=64, nnz_train=U * 20, nnz_test=U * 5, seed=3, device="cuda")
+    c = _native.Context(0)
+    c.set_train_csr(d["train_indptr"], d["train_indices"], I)
+    c.set_test_csr(d["test_indptr"], d["test_indices"], I)
+    c.set_option("rank", 1)
+    c.set_option("sample_tiles", 2)
+    c.set_option("exact_seg_rows", seg_rows)
+    ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"]).cuda()
+    S = oracle.scores(d["user_emb"], d["item_emb"], None)
+    oracle.mask_rows(S, d["train_indptr"], d["train_indices"])
+    metric, K = [1, 2, 3, 4, 5], 20
+    eper, etop = oracle.eval_scores(S, d["test_indptr"], d["test_indices"], metric, K, return_topk=True)
+    for prec in ("3xtf32", "tf32r"):
+        for rep in range(2):
+            idx = torch.empty((U, K), dtype=torch.int32, device="cuda")
+            val = torch.empty((U, K), dtype=torch.float32, device="cuda")
+            per = torch.empty((U, len(metric) * K), dtype=torch.float32, device="cuda")
+            sums = torch.zeros(len(metric) * K, dtype=torch.float64, device="cuda")
+            c.eval_fused(ue, ie, None, 0, metric, K, precision=prec, topk_idx=idx, topk_val=val, per_user=per, sums=sums)
+            torch.cuda.synchronize()
+            assert c.fused_stats()["exact_rows"] > 0.2 * U
+            _check_fused(idx.cpu().numpy(), val.cpu().numpy(), per.cpu().numpy(), sums.cpu().numpy(),
+                         d["user_emb"], d["item_emb"], None, (d["train_indptr"], d["train_indices"]),
+                         (d["test_indptr"], d["test_indices"]), metric, K)
+    c.close()
