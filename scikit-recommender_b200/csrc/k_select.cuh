@@ -171,16 +171,27 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         const int *off = s_off[warp];
         uint32_t vmin = 0xffffffffu, vmax = 0u;
         const uint2 *row_src = cand + row * n_sub * (int64_t)sub_stride;
-        for (int j = lane; j < n; j += 32) {
-            int s = 0;
+        for (int j0 = lane; j0 < n; j0 += 128) {  // four independent loads in flight per lane
+            uint2 e[4];
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (off[s + step] <= j) s += step;
-            uint2 e = row_src[(int64_t)s * sub_stride + (j - off[s])];
-            e.x = ord_f32(__uint_as_float(e.x));
-            vmin = min(vmin, e.x);
-            vmax = max(vmax, e.x);
-            ent[j] = e;
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + 32 * q;
+                int s = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                    if (off[s + step] <= j) s += step;
+                e[q] = (j < n) ? row_src[(int64_t)s * sub_stride + (j - off[s])] : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + 32 * q;
+                if (j < n) {
+                    e[q].x = ord_f32(__uint_as_float(e[q].x));
+                    vmin = min(vmin, e[q].x);
+                    vmax = max(vmax, e[q].x);
+                    ent[j] = e[q];
+                }
+            }
         }
         vmin = __reduce_min_sync(0xffffffffu, vmin);
         vmax = __reduce_max_sync(0xffffffffu, vmax);
@@ -296,35 +307,43 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             __syncwarp();
             const bool vec_ok = ((R.ld_v & 3) == 0) && ((reinterpret_cast<uintptr_t>(R.V) & 15) == 0);
             uint32_t omin = 0xffffffffu, omax = 0u;
-            for (int i0 = 0; i0 < m; i0 += 64) {  // two candidates per lane in flight: two independent FMA chains
-                const int ia = i0 + lane, ib = ia + 32;
-                const bool va = ia < m, vb = ib < m;
-                const uint32_t item_a = va ? ~(uint32_t)skey[ia] : 0u, item_b = vb ? ~(uint32_t)skey[ib] : 0u;
-                const float *pa = R.V + (int64_t)item_a * R.ld_v, *pb = R.V + (int64_t)item_b * R.ld_v;
-                float a = 0.0f, b = 0.0f;
+            for (int i0 = 0; i0 < m; i0 += 32) {
+                // one candidate per lane; its row is fetched 8 float4 at a time, all loads issued before the first FMA
+                // (with the loads inside the FMA loop every 4 k-values waited a full L2 round trip: 16 trips per row)
+                const int ia = i0 + lane;
+                const bool va = ia < m;
+                const uint32_t item_a = va ? ~(uint32_t)skey[ia] : 0u;
+                const float *pa = R.V + (int64_t)item_a * R.ld_v;
+                float a = 0.0f;
                 int k = 0;
                 if (vec_ok) {
+                    for (; k + 32 <= R.d; k += 32) {
+                        float4 x[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) x[q] = __ldg(reinterpret_cast<const float4 *>(pa + k) + q);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 w = *reinterpret_cast<const float4 *>(u + k + 4 * q);
+                            a = fmaf(w.x, x[q].x, a);
+                            a = fmaf(w.y, x[q].y, a);
+                            a = fmaf(w.z, x[q].z, a);
+                            a = fmaf(w.w, x[q].w, a);
+                        }
+                    }
                     for (; k + 4 <= R.d; k += 4) {
                         const float4 x = __ldg(reinterpret_cast<const float4 *>(pa + k));
-                        const float4 y = __ldg(reinterpret_cast<const float4 *>(pb + k));
                         const float4 w = *reinterpret_cast<const float4 *>(u + k);
-                        a = fmaf(w.x, x.x, a); b = fmaf(w.x, y.x, b);
-                        a = fmaf(w.y, x.y, a); b = fmaf(w.y, y.y, b);
-                        a = fmaf(w.z, x.z, a); b = fmaf(w.z, y.z, b);
-                        a = fmaf(w.w, x.w, a); b = fmaf(w.w, y.w, b);
+                        a = fmaf(w.x, x.x, a);
+                        a = fmaf(w.y, x.y, a);
+                        a = fmaf(w.z, x.z, a);
+                        a = fmaf(w.w, x.w, a);
                     }
                 }
-                for (; k < R.d; ++k) { a = fmaf(u[k], __ldg(pa + k), a); b = fmaf(u[k], __ldg(pb + k), b); }
-                if (R.bias != nullptr) { a += __ldg(R.bias + item_a); b += __ldg(R.bias + item_b); }
+                for (; k < R.d; ++k) a = fmaf(u[k], __ldg(pa + k), a);
+                if (R.bias != nullptr) a += __ldg(R.bias + item_a);
                 if (va) {
                     const u64 key = make_key(a, item_a);
                     skey[ia] = key;
-                    omin = min(omin, (uint32_t)(key >> 32));
-                    omax = max(omax, (uint32_t)(key >> 32));
-                }
-                if (vb) {
-                    const u64 key = make_key(b, item_b);
-                    skey[ib] = key;
                     omin = min(omin, (uint32_t)(key >> 32));
                     omax = max(omax, (uint32_t)(key >> 32));
                 }
