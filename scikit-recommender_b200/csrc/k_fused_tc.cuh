@@ -246,12 +246,19 @@ struct TcArgs {
 };
 
 constexpr int TC_TRACE_SLOTS = 16;
+constexpr int TC_MASK_PF = 4;  // mask builder: key prefetch distance in tiles (< 32)
 // slots: 0 producer got the stage of kb 0, 1 producer issued the last TMA of the tile, 2 issuer: accumulator free,
 // 3 issuer: first stage full, 4 issuer: tile committed, 5 mask: buffer free, 6 mask: bitmap ready,
 // 7/10 epilogue warp 0/15: tile full, 8/11: accumulator in registers (released), 9/12: tile processed
 #ifndef SKR_TC_TRACE
 #define SKR_TC_TRACE 0
 #endif
+// ablation switches (TcArgs::dbg) are compiled in only for tools/dbg_timing.py and tools/trace_tiles.py
+// (SKR_NVCC_EXTRA="-DSKR_TC_DBG=1"): the tests on them cost ~10 instructions per tile in the epilogue loop
+#ifndef SKR_TC_DBG
+#define SKR_TC_DBG 0
+#endif
+#define TC_DBG(word, bit) (SKR_TC_DBG && ((word) & (bit)))
 __device__ __forceinline__ void tc_trace(const TcArgs &A, int tile, int slot)
 {
     if (SKR_TC_TRACE && A.trace != nullptr && (int)blockIdx.x == A.trace_cta && tile < A.trace_tiles)
@@ -282,7 +289,7 @@ __device__ __forceinline__ void sorted_insert(float (&v)[TC_R], float x)
 // list v.  COLLECT: survivor mask against the row threshold, survivors appended to the sub-list.
 template <bool SAMPLE, bool BIAS>
 __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const float *__restrict__ bias32, uint32_t mword, float thr, int col0,
-                                           bool my_valid, int cap, bool no_append, float4 *my_stage, uint2 *wbase, int &wn, float (&v)[TC_R])
+                                           bool my_valid, int cap, int dbg, float4 *my_stage, uint2 *wbase, int &wn, float (&v)[TC_R])
 {
     float s[32];
     if (BIAS) {
@@ -315,7 +322,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
         mx = fmaxf(mx, fmaxf(fmaxf(m1[6], m1[7]), m1[8]));
         mx = fmaxf(mx, fmaxf(m1[9], m1[10]));
         if (my_valid && mx > v[TC_R - 1]) sorted_insert(v, mx);
-    } else if (!no_append) {
+    } else if (!TC_DBG(dbg, 4)) {
         // Detection costs two instructions per score on two different pipes and no predicates:
         // d = s - T0 (FMA pipe), then a funnel shift (ALU pipe) collects the sign bit of d; bit q of
         // `pass` ends up set iff s[q] >= T0 and item q is not masked.
@@ -331,6 +338,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
         // then reverse
         const uint32_t m = (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
         uint32_t pass = ~__brev(m) & ~mword;
+        if (TC_DBG(dbg, 32)) pass &= (uint32_t)(wn >> 30);  // timing experiment: detection only
         if (pass != 0u) {
             // rare per lane: park my 32 scores in shared memory so they can be indexed, then append
             // each survivor as (score bits, item) to my list in HBM
@@ -342,7 +350,8 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
                 const int q = __ffs(pass) - 1;
                 pass &= pass - 1u;
                 const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
-                if (wn < cap) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
+                if (wn < cap && !TC_DBG(dbg, 64)) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
+                if (TC_DBG(dbg, 64)) wn += (int)(__float_as_uint(sc) >> 31);  // timing experiment: no global store
                 ++wn;
             } while (pass != 0u);
         }
@@ -423,7 +432,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 mbar_wait(empty + s, ph ^ 1u, A.err_flag, 1);
                 if (elect_one()) {
                     if (kb == 0) tc_trace(A, i, 0);
-                    if (A.dbg & 8) {
+                    if (TC_DBG(A.dbg, 8)) {
                         mbar_arrive(full + s);
                     } else {
                         mbar_expect_tx(full + s, STAGE_BYTES);
@@ -444,7 +453,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         // tcgen05.mma in an ELECT / 3 x R2UR / branch loop (~100 cycles per MMA, measured) because it cannot
         // prove the descriptors uniform; here they are uniform registers and an MMA is a single instruction.
         const int p = (role == 1) ? 0 : 1;
-        const bool do_mma = !(A.dbg & 2);
+        const bool do_mma = !TC_DBG(A.dbg, 2);
         mbar_wait(a_ready, 0, A.err_flag, 2);
         tc_fence_after();
         const uint32_t a_hi0 = tmem_base;
@@ -503,31 +512,51 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             keys = P.mask_keys + __ldg(P.mask_tile_ptr + rt_abs);
             offs = P.mask_tile_off + rt_abs * (int64_t)(P.n_ct + 1);
         }
-        uint32_t off_b = 0, off_e = 0, nkey = 0xffffffffu;
-        for (int i = 0; i < n_tiles; ++i) {
+        // Lane l holds the key range of tile (32-tile batch + l) for the current batch (off_*) and the next (nxt_*).
+        // The first 32 keys of a tile are fetched TC_MASK_PF tiles ahead: one tile of bitmap work is shorter than
+        // an L2 round trip, and with a one-tile lookahead this warp paced the whole pipeline in the single-pass modes.
+        uint32_t off_b = 0, off_e = 0, nxt_b = 0, nxt_e = 0;
+        auto load_offs = [&](int base, uint32_t &ob, uint32_t &oe) {
+            const int ti = base + lane;
+            ob = oe = 0;
+            if (keys != nullptr && ti < n_tiles) {
+                const int t = t0 + ti * t_step;
+                ob = __ldg(offs + t);
+                oe = __ldg(offs + t + 1);
+            }
+        };
+        // first keys of tile x, x in the current or the next batch relative to tile i
+        auto fetch = [&](int x, int i) -> uint32_t {
+            if (keys == nullptr || x >= n_tiles) return 0xffffffffu;
+            const bool nx = (x >> 5) != (i >> 5);
+            const uint32_t nb = __shfl_sync(0xffffffffu, nx ? nxt_b : off_b, x & 31);
+            const uint32_t ne = __shfl_sync(0xffffffffu, nx ? nxt_e : off_e, x & 31);
+            return (nb + lane < ne) ? __ldg(keys + nb + lane) : 0xffffffffu;
+        };
+        load_offs(0, off_b, off_e);
+        load_offs(32, nxt_b, nxt_e);
+        uint32_t nk[TC_MASK_PF];
+#pragma unroll
+        for (int j = 0; j < TC_MASK_PF; ++j) nk[j] = fetch(j, 0);
+        for (int i0 = 0; i0 < n_tiles; i0 += TC_MASK_PF) {
+#pragma unroll
+          for (int j = 0; j < TC_MASK_PF; ++j) {
+            const int i = i0 + j;
+            if (i >= n_tiles) break;
             const int b = i % NBUF;
             const int col0 = (t0 + i * t_step) * TN;
-            if (keys != nullptr && (i & 31) == 0) {
-                const int ti = i + lane;
-                off_b = off_e = 0;
-                if (ti < n_tiles) {
-                    const int t = t0 + ti * t_step;
-                    off_b = __ldg(offs + t);
-                    off_e = __ldg(offs + t + 1);
-                }
-                const uint32_t nb = __shfl_sync(0xffffffffu, off_b, 0), ne = __shfl_sync(0xffffffffu, off_e, 0);
-                nkey = (nb + lane < ne) ? __ldg(keys + nb + lane) : 0xffffffffu;
+            if ((i & 31) == 0 && i != 0) {
+                off_b = nxt_b;
+                off_e = nxt_e;
+                load_offs(i + 32, nxt_b, nxt_e);
             }
             const uint32_t kb0 = __shfl_sync(0xffffffffu, off_b, i & 31), ke0 = __shfl_sync(0xffffffffu, off_e, i & 31);
-            uint32_t key = nkey;
-            if (keys != nullptr && ((i + 1) & 31) != 0 && i + 1 < n_tiles) {
-                const uint32_t nb = __shfl_sync(0xffffffffu, off_b, (i + 1) & 31), ne = __shfl_sync(0xffffffffu, off_e, (i + 1) & 31);
-                nkey = (nb + lane < ne) ? __ldg(keys + nb + lane) : 0xffffffffu;
-            }
+            uint32_t key = nk[j];
+            nk[j] = fetch(i + TC_MASK_PF, i);
             mbar_wait(tile_empty + b, (uint32_t)(((i / NBUF) & 1) ^ 1), A.err_flag, 5);
             if (lane == 0) tc_trace(A, i, 5);
             uint32_t *bm = bitmap + b * 4 * TM;
-            if (A.dbg & 16) {  // timing ablation: no bitmap work at all
+            if (TC_DBG(A.dbg, 16)) {  // timing ablation: no bitmap work at all
                 if (lane == 0) mbar_arrive(tile_full + b);
                 continue;
             }
@@ -551,6 +580,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) tc_trace(A, i, 15);
             if (lane == 0) { mbar_arrive(tile_full + b); tc_trace(A, i, 6); }
+          }
         }
     } else {
         // ===== epilogue: thread <-> user row (TMEM lane), warp <-> 32 columns of every tile ========
@@ -622,7 +652,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             if (tr_me) tc_trace(A, i, tslot);
             uint32_t raw[32];
             uint32_t mword = 0u;
-            if (!(A.dbg & 1)) {
+            if (!TC_DBG(A.dbg, 1)) {
                 mword = my_bm[b * 4 * TM];
                 tmem_ld32_wait(my_acc + (uint32_t)(b * TN), raw);
             }
@@ -632,14 +662,14 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             if (lane == 0) mbar_arrive(tile_empty + b);
             if (tr_me) tc_trace(A, i, tslot + 1);
             if (++b == NBUF) { b = 0; bph ^= 1u; }
-            if (A.dbg & 1) continue;
+            if (TC_DBG(A.dbg, 1)) continue;
 
             // two copies of the per-tile work, so that without a bias the scores are consumed in the very
             // registers tcgen05.ld wrote (one shared copy costs 32 register moves per tile)
             if (P.bias != nullptr)
-                tc_process<SAMPLE, true>(raw, P.bias + col0, mword, thr, col0, my_valid, A.cap, (A.dbg & 4) != 0, my_stage, wbase, wn, v);
+                tc_process<SAMPLE, true>(raw, P.bias + col0, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
             else
-                tc_process<SAMPLE, false>(raw, nullptr, mword, thr, col0, my_valid, A.cap, (A.dbg & 4) != 0, my_stage, wbase, wn, v);
+                tc_process<SAMPLE, false>(raw, nullptr, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
             if (tr_me) tc_trace(A, i, tslot + 2);
         }
 

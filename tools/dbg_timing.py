@@ -10,13 +10,13 @@ ctx.set_train_csr(d["train_indptr"], d["train_indices"], d["items"])
 ctx.set_test_csr(d["test_indptr"], d["test_indices"], d["items"])
 ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"]).cuda()
 sums = torch.zeros(150, dtype=torch.float64, device="cuda")
-for prec in ("3xtf32", "1xtf32"):
+for prec in ("1xtf32",):
     for stages in (0,):
-        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (2, "no MMA"), (3, "no MMA, no epilogue"), (19, "no MMA, no epilogue, no bitmaps"), (16, "no bitmaps"), (9, "no TMA, no epilogue (MMA only)")):
+        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (32, "detection, no slow path"), (64, "slow path, no global store"), (2, "no MMA"), (3, "no MMA, no epilogue"), (19, "no MMA, no epilogue, no bitmaps"), (16, "no bitmaps"), (9, "no TMA, no epilogue (MMA only)"), (9 + 128, "MMA only, same A slice"), (9 + 256, "MMA only, same B slice"), (9 + 384, "MMA only, same A and B")):
             ctx.set_option("dbg", dbg)
             ms = []
             for _ in range(3):
                 ctx.eval_fused(ue, ie, None, 0, [1, 2, 4], 50, precision=prec, sums=sums)
                 torch.cuda.synchronize()
                 ms.append(ctx.fused_kernel_ms(0))
-            print("%s stages=%d dbg=%2d %-32s collect %.3f ms  prepass %.3f ms" % (prec, stages, dbg, name, min(ms), ctx.fused_prepass_ms(0)), flush=True)
+            print("%s stages=%d dbg=%3d %-32s collect %.3f ms  prepass %.3f ms" % (prec, stages, dbg, name, min(ms), ctx.fused_prepass_ms(0)), flush=True)

@@ -28,6 +28,7 @@ for _ in range(3):
     ctx.eval_fused(ue, ie, b, 0, ids, K, precision=prec, sums=sums)
 torch.cuda.synchronize()
 ctx.set_option("trace_cta", cta)
+ctx.set_option("dbg", int(os.environ.get("SKR_DBG", "0")))  # ablation switches (results invalid), see TcArgs::dbg
 ctx.eval_fused(ue, ie, b, 0, ids, K, precision=prec, sums=sums)
 torch.cuda.synchronize()
 plan = ctx.fused_stats()
