@@ -73,6 +73,7 @@ __host__ __device__ inline size_t tc_smem_bytes()
            + (size_t)TC_RING_BYTES
            + (size_t)TC_MAX_BUF * 4 * TM * 4     // train-mask bitmaps, one per accumulator buffer
            + (size_t)8 * TC_EPI_THREADS * 16     // score staging: one 32-float row per epilogue thread, [8][512] float4
+           + (size_t)TC_TILE_BYTES               // constant B tile of the threshold MMA (single-pass COLLECT)
            + 256;                                // barriers + tmem pointer
 }
 
@@ -232,6 +233,8 @@ struct TcArgs {
     float *samp;
     // COLLECT: per-row thresholds (k_sample_thr) and candidate lists
     const float *thr;        // [n_rows]
+    const float *thr_hi;     // [n_rows] single-pass COLLECT with NKB <= 3: thr = fl(hi + lo), hi and lo TF32 values (k_sample_thr)
+    const float *thr_lo;
     int cap;                 // entries per (row, chunk, column quarter) sub-list
     uint2 *cand;             // [n_rows, S*4, cap] (score bits, item)
     uint32_t *cand_cnt;      // [n_rows, S*4] entries offered (> cap means overflow)
@@ -287,7 +290,7 @@ __device__ __forceinline__ void sorted_insert(float (&v)[TC_R], float x)
 
 // One thread's share of a tile: 32 scores of its row.  SAMPLE: fold the group maximum into the sorted
 // list v.  COLLECT: survivor mask against the row threshold, survivors appended to the sub-list.
-template <bool SAMPLE, bool BIAS>
+template <bool SAMPLE, bool BIAS, bool PRESUB>
 __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const float *__restrict__ bias32, uint32_t mword, float thr, int col0,
                                            bool my_valid, int cap, int dbg, float4 *my_stage, uint2 *wbase, int &wn, float (&v)[TC_R])
 {
@@ -325,14 +328,15 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
     } else if (!TC_DBG(dbg, 4)) {
         // Detection costs two instructions per score on two different pipes and no predicates:
         // d = s - T0 (FMA pipe), then a funnel shift (ALU pipe) collects the sign bit of d; bit q of
-        // `pass` ends up set iff s[q] >= T0 and item q is not masked.
+        // `pass` ends up set iff s[q] >= T0 and item q is not masked.  PRESUB: the accumulator already
+        // holds score - T0 (threshold MMA, see the kernel), so the subtraction is gone.
         uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;  // four independent chains of 8 for ILP
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            m0 = __funnelshift_l(__float_as_uint(s[q] - thr), m0, 1);
-            m1 = __funnelshift_l(__float_as_uint(s[q + 8] - thr), m1, 1);
-            m2 = __funnelshift_l(__float_as_uint(s[q + 16] - thr), m2, 1);
-            m3 = __funnelshift_l(__float_as_uint(s[q + 24] - thr), m3, 1);
+            m0 = __funnelshift_l(__float_as_uint(PRESUB ? s[q] : s[q] - thr), m0, 1);
+            m1 = __funnelshift_l(__float_as_uint(PRESUB ? s[q + 8] : s[q + 8] - thr), m1, 1);
+            m2 = __funnelshift_l(__float_as_uint(PRESUB ? s[q + 16] : s[q + 16] - thr), m2, 1);
+            m3 = __funnelshift_l(__float_as_uint(PRESUB ? s[q + 24] : s[q + 24] - thr), m3, 1);
         }
         // chain j holds items 8j..8j+7 with item 8j in bit 7: assemble so that item 0 lands in bit 31,
         // then reverse
@@ -349,7 +353,8 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
             do {
                 const int q = __ffs(pass) - 1;
                 pass &= pass - 1u;
-                const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
+                float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
+                if (PRESUB) sc += thr;  // back to the score: the sub-lists hold scores, not margins
                 if (wn < cap && !TC_DBG(dbg, 64)) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
                 if (TC_DBG(dbg, 64)) wn += (int)(__float_as_uint(sc) >> 31);  // timing experiment: no global store
                 ++wn;
@@ -367,7 +372,13 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     constexpr int STAGE_BYTES = (PASSES == 3) ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
     static_assert(NKB >= 1 && NKB <= 4 && (PASSES == 1 || PASSES == 3), "tile shape");
     static_assert(STAGES * STAGE_BYTES == TC_RING_BYTES, "ring size");
-    constexpr int A_COLS = TC_KB * NKB * (PASSES == 3 ? 2 : 1);
+    // Single-pass COLLECT (precision tf32r / 1xtf32): one extra K = 8 MMA per tile starts the accumulator at -T0[row]
+    // (A' = [-hi, -lo, 0 x 6] per row in TMEM, B' = [1, 1, 0 x 6] for every column, a constant shared-memory tile),
+    // so the epilogue tests sign bits instead of subtracting: the single-pass modes are bound by the epilogue's
+    // instruction issue, not by the tensor pipe.  Needs 16 more TMEM columns, which d = 128 (NKB = 4) does not leave.
+    constexpr bool PRESUB = !SAMPLE && PASSES == 1 && NKB <= 3;
+    constexpr int A_THR_COL = TC_KB * NKB * (PASSES == 3 ? 2 : 1);  // first column of A'
+    constexpr int A_COLS = A_THR_COL + (PRESUB ? 16 : 0);
     constexpr int NBUF = (A_COLS <= 512 - 3 * TN) ? 3 : 2;
     constexpr int ACC_COL = 512 - NBUF * TN;  // first accumulator column
 
@@ -378,7 +389,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     unsigned char *b_tiles = smem;
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + TC_RING_BYTES);        // [NBUF][4][TM]
     float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + TC_MAX_BUF * 4 * TM);  // [8][TC_EPI_THREADS]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 8 * TC_EPI_THREADS);
+    unsigned char *thr_tile = reinterpret_cast<unsigned char *>(stage_buf + 8 * TC_EPI_THREADS);  // [TN][128 B], SWIZZLE_128B, 1024-aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(thr_tile + TC_TILE_BYTES);
     uint64_t *full = bars;                            // [TC_MAX_STAGES] TMA landed
     uint64_t *empty = bars + TC_MAX_STAGES;           // [TC_MAX_STAGES] MMAs that read the stage are done
     uint64_t *tile_full = bars + 2 * TC_MAX_STAGES;   // [NBUF] accumulator complete (MMA commit) + bitmap built (mask warp)
@@ -403,8 +415,18 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             mbar_init(tile_full + b, 2);
             mbar_init(tile_empty + b, TC_EPI_WARPS);
         }
-        mbar_init(a_ready, 4 * NKB);
+        mbar_init(a_ready, 4 * NKB + (PRESUB ? 4 : 0));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (PRESUB) {
+        // B' in the K-major SWIZZLE_128B layout the item tiles use: logical 16-byte chunk c of row r sits at
+        // chunk position c ^ (r & 7); chunk 0 holds k = 0..3 = (1, 1, 0, 0), everything else is zero
+        uint4 *t4 = reinterpret_cast<uint4 *>(thr_tile);
+        for (int j = tid; j < TC_TILE_BYTES / 16; j += TC_THREADS) {
+            const int r8 = (j >> 3) & 7, pos = j & 7;
+            t4[j] = ((pos ^ r8) == 0) ? make_uint4(0x3f800000u, 0x3f800000u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
     }
     if (role == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bhi) : "memory");
@@ -459,6 +481,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         const uint32_t a_hi0 = tmem_base;
         const uint32_t a_lo0 = tmem_base + (uint32_t)(NKB * TC_KB);
         const uint64_t desc0 = make_b_desc(smem_u32(b_tiles));
+        const uint64_t desc_thr = make_b_desc(smem_u32(thr_tile));
         for (int i = p; i < n_tiles; i += 2) {
             const int b = i % NBUF;
             const uint32_t d_tmem = tmem_base + (uint32_t)(ACC_COL + b * TN);
@@ -476,11 +499,12 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 if (elect_one()) {
                     if (kb == 0) tc_trace(A, i, 3);
                     if (do_mma) {
+                        if (PRESUB && kb == 0) tc_mma_ts(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC, 0u);  // acc = -T0[row]
 #pragma unroll
                         for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 = 32 bytes
                             const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
                             const uint64_t dhi = ds + (uint64_t)(k8 * 2);
-                            const uint32_t acc = (kb | k8) ? 1u : 0u;
+                            const uint32_t acc = (PRESUB || (kb | k8)) ? 1u : 0u;
                             if (PASSES == 3) {
                                 const uint64_t dlo = dhi + (uint64_t)(TC_TILE_BYTES >> 4);
                                 tc_mma_ts(d_tmem, a_lo0 + acol, dhi, TC_IDESC, acc);
@@ -627,7 +651,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         }
 
         // COLLECT: fixed per-row threshold from the sampled pre-pass; survivors go to this thread's sub-list
-        float thr = PINF;  // rows beyond n_rows collect nothing
+        // rows beyond n_rows collect nothing (PRESUB: 2^126, a TF32 value; inf would make the threshold MMA produce NaN)
+        float thr = PRESUB ? __int_as_float(0x7e800000) : PINF;
+        float thr_hi = thr, thr_lo = 0.0f;
         uint2 *wbase = nullptr;
         int wn = 0;
         float v[TC_R];  // SAMPLE: largest group maxima so far, descending
@@ -635,7 +661,23 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         for (int q = 0; q < TC_R; ++q) v[q] = NINF;
         if (!SAMPLE && my_valid) {
             thr = __ldg(A.thr + my_row);
+            if (PRESUB) {
+                thr_hi = __ldg(A.thr_hi + my_row);
+                thr_lo = __ldg(A.thr_lo + my_row);
+            }
             wbase = A.cand + ((my_row * P.S + c) * 4 + cq) * (int64_t)A.cap;
+        }
+        if (PRESUB && cq == 3) {  // A': -T0 as TF32 hi + lo (k_sample_thr), 16 columns reserved, 8 read
+            uint32_t x[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) x[q] = 0u;
+            x[0] = __float_as_uint(-thr_hi);
+            x[1] = __float_as_uint(-thr_lo);
+            tmem_st16(lane_addr + (uint32_t)A_THR_COL, x);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
         }
         float4 *my_stage = stage_buf + tid;  // element q of my row: float (q & 3) of my_stage[(q >> 2) * TC_EPI_THREADS]
         const uint32_t *my_bm = bitmap + cq * TM + r;
@@ -667,9 +709,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             // two copies of the per-tile work, so that without a bias the scores are consumed in the very
             // registers tcgen05.ld wrote (one shared copy costs 32 register moves per tile)
             if (P.bias != nullptr)
-                tc_process<SAMPLE, true>(raw, P.bias + col0, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
+                tc_process<SAMPLE, true, PRESUB>(raw, P.bias + col0, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
             else
-                tc_process<SAMPLE, false>(raw, nullptr, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
+                tc_process<SAMPLE, false, PRESUB>(raw, nullptr, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
             if (tr_me) tc_trace(A, i, tslot + 2);
         }
 
@@ -706,12 +748,16 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 //   very loose bound: every one of <= d additions may lose a full ulp of the running sum, twice);
 //   the exact kernels' own FMA chain: <= d 2^-24 sum |u_k i_k|; the two bias additions: 2^-23 |score|;
 //   sum |u_k i_k| <= ||u|| max_j ||i_j|| (Cauchy-Schwarz), |score| <= that + max |b|.
-// eps = 1.25 [(2^-10 + (1.25 d + 2) 2^-22) ||u|| N_max + 2^-22 B_max]: the 1.25 covers the FP32 evaluation of
+//   threshold MMA (single-pass kernel, PRESUB): the accumulator starts at -T0, |T0| <= ||u|| N_max + B_max, so the
+//   partial sums are at most twice as large, and the epilogue's add-back rounds once more: covered by doubling
+//   the accumulation term (and a few ulps);
+// eps = 1.25 [(2^-10 + (2.5 d + 8) 2^-22) ||u|| N_max + 2^-22 B_max]: the 1.25 covers the FP32 evaluation of
 // the norms and leaves slack (tests assert the observed error stays below eps / 2).  eps_coef carries the
 // bracket's first factor, stats = {N_max^2, B_max} from k_item_stats.
 __global__ void __launch_bounds__(256)
 k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
-             int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out)
+             int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
+             float *__restrict__ thr_lo_out)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
@@ -742,6 +788,28 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
         if (!(e2 < INF)) e2 = INF;  // overflow / NaN operands: collect everything, the exact kernel settles the row
         t0 = (e2 < INF) ? __fsub_rd(t0, e2) : -INF;
         if (lane == 0) eps2_out[row] = e2;
+    }
+    if (thr_hi_out != nullptr) {
+        // The single-pass main kernel subtracts the threshold inside the tensor core (threshold MMA): it needs
+        // T = hi + lo with TF32 hi, lo and T <= t0 (collect a superset).  hi = rna(t0); t0 - hi is exact; lo is that
+        // remainder rounded towards -inf on the TF32 grid.  thr = fl(hi + lo) <= t0 is what the epilogue adds back and
+        // what k_select_cands compares against.  Without a usable threshold (-inf: fewer than r finite samples;
+        // NaN) the row collects nothing and k_select_cands hands it to the exact kernel.
+        float hi = __int_as_float(0x7e800000), lo = 0.0f;  // 2^126
+        if (fabsf(t0) < 1.0e37f) {
+            hi = __uint_as_float(to_tf32(t0));
+            const float rem = t0 - hi;
+            uint32_t lb = __float_as_uint(rem);
+            const bool inexact = (lb & 0x1fffu) != 0u;
+            lb &= ~0x1fffu;
+            if (rem < 0.0f && inexact) lb += 0x2000u;  // magnitude up = value down
+            lo = __uint_as_float(lb);
+        }
+        t0 = hi + lo;
+        if (lane == 0) {
+            thr_hi_out[row] = hi;
+            thr_lo_out[row] = lo;
+        }
     }
     if (lane == 0) thr[row] = t0;
 }

@@ -263,7 +263,7 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         if (RESCORE && ok) {
             // every candidate down to cut - 2 eps must be looked at; complete only if the main pass collected that far
             const float lb = __fsub_rd(unord_f32(cut), __ldg(R.eps2 + row));
-            ok = lb >= __ldg(R.thr_c + row);
+            ok = lb > __ldg(R.thr_c + row);  // strict: a margin that rounds to -0/+0 in the threshold MMA may go either way
             const uint32_t ol = ord_f32(lb);
             T = (ol > vmin) ? ol - vmin : 0u;
             if (!ok) {

@@ -974,7 +974,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
 
         if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 4 * TC_R * sizeof(float)))) return rc;
         if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * cap * sizeof(uint2)))) return rc;
-        if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(float)))) return rc;
+        if ((rc = ensure(ctx, ctx->thr, (size_t)3 * n_rows * sizeof(float)))) return rc;  // thr | TF32 hi | TF32 lo (threshold MMA)
         if ((rc = ensure(ctx, ctx->cand_cnt, (size_t)n_rows * n_sub * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
         int *fail_count = (int *)ctx->fail_list.p;             // [0] = count, [1..] = rows
@@ -1003,6 +1003,9 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 4.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
         const bool rescore = (precision == SKR_PREC_TF32R);
         const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
+        const bool presub = (passes == 1) && (nkb <= 3);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
+        A.thr_hi = presub ? A.thr + n_rows : nullptr;
+        A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
         float eps_coef = 0.0f;
         if (rescore) {
             if ((rc = ensure(ctx, ctx->stats, 2 * sizeof(float)))) return rc;
@@ -1010,14 +1013,15 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
             k_item_stats<<<(unsigned)std::min<int64_t>((n_items + 7) / 8, 4 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, bias_dev,
                                                                                                    (uint32_t *)ctx->stats.p);
             ctx->launches++;
-            eps_coef = (float)(ldexp(1.0, -10) + (1.25 * d + 2.0) * ldexp(1.0, -22));
+            eps_coef = (float)(ldexp(1.0, -10) + (2.5 * d + 8.0) * ldexp(1.0, -22));
         }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)P.n_rt, st, mhi, mlo, A, P))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
         k_sample_thr<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
-                                                                   (const float *)ctx->stats.p, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr);
+                                                                   (const float *)ctx->stats.p, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr,
+                                                                   (float *)A.thr_hi, (float *)A.thr_lo);
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
             A.trace_tiles = ctx->work_max_tiles;

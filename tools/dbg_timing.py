@@ -12,7 +12,7 @@ ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"])
 sums = torch.zeros(150, dtype=torch.float64, device="cuda")
 for prec in ("1xtf32",):
     for stages in (0,):
-        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (32, "detection, no slow path"), (64, "slow path, no global store"), (2, "no MMA"), (3, "no MMA, no epilogue"), (19, "no MMA, no epilogue, no bitmaps"), (16, "no bitmaps"), (9, "no TMA, no epilogue (MMA only)"), (9 + 128, "MMA only, same A slice"), (9 + 256, "MMA only, same B slice"), (9 + 384, "MMA only, same A and B")):
+        for dbg, name in ((0, "full"), (1, "no epilogue work"), (4, "ld+mask only, no appends"), (32, "detection, no slow path"), (64, "slow path, no global store"), (2, "no MMA"), (3, "no MMA, no epilogue"), (19, "no MMA, no epilogue, no bitmaps"), (16, "no bitmaps"), (9, "no TMA, no epilogue (MMA only)"), (25, "MMA only, no bitmaps")):
             ctx.set_option("dbg", dbg)
             ms = []
             for _ in range(3):
