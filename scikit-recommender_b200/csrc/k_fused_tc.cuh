@@ -236,7 +236,7 @@ struct TcArgs {
     const float *thr_hi;     // [n_rows] single-pass COLLECT with NKB <= 3: thr = fl(hi + lo), hi and lo TF32 values (k_sample_thr)
     const float *thr_lo;
     int cap;                 // entries per (row, chunk, column quarter) sub-list
-    uint2 *cand;             // [n_rows, S*4, cap] (score bits, item)
+    uint2 *cand;             // [n_rows, S*4, cap] (score bits, item); PRESUB kernels store score - thr[row]
     uint32_t *cand_cnt;      // [n_rows, S*4] entries offered (> cap means overflow)
     // COLLECT work list: CTA b scores item tiles [t0, t0 + n) of user tile rt into sub-list slot `slot` of its rows;
     // built on the host with unequal chunk counts per user tile and ordered largest first, so that the hardware's
@@ -351,10 +351,10 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
                 my_stage[q * TC_EPI_THREADS] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             const float *row_f = reinterpret_cast<const float *>(my_stage);
             do {
-                const int q = __ffs(pass) - 1;
-                pass &= pass - 1u;
-                float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
-                if (PRESUB) sc += thr;  // back to the score: the sub-lists hold scores, not margins
+                const int q = 31 - __clz(pass);  // highest first: one FLO instead of BREV + FLO; the lists are unordered
+                pass ^= 1u << q;
+                // PRESUB: the sub-lists hold margins (score - T0); k_select_cands adds T0 back
+                const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
                 if (wn < cap && !TC_DBG(dbg, 64)) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
                 if (TC_DBG(dbg, 64)) wn += (int)(__float_as_uint(sc) >> 31);  // timing experiment: no global store
                 ++wn;

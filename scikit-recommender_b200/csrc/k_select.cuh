@@ -122,8 +122,9 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count,
                const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
                const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
-               float *__restrict__ topk_val_out, double *__restrict__ acc_out, RescoreArgs R)
+               float *__restrict__ topk_val_out, double *__restrict__ acc_out, RescoreArgs R, const float *__restrict__ add_back)
 {
+    // add_back (nullable): the lists hold margins score - add_back[row] (single-pass main kernel with the threshold MMA)
     constexpr int CAP = 32 * PER;
     constexpr int CAPS = RESCORE ? CAP / 2 : CAP;  // size at which the search for the cut stops
     constexpr int SEL_MAX = sel_max(PER, RESCORE);
@@ -171,6 +172,7 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
         const int *off = s_off[warp];
         uint32_t vmin = 0xffffffffu, vmax = 0u;
         const uint2 *row_src = cand + row * n_sub * (int64_t)sub_stride;
+        const float t_add = (add_back != nullptr) ? __ldg(add_back + row) : 0.0f;
         for (int j0 = lane; j0 < n; j0 += 128) {  // four independent loads in flight per lane
             uint2 e[4];
 #pragma unroll
@@ -186,7 +188,7 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             for (int q = 0; q < 4; ++q) {
                 const int j = j0 + 32 * q;
                 if (j < n) {
-                    e[q].x = ord_f32(__uint_as_float(e[q].x));
+                    e[q].x = ord_f32((add_back != nullptr) ? __uint_as_float(e[q].x) + t_add : __uint_as_float(e[q].x));
                     vmin = min(vmin, e[q].x);
                     vmax = max(vmax, e[q].x);
                     ent[j] = e[q];

@@ -297,13 +297,13 @@ int run_row_exact(skr_ctx *ctx, const ExactArgs &E, int32_t *fail_list, int *fai
 
 int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
                        const MetricIds &m, int K, const ExactArgs &E, int32_t *fail_list, int *fail_count, int32_t *topk_idx,
-                       float *topk_val, float *per_user, double *sums, u64 *keys_only, RescoreArgs RA, cudaStream_t st)
+                       float *topk_val, float *per_user, double *sums, u64 *keys_only, RescoreArgs RA, const float *add_back, cudaStream_t st)
 {
     const bool rescore = RA.U != nullptr;
     // kernel instantiations: the sort capacity is 64 / 128 keys (K <= 64 / 128); re-scoring doubles it (error band) and
     // splits the job in two kernels: candidates -> exact keys of the survivors, then sort + metrics
     typedef void (*SelKernel)(const uint2 *, const uint32_t *, int, int, int, int, int64_t, int64_t, u64 *, int32_t *, int *, const int64_t *,
-                              const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs);
+                              const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs, const float *);
     typedef void (*SortKernel)(const u64 *, const int *, int, int64_t, int64_t, u64 *, const int64_t *, const int32_t *, MetricIds, const double *,
                                const float *, float *, int32_t *, float *, double *);
     const int per = rescore ? (K <= 64 ? 4 : 8) : (K <= 64 ? 2 : 4);
@@ -320,7 +320,7 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     const int g_sel = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
     if (keys_only != nullptr) {  // per-shard lists: sorted keys out, no metrics
         sel<<<g_sel, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA);
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back);
         if (rescore) {
             srt<<<g_sel, SEL_WARPS * 32, 0, st>>>(RA.rs_keys, RA.rs_cnt, K, n_rows, row0, keys_only, nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr,
                                                   nullptr, nullptr);
@@ -363,13 +363,13 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     }
     if (rescore) {
         sel<<<g_sel, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, nullptr, nullptr, m, nullptr,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA);
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back);
         srt<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(RA.rs_keys, RA.rs_cnt, K, n_rows, row0, nullptr, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc,
                                                     ctx->d_idcg, pu, topk_idx, topk_val, acc);
         ctx->launches++;
     } else {
         sel<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
-                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA);
+                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA, add_back);
     }
     SKR_AFTER(ctx, st, "k_select_cands / k_sort_metrics");
     if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys, st))) return rc;
@@ -999,8 +999,9 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.trace_cta = -1;
         A.trace_tiles = 0;
         // AUTO: re-scoring costs a fixed ~60 candidate rows per user, the two extra MMA passes of 3xTF32 grow with
-        // the catalogue: measured break-even between c2 (I d = 2.6 M, 3xTF32 5 % faster) and c3b (5.9 M, tf32r 11 % faster)
-        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 4.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
+        // the catalogue: measured on one B200, tf32r is 5 % faster at c2 (I d = 2.6 M) and 22 % at c3b (5.9 M); below
+        // ~1 M the sampled thresholds stop working for either and the choice does not matter
+        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 2.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
         const bool rescore = (precision == SKR_PREC_TF32R);
         const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
         const bool presub = (passes == 1) && (nkb <= 3);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
@@ -1045,7 +1046,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         RescoreArgs RA = {nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (rescore) RA = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (const float *)ctx->thr.p, (const float *)ctx->eps2.p, nullptr, nullptr};
         rc = run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
-                                per_user_dev, sums_dev, keys_only, RA, st);
+                                per_user_dev, sums_dev, keys_only, RA, presub ? A.thr : nullptr, st);
         if (rc || keys_only == nullptr) return rc;
     } else {
         if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;
