@@ -35,18 +35,26 @@
 // barrier latency.  Hence: k-blocks and passes are template parameters (the issue loop is straight-line
 // code), 16 epilogue warps each own one 32-column group of the tile (thread <-> TMEM lane <-> user row;
 // four warps per SM sub-partition hide each other's latencies), the accumulator-ready and mask-ready
-// signals share one barrier per buffer, and the mask builder keeps tile offsets in registers (one
-// coalesced load per 32 tiles) and fetches keys one tile ahead.
+// signals share one barrier per buffer, and the mask builders keep tile offsets in registers (one
+// coalesced load per 32 tiles) and fetch keys four of their tiles ahead.
 //
-// Warp roles (640 threads): warps 0-15 epilogue (lane quarter = warp & 3, column quarter = warp >> 2),
+// Later measurements (single-pass modes, c2): the epilogue was bound by shared-memory store traffic, not by
+// instruction issue -- parking all 32 scores of every lane that has a survivor moved ~450 store wavefronts per
+// tile; predicating the stores per 4-score group cut the kernel from 0.355 to 0.304 ms.  One bitmap builder
+// (~600-750 cycles per tile, an L2 round trip for its keys with a one-tile lookahead) paced the SAMPLE pass and the
+// MMA-only ablation; two builders on alternate tiles with a deeper prefetch removed that.  Subtracting the
+// threshold inside the tensor core (PRESUB below) takes 32 FADDs per thread and tile out of the epilogue.
+//
+// Warp roles (672 threads): warps 0-15 epilogue (lane quarter = warp & 3, column quarter = warp >> 2),
 // warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer of the even tiles, warp 18 train-mask bitmap
-// builder, warp 19 MMA issuer of the odd tiles.  Accumulators and bitmaps are double buffered so the
-// epilogue of tile n overlaps the MMAs of tile n+1.
+// builder of the even tiles, warp 19 MMA issuer of the odd tiles, warp 20 bitmap builder of the odd tiles.
+// Accumulators and bitmaps are multi-buffered so the epilogue of tile n overlaps the MMAs of tile n+1.
+// (21 warps put six on one SM sub-partition: 80 registers per thread instead of 96.)
 //
-// TMEM columns: [0, 32*NKB) A_hi, [32*NKB, 64*NKB) A_lo (3xTF32 only), then NBUF accumulators of 128 columns
-// at the top: three when A fits 128 columns (d <= 64, or any d <= 128 in one pass), otherwise two.  The third
-// buffer lets the issuers run a tile further ahead of the epilogue, which is what bounds the single-pass
-// modes (their accumulator round trip, not the tensor pipe).
+// TMEM columns: [0, 32*NKB) A_hi, [32*NKB, 64*NKB) A_lo (3xTF32 only), 16 columns for the threshold operand
+// (single-pass COLLECT, NKB <= 3), then NBUF accumulators of 128 columns at the top: three when A fits 128
+// columns (d <= 64, or d <= 96 in one pass, d <= 128 in one pass without PRESUB), otherwise two.  The third
+// buffer lets the issuers run a tile further ahead of the epilogue.
 #pragma once
 #include <cuda.h>
 #include "fused_common.cuh"
@@ -55,7 +63,7 @@ namespace skr {
 
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
-constexpr int TC_THREADS = TC_EPI_THREADS + 128;
+constexpr int TC_THREADS = TC_EPI_THREADS + 160;      // + 5 helper warps
 constexpr int TC_KB = 32;                             // floats per k-block (one 128-byte swizzle row)
 constexpr int TC_TILE_BYTES = TN * TC_KB * 4;         // 16 KB: one operand tile of one k-block
 constexpr int TC_RING_BYTES = 8 * TC_TILE_BYTES;      // 4 stages of hi+lo (3xTF32) or 8 stages of hi (1xTF32)
@@ -249,7 +257,7 @@ struct TcArgs {
 };
 
 constexpr int TC_TRACE_SLOTS = 16;
-constexpr int TC_MASK_PF = 4;  // mask builder: key prefetch distance in tiles (< 32)
+constexpr int TC_MASK_PF = 4;  // mask builders: key prefetch distance in own tiles (2 * TC_MASK_PF < 32)
 // slots: 0 producer got the stage of kb 0, 1 producer issued the last TMA of the tile, 2 issuer: accumulator free,
 // 3 issuer: first stage full, 4 issuer: tile committed, 5 mask: buffer free, 6 mask: bitmap ready,
 // 7/10 epilogue warp 0/15: tile full, 8/11: accumulator in registers (released), 9/12: tile processed
@@ -405,7 +413,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     // Epilogue = warps 0-15, helpers = warps 16-19: the warp scheduler favours higher warp ids, and the
     // latency-critical single-thread roles (TMA producer, MMA issuers) must not queue behind the epilogue.
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int role = warp - TC_EPI_WARPS;  // 0 TMA producer, 1 MMA issuer (even tiles) + TMEM allocator, 2 mask builder, 3 MMA issuer (odd tiles)
+    const int role = warp - TC_EPI_WARPS;  // 0 TMA producer, 1 MMA issuer (even tiles) + TMEM allocator, 2 mask builder (even), 3 MMA issuer (odd tiles), 4 mask builder (odd)
     // tiles of this work item: COLLECT t0 + i (work list), SAMPLE i * stride
     int4 wk = make_int4((int)blockIdx.x, 0, A.n_samp, 0);
     if (!SAMPLE) wk = __ldg(A.work + blockIdx.x);
@@ -528,7 +536,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 __syncwarp();
             }
         }
-    } else if (role == 2) {
+    } else if (role == 2 || role == 4) {
         // ===== train-mask bitmap builder ===========================================================
         // Keys of this user tile are sorted by item; mask_tile_off gives, per item tile, where its keys
         // start.  Lane l holds the key range of tile (32-tile batch start + l): one coalesced load per
@@ -540,9 +548,12 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             keys = P.mask_keys + __ldg(P.mask_tile_ptr + rt_abs);
             offs = P.mask_tile_off + rt_abs * (int64_t)(P.n_ct + 1);
         }
+        // Two builders take alternate tiles: one tile of bitmap work (zero, scatter, arrive: ~600 cycles with the
+        // epilogue competing for issue slots) is longer than the single-pass MMA of a tile.
         // Lane l holds the key range of tile (32-tile batch + l) for the current batch (off_*) and the next (nxt_*).
-        // The first 32 keys of a tile are fetched TC_MASK_PF tiles ahead: one tile of bitmap work is shorter than
-        // an L2 round trip, and with a one-tile lookahead this warp paced the whole pipeline in the single-pass modes.
+        // The first 32 keys of a tile are fetched TC_MASK_PF of this warp's tiles ahead: one tile of bitmap work is
+        // shorter than an L2 round trip, and with a one-tile lookahead this warp paced the whole pipeline.
+        const int mp = (role == 2) ? 0 : 1;
         uint32_t off_b = 0, off_e = 0, nxt_b = 0, nxt_e = 0;
         auto load_offs = [&](int base, uint32_t &ob, uint32_t &oe) {
             const int ti = base + lane;
@@ -553,7 +564,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 oe = __ldg(offs + t + 1);
             }
         };
-        // first keys of tile x, x in the current or the next batch relative to tile i
+        // first keys of tile x, x in the batch of tile i or the one after it
         auto fetch = [&](int x, int i) -> uint32_t {
             if (keys == nullptr || x >= n_tiles) return 0xffffffffu;
             const bool nx = (x >> 5) != (i >> 5);
@@ -563,24 +574,26 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         };
         load_offs(0, off_b, off_e);
         load_offs(32, nxt_b, nxt_e);
+        int batch = 0;
         uint32_t nk[TC_MASK_PF];
 #pragma unroll
-        for (int j = 0; j < TC_MASK_PF; ++j) nk[j] = fetch(j, 0);
-        for (int i0 = 0; i0 < n_tiles; i0 += TC_MASK_PF) {
+        for (int j = 0; j < TC_MASK_PF; ++j) nk[j] = fetch(mp + 2 * j, 0);
+        for (int i0 = mp; i0 < n_tiles; i0 += 2 * TC_MASK_PF) {
 #pragma unroll
           for (int j = 0; j < TC_MASK_PF; ++j) {
-            const int i = i0 + j;
+            const int i = i0 + 2 * j;
             if (i >= n_tiles) break;
             const int b = i % NBUF;
             const int col0 = (t0 + i * t_step) * TN;
-            if ((i & 31) == 0 && i != 0) {
+            if ((i >> 5) != batch) {
+                batch = i >> 5;
                 off_b = nxt_b;
                 off_e = nxt_e;
-                load_offs(i + 32, nxt_b, nxt_e);
+                load_offs(batch * 32 + 32, nxt_b, nxt_e);
             }
             const uint32_t kb0 = __shfl_sync(0xffffffffu, off_b, i & 31), ke0 = __shfl_sync(0xffffffffu, off_e, i & 31);
             uint32_t key = nk[j];
-            nk[j] = fetch(i + TC_MASK_PF, i);
+            nk[j] = fetch(i + 2 * TC_MASK_PF, i);
             mbar_wait(tile_empty + b, (uint32_t)(((i / NBUF) & 1) ^ 1), A.err_flag, 5);
             if (lane == 0) tc_trace(A, i, 5);
             uint32_t *bm = bitmap + b * 4 * TM;
