@@ -237,7 +237,7 @@ def run_ours(args):
     if world > 1:
         td.barrier()
     torch.cuda.synchronize()
-    launches = ctx.launch_count - launches0 + args.steps * (2 if world == 1 else 4)  # + L2 flush, sums.zero_ (, count fill, all-reduce) per step
+    launches = ctx.launch_count - launches0  # this library's kernels only (torch adds the L2 flush and sums.zero_() per step, NCCL the all-reduce)
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kernel_ms = [ctx.fused_kernel_ms(i) for i in range(args.steps)]
     prepass_ms = [ctx.fused_prepass_ms(i) for i in range(args.steps)]

@@ -770,7 +770,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 //   the accumulation term (and a few ulps);
 // eps = 1.25 [(2^-10 + (2.5 d + 8) 2^-22) ||u|| N_max + 2^-22 B_max]: the 1.25 covers the FP32 evaluation of
 // the norms and leaves slack (tests assert the observed error stays below eps / 2).  eps_coef carries the
-// bracket's first factor, stats = {N_max^2, B_max} from k_item_stats.
+// bracket's first factor, stats = {N_max^2, B_max} from k_split_tf32.
 __global__ void __launch_bounds__(256)
 k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
              int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
@@ -831,49 +831,43 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
     if (lane == 0) thr[row] = t0;
 }
 
-// max_j ||item_j||^2 and max_j |bias_j| (non-negative floats order like their bit patterns: atomicMax on uint)
+// ---- operand preparation ---------------------------------------------------------------------------
+// item table -> hi/lo TF32 tables [n, d_pad] (zero padded in k), one warp per item row.  The same pass takes
+// max_j ||item_j||^2 and max_j |bias_j| for the tf32r error band (non-negative floats order like their bit
+// patterns: atomicMax on uint) into stats_cur, and resets the words later kernels count into: the fail-list
+// length, and the statistics slot of the NEXT evaluate (the two slots alternate, so nothing races with the
+// atomics of this launch).  A stale slot after a failed call can only enlarge the band.
 __global__ void __launch_bounds__(256)
-k_item_stats(const float *__restrict__ V, int64_t ld_v, int64_t n_items, int d, const float *__restrict__ bias, uint32_t *__restrict__ stats)
+k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, float *__restrict__ hi, float *__restrict__ lo,
+             const float *__restrict__ bias, int *__restrict__ zero_a, uint32_t *__restrict__ stats_cur, uint32_t *__restrict__ stats_next)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (zero_a != nullptr) *zero_a = 0;
+        if (stats_next != nullptr) { stats_next[0] = 0u; stats_next[1] = 0u; }
+    }
     float best = 0.0f, bb = 0.0f;
-    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n_items; row += (int64_t)gridDim.x * 8) {
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
         float ss = 0.0f;
-        for (int k = lane; k < d; k += 32) {
-            const float v = __ldg(V + row * ld_v + k);
-            ss = fmaf(v, v, ss);
+        for (int k = lane; k < d_pad; k += 32) {
+            const float x = (k < d) ? __ldg(X + row * ld + k) : 0.0f;
+            const uint32_t h = to_tf32(x);
+            hi[row * d_pad + k] = __uint_as_float(h);
+            lo[row * d_pad + k] = __uint_as_float(to_tf32(x - __uint_as_float(h)));
+            ss = fmaf(x, x, ss);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        best = fmaxf(best, ss);
-        if (bias != nullptr && lane == 0) bb = fmaxf(bb, fabsf(__ldg(bias + row)));
+        best = fmaxf(best, (ss == ss) ? ss : __int_as_float(0x7f800000));
+        if (bias != nullptr && lane == 0) {
+            const float v = fabsf(__ldg(bias + row));
+            bb = fmaxf(bb, (v == v) ? v : __int_as_float(0x7f800000));
+        }
     }
-    if (lane == 0) {
-        if (!(best == best)) best = __int_as_float(0x7f800000);
-        atomicMax(stats, __float_as_uint(best));
-        if (bias != nullptr) atomicMax(stats + 1, __float_as_uint(bb == bb ? bb : __int_as_float(0x7f800000)));
+    if (lane == 0 && stats_cur != nullptr) {
+        atomicMax(stats_cur, __float_as_uint(best));
+        if (bias != nullptr) atomicMax(stats_cur + 1, __float_as_uint(bb));
     }
-}
-
-// ---- operand preparation ---------------------------------------------------------------------------
-// item table -> hi/lo TF32 tables [n, d_pad] (zero padded in k), one thread per output element
-// (also resets the two words the later kernels count into -- fail-list length and, for tf32r, the item statistics --
-// which saves two memset nodes per evaluate)
-__global__ void k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad,
-                             float *__restrict__ hi, float *__restrict__ lo, int *__restrict__ zero_a, uint32_t *__restrict__ zero_b2)
-{
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx == 0) {
-        if (zero_a != nullptr) *zero_a = 0;
-        if (zero_b2 != nullptr) { zero_b2[0] = 0u; zero_b2[1] = 0u; }
-    }
-    if (idx >= n * d_pad) return;
-    const int64_t r = idx / d_pad;
-    const int k = (int)(idx - r * d_pad);
-    const float x = (k < d) ? X[r * ld + k] : 0.0f;
-    const uint32_t h = to_tf32(x);
-    hi[idx] = __uint_as_float(h);
-    lo[idx] = __uint_as_float(to_tf32(x - __uint_as_float(h)));
 }
 
 __global__ void k_pad_bias(const float *__restrict__ bias, int n, int n_pad, float *__restrict__ out)

@@ -87,6 +87,7 @@ struct skr_ctx {
     EncodeTiledFn encode = nullptr;
     std::vector<cudaEvent_t> ev0, ev1, ev2;  // ring: ev2 before the pre-pass, ev0/ev1 around the main scoring kernel
     int64_t ev_calls = 0;
+    int stats_slot = 0;  // which half of `stats` the next evaluate fills (k_split_tf32 resets the other)
 };
 
 namespace {
@@ -932,11 +933,17 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
         if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;
         if ((rc = ensure(ctx, ctx->blo, tbytes))) return rc;
-        const int64_t n_el = n_items * d_pad;
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
-        if ((rc = ensure(ctx, ctx->stats, 2 * sizeof(float)))) return rc;
-        k_split_tf32<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p, (float *)ctx->blo.p,
-                                                                     (int *)ctx->fail_list.p, (uint32_t *)ctx->stats.p);
+        if (ctx->stats.cap == 0) {  // two slots of {max ||item||^2, max |bias|}, alternating between evaluates
+            if ((rc = ensure(ctx, ctx->stats, 4 * sizeof(uint32_t)))) return rc;
+            SKR_CUDA(ctx, cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(uint32_t), st));
+        }
+        uint32_t *stats_cur = (uint32_t *)ctx->stats.p + 2 * ctx->stats_slot;
+        uint32_t *stats_next = (uint32_t *)ctx->stats.p + 2 * (ctx->stats_slot ^ 1);
+        ctx->stats_slot ^= 1;
+        k_split_tf32<<<(unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
+                                                                                                  (float *)ctx->blo.p, bias_dev, (int *)ctx->fail_list.p, stats_cur,
+                                                                                                  stats_next);
         ctx->launches++;
         CUtensorMap mhi, mlo;
         if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
@@ -1009,11 +1016,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
         float eps_coef = 0.0f;
         if (rescore) {
-            if ((rc = ensure(ctx, ctx->stats, 2 * sizeof(float)))) return rc;
             if ((rc = ensure(ctx, ctx->eps2, (size_t)n_rows * sizeof(float)))) return rc;
-            k_item_stats<<<(unsigned)std::min<int64_t>((n_items + 7) / 8, 4 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, bias_dev,
-                                                                                                   (uint32_t *)ctx->stats.p);
-            ctx->launches++;
             eps_coef = (float)(ldexp(1.0, -10) + (2.5 * d + 8.0) * ldexp(1.0, -22));
         }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
@@ -1021,7 +1024,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)P.n_rt, st, mhi, mlo, A, P))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
         k_sample_thr<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
-                                                                   (const float *)ctx->stats.p, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr,
+                                                                   (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr,
                                                                    (float *)A.thr_hi, (float *)A.thr_lo);
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
