@@ -847,21 +847,37 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
         if (stats_next != nullptr) { stats_next[0] = 0u; stats_next[1] = 0u; }
     }
     float best = 0.0f, bb = 0.0f;
-    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
-        float ss = 0.0f;
-        for (int k = lane; k < d_pad; k += 32) {
-            const float x = (k < d) ? __ldg(X + row * ld + k) : 0.0f;
-            const uint32_t h = to_tf32(x);
-            hi[row * d_pad + k] = __uint_as_float(h);
-            lo[row * d_pad + k] = __uint_as_float(to_tf32(x - __uint_as_float(h)));
-            ss = fmaf(x, x, ss);
-        }
+    // four rows per warp and step, all loads issued before the first store (d_pad <= 128: at most 4 values per lane and row)
+    for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 4; row0 < n; row0 += (int64_t)gridDim.x * 32) {
+        float x[4][4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        best = fmaxf(best, (ss == ss) ? ss : __int_as_float(0x7f800000));
-        if (bias != nullptr && lane == 0) {
-            const float v = fabsf(__ldg(bias + row));
-            bb = fmaxf(bb, (v == v) ? v : __int_as_float(0x7f800000));
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = lane + 32 * q;
+                x[r][q] = (row0 + r < n && k < d) ? __ldg(X + (row0 + r) * ld + k) : 0.0f;
+            }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (row0 + r >= n) break;
+            float ss = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = lane + 32 * q;
+                if (k < d_pad) {
+                    const uint32_t h = to_tf32(x[r][q]);
+                    hi[(row0 + r) * d_pad + k] = __uint_as_float(h);
+                    lo[(row0 + r) * d_pad + k] = __uint_as_float(to_tf32(x[r][q] - __uint_as_float(h)));
+                    ss = fmaf(x[r][q], x[r][q], ss);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            best = fmaxf(best, (ss == ss) ? ss : __int_as_float(0x7f800000));
+            if (bias != nullptr && lane == 0) {
+                const float v = fabsf(__ldg(bias + row0 + r));
+                bb = fmaxf(bb, (v == v) ? v : __int_as_float(0x7f800000));
+            }
         }
     }
     if (lane == 0 && stats_cur != nullptr) {

@@ -941,7 +941,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         uint32_t *stats_cur = (uint32_t *)ctx->stats.p + 2 * ctx->stats_slot;
         uint32_t *stats_next = (uint32_t *)ctx->stats.p + 2 * (ctx->stats_slot ^ 1);
         ctx->stats_slot ^= 1;
-        k_split_tf32<<<(unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
+        k_split_tf32<<<(unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
                                                                                                   (float *)ctx->blo.p, bias_dev, (int *)ctx->fail_list.p, stats_cur,
                                                                                                   stats_next);
         ctx->launches++;
