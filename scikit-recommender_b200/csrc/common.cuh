@@ -5,6 +5,13 @@
 
 namespace skr {
 
+// Programmatic dependent launch: kernels of one evaluate are launched with programmatic stream serialisation, so
+// the next kernel's blocks are set up while this one drains.  pdl_wait() must precede the first access to anything
+// an earlier kernel of the stream wrote (it is a no-op for a plain launch); pdl_trigger() lets the dependent grid be
+// scheduled once every block of this grid has got this far.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 typedef unsigned long long u64;
 
 // ---------------------------------------------------------------------------------------------

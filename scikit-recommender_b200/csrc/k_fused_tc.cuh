@@ -379,6 +379,7 @@ template <int NKB, int PASSES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, TcArgs A, FusedParams P)
 {
+    pdl_trigger();  // the wait comes after the prologue, which touches nothing an earlier kernel wrote
     constexpr bool SAMPLE = (MODE == TC_MODE_SAMPLE);
     constexpr int STAGES = (PASSES == 3) ? 4 : 8;
     constexpr int STAGE_BYTES = (PASSES == 3) ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
@@ -452,6 +453,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // barriers, TMEM, the constant threshold tile and the work item (host-written, constant) are set up: everything
+    // below reads what the previous kernels of this evaluate produced (item tables, thresholds, bitmaps' keys)
+    pdl_wait();
 
     if (role == 0) {
         // ===== TMA producer: item k-block tiles (hi, lo) through the stage ring ==================
@@ -776,6 +780,8 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
              int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
              float *__restrict__ thr_lo_out)
 {
+    pdl_wait();
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= n_rows) return;
@@ -841,6 +847,8 @@ __global__ void __launch_bounds__(256)
 k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, float *__restrict__ hi, float *__restrict__ lo,
              const float *__restrict__ bias, int *__restrict__ zero_a, uint32_t *__restrict__ stats_cur, uint32_t *__restrict__ stats_next)
 {
+    pdl_wait();
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (zero_a != nullptr) *zero_a = 0;
@@ -888,6 +896,8 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
 
 __global__ void k_pad_bias(const float *__restrict__ bias, int n, int n_pad, float *__restrict__ out)
 {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_pad) out[i] = (i < n) ? bias[i] : 0.0f;
 }

@@ -112,6 +112,8 @@ k_metrics(const u64 *__restrict__ keys, const int32_t *__restrict__ idx_in, int 
           MetricIds mids, const double *__restrict__ disc, const float *__restrict__ idcg, float *__restrict__ per_user,
           int32_t *__restrict__ topk_idx_out, float *__restrict__ topk_val_out, double *__restrict__ acc_out)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ double k4_acc[];  // [K4_WARPS][M*K] when acc_out != null
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MK = mids.n * K;
@@ -147,6 +149,8 @@ k_metrics(const u64 *__restrict__ keys, const int32_t *__restrict__ idx_in, int 
 __global__ void __launch_bounds__(256)
 k_colsum_fold(const double *__restrict__ partial, int n_blk, int n_cols, double *__restrict__ sums)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ double s_t[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x;

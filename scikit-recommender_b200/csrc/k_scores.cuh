@@ -206,6 +206,8 @@ k_row_exact(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_
             const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K, int n_seg, int seg_items,
             int max_seg_rows, u64 *__restrict__ part, u64 *__restrict__ out_keys)
 {
+    pdl_wait();
+    pdl_trigger();
     __shared__ u64 keys[K2_P];
     __shared__ uint32_t bitmap[K2_CHUNK / 32];
     __shared__ int s_cnt;
@@ -251,6 +253,8 @@ __global__ void __launch_bounds__(128)
 k_merge_fail(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_count, const u64 *__restrict__ part, int n_seg, int K,
              int max_seg_rows, u64 *__restrict__ out_keys)
 {
+    pdl_wait();
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_fail = min(*fail_count, max_seg_rows);
     const int n = n_seg * K;

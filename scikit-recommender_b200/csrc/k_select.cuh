@@ -124,6 +124,8 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
                float *__restrict__ topk_val_out, double *__restrict__ acc_out, RescoreArgs R, const float *__restrict__ add_back)
 {
+    pdl_wait();
+    pdl_trigger();
     // add_back (nullable): the lists hold margins score - add_back[row] (single-pass main kernel with the threshold MMA)
     constexpr int CAP = 32 * PER;
     constexpr int CAPS = RESCORE ? CAP / 2 : CAP;  // size at which the search for the cut stops
@@ -375,6 +377,8 @@ k_sort_metrics(const u64 *__restrict__ rs_keys, const int *__restrict__ rs_cnt, 
                const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
                float *__restrict__ topk_val_out, double *__restrict__ acc_out)
 {
+    pdl_wait();
+    pdl_trigger();
     constexpr int CAP = 32 * PER;
     __shared__ u64 s_key[SEL_WARPS][CAP];
     extern __shared__ double sel_acc[];  // [SEL_WARPS][M*K] when acc_out != null

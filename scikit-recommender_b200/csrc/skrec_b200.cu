@@ -120,6 +120,24 @@ int fail(skr_ctx *ctx, int code, const char *fmt, ...)
                         cudaGetErrorString(e__));                                                    \
     } while (0)
 
+// launch with programmatic stream serialisation (see pdl_wait in common.cuh)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int ensure(skr_ctx *ctx, Buf &b, size_t bytes)
 {
     if (bytes <= b.cap) return SKR_OK;
@@ -243,11 +261,11 @@ int run_metrics(skr_ctx *ctx, const u64 *keys, const int32_t *idx_in, int64_t n_
         acc = (double *)ctx->partial.p;
         if (acc_smem > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_smem));
     }
-    k_metrics<<<grid, K4_WARPS * 32, fused_sums ? acc_smem : 0, st>>>(keys, idx_in, K, n_rows, row0, nullptr, nullptr, ctx->d_te_indptr, ctx->d_te_idx,
-                                                                    m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc);
+    SKR_CUDA(ctx, launch_pdl(k_metrics, dim3((unsigned)(grid)), dim3((unsigned)(K4_WARPS * 32)), (size_t)(fused_sums ? acc_smem : 0), st, keys, idx_in, K, n_rows, row0, nullptr, nullptr, ctx->d_te_indptr, ctx->d_te_idx,
+                                                                    m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc));
     ctx->launches++;
     if (fused_sums) {
-        k_colsum_fold<<<MK, 256, 0, st>>>(acc, grid, MK, sums);
+        SKR_CUDA(ctx, launch_pdl(k_colsum_fold, dim3((unsigned)(MK)), dim3((unsigned)(256)), (size_t)(0), st, acc, grid, MK, sums));
         ctx->launches++;
     } else if (sums) {
         const int nblk = (int)std::min<int64_t>(n_rows, 2 * ctx->n_sm);
@@ -280,16 +298,16 @@ int run_row_exact(skr_ctx *ctx, const ExactArgs &E, int32_t *fail_list, int *fai
     const int64_t max_fail = std::min<int64_t>(n_rows, ctx->opt_exact_seg_rows >= 0 ? ctx->opt_exact_seg_rows : 256);
     int rc = ensure(ctx, ctx->part, (size_t)max_fail * n_seg * K * sizeof(u64));
     if (rc) return rc;
-    k_row_exact<<<dim3((unsigned)std::max(1, 4 * ctx->n_sm / n_seg), (unsigned)n_seg), K2_THREADS, 0, st>>>(fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
-                                                                  E.tr_indptr, E.tr_idx, K, n_seg, seg_items, (int)max_fail, (u64 *)ctx->part.p, keys_out);
+    SKR_CUDA(ctx, launch_pdl(k_row_exact, dim3((unsigned)std::max(1, 4 * ctx->n_sm / n_seg), (unsigned)n_seg), dim3((unsigned)(K2_THREADS)), (size_t)(0), st, fail_list, fail_count, E.U, E.ld_u, E.V, E.ld_v, E.d, E.bias, E.n_items, row0,
+                                                                  E.tr_indptr, E.tr_idx, K, n_seg, seg_items, (int)max_fail, (u64 *)ctx->part.p, keys_out));
     SKR_AFTER(ctx, st, "k_row_exact");
     const int n = n_seg * K;
     const unsigned g = (unsigned)ctx->n_sm;
-    if (n <= 64) k_merge_fail<2><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
-    else if (n <= 128) k_merge_fail<4><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
-    else if (n <= 256) k_merge_fail<8><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
-    else if (n <= 512) k_merge_fail<16><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
-    else k_merge_fail<32><<<g, 128, 0, st>>>(fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out);
+    if (n <= 64) SKR_CUDA(ctx, launch_pdl(k_merge_fail<2>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
+    else if (n <= 128) SKR_CUDA(ctx, launch_pdl(k_merge_fail<4>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
+    else if (n <= 256) SKR_CUDA(ctx, launch_pdl(k_merge_fail<8>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
+    else if (n <= 512) SKR_CUDA(ctx, launch_pdl(k_merge_fail<16>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
+    else SKR_CUDA(ctx, launch_pdl(k_merge_fail<32>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
     ctx->launches += 2;
     SKR_AFTER(ctx, st, "k_merge_fail");
     SKR_CUDA(ctx, cudaGetLastError());
@@ -320,11 +338,11 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     }
     const int g_sel = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
     if (keys_only != nullptr) {  // per-shard lists: sorted keys out, no metrics
-        sel<<<g_sel, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back);
+        SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m,
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back));
         if (rescore) {
-            srt<<<g_sel, SEL_WARPS * 32, 0, st>>>(RA.rs_keys, RA.rs_cnt, K, n_rows, row0, keys_only, nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr,
-                                                  nullptr, nullptr);
+            SKR_CUDA(ctx, launch_pdl(srt, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, RA.rs_keys, RA.rs_cnt, K, n_rows, row0, keys_only, nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr,
+                                                  nullptr, nullptr));
             ctx->launches++;
         }
         if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys_only, st))) return rc;
@@ -363,23 +381,23 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
         else SKR_CUDA(ctx, cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
     }
     if (rescore) {
-        sel<<<g_sel, SEL_WARPS * 32, 0, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, nullptr, nullptr, m, nullptr,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back);
-        srt<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(RA.rs_keys, RA.rs_cnt, K, n_rows, row0, nullptr, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc,
-                                                    ctx->d_idcg, pu, topk_idx, topk_val, acc);
+        SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, nullptr, nullptr, m, nullptr,
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back));
+        SKR_CUDA(ctx, launch_pdl(srt, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(dyn_sel), st, RA.rs_keys, RA.rs_cnt, K, n_rows, row0, nullptr, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc,
+                                                    ctx->d_idcg, pu, topk_idx, topk_val, acc));
         ctx->launches++;
     } else {
-        sel<<<g_sel, SEL_WARPS * 32, dyn_sel, st>>>(cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
-                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA, add_back);
+        SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(dyn_sel), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
+                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA, add_back));
     }
     SKR_AFTER(ctx, st, "k_select_cands / k_sort_metrics");
     if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys, st))) return rc;
-    k_metrics<<<g_fix, K4_WARPS * 32, fused_sums ? acc_k4 : 0, st>>>(keys, nullptr, K, n_rows, row0, fail_list, fail_count, ctx->d_te_indptr,
+    SKR_CUDA(ctx, launch_pdl(k_metrics, dim3((unsigned)(g_fix)), dim3((unsigned)(K4_WARPS * 32)), (size_t)(fused_sums ? acc_k4 : 0), st, keys, nullptr, K, n_rows, row0, fail_list, fail_count, ctx->d_te_indptr,
                                                                      ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val,
-                                                                     acc ? acc + (size_t)g_sel * MK : nullptr);
+                                                                     acc ? acc + (size_t)g_sel * MK : nullptr));
     ctx->launches += 2;
     if (fused_sums) {
-        k_colsum_fold<<<MK, 256, 0, st>>>(acc, g_sel + g_fix, MK, sums);
+        SKR_CUDA(ctx, launch_pdl(k_colsum_fold, dim3((unsigned)(MK)), dim3((unsigned)(256)), (size_t)(0), st, acc, g_sel + g_fix, MK, sums));
         ctx->launches++;
     } else if (sums) {
         const int nblk = (int)std::min<int64_t>(n_rows, 2 * ctx->n_sm);
@@ -505,7 +523,7 @@ int launch_tc(skr_ctx *ctx, int nkb, int passes, int mode, unsigned grid, cudaSt
                : nkb == 3 ? tc_kernel_for<3>(passes, mode) : tc_kernel_for<4>(passes, mode);
     const size_t smem = tc_smem_bytes();
     SKR_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TC_THREADS, smem, st>>>(mhi, mlo, A, P);
+    SKR_CUDA(ctx, launch_pdl(k, dim3((unsigned)(grid)), dim3((unsigned)(TC_THREADS)), (size_t)(smem), st, mhi, mlo, A, P));
     return SKR_OK;
 }
 
@@ -785,7 +803,7 @@ int skr_colsum_rows(skr_ctx *ctx, const float *per_user_dev, int64_t n_cols, con
     int rc = ensure(ctx, ctx->partial, (size_t)nblk * n_cols * sizeof(double));
     if (rc) return rc;
     k_colsum_partial<<<nblk, 256, 0, st>>>(per_user_dev, n_list, (int)n_cols, (double *)ctx->partial.p, row_list_dev);
-    k_colsum_fold<<<(unsigned)n_cols, 256, 0, st>>>((const double *)ctx->partial.p, nblk, (int)n_cols, sums_dev);
+    SKR_CUDA(ctx, launch_pdl(k_colsum_fold, dim3((unsigned)((unsigned)n_cols)), dim3((unsigned)(256)), (size_t)(0), st, (const double *)ctx->partial.p, nblk, (int)n_cols, sums_dev));
     ctx->launches += 2;
     SKR_CUDA(ctx, cudaGetLastError());
     return SKR_OK;
@@ -919,7 +937,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
     if (bias_dev) {
         const int n_pad = P.n_ct * TN;
         if ((rc = ensure(ctx, ctx->bias, (size_t)n_pad * sizeof(float)))) return rc;
-        k_pad_bias<<<(n_pad + 255) / 256, 256, 0, st>>>(bias_dev, (int)n_items, n_pad, (float *)ctx->bias.p);
+        SKR_CUDA(ctx, launch_pdl(k_pad_bias, dim3((unsigned)((n_pad + 255) / 256)), dim3((unsigned)(256)), (size_t)(0), st, bias_dev, (int)n_items, n_pad, (float *)ctx->bias.p));
         ctx->launches++;
         P.bias = (const float *)ctx->bias.p;
     }
@@ -941,9 +959,9 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         uint32_t *stats_cur = (uint32_t *)ctx->stats.p + 2 * ctx->stats_slot;
         uint32_t *stats_next = (uint32_t *)ctx->stats.p + 2 * (ctx->stats_slot ^ 1);
         ctx->stats_slot ^= 1;
-        k_split_tf32<<<(unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm), 256, 0, st>>>(item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
+        SKR_CUDA(ctx, launch_pdl(k_split_tf32, dim3((unsigned)((unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm))), dim3((unsigned)(256)), (size_t)(0), st, item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
                                                                                                   (float *)ctx->blo.p, bias_dev, (int *)ctx->fail_list.p, stats_cur,
-                                                                                                  stats_next);
+                                                                                                  stats_next));
         ctx->launches++;
         CUtensorMap mhi, mlo;
         if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
@@ -1023,9 +1041,9 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)P.n_rt, st, mhi, mlo, A, P))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
-        k_sample_thr<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>((const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
+        SKR_CUDA(ctx, launch_pdl(k_sample_thr, dim3((unsigned)((unsigned)((n_rows + 7) / 8))), dim3((unsigned)(256)), (size_t)(0), st, (const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
                                                                    (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr,
-                                                                   (float *)A.thr_hi, (float *)A.thr_lo);
+                                                                   (float *)A.thr_hi, (float *)A.thr_lo));
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
             A.trace_tiles = ctx->work_max_tiles;
