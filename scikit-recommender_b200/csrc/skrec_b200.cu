@@ -69,6 +69,7 @@ struct skr_ctx {
     // workspace, grow-only
     Buf trace, work, stats, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
+    double *h_pin = nullptr;  // pinned host staging for the small results ([sums | watchdog flag]), SKR_PIN_DOUBLES doubles
     int64_t launches = 0;
     const char *last_fused = "none";
     int64_t opt_chunks = 0;
@@ -137,6 +138,8 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+
+constexpr int SKR_PIN_DOUBLES = 2048;
 
 int ensure(skr_ctx *ctx, Buf &b, size_t bytes)
 {
@@ -612,6 +615,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     cudaSetDevice(ctx->device);
     free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr); free_dev(ctx->d_mask_tile_off);
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
                    &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt, &ctx->work};
@@ -1152,15 +1156,20 @@ int skr_eval_merged_topk(skr_ctx *ctx, const uint64_t *keys_all_dev, int n_shard
 static int finish_host(skr_ctx *ctx, int64_t n_rows, int MK, int K, int32_t *topk_idx_host, float *per_user_host, double *sums_host,
                        const int32_t *d_idx, const float *d_pu, const double *d_sums, cudaStream_t st)
 {
-    std::vector<double> tmp((size_t)MK);
     if (topk_idx_host) SKR_CUDA(ctx, cudaMemcpyAsync(topk_idx_host, d_idx, (size_t)n_rows * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (per_user_host) SKR_CUDA(ctx, cudaMemcpyAsync(per_user_host, d_pu, (size_t)n_rows * MK * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (sums_host) SKR_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_sums, (size_t)MK * sizeof(double), cudaMemcpyDeviceToHost, st));
+    // sums and the watchdog flag land in one pinned buffer: two asynchronous copies and a single synchronisation
+    // (a pageable destination and a separate blocking copy of the flag cost two more round trips per call)
+    if (ctx->h_pin == nullptr) SKR_CUDA(ctx, cudaMallocHost((void **)&ctx->h_pin, (size_t)SKR_PIN_DOUBLES * sizeof(double)));
+    const bool pinned = MK + 1 <= SKR_PIN_DOUBLES;
+    std::vector<double> tmp(pinned ? 0 : (size_t)MK);
+    double *dst = pinned ? ctx->h_pin : tmp.data();
+    int *flag_p = reinterpret_cast<int *>(ctx->h_pin + (SKR_PIN_DOUBLES - 1));
+    if (sums_host) SKR_CUDA(ctx, cudaMemcpyAsync(dst, d_sums, (size_t)MK * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SKR_CUDA(ctx, cudaMemcpyAsync(flag_p, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SKR_CUDA(ctx, cudaStreamSynchronize(st));
-    if (sums_host) for (int i = 0; i < MK; ++i) sums_host[i] += tmp[(size_t)i];
-    int flag = 0;
-    SKR_CUDA(ctx, cudaMemcpy(&flag, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag) return fail(ctx, SKR_ERR_CUDA, "kernel watchdog tripped (code %d)", flag);
+    if (sums_host) for (int i = 0; i < MK; ++i) sums_host[i] += dst[i];
+    if (*flag_p) return fail(ctx, SKR_ERR_CUDA, "kernel watchdog tripped (code %d)", *flag_p);
     return SKR_OK;
 }
 
@@ -1213,10 +1222,17 @@ int skr_eval_fused_host(skr_ctx *ctx, const float *user_vecs_host, int64_t n_row
         SKR_CUDA(ctx, cudaMemsetAsync(ctx->stage_a.p, 0, (size_t)n_rows * dp * sizeof(float), st));
         SKR_CUDA(ctx, cudaMemsetAsync(ctx->stage_b.p, 0, (size_t)n_items * dp * sizeof(float), st));
     }
-    SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_a.p, (size_t)dp * sizeof(float), user_vecs_host, (size_t)ld_u * sizeof(float),
-                                    (size_t)d * sizeof(float), (size_t)n_rows, cudaMemcpyHostToDevice, st));
-    SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_b.p, (size_t)dp * sizeof(float), item_vecs_host, (size_t)ld_i * sizeof(float),
-                                    (size_t)d * sizeof(float), (size_t)n_items, cudaMemcpyHostToDevice, st));
+    // packed tables (the usual case) go as one flat copy each: a pitched copy of 256-byte rows is descriptor-bound
+    if (ld_u == dp && d == dp)
+        SKR_CUDA(ctx, cudaMemcpyAsync(ctx->stage_a.p, user_vecs_host, (size_t)n_rows * dp * sizeof(float), cudaMemcpyHostToDevice, st));
+    else
+        SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_a.p, (size_t)dp * sizeof(float), user_vecs_host, (size_t)ld_u * sizeof(float),
+                                        (size_t)d * sizeof(float), (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    if (ld_i == dp && d == dp)
+        SKR_CUDA(ctx, cudaMemcpyAsync(ctx->stage_b.p, item_vecs_host, (size_t)n_items * dp * sizeof(float), cudaMemcpyHostToDevice, st));
+    else
+        SKR_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_b.p, (size_t)dp * sizeof(float), item_vecs_host, (size_t)ld_i * sizeof(float),
+                                        (size_t)d * sizeof(float), (size_t)n_items, cudaMemcpyHostToDevice, st));
     if (bias_host) SKR_CUDA(ctx, cudaMemcpyAsync(ctx->stage_c.p, bias_host, (size_t)n_items * sizeof(float), cudaMemcpyHostToDevice, st));
     SKR_CUDA(ctx, cudaMemsetAsync(ctx->sums.p, 0, (size_t)MK * sizeof(double), st));
     rc = skr_eval_fused(ctx, (const float *)ctx->stage_a.p, n_rows, dp, (const float *)ctx->stage_b.p, n_items, dp, (int)dp,
