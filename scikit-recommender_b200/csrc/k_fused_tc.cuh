@@ -179,16 +179,6 @@ __device__ __forceinline__ uint32_t to_tf32(float x)
 #define SKR_W32(a, o) \
     "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7])
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : SKR_R32(r, 0), SKR_R32(r, 8), SKR_R32(r, 16), SKR_R32(r, 24)
-        : "r"(taddr)
-        : "memory");
-}
 // load + wait in one statement: the registers are defined only once the data has landed
 __device__ __forceinline__ void tmem_ld32_wait(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -201,16 +191,6 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t taddr, uint32_t (&r)[32]
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};"
-        ::SKR_W32(r, 0), SKR_W32(r, 8), SKR_W32(r, 16), SKR_W32(r, 24), "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
