@@ -411,12 +411,17 @@ class RankingEvaluator(object):
             x = np.ascontiguousarray(x)
         return x
 
-    def _fused_can_take(self, d):
-        """Shapes the fused kernels cover: top-K <= 128; d <= 128 on tensor cores, else FP32 FMA with d % 4 == 0."""
+    def _fused_can_take(self, d, n_items=None):
+        """Shapes the fused kernels cover: top-K <= 128; d <= 128 on tensor cores, else FP32 FMA with d % 4 == 0.
+        With precision "auto" a catalogue too small for sampled thresholds (about 160 items per requested rank:
+        ml-1m at top-50) goes to the score-block path as well -- the fused kernels would still be exact there, but
+        through their per-row fallback, which is slower than a GEMM plus the HBM-bound top-K kernel."""
         if self.max_top > 128:
             return False
         if self.precision in ("3xtf32", "tf32r", "1xtf32"):
             return True  # an explicit tensor-core request fails loudly in the library if the shape is out of range
+        if self.precision == "auto" and n_items is not None and n_items < max(3072, 160 * self.max_top):
+            return False
         return d <= 128 or (d % 4 == 0 and d <= 1024)
 
     def _evaluate_by_blocks(self, uv, iv, b, users, key, dev, want_pu):
@@ -442,7 +447,7 @@ class RankingEvaluator(object):
         import torch
         user_vecs, item_vecs, bias = model.eval_embeddings(users)
         MK = self.metrics_num * self.max_top
-        if not self._fused_can_take(int(item_vecs.shape[1])):
+        if not self._fused_can_take(int(item_vecs.shape[1]), int(item_vecs.shape[0])):
             uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
             assert uv.shape[0] == len(users) and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
             return self._evaluate_by_blocks(uv, iv, b, users, key, dev, want_pu)

@@ -579,7 +579,7 @@ def test_top_k_and_arg_top_k_like_pyx_sort(torch_cuda):
 
 def test_adapters_through_the_evaluator(torch_cuda):
     from skrec_b200 import RankingEvaluator, adapters, synth
-    data = synth.make(users=400, items=2500, d=32, nnz_train=9000, nnz_test=2500, seed=21, bias=True)
+    data = synth.make(users=400, items=4000, d=32, nnz_train=9000, nnz_test=2500, seed=21, bias=True)
     metric, top_k = ["Precision", "Recall", "MAP", "NDCG", "MRR"], [5, 20]
     ids = [synth.METRIC_IDS[m] for m in metric]
     cols = np.array(top_k) - 1
@@ -790,6 +790,23 @@ def test_evaluator_routes_shapes_outside_the_fused_kernels(torch_cuda):
         ev = RankingEvaluator(data["train"], data["test"], metric=metric, top_k=top_k, device=0, batch_size=128)
         got = np.array(list(ev.evaluate(model).values()), np.float32)
         assert ev.last_stats["path"] == "scores:device_blocks"
+        per, _ = oracle.evaluate_dicts(synth.PredictOnlyModel(data["user_emb"], data["item_emb"], data["bias"]).predict,
+                                       data["train"], data["test"], ids, max(top_k))
+        expect = oracle.mean_f32(per).reshape(len(ids), max(top_k))[:, np.array(top_k) - 1].ravel()
+        assert np.max(np.abs(got - expect)) <= TOL_METRIC
+
+
+def test_evaluator_routes_small_catalogues_by_requested_rank(torch_cuda):
+    """ml-1m-sized catalogue: top-20 fits the sampled-threshold plan (fused), top-50 does not (score blocks); same numbers."""
+    from skrec_b200 import RankingEvaluator, adapters, synth
+    data = synth.make(users=500, items=3706, d=64, nnz_train=20000, nnz_test=2500, seed=77, bias=True)
+    metric = ["Precision", "Recall", "NDCG"]
+    ids = [synth.METRIC_IDS[m] for m in metric]
+    model = adapters.dot_product(data["user_emb"], data["item_emb"], data["bias"])
+    for top_k, path in (([10, 20], "fused:"), ([20, 50], "scores:device_blocks")):
+        ev = RankingEvaluator(data["train"], data["test"], metric=metric, top_k=top_k, device=0)
+        got = np.array(list(ev.evaluate(model).values()), np.float32)
+        assert ev.last_stats["path"].startswith(path), ev.last_stats["path"]
         per, _ = oracle.evaluate_dicts(synth.PredictOnlyModel(data["user_emb"], data["item_emb"], data["bias"]).predict,
                                        data["train"], data["test"], ids, max(top_k))
         expect = oracle.mean_f32(per).reshape(len(ids), max(top_k))[:, np.array(top_k) - 1].ravel()
