@@ -662,6 +662,23 @@ def test_fused_tf32r_equals_fp32_path_bit_for_bit(torch_cuda, ctx, U, I, d, bias
     _check_fused(*got, ue, ie, b, tr, te, metric, K)
 
 
+@pytest.mark.parametrize("d,bias", [(32, True), (64, False), (96, True), (128, True)])
+def test_fused_tf32r_with_working_thresholds_equals_fp32_path(torch_cuda, ctx, d, bias):
+    """Catalogue large enough for the sampled thresholds to settle (nearly) every row in the candidate path -- small
+    shapes go through the exact fallback and would not exercise the threshold MMA (d <= 96) or the FADD epilogue (d = 128)."""
+    U, I, K = 300, 16384, 50
+    ue, ie, b, tr, te = _fused_case(1000 + d, U, I, d, bias, 40)
+    metric = [1, 2, 4]
+    got = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "tf32r")
+    assert ctx.last_fused_kernel == "tcgen05_tf32r"
+    assert ctx.fused_stats()["exact_rows"] <= U // 20
+    ref = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "fp32")
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    x3 = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "3xtf32")
+    assert ctx.fused_stats()["exact_rows"] <= U // 20
+    _check_fused(*x3, ue, ie, b, tr, te, metric, K, tol_score=TOL_SCORE * max(1.0, 0.5 * np.sqrt(d)))
+
+
 def test_tf32_error_stays_inside_the_band_tf32r_assumes(torch_cuda, ctx):
     """|s_tf32 - s_fp32| of the single-pass kernel (threshold MMA and the epilogue's add-back included) against eps
     of k_sample_thr (k_fused_tc.cuh), on the candidates the kernel reports: the bound must hold with slack."""
