@@ -439,7 +439,7 @@ static long lpt_makespan(const std::vector<int4> &items, int n_sm, int overhead)
     return *std::max_element(load.begin(), load.end());
 }
 
-static WorkPlan make_work(int n_rt, int n_ct, int s_lo, int n_plus, int n_sm)
+static WorkPlan make_work(int n_rt, int n_ct, int s_lo, int n_plus, int n_sm, int overhead)
 {
     // n_plus user tiles get s_lo + 1 chunks, the others s_lo
     WorkPlan wp;
@@ -455,17 +455,19 @@ static WorkPlan make_work(int n_rt, int n_ct, int s_lo, int n_plus, int n_sm)
     }
     std::stable_sort(wp.items.begin(), wp.items.end(), [](const int4 &a, const int4 &b) { return a.z > b.z; });
     for (const int4 &w : wp.items) wp.max_tiles = std::max(wp.max_tiles, w.z);
-    wp.makespan = lpt_makespan(wp.items, n_sm, 6);
+    wp.makespan = lpt_makespan(wp.items, n_sm, overhead);
     return wp;
 }
 
-static WorkPlan plan_work(const skr_ctx *ctx, int n_rt, int n_ct)
+static WorkPlan plan_work(const skr_ctx *ctx, int n_rt, int n_ct, int overhead)
 {
+    // overhead: a CTA's fixed cost (prologue, pipeline fill, tail) in tile times -- ~5 us, i.e. 6 three-pass tiles or 10
+    // single-pass tiles at d = 64
     const int smax = std::min(n_ct, 8);  // 4 sub-lists per chunk, at most 32 per row
-    if (ctx->opt_chunks > 0) return make_work(n_rt, n_ct, (int)std::min<int64_t>(ctx->opt_chunks, smax), 0, ctx->n_sm);
-    WorkPlan best = make_work(n_rt, n_ct, 1, 0, ctx->n_sm);
+    if (ctx->opt_chunks > 0) return make_work(n_rt, n_ct, (int)std::min<int64_t>(ctx->opt_chunks, smax), 0, ctx->n_sm, overhead);
+    WorkPlan best = make_work(n_rt, n_ct, 1, 0, ctx->n_sm, overhead);
     for (int s = 2; s <= smax; ++s) {
-        WorkPlan w = make_work(n_rt, n_ct, s, 0, ctx->n_sm);
+        WorkPlan w = make_work(n_rt, n_ct, s, 0, ctx->n_sm, overhead);
         if (w.makespan < best.makespan) best = w;
     }
     for (int k = 1; k <= 16; ++k) {  // k full waves
@@ -473,7 +475,7 @@ static WorkPlan plan_work(const skr_ctx *ctx, int n_rt, int n_ct)
         const int s_lo = (int)(C / n_rt), n_plus = (int)(C - (long)s_lo * n_rt);
         if (s_lo < 1 || n_plus == 0) continue;
         if (s_lo + 1 > smax) break;
-        WorkPlan w = make_work(n_rt, n_ct, s_lo, n_plus, ctx->n_sm);
+        WorkPlan w = make_work(n_rt, n_ct, s_lo, n_plus, ctx->n_sm, overhead);
         if (w.makespan < best.makespan) best = w;
     }
     return best;
@@ -984,13 +986,20 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         r = std::max(1, std::min(r, TC_MAX_RANK));
         if (ctx->opt_rank > 0) r = (int)std::min<int64_t>(ctx->opt_rank, TC_MAX_RANK);
         const double expect = r / f_eff;  // candidates per row
-        // work list of the main pass (cached: it depends only on the tile counts)
-        if (ctx->work_key[0] != P.n_rt || ctx->work_key[1] != P.n_ct || ctx->work_key[2] != (int)ctx->opt_chunks) {
-            const WorkPlan wp = plan_work(ctx, P.n_rt, P.n_ct);
+        // AUTO: re-scoring costs a fixed ~60 candidate rows per user, the two extra MMA passes of 3xTF32 grow with
+        // the catalogue: measured on one B200, tf32r is 5 % faster at c2 (I d = 2.6 M) and 22 % at c3b (5.9 M); below
+        // ~1 M the sampled thresholds stop working for either and the choice does not matter
+        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 2.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
+        const bool rescore = (precision == SKR_PREC_TF32R);
+        const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
+        // work list of the main pass (cached: it depends only on the tile counts and the cost of a tile)
+        const int cta_overhead = (passes == 1) ? (nkb <= 2 ? 10 : 6) : (nkb <= 2 ? 6 : 4);
+        if (ctx->work_key[0] != P.n_rt || ctx->work_key[1] != P.n_ct || ctx->work_key[2] != (int)ctx->opt_chunks || ctx->work_key[3] != cta_overhead) {
+            const WorkPlan wp = plan_work(ctx, P.n_rt, P.n_ct, cta_overhead);
             if ((rc = ensure(ctx, ctx->work, wp.items.size() * sizeof(int4)))) return rc;
             SKR_CUDA(ctx, cudaMemcpyAsync(ctx->work.p, wp.items.data(), wp.items.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
             SKR_CUDA(ctx, cudaStreamSynchronize(st));  // the host vector goes away; happens once per shape
-            ctx->work_key[0] = P.n_rt; ctx->work_key[1] = P.n_ct; ctx->work_key[2] = (int)ctx->opt_chunks;
+            ctx->work_key[0] = P.n_rt; ctx->work_key[1] = P.n_ct; ctx->work_key[2] = (int)ctx->opt_chunks; ctx->work_key[3] = cta_overhead;
             ctx->work_ctas = (int)wp.items.size(); ctx->work_slots = wp.slots; ctx->work_min_slots = wp.min_slots;
             ctx->work_max_tiles = wp.max_tiles; ctx->work_mixed = wp.mixed;
         }
@@ -1027,12 +1036,6 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.trace = nullptr;
         A.trace_cta = -1;
         A.trace_tiles = 0;
-        // AUTO: re-scoring costs a fixed ~60 candidate rows per user, the two extra MMA passes of 3xTF32 grow with
-        // the catalogue: measured on one B200, tf32r is 5 % faster at c2 (I d = 2.6 M) and 22 % at c3b (5.9 M); below
-        // ~1 M the sampled thresholds stop working for either and the choice does not matter
-        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 2.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
-        const bool rescore = (precision == SKR_PREC_TF32R);
-        const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
         const bool presub = (passes == 1) && (nkb <= 3);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
         A.thr_hi = presub ? A.thr + n_rows : nullptr;
         A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
