@@ -1036,7 +1036,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.trace = nullptr;
         A.trace_cta = -1;
         A.trace_tiles = 0;
-        const bool presub = (passes == 1) && (nkb <= 3);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
+        const bool presub = (passes == 1);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
         A.thr_hi = presub ? A.thr + n_rows : nullptr;
         A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
         float eps_coef = 0.0f;
