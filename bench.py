@@ -91,6 +91,26 @@ class ClockSampler(object):
                 "window": "warm-up + timed steps + e2e steps"}
 
 
+C4_RANKS = 8  # c4 is quoted user-sharded over 8 B200: one rank's share is 125,000 of the 1,000,000 users
+
+
+def rank_config(name, users=None):
+    """The workload one rank holds.  c1-c3: the whole config (N > 1 gives every rank its own slice of that size).
+    c4 (1M x 1M): one GPU's share of the 8-way user sharding -- 125,000 users against the full 1M-item table, interactions
+    scaled with the users (50 train / 10 test items per user) -- so `--gpus 8` is exactly c4 and `--gpus 1` one eighth of it."""
+    from skrec_b200 import synth
+    cfg = dict(synth.CONFIGS[name])
+    if name == "c4" and users is None:
+        users = cfg["users"] // C4_RANKS
+    if users is not None and users != cfg["users"]:
+        f = float(users) / cfg["users"]
+        cfg["nnz_train"] = max(users, int(round(cfg["nnz_train"] * f)))
+        cfg["nnz_test"] = max(users, int(round(cfg["nnz_test"] * f)))
+        cfg["name"] = "%s, %d-user slice" % (cfg["name"], users)
+        cfg["users"] = int(users)
+    return cfg
+
+
 def reference_users_per_s(data, cfg, users, cores, batch_size=256, repeats=1):
     """The unmodified reference RankingEvaluator.evaluate (oracle/_ref) on `users`; best of repeats."""
     import torch
@@ -128,8 +148,11 @@ def run_reference(args):
         return 0
     import warnings
     warnings.filterwarnings("ignore")
-    cfg = synth.CONFIGS[args.config]
-    data = synth.make_config(args.config)
+    # c4: a 2,048-user slice against the full 1M-item table (a full pass would stream 4 TB of scores)
+    cfg = rank_config(args.config, users=2048 if args.config == "c4" else args.users_per_gpu)
+    if args.config == "c4":
+        cfg["item_seed"] = cfg["seed"] + 7
+    data = synth.make(**cfg)
     cores = os.cpu_count() or 1
     U = data["users"]
     rate, _, _ = reference_users_per_s(data, cfg, list(range(min(U, 1024))), cores)
@@ -171,8 +194,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         td.init_process_group("nccl", device_id=dev)
 
-    cfg = dict(synth.CONFIGS[args.config])
-    if world > 1:  # each rank: its own user slice of one replicated catalogue
+    cfg = rank_config(args.config, users=args.users_per_gpu)
+    if world > 1 or args.config == "c4":  # each rank: its own user slice of one replicated catalogue
         cfg["item_seed"] = cfg["seed"] + 7
         cfg["seed"] = cfg["seed"] + 1000 * rank
     data = synth.make(device=dev, **cfg)
@@ -334,9 +357,12 @@ def run_ours(args):
             n = U if U <= 60000 else 2048
             rate, secs, ref_rep = reference_users_per_s(data, cfg, list(range(n)), cores, repeats=2)
             ref_vals = np.array(list(ref_rep.values()), np.float32)
+            gpu_vals = means
+            if n != U:  # the same users through the GPU evaluator, so the sample is a parity check too
+                gpu_vals = np.array(list(evaluator.evaluate(model, test_users=list(range(n))).values()), np.float32)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "%d of %d users, 1 pass, best of 2 (%.2f s), batch 256, unmodified reference RankingEvaluator + torch CPU predict" % (n, U, secs),
-                   "max_abs_metric_diff_vs_gpu": float(np.max(np.abs(ref_vals - means))) if n == U else None}
+                   "max_abs_metric_diff_vs_gpu": float(np.max(np.abs(ref_vals - gpu_vals)))}
         else:
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref not present"}
 
@@ -359,13 +385,16 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="default 200 (c1-c3), 20 (c4: a step is ~70 ms)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3a", "c3b"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3a", "c3b", "c4"])
+    ap.add_argument("--users-per-gpu", type=int, default=None, help="evaluate a slice of this many users per rank (interactions scaled with it)")
     ap.add_argument("--precision", default="auto", choices=["auto", "3xtf32", "fp32", "1xtf32", "tf32r"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.config == "c4" else 200
     args.steps = max(1, args.steps)
     if args.impl == "reference":
         return run_reference(args)

@@ -101,3 +101,23 @@ def test_evaluate_requires_predict_and_a_gpu():
                 return np.zeros((len(users), 10), np.float32)
         with pytest.raises(RuntimeError):  # no CPU fallback
             ev.evaluate(M())
+
+
+def test_bench_rank_config_c4_is_one_eighth_of_the_users():
+    """bench.py --config c4: a rank holds 125,000 of the 1M users against the full item table, interactions scaled
+    with the users; c1-c3 stay whole; --users-per-gpu slices any config."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("skr_bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from skrec_b200 import synth
+    c4 = bench.rank_config("c4")
+    assert (c4["users"], c4["items"], c4["d"]) == (125_000, 1_000_000, 128)
+    assert c4["nnz_train"] == 6_250_000 and c4["nnz_test"] == 1_250_000
+    assert c4["top_k"] == [10, 20, 50, 100] and len(c4["metric"]) == 5
+    assert bench.rank_config("c2") == synth.CONFIGS["c2"]
+    half = bench.rank_config("c2", users=1000)
+    assert half["users"] == 1000 and half["items"] == synth.CONFIGS["c2"]["items"]
+    assert abs(half["nnz_train"] - 810_128 * 1000 / 29858) <= 1
+    assert synth.CONFIGS["c4"]["users"] == 1_000_000  # the table itself is not touched

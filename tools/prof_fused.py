@@ -1,4 +1,4 @@
-"""ncu target: a few launches of the fused scoring kernel on the c2 workload (development aid)."""
+"""ncu target: a few launches of the fused scoring kernel on a bench workload (c2 default; c3a, c3b, c4 = 125,000-user share) (development aid)."""
 import os
 import sys
 
@@ -11,8 +11,14 @@ from skrec_b200 import _native, synth  # noqa: E402
 prec = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfgname = sys.argv[3] if len(sys.argv) > 3 else "c2"
-d = synth.make_config(cfgname, device="cuda")
-cfg = d["config"]
+if cfgname == "c4":  # one GPU's share of the 8-way user sharding, like bench.py --config c4
+    import bench  # noqa: E402
+    cfg = bench.rank_config("c4")
+    cfg["item_seed"] = cfg["seed"] + 7
+    d = synth.make(device="cuda", **cfg)
+else:
+    d = synth.make_config(cfgname, device="cuda")
+    cfg = d["config"]
 ctx = _native.Context(0)
 ctx.set_train_csr(d["train_indptr"], d["train_indices"], d["items"])
 ctx.set_test_csr(d["test_indptr"], d["test_indices"], d["items"])
