@@ -339,7 +339,12 @@ def run_ours(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(ctx.last_fused_kernel)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full): "<kernel>" is the c2 capture,
+        # "<kernel>@<config>" the others; configs without a capture report null
+        tj = json.load(open(tp))
+        traffic = tj.get("%s@%s" % (ctx.last_fused_kernel, args.config), tj.get(ctx.last_fused_kernel) if args.config == "c2" else None)
+        if args.users_per_gpu is not None:
+            traffic = None
     roofline = {"bound": "tensor", "kernel": ctx.last_fused_kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "prepass_kernel_ms": float(np.mean(prepass_ms)), "plan": plan,
