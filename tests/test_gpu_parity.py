@@ -729,6 +729,51 @@ def test_c2_full_size_tf32r_equals_fp32_path(torch_cuda, ctx, c2_data):
     assert stats["exact_rows"] < 0.01 * d["users"]  # the fast path settles (almost) every row
 
 
+def test_c4_catalogue_size_tf32r_equals_fp32_path_and_oracle_sample(torch_cuda, ctx):
+    """BASELINE.json configs[3] at the full catalogue size (1M items, d=128, bias, top-100, five metrics) on a 2,048-user
+    slice of one GPU's share: the tensor-core path (TF32 candidates + exact re-scoring) gives the FP32 kernel's items,
+    scores and per-user metric vectors bit for bit, and both agree with the oracle on a 32-user sample."""
+    from skrec_b200 import synth
+    torch = torch_cuda
+    cfg = dict(synth.CONFIGS["c4"])
+    U = 2048
+    cfg.update(users=U, nnz_train=U * 50, nnz_test=U * 10)
+    d = synth.make(device="cuda", **cfg)
+    tr = (d["train_indptr"], d["train_indices"])
+    te = (d["test_indptr"], d["test_indices"])
+    metric, K = [1, 2, 3, 4, 5], 100
+    a = _run_fused(torch, ctx, d["user_emb"], d["item_emb"], d["bias"], tr, te, metric, K, "tf32r")
+    assert ctx.last_fused_kernel == "tcgen05_tf32r"
+    stats = ctx.fused_stats()
+    b = _run_fused(torch, ctx, d["user_emb"], d["item_emb"], d["bias"], tr, te, metric, K, "fp32")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert stats["exact_rows"] < 0.01 * U  # the sampled thresholds settle (almost) every row
+    # every list: K distinct, unmasked items in descending (score, -id) order
+    assert np.all((a[1][:, :-1] > a[1][:, 1:]) | ((a[1][:, :-1] == a[1][:, 1:]) & (a[0][:, :-1] < a[0][:, 1:])))
+    rows = np.repeat(np.arange(U), np.diff(tr[0]))
+    train_keys = rows.astype(np.int64) * d["items"] + tr[1]
+    list_keys = (np.arange(U, dtype=np.int64)[:, None] * d["items"] + a[0]).ravel()
+    assert not np.isin(list_keys, train_keys).any()
+    # oracle on a sample of users
+    sample = np.arange(0, U, U // 32)[:32]
+    S = oracle.scores(d["user_emb"][sample], d["item_emb"], d["bias"])
+    sp, si = oracle.dicts_to_csr(sample.tolist(), d["train"])
+    oracle.mask_rows(S, sp, si)
+    ep, ei = oracle.dicts_to_csr(sample.tolist(), d["test"], dedup_sort=True)
+    eper, etop = oracle.eval_scores(S, ep, ei, metric, K, return_topk=True)
+    got = a[0][sample]
+    diff = got != etop
+    if diff.any():
+        gs = np.take_along_axis(S, got.astype(np.int64), 1)
+        es = np.take_along_axis(S, etop.astype(np.int64), 1)
+        assert np.max(np.abs(gs[diff] - es[diff])) < TOL_NEAR_TIE
+    assert diff.mean() < 0.02
+    assert np.max(np.abs(a[2][sample].astype(np.float64).mean(0) - eper.astype(np.float64).mean(0))) <= TOL_METRIC
+    same = ~diff.any(axis=1)
+    assert np.array_equal(a[2][sample][same], eper[same])
+    assert eper[:, 4 * K - 1].mean() > 0.005  # NDCG@100 of the planted test items: the check is not vacuous
+
+
 # ---- randomized shape sweep: every fused precision against the oracle on ragged / awkward shapes -------------
 def _sweep_cases():
     g = np.random.default_rng(2026)
