@@ -175,6 +175,15 @@ int skr_fused_prepass_ms(skr_ctx *ctx, int back, float *ms_out);
  * threshold rank r, sub-list capacity, item chunks, TMA stages, rows re-done by the exact kernel.
  * Synchronises the device. */
 int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out);
+/* Host only -- no CUDA call, usable without a GPU: the work list the tcgen05 main pass runs for n_user_tiles x
+ * n_item_tiles tiles (128 users x 128 items each) on n_sm SMs.  A work item is (user tile, first item tile, number of
+ * item tiles, chunk index of that user tile); items come largest first (the block scheduler then runs
+ * longest-processing-time-first), user tiles get `slots` or `slots - 1` chunks so that the CTA count fills whole waves.
+ * cta_overhead: fixed cost of a CTA in tile times; chunks: 0 = automatic, else the "chunks" option.
+ * items_out (nullable): int32 [max_items][4]; info_out (nullable): [5] = slots, min_slots, largest item, mixed, simulated
+ * makespan in tile times.  Returns the number of work items, or a negative SKR_ERR_*. */
+int64_t skr_plan_work_host(int n_user_tiles, int n_item_tiles, int n_sm, int cta_overhead, int chunks, int32_t *items_out,
+                           int64_t max_items, int64_t *info_out);
 /* Development aid: with skr_set_option("trace_cta", c >= 0) the main tcgen05 pass records, for CTA c,
  * SM-clock timestamps of its pipeline events per item tile (16 slots per tile, see k_fused_tc.cuh);
  * this copies up to n_out of them to the host.  Synchronises the device. */

@@ -19,6 +19,7 @@ SYMBOLS = (
     "skr_abi_version", "skr_ctx_create", "skr_ctx_destroy", "skr_last_error", "skr_set_train_csr",
     "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
     "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace", "skr_topk_fused", "skr_eval_merged_topk", "skr_topk_scores", "skr_topk_scores_host", "skr_colsum_rows",
+    "skr_plan_work_host",
 )
 
 _lib = None
@@ -71,12 +72,28 @@ def lib():
     L.skr_fused_prepass_ms.argtypes = [_vp, _int, ctypes.POINTER(ctypes.c_float)]
     L.skr_fused_stats.argtypes = [_vp, ctypes.POINTER(_i64), _int]
     L.skr_fused_trace.argtypes = [_vp, ctypes.POINTER(_i64), _i64]
+    L.skr_plan_work_host.argtypes = [_int, _int, _int, _int, _int, _vp, _i64, ctypes.POINTER(_i64)]
+    L.skr_plan_work_host.restype = _i64
     for name in SYMBOLS:
         getattr(L, name)
     if L.skr_abi_version() != 1:
         raise ImportError("libskrec_b200.so ABI version %d, expected 1" % L.skr_abi_version())
     _lib = L
     return L
+
+
+def plan_work(n_user_tiles, n_item_tiles, n_sm=148, cta_overhead=10, chunks=0):
+    """Work list of the tcgen05 main pass (host only, no GPU needed): -> (int32 [n, 4] of (user tile, first item tile,
+    item tiles, chunk index), dict(slots, min_slots, max_tiles, mixed, makespan))."""
+    L = lib()
+    info = (_i64 * 5)()
+    n = L.skr_plan_work_host(int(n_user_tiles), int(n_item_tiles), int(n_sm), int(cta_overhead), int(chunks), None, 0, info)
+    if n < 0:
+        raise NativeError(int(n), "skr_plan_work_host: invalid argument")
+    items = np.empty((int(n), 4), np.int32)
+    L.skr_plan_work_host(int(n_user_tiles), int(n_item_tiles), int(n_sm), int(cta_overhead), int(chunks),
+                         ctypes.c_void_p(items.ctypes.data), int(n), info)
+    return items, dict(zip(("slots", "min_slots", "max_tiles", "mixed", "makespan"), [int(x) for x in info]))
 
 
 def _np_ptr(a):

@@ -459,23 +459,26 @@ static WorkPlan make_work(int n_rt, int n_ct, int s_lo, int n_plus, int n_sm, in
     return wp;
 }
 
-static WorkPlan plan_work(const skr_ctx *ctx, int n_rt, int n_ct, int overhead)
+static WorkPlan plan_work(int n_sm, int64_t opt_chunks, int n_rt, int n_ct, int overhead);
+static WorkPlan plan_work(const skr_ctx *ctx, int n_rt, int n_ct, int overhead) { return plan_work(ctx->n_sm, ctx->opt_chunks, n_rt, n_ct, overhead); }
+
+static WorkPlan plan_work(int n_sm, int64_t opt_chunks, int n_rt, int n_ct, int overhead)
 {
     // overhead: a CTA's fixed cost (prologue, pipeline fill, tail) in tile times -- ~5 us, i.e. 6 three-pass tiles or 10
     // single-pass tiles at d = 64
     const int smax = std::min(n_ct, 8);  // 4 sub-lists per chunk, at most 32 per row
-    if (ctx->opt_chunks > 0) return make_work(n_rt, n_ct, (int)std::min<int64_t>(ctx->opt_chunks, smax), 0, ctx->n_sm, overhead);
-    WorkPlan best = make_work(n_rt, n_ct, 1, 0, ctx->n_sm, overhead);
+    if (opt_chunks > 0) return make_work(n_rt, n_ct, (int)std::min<int64_t>(opt_chunks, smax), 0, n_sm, overhead);
+    WorkPlan best = make_work(n_rt, n_ct, 1, 0, n_sm, overhead);
     for (int s = 2; s <= smax; ++s) {
-        WorkPlan w = make_work(n_rt, n_ct, s, 0, ctx->n_sm, overhead);
+        WorkPlan w = make_work(n_rt, n_ct, s, 0, n_sm, overhead);
         if (w.makespan < best.makespan) best = w;
     }
     for (int k = 1; k <= 16; ++k) {  // k full waves
-        const long C = (long)k * ctx->n_sm;
+        const long C = (long)k * n_sm;
         const int s_lo = (int)(C / n_rt), n_plus = (int)(C - (long)s_lo * n_rt);
         if (s_lo < 1 || n_plus == 0) continue;
         if (s_lo + 1 > smax) break;
-        WorkPlan w = make_work(n_rt, n_ct, s_lo, n_plus, ctx->n_sm, overhead);
+        WorkPlan w = make_work(n_rt, n_ct, s_lo, n_plus, n_sm, overhead);
         if (w.makespan < best.makespan) best = w;
     }
     return best;
@@ -676,6 +679,29 @@ int skr_fused_prepass_ms(skr_ctx *ctx, int back, float *ms_out)
     SKR_CUDA(ctx, cudaEventSynchronize(ctx->ev0[i]));
     SKR_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev2[i], ctx->ev0[i]));
     return SKR_OK;
+}
+
+int64_t skr_plan_work_host(int n_user_tiles, int n_item_tiles, int n_sm, int cta_overhead, int chunks, int32_t *items_out, int64_t max_items,
+                           int64_t *info_out)
+{
+    if (n_user_tiles <= 0 || n_item_tiles <= 0 || n_sm <= 0 || cta_overhead < 0 || chunks < 0) return SKR_ERR_INVALID;
+    const WorkPlan wp = plan_work(n_sm, chunks, n_user_tiles, n_item_tiles, cta_overhead);
+    const int64_t n = (int64_t)wp.items.size();
+    if (items_out != nullptr)
+        for (int64_t i = 0; i < n && i < max_items; ++i) {
+            items_out[4 * i + 0] = wp.items[(size_t)i].x;
+            items_out[4 * i + 1] = wp.items[(size_t)i].y;
+            items_out[4 * i + 2] = wp.items[(size_t)i].z;
+            items_out[4 * i + 3] = wp.items[(size_t)i].w;
+        }
+    if (info_out != nullptr) {
+        info_out[0] = wp.slots;
+        info_out[1] = wp.min_slots;
+        info_out[2] = wp.max_tiles;
+        info_out[3] = wp.mixed ? 1 : 0;
+        info_out[4] = wp.makespan;
+    }
+    return n;
 }
 
 int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out)
