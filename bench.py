@@ -345,11 +345,15 @@ def run_ours(args):
         traffic = tj.get("%s@%s" % (ctx.last_fused_kernel, args.config), tj.get(ctx.last_fused_kernel) if args.config == "c2" else None)
         if args.users_per_gpu is not None:
             traffic = None
+    cublas_tf32 = None  # cuBLAS TF32 8192^3 on a B200 of this pool (tools/tf32_peak.py): a cross-check of the derived peak
+    cp = os.path.join(ROOT, "profiles", "r1_run9_tf32_peak.json")
+    if os.path.exists(cp):
+        cublas_tf32 = json.load(open(cp))["cublas_8192_cubed"]["tf32"]["best_tflops"]
     roofline = {"bound": "tensor", "kernel": ctx.last_fused_kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "prepass_kernel_ms": float(np.mean(prepass_ms)), "plan": plan,
                 "algorithmic_flops_per_launch": flops, "mma_passes": passes, "tensor_pipe_utilisation_est": passes * achieved / peak,
-                "peak_note": peak_note}
+                "peak_note": peak_note, "cublas_tf32_8192_tflops": cublas_tf32}
 
     # ---- the reference on this box's host cores, same workload -----------------------------------
     cpu = None
