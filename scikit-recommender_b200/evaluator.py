@@ -103,6 +103,30 @@ def _csr_rows(indptr, indices, rows, col_range=None):
     return optr, np.ascontiguousarray(oidx, dtype=np.int32)
 
 
+def _pairs_to_csr(pairs, num_users, num_items):
+    """(user, item) pairs [n, 2] -> (indptr int64 [num_users + 1], indices int32), items in the pairs' order per user."""
+    users = np.ascontiguousarray(pairs[:, 0], dtype=np.int64)
+    items = np.ascontiguousarray(pairs[:, 1], dtype=np.int64)
+    if users.size and (users.max() >= num_users or items.max() >= num_items):
+        raise ValueError("interaction pair outside [0, %d) x [0, %d)" % (num_users, num_items))
+    indptr = np.zeros(int(num_users) + 1, dtype=np.int64)
+    np.cumsum(np.bincount(users, minlength=int(num_users)), out=indptr[1:])
+    order = np.argsort(users, kind="stable")
+    return indptr, items[order].astype(np.int32)
+
+
+def _read_pairs(path, sep="\t"):
+    """First two columns of a header-less interaction file -> int64 [n, 2] (the files `_read_csv` loads, dataset.py:36-42)."""
+    import os
+    if not os.path.isfile(path):
+        raise FileNotFoundError("'%s' does not exist." % path)  # dataset.py:389-395 (`handle=raise_error`)
+    import pandas as pd
+    df = pd.read_csv(path, sep=sep, header=None, usecols=[0, 1])
+    if df.isnull().values.any():
+        raise ValueError("'%s' has empty fields, please check the file or the separator." % path)
+    return df.to_numpy(dtype=np.int64)
+
+
 def _rows_to_csr(users, d, col_range=None):
     if isinstance(d, _LazyRows):
         return _csr_rows(d.indptr, d.indices, users, col_range)
@@ -226,6 +250,36 @@ class RankingEvaluator(object):
         self.user_pos_train = _LazyRows(tr[0], tr[1], None) if tr is not None else dict()
         self._csr = (tr, te)
         return self
+
+    @classmethod
+    def from_pairs(cls, train_pairs, test_pairs, num_users=None, num_items=None, **kwargs):
+        """Build the evaluator from (user, item) interaction pairs -- int arrays [n, 2], what
+        `ImplicitFeedback.to_user_item_pairs()` gives (dataset.py:117-120); `train_pairs` may be None.
+        Rows keep the pairs' order per user, like `to_user_dict()` (dataset.py:148-156: groupby user, items in
+        file order); users and items are the ids as they come (already remapped by the reference's preprocessor).
+        `num_users` / `num_items` default to max id + 1 over both sets (dataset.py:407-411)."""
+        tr = None if train_pairs is None else np.asarray(train_pairs).reshape(-1, 2)
+        te = np.asarray(test_pairs).reshape(-1, 2)
+        assert te.shape[0] > 0, "'user_test_dict' can be empty."
+        both = [x for x in (tr, te) if x is not None and x.shape[0] > 0]
+        lo = min(int(x.min()) for x in both)
+        if lo < 0:
+            raise ValueError("negative user or item id in the interaction pairs")
+        if num_users is None:
+            num_users = max(int(x[:, 0].max()) for x in both) + 1
+        if num_items is None:
+            num_items = max(int(x[:, 1].max()) for x in both) + 1
+        return cls.from_csr(None if tr is None else _pairs_to_csr(tr, num_users, num_items),
+                            _pairs_to_csr(te, num_users, num_items), **kwargs)
+
+    @classmethod
+    def from_files(cls, train_file, test_file, sep="\t", num_users=None, num_items=None, **kwargs):
+        """Build the evaluator straight from the reference's `<prefix>.train` / `<prefix>.test` interaction files
+        (dataset.py:388-395: header-less, `sep`-separated, columns user, item[, rating][, time] with integer ids),
+        bypassing the DataFrame -> ImplicitFeedback -> dict-of-arrays -> pickle-cache chain (dataset.py:131-156,
+        300-362).  Only the first two columns are read.  `train_file` may be None."""
+        tr = None if train_file is None else _read_pairs(train_file, sep)
+        return cls.from_pairs(tr, _read_pairs(test_file, sep), num_users=num_users, num_items=num_items, **kwargs)
 
     def set_train_data(self, user_train_dict: Optional[Dict[int, np.ndarray]] = None):
         self.user_pos_train = user_train_dict if user_train_dict is not None else dict()

@@ -1,5 +1,7 @@
 """Host logic of the rows next to the hot path: score-provider adapters (algebra against the
 reference models' scoring expressions), CSR ingestion helpers, the lazy {user: items} view.  No GPU."""
+from collections import OrderedDict
+
 import numpy as np
 import pytest
 import torch
@@ -97,3 +99,73 @@ def test_from_csr_builds_the_same_evaluator_state_without_a_gpu():
             e.evaluate(adapters.dot_product(np.zeros((30, 4), np.float32), np.zeros((50, 4), np.float32)))
         else:
             raise RuntimeError("gpu present")
+
+
+def _pairs_case(seed, n_users=40, n_items=60, n_train=400, n_test=90):
+    g = _g(seed)
+    def draw(n):
+        p = np.unique(np.stack([g.integers(0, n_users, n), g.integers(0, n_items, n)], 1), axis=0)
+        return p[g.permutation(p.shape[0])]  # file order is not sorted by user
+    return draw(n_train), draw(n_test)
+
+
+def test_from_pairs_equals_the_reference_dict_construction():
+    """`to_user_dict()` restated (dataset.py:148-156: groupby user ascending, items in file order) against from_pairs."""
+    import pandas as pd
+    tr, te = _pairs_case(11)
+    def to_user_dict(p):
+        df = pd.DataFrame(p, columns=["user", "item"])
+        return OrderedDict((u, d["item"].to_numpy(dtype=np.int32)) for u, d in df.groupby("user"))
+    dtr, dte = to_user_dict(tr), to_user_dict(te)
+    a = ev.RankingEvaluator(dtr, dte, metric=["Recall", "NDCG"], top_k=[5, 20])
+    b = ev.RankingEvaluator.from_pairs(tr, te, metric=["Recall", "NDCG"], top_k=[5, 20])
+    assert b._all_users == list(dte.keys()) == a._all_users
+    for u in dte:
+        assert np.array_equal(b.user_pos_test[u], dte[u])
+    for u in dtr:
+        assert np.array_equal(b.user_pos_train[u], dtr[u])
+    assert all(b.user_pos_train[u].size == 0 for u in range(40) if u not in dtr)
+    # the CSRs the native context would be given are identical row for row
+    users = a._all_users
+    for d_dict, d_lazy in ((dte, b.user_pos_test), (dtr, b.user_pos_train)):
+        p0, i0 = ev._rows_to_csr(users, d_dict)
+        p1, i1 = ev._rows_to_csr(users, d_lazy)
+        assert np.array_equal(p0, p1) and np.array_equal(i0, i1)
+        p0, i0 = ev._rows_to_csr(users, d_dict, (10, 35))  # an item shard's column partition
+        p1, i1 = ev._rows_to_csr(users, d_lazy, (10, 35))
+        assert np.array_equal(p0, p1) and np.array_equal(i0, i1)
+    assert a.metrics_list == b.metrics_list and a.max_top == b.max_top
+    # sizes: inferred like dataset.py:407-411, or given
+    c = ev.RankingEvaluator.from_pairs(None, te, num_users=100, num_items=200)
+    assert len(c.user_pos_train) == 0 and c._csr[1][0].size == 101
+    with pytest.raises(ValueError):
+        ev.RankingEvaluator.from_pairs(tr, te, num_users=5)
+    with pytest.raises(ValueError):
+        ev.RankingEvaluator.from_pairs(tr, np.array([[0, -1]]))
+
+
+def test_from_files_reads_the_reference_interaction_files(tmp_path):
+    tr, te = _pairs_case(12)
+    g = _g(3)
+    # UIRT columns, tab separated, no header (dataset.py:27-30, 388-395); only user and item matter
+    def write(path, p):
+        with open(path, "w") as f:
+            for u, i in p:
+                f.write("%d\t%d\t%.1f\t%d\n" % (u, i, 1.0, int(g.integers(1, 10 ** 9))))
+    write(tmp_path / "toy.train", tr)
+    write(tmp_path / "toy.test", te)
+    a = ev.RankingEvaluator.from_pairs(tr, te, top_k=10)
+    b = ev.RankingEvaluator.from_files(str(tmp_path / "toy.train"), str(tmp_path / "toy.test"), top_k=10)
+    for x, y in zip(a._csr[0] + a._csr[1], b._csr[0] + b._csr[1]):
+        assert np.array_equal(x, y)
+    assert a._all_users == b._all_users
+    c = ev.RankingEvaluator.from_files(None, str(tmp_path / "toy.test"), top_k=10)
+    assert len(c.user_pos_train) == 0
+    with pytest.raises(FileNotFoundError):
+        ev.RankingEvaluator.from_files(str(tmp_path / "missing.train"), str(tmp_path / "toy.test"))
+    # comma separated UI file
+    with open(tmp_path / "toy_ui.test", "w") as f:
+        for u, i in te:
+            f.write("%d,%d\n" % (u, i))
+    d = ev.RankingEvaluator.from_files(None, str(tmp_path / "toy_ui.test"), sep=",", top_k=10)
+    assert np.array_equal(d._csr[1][1], b._csr[1][1])
