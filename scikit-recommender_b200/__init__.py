@@ -3,7 +3,7 @@
 Public surface = the reference's evaluation API (skrec/utils/py/evaluator.py,
 skrec/utils/py/cython/pyx_eval_matrix.pyx): `RankingEvaluator`, `MetricReport`, `EarlyStopping`,
 `eval_score_matrix`, plus the sibling native API `top_k` / `arg_top_k` (pyx_sort.pyx) and the score-provider
-`adapters`.  Everything is computed by the sm_100a kernels in csrc/ behind the C ABI of
+`adapters`, and `group_users_by_interactions` (dataset.py:707-765) for `evaluate_groups`.  Everything is computed by the sm_100a kernels in csrc/ behind the C ABI of
 include/skrec_b200.h; importing this package does not need a GPU, evaluating does.
 """
 from .report import MetricReport, EarlyStopping
@@ -11,6 +11,8 @@ from .evaluator import RankingEvaluator
 from .eval_matrix import eval_score_matrix
 from .sort import top_k, arg_top_k
 from . import adapters
+from .groups import UserGroup, group_users_by_interactions
 
-__all__ = ["MetricReport", "RankingEvaluator", "EarlyStopping", "eval_score_matrix", "top_k", "arg_top_k", "adapters"]
+__all__ = ["MetricReport", "RankingEvaluator", "EarlyStopping", "eval_score_matrix", "top_k", "arg_top_k", "adapters",
+           "UserGroup", "group_users_by_interactions"]
 __version__ = "0.1.0"

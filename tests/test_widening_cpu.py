@@ -169,3 +169,75 @@ def test_from_files_reads_the_reference_interaction_files(tmp_path):
             f.write("%d,%d\n" % (u, i))
     d = ev.RankingEvaluator.from_files(None, str(tmp_path / "toy_ui.test"), sep=",", top_k=10)
     assert np.array_equal(d._csr[1][1], b._csr[1][1])
+
+
+# ---- user activity groups (dataset.py:707-765), the caller above evaluate_groups ------------------------------
+def _groups_golden():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "user_groups.json")))
+
+
+def _groups_case_dict(c):
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("mk_groups", os.path.join(os.path.dirname(__file__), "golden", "make_groups_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m, m.make_case(c["seed"], c["n_users"], c["sigma"], c.get("skip_every", 0))
+
+
+def _same_groups(got, want):
+    assert [g.label for g in got] == [w["label"] for w in want]
+    for gi, (g, w) in enumerate(zip(got, want)):
+        assert g.num_users == w["num_users"] and np.array_equal(g.users, np.array(w["users"]))
+        assert np.array_equal(g.activities, np.array(w["activities"]))
+        assert int(g.num_interactions) == w["num_interactions"][gi]  # the reference stores the list of all groups' totals
+
+
+def test_user_groups_equal_the_reference_function_golden():
+    from skrec_b200 import groups
+    for entry in _groups_golden():
+        c = entry["case"]
+        _, d = _groups_case_dict(c)
+        _same_groups(groups.group_users_by_interactions(d, num_groups=c["num_groups"]), entry["groups"])
+        # the same interactions as a CSR pair / scipy matrix / the evaluator's lazy view
+        n_users = c["n_users"]
+        cnt = np.array([len(d[u]) if u in d else 0 for u in range(n_users)], np.int64)
+        indptr = np.r_[0, np.cumsum(cnt)].astype(np.int64)
+        indices = np.concatenate([d[u] for u in d]).astype(np.int32)
+        _same_groups(groups.group_users_by_interactions((indptr, indices), num_groups=c["num_groups"]), entry["groups"])
+        _same_groups(groups.group_users_by_interactions(ev._LazyRows(indptr, indices), num_groups=c["num_groups"]), entry["groups"])
+        import scipy.sparse as sp
+        m = sp.csr_matrix((np.ones(indices.size, np.float32), indices, indptr), shape=(n_users, int(indices.max()) + 1))
+        _same_groups(groups.group_users_by_interactions(m, num_groups=c["num_groups"]), entry["groups"])
+
+
+def test_user_groups_against_the_reference_source_live():
+    import os
+    if not os.path.exists("/root/reference/skrec/io/dataset.py"):
+        pytest.skip("reference sources are only present in the build container")
+    from skrec_b200 import groups
+    m, _ = _groups_case_dict(dict(seed=0, n_users=8, sigma=1.0))
+    fn = m.reference_function()
+    for seed in range(20, 32):
+        g = _g(seed)
+        c = dict(seed=seed, n_users=int(g.integers(50, 2000)), sigma=float(g.uniform(0.5, 1.6)), num_groups=int(g.integers(2, 6)),
+                 skip_every=int(g.choice([0, 5, 9])))
+        d = m.make_case(c["seed"], c["n_users"], c["sigma"], c["skip_every"])
+        want = fn(m._Dataset(d), num_groups=c["num_groups"])
+        got = groups.group_users_by_interactions(d, num_groups=c["num_groups"])
+        assert [x.label for x in got] == [x.label for x in want]
+        for a, b in zip(got, want):
+            assert np.array_equal(a.users, b.users) and np.array_equal(a.activities, b.activities) and a.num_users == b.num_users
+
+
+def test_user_group_objects_feed_the_evaluator():
+    from skrec_b200 import groups
+    entry = _groups_golden()[0]
+    _, d = _groups_case_dict(entry["case"])
+    gs = groups.group_users_by_interactions(d)
+    assert sum(len(g) for g in gs) == len(d) and sorted(u for g in gs for u in g) == sorted(d.keys())
+    assert list(gs[0])[:3] == gs[0].users[:3].tolist()
+    with pytest.raises(IndexError):  # two activity levels cannot make four groups (the reference fails the same way)
+        groups.group_users_by_interactions({0: np.arange(3), 1: np.arange(3), 2: np.arange(5)}, num_groups=4)
