@@ -13,15 +13,22 @@ transform of it per user, which leaves every rank list and therefore every metri
 |---|---|---|
 | BPRMF                                                | u.i + b_i            (BPRMF.py:84-88)                | dot_product(U, I, b) |
 | LightGCN, LayerGCN, LightGCL, SLMRec, SGL-style GCNs | u_final.i_final      (LightGCN.py:102-107)           | dot_product(U_final, I_final) |
-| SelfCF, BM3                                          | u_on.i_tg + u_tg.i_on (SelfCF.py:235-241)            | two_tower_sum(u_on, i_tg, u_tg, i_on) |
+| FREEDOM, LATTICE, MGCN, DENS, AOBPR                  | u.i on the propagated / learnt tables (FREEDOM.py:254-260, LATTICE.py:296-302, MGCN.py:355-361, DENS.py:315-316, AOBPR.py:94-97) | dot_product(U, I) |
+| BM3                                                  | pred(u_on).pred(i_on) (BM3.py:206-210)               | dot_product(pred(U_on), pred(I_on)) |
+| SLMRec                                               | sigmoid(u.i)         (SLMRec.py:366-370)             | dot_product(U, I)  (monotone: the sigmoid is dropped) |
+| SASRec, SRGNN                                        | h_last.i             (SASRec.py:463, SRGNN.py:176)   | dot_product(H_last, I): one query row per evaluated user |
+| GRU4Rec, GRU4RecPlus                                 | act(h.i + b_i)       (GRU4Rec.py:157-158)            | dot_product(H, I, b)  (monotone final activation dropped) |
+| HGN                                                  | (u + union + sum_l e_l).W2 + b2 (HGN.py:147-163)     | summed_query([u, union, e.sum(1)], W2, b2) |
+| SelfCF                                               | u_on.i_tg + u_tg.i_on (SelfCF.py:235-241)            | two_tower_sum(u_on, i_tg, u_tg, i_on) |
 | FPMC                                                 | ui.iu + last.il      (FPMC.py:81-87)                 | two_tower_sum(UI, IU, LI[last], IL) |
 | MultVAE, CDAE                                        | h(x_u).W^T + c       (MultVAE.py:138-141)            | decoder_layer(H, W, c) |
 | CML                                                  | -||u - i||           (CML.py:152)                    | neg_euclidean(U, I)  (monotone: 2u.i - ||i||^2) |
 | Pop                                                  | popularity count     (Pop.py:41-44)                  | item_scores(counts) |
+| TransRec                                             | -||u + g + last - i|| + b_i (TransRec.py:86-93)      | none: the square root next to a per-item bias is not a monotone image of a dot product; use `predict` (score-block path) |
 """
 import numpy as np
 
-__all__ = ["EmbeddingScorer", "dot_product", "two_tower_sum", "decoder_layer", "neg_euclidean", "item_scores"]
+__all__ = ["EmbeddingScorer", "dot_product", "two_tower_sum", "summed_query", "decoder_layer", "neg_euclidean", "item_scores"]
 
 
 def _t(x):
@@ -91,6 +98,18 @@ def two_tower_sum(u_a, i_a, u_b, i_b, item_bias=None, user_index=None):
     import torch
     u_a, i_a, u_b, i_b = _t(u_a), _t(i_a), _t(u_b), _t(i_b)
     return EmbeddingScorer(torch.cat([u_a, u_b], 1), torch.cat([i_a, i_b], 1), item_bias, user_index, "two_tower_sum")
+
+
+def summed_query(parts, item_table, item_bias=None, user_index=None):
+    """score = sum_p (q_p . i) + b_i  ==  (sum_p q_p) . i + b_i: several query vectors of one user against the same item
+    table (HGN.py:147-163 adds user_emb.W2^T, union_out.W2^T and the sum over the sequence of item_embs.W2^T).
+    The parts are added first, in the order given -- a float reassociation of the reference's sum of products."""
+    parts = [_t(p).float() for p in parts]
+    q = parts[0].clone()
+    for p in parts[1:]:
+        assert p.shape == q.shape, "query parts must have the same shape [B, d]"
+        q += p
+    return EmbeddingScorer(q, item_table, item_bias, user_index, "summed_query")
 
 
 def decoder_layer(hidden_rows, weight, bias=None, user_index=None):

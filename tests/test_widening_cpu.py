@@ -241,3 +241,34 @@ def test_user_group_objects_feed_the_evaluator():
     assert list(gs[0])[:3] == gs[0].users[:3].tolist()
     with pytest.raises(IndexError):  # two activity levels cannot make four groups (the reference fails the same way)
         groups.group_users_by_interactions({0: np.arange(3), 1: np.arange(3), 2: np.arange(5)}, num_groups=4)
+
+
+def test_summed_query_equals_hgn_expression():
+    g = _g(21)
+    B, L, d, n = 9, 5, 16, 40
+    u, union = g.standard_normal((B, d)).astype(np.float32), g.standard_normal((B, d)).astype(np.float32)
+    e = g.standard_normal((B, L, d)).astype(np.float32)
+    W2, b2 = g.standard_normal((n, d)).astype(np.float32), g.standard_normal(n).astype(np.float32)
+    tu, tun, te, tw, tb = (torch.from_numpy(x) for x in (u, union, e, W2, b2))
+    # HGN.py:147-163
+    res = tu.mm(tw.T) + tb
+    res += tun.mm(tw.T)
+    res += torch.matmul(te, tw.T.unsqueeze(dim=0)).sum(dim=1)
+    sc = adapters.summed_query([u, union, e.sum(1)], W2, b2)
+    uv, iv, bias = sc.eval_embeddings(list(range(B)))
+    assert np.allclose((uv @ iv.T + bias).numpy(), res.numpy(), atol=1e-4)
+    assert np.allclose(sc.predict([3, 1]), res.numpy()[[3, 1]], atol=1e-4)
+    assert sc.note == "summed_query" and "summed_query" in adapters.__all__
+
+
+def test_monotone_activations_leave_every_rank_list_unchanged():
+    """SLMRec (sigmoid, SLMRec.py:366-370) and GRU4Rec (final activation, GRU4Rec.py:157-158): dropping a strictly
+    increasing activation changes scores, not the order of any user's items."""
+    g = _g(22)
+    U, I, b = g.standard_normal((6, 8)).astype(np.float32), g.standard_normal((50, 8)).astype(np.float32), g.standard_normal(50).astype(np.float32)
+    raw = adapters.dot_product(U, I, b).predict(list(range(6)))
+    for act in (torch.sigmoid, torch.tanh):
+        ref = act(torch.from_numpy(U) @ torch.from_numpy(I).T + torch.from_numpy(b)).double().numpy()
+        keep = np.abs(np.diff(np.sort(ref, 1), axis=1)).min() > 0  # no two scores collapse in the activation's float image
+        if keep:
+            assert np.array_equal(np.argsort(-ref, 1, kind="stable"), np.argsort(-raw.astype(np.float64), 1, kind="stable"))
