@@ -819,7 +819,8 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------
-// item table -> hi/lo TF32 tables [n, d_pad] (zero padded in k), one warp per item row.  The same pass takes
+// item table -> hi/lo TF32 tables [n, d_pad] (zero padded in k), one warp per item row (lo == null: the single-pass
+// kernels read only hi, the lo table is neither allocated nor written).  The same pass takes
 // max_j ||item_j||^2 and max_j |bias_j| for the tf32r error band (non-negative floats order like their bit
 // patterns: atomicMax on uint) into stats_cur, and resets the words later kernels count into: the fail-list
 // length, and the statistics slot of the NEXT evaluate (the two slots alternate, so nothing races with the
@@ -856,7 +857,7 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
                 if (k < d_pad) {
                     const uint32_t h = to_tf32(x[r][q]);
                     hi[(row0 + r) * d_pad + k] = __uint_as_float(h);
-                    lo[(row0 + r) * d_pad + k] = __uint_as_float(to_tf32(x[r][q] - __uint_as_float(h)));
+                    if (lo != nullptr) lo[(row0 + r) * d_pad + k] = __uint_as_float(to_tf32(x[r][q] - __uint_as_float(h)));
                     ss = fmaf(x[r][q], x[r][q], ss);
                 }
             }

@@ -67,7 +67,7 @@ struct skr_ctx {
     float *d_idcg = nullptr;  // iDCG after n terms (metric.h:82), host-accumulated
     int disc_n = 0;
     // workspace, grow-only
-    Buf trace, work, stats, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
+    Buf trace, stats, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
     double *h_pin = nullptr;  // pinned host staging for the small results ([sums | watchdog flag]), SKR_PIN_DOUBLES doubles
     int64_t launches = 0;
@@ -77,14 +77,22 @@ struct skr_ctx {
     int64_t opt_sample_tiles = 0;
     int64_t opt_rank = 0;
     int64_t opt_dbg = 0;
+    int64_t opt_chunk_rows = 0;      // rows per chunk of the fused pipeline (0 = default)
     int64_t opt_exact_seg_rows = -1;  // development: how many failed rows are cut in segments (-1 = default)
     bool debug_sync = false;  // SKR_DEBUG_SYNC=1: synchronise and check after every kernel, naming the one that failed
     int64_t opt_trace_cta = -1;  // >= 0: record the tile timeline of that CTA of the main pass (development aid)
     struct Plan { int n_samp, stride, r, cap, S, stages; } last_plan = {0, 0, 0, 0, 0, 0};
-    // cached COLLECT work list (see plan_work)
-    int work_key[4] = {-1, -1, -1, -1};
-    int work_ctas = 0, work_slots = 0, work_min_slots = 0, work_max_tiles = 0;
-    bool work_mixed = false;
+    // cached COLLECT work lists (see plan_work): a row-chunked evaluate alternates between the shape of the full
+    // chunks and the shape of the last one, and building a list costs a host simulation plus a synchronous upload
+    struct WorkCache {
+        int key[4] = {-1, -1, -1, -1};
+        Buf buf;
+        int ctas = 0, slots = 0, min_slots = 0, max_tiles = 0;
+        bool mixed = false;
+        int64_t used = 0;
+    } work_cache[4];
+    int64_t work_clock = 0;
+    uint32_t *stats_cur_ptr = nullptr;  // item statistics slot the current evaluate reads (chunks after the first reuse it)
     EncodeTiledFn encode = nullptr;
     std::vector<cudaEvent_t> ev0, ev1, ev2;  // ring: ev2 before the pre-pass, ev0/ev1 around the main scoring kernel
     int64_t ev_calls = 0;
@@ -623,8 +631,9 @@ int skr_ctx_destroy(skr_ctx *ctx)
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
-                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt, &ctx->work};
+                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt};
     for (Buf *b : bufs) free_dev(b->p);
+    for (auto &w : ctx->work_cache) free_dev(w.buf.p);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev2) cudaEventDestroy(e);
@@ -640,6 +649,7 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "sample_tiles")) { ctx->opt_sample_tiles = value; return SKR_OK; }
     if (!strcmp(name, "rank")) { ctx->opt_rank = value; return SKR_OK; }
     if (!strcmp(name, "dbg")) { ctx->opt_dbg = value; return SKR_OK; }
+    if (!strcmp(name, "chunk_rows")) { ctx->opt_chunk_rows = value < 0 ? 0 : value; return SKR_OK; }
     if (!strcmp(name, "exact_seg_rows")) { ctx->opt_exact_seg_rows = value; return SKR_OK; }
     if (!strcmp(name, "trace_cta")) { ctx->opt_trace_cta = value; return SKR_OK; }
     if (!strcmp(name, "event_ring")) {
@@ -707,6 +717,7 @@ int64_t skr_plan_work_host(int n_user_tiles, int n_item_tiles, int n_sm, int cta
 int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out)
 {
     if (!ctx || !out || n_out < 7) return SKR_ERR_INVALID;
+    if (n_out >= 8) out[7] = ctx->ev_calls;  // timed scoring launches since the last "event_ring" option (one per row chunk)
     int n_fail = 0;
     SKR_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->fail_list.p) SKR_CUDA(ctx, cudaMemcpy(&n_fail, ctx->fail_list.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -912,10 +923,12 @@ int skr_eval_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64
 
 // The fused pipeline.  keys_only == null: metrics of the rows (skr_eval_fused).  keys_only != null: the rows'
 // sorted top-K rank keys over this item table with item ids shifted by item_offset, no metrics (skr_topk_fused).
-static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
-                          int64_t n_items, int64_t ld_i, int d, const float *bias_dev, int64_t row0, const MetricIds &m, int top_k,
-                          int precision, int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev, double *sums_dev,
-                          u64 *keys_only, int64_t item_offset, void *stream)
+// One row chunk of the fused pipeline.  first_chunk: the item-side preparation (bias padding, TF32 split, item
+// statistics) runs; later chunks of the same evaluate reuse it.
+static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
+                       int64_t n_items, int64_t ld_i, int d, const float *bias_dev, int64_t row0, const MetricIds &m, int top_k,
+                       int precision, int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev, double *sums_dev,
+                       u64 *keys_only, int64_t item_offset, void *stream, bool first_chunk)
 {
     int rc;
     if (!user_vecs_dev || !item_vecs_dev || n_rows <= 0 || d <= 0) return fail(ctx, SKR_ERR_INVALID, "eval_fused: empty input");
@@ -969,8 +982,10 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
     if (bias_dev) {
         const int n_pad = P.n_ct * TN;
         if ((rc = ensure(ctx, ctx->bias, (size_t)n_pad * sizeof(float)))) return rc;
-        SKR_CUDA(ctx, launch_pdl(k_pad_bias, dim3((unsigned)((n_pad + 255) / 256)), dim3((unsigned)(256)), (size_t)(0), st, bias_dev, (int)n_items, n_pad, (float *)ctx->bias.p));
-        ctx->launches++;
+        if (first_chunk) {
+            SKR_CUDA(ctx, launch_pdl(k_pad_bias, dim3((unsigned)((n_pad + 255) / 256)), dim3((unsigned)(256)), (size_t)(0), st, bias_dev, (int)n_items, n_pad, (float *)ctx->bias.p));
+            ctx->launches++;
+        }
         P.bias = (const float *)ctx->bias.p;
     }
     const unsigned grid = (unsigned)(P.n_rt * P.S);
@@ -978,26 +993,39 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
     const size_t slot = (size_t)(ctx->ev_calls % (int64_t)ring);
 
     if (use_tc) {
-        // operand prep: item table -> hi/lo TF32 tables, TMA descriptors
+        // AUTO: re-scoring costs a fixed ~60 candidate rows per user, the two extra MMA passes of 3xTF32 grow with
+        // the catalogue: measured on one B200, tf32r is 5 % faster at c2 (I d = 2.6 M) and 22 % at c3b (5.9 M); below
+        // ~1 M the sampled thresholds stop working for either and the choice does not matter
+        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 2.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
+        const bool rescore = (precision == SKR_PREC_TF32R);
+        const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
+        // operand prep: item table -> hi (and, for three passes, lo) TF32 tables, TMA descriptors
         const int d_pad = nkb * TC_KB;
         const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
         if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;
-        if ((rc = ensure(ctx, ctx->blo, tbytes))) return rc;
+        if (passes == 3 && (rc = ensure(ctx, ctx->blo, tbytes))) return rc;
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
         if (ctx->stats.cap == 0) {  // two slots of {max ||item||^2, max |bias|}, alternating between evaluates
             if ((rc = ensure(ctx, ctx->stats, 4 * sizeof(uint32_t)))) return rc;
             SKR_CUDA(ctx, cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(uint32_t), st));
         }
-        uint32_t *stats_cur = (uint32_t *)ctx->stats.p + 2 * ctx->stats_slot;
-        uint32_t *stats_next = (uint32_t *)ctx->stats.p + 2 * (ctx->stats_slot ^ 1);
-        ctx->stats_slot ^= 1;
-        SKR_CUDA(ctx, launch_pdl(k_split_tf32, dim3((unsigned)((unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm))), dim3((unsigned)(256)), (size_t)(0), st, item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
-                                                                                                  (float *)ctx->blo.p, bias_dev, (int *)ctx->fail_list.p, stats_cur,
-                                                                                                  stats_next));
-        ctx->launches++;
+        if (first_chunk || ctx->stats_cur_ptr == nullptr) {
+            uint32_t *stats_cur = (uint32_t *)ctx->stats.p + 2 * ctx->stats_slot;
+            uint32_t *stats_next = (uint32_t *)ctx->stats.p + 2 * (ctx->stats_slot ^ 1);
+            ctx->stats_slot ^= 1;
+            ctx->stats_cur_ptr = stats_cur;
+            SKR_CUDA(ctx, launch_pdl(k_split_tf32, dim3((unsigned)((unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm))), dim3((unsigned)(256)), (size_t)(0), st, item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
+                                                                                                      passes == 3 ? (float *)ctx->blo.p : (float *)nullptr, bias_dev, (int *)ctx->fail_list.p, stats_cur,
+                                                                                                      stats_next));
+            ctx->launches++;
+        } else {
+            SKR_CUDA(ctx, cudaMemsetAsync(ctx->fail_list.p, 0, sizeof(int), st));  // the split kernel's other job: empty fail list
+        }
+        uint32_t *stats_cur = ctx->stats_cur_ptr;
         CUtensorMap mhi, mlo;
         if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
-        if ((rc = make_tmap(ctx, &mlo, (const float *)ctx->blo.p, n_items, d_pad))) return rc;
+        if (passes == 3) { if ((rc = make_tmap(ctx, &mlo, (const float *)ctx->blo.p, n_items, d_pad))) return rc; }
+        else mlo = mhi;  // single-pass kernels never touch the lo table: it is not even built
 
         // sampling plan (k_fused_tc.cuh header): fraction f ~ 6/K of the item tiles, threshold = r-th largest
         // sampled group maximum with r = K f + 4.5 sqrt(K f) + 8 (a ~4-sigma margin against fewer than K survivors)
@@ -1012,28 +1040,30 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         r = std::max(1, std::min(r, TC_MAX_RANK));
         if (ctx->opt_rank > 0) r = (int)std::min<int64_t>(ctx->opt_rank, TC_MAX_RANK);
         const double expect = r / f_eff;  // candidates per row
-        // AUTO: re-scoring costs a fixed ~60 candidate rows per user, the two extra MMA passes of 3xTF32 grow with
-        // the catalogue: measured on one B200, tf32r is 5 % faster at c2 (I d = 2.6 M) and 22 % at c3b (5.9 M); below
-        // ~1 M the sampled thresholds stop working for either and the choice does not matter
-        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 2.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
-        const bool rescore = (precision == SKR_PREC_TF32R);
-        const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
         // work list of the main pass (cached: it depends only on the tile counts and the cost of a tile)
         const int cta_overhead = (passes == 1) ? (nkb <= 2 ? 10 : 6) : (nkb <= 2 ? 6 : 4);
-        if (ctx->work_key[0] != P.n_rt || ctx->work_key[1] != P.n_ct || ctx->work_key[2] != (int)ctx->opt_chunks || ctx->work_key[3] != cta_overhead) {
-            const WorkPlan wp = plan_work(ctx, P.n_rt, P.n_ct, cta_overhead);
-            if ((rc = ensure(ctx, ctx->work, wp.items.size() * sizeof(int4)))) return rc;
-            SKR_CUDA(ctx, cudaMemcpyAsync(ctx->work.p, wp.items.data(), wp.items.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-            SKR_CUDA(ctx, cudaStreamSynchronize(st));  // the host vector goes away; happens once per shape
-            ctx->work_key[0] = P.n_rt; ctx->work_key[1] = P.n_ct; ctx->work_key[2] = (int)ctx->opt_chunks; ctx->work_key[3] = cta_overhead;
-            ctx->work_ctas = (int)wp.items.size(); ctx->work_slots = wp.slots; ctx->work_min_slots = wp.min_slots;
-            ctx->work_max_tiles = wp.max_tiles; ctx->work_mixed = wp.mixed;
+        const int wkey[4] = {P.n_rt, P.n_ct, (int)ctx->opt_chunks, cta_overhead};
+        skr_ctx::WorkCache *wc = nullptr, *lru = &ctx->work_cache[0];
+        for (auto &w : ctx->work_cache) {
+            if (w.key[0] == wkey[0] && w.key[1] == wkey[1] && w.key[2] == wkey[2] && w.key[3] == wkey[3]) wc = &w;
+            if (w.used < lru->used) lru = &w;
         }
-        P.S = ctx->work_slots;
-        const unsigned grid_tc = (unsigned)ctx->work_ctas;
+        if (wc == nullptr) {
+            wc = lru;
+            const WorkPlan wp = plan_work(ctx, P.n_rt, P.n_ct, cta_overhead);
+            if ((rc = ensure(ctx, wc->buf, wp.items.size() * sizeof(int4)))) return rc;
+            SKR_CUDA(ctx, cudaMemcpyAsync(wc->buf.p, wp.items.data(), wp.items.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+            SKR_CUDA(ctx, cudaStreamSynchronize(st));  // the host vector goes away; happens once per shape
+            for (int q = 0; q < 4; ++q) wc->key[q] = wkey[q];
+            wc->ctas = (int)wp.items.size(); wc->slots = wp.slots; wc->min_slots = wp.min_slots;
+            wc->max_tiles = wp.max_tiles; wc->mixed = wp.mixed;
+        }
+        wc->used = ++ctx->work_clock;
+        P.S = wc->slots;
+        const unsigned grid_tc = (unsigned)wc->ctas;
         const int n_sub = 4 * P.S;        // one sub-list per (item chunk, column quarter of the tile)
         // capacity of a sub-list: twice the expected share of the user tiles with the fewest chunks
-        int cap = next_pow2((int)(2.0 * expect / (4 * ctx->work_min_slots)) + 16);
+        int cap = next_pow2((int)(2.0 * expect / (4 * wc->min_slots)) + 16);
         cap = std::max(16, std::min(cap, 512));
 
         if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 4 * TC_R * sizeof(float)))) return rc;
@@ -1056,8 +1086,8 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         A.cap = cap;
         A.cand = (uint2 *)ctx->cand.p;
         A.cand_cnt = (uint32_t *)ctx->cand_cnt.p;
-        A.work = (const int4 *)ctx->work.p;
-        if (ctx->work_mixed)  // user tiles with fewer chunks leave their last sub-lists untouched: they must read as empty
+        A.work = (const int4 *)wc->buf.p;
+        if (wc->mixed)  // user tiles with fewer chunks leave their last sub-lists untouched: they must read as empty
             SKR_CUDA(ctx, cudaMemsetAsync(ctx->cand_cnt.p, 0, (size_t)n_rows * n_sub * sizeof(uint32_t), st));
         A.trace = nullptr;
         A.trace_cta = -1;
@@ -1079,7 +1109,7 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
                                                                    (float *)A.thr_hi, (float *)A.thr_lo));
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
-            A.trace_tiles = ctx->work_max_tiles;
+            A.trace_tiles = wc->max_tiles;
             const size_t tb = (size_t)A.trace_tiles * TC_TRACE_SLOTS * sizeof(long long);
             if ((rc = ensure(ctx, ctx->trace, tb))) return rc;
             SKR_CUDA(ctx, cudaMemsetAsync(ctx->trace.p, 0, tb, st));
@@ -1131,6 +1161,32 @@ static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_ro
         ctx->launches++;
     }
     SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
+// The fused pipeline over any number of rows: row chunks of at most `chunk_rows` (option "chunk_rows", default 131,072 =
+// 1,024 user tiles) bound the workspace (candidate lists: 1 GB per chunk at c4 instead of 8 GB for 10^6 rows) while
+// the item-side preparation is done once.  Chunks are near-equal multiples of 128 rows, so at most two shapes occur.
+static int fused_pipeline(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
+                          int64_t n_items, int64_t ld_i, int d, const float *bias_dev, int64_t row0, const MetricIds &m, int top_k,
+                          int precision, int32_t *topk_idx_dev, float *topk_val_dev, float *per_user_dev, double *sums_dev,
+                          u64 *keys_only, int64_t item_offset, void *stream)
+{
+    const int64_t max_rows = ctx->opt_chunk_rows > 0 ? ((ctx->opt_chunk_rows + TM - 1) / TM) * TM : (int64_t)131072;
+    if (n_rows <= max_rows)
+        return fused_chunk(ctx, user_vecs_dev, n_rows, ld_u, item_vecs_dev, n_items, ld_i, d, bias_dev, row0, m, top_k, precision, topk_idx_dev,
+                           topk_val_dev, per_user_dev, sums_dev, keys_only, item_offset, stream, true);
+    const int64_t n_chunks = (n_rows + max_rows - 1) / max_rows;
+    const int64_t step = (((n_rows + n_chunks - 1) / n_chunks) + TM - 1) / TM * TM;
+    const int MK = m.n * top_k;
+    for (int64_t c0 = 0; c0 < n_rows; c0 += step) {
+        const int64_t n = std::min(step, n_rows - c0);
+        int rc = fused_chunk(ctx, user_vecs_dev + c0 * ld_u, n, ld_u, item_vecs_dev, n_items, ld_i, d, bias_dev, row0 + c0, m, top_k, precision,
+                             topk_idx_dev ? topk_idx_dev + c0 * top_k : nullptr, topk_val_dev ? topk_val_dev + c0 * top_k : nullptr,
+                             per_user_dev ? per_user_dev + c0 * MK : nullptr, sums_dev, keys_only ? keys_only + c0 * top_k : nullptr,
+                             item_offset, stream, c0 == 0);
+        if (rc) return rc;
+    }
     return SKR_OK;
 }
 

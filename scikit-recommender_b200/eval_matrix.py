@@ -9,6 +9,8 @@ silently misread; ties rank the lower item id first.
 """
 import numpy as np
 
+from .evaluator import _as_i32
+
 _ctx_cache = {}
 
 
@@ -35,8 +37,9 @@ def eval_score_matrix(score_matrix, test_items, metric, top_k, thread_num=None, 
         raise ValueError("len(test_items) != number of score rows")
     indptr = np.zeros(len(test_items) + 1, dtype=np.int64)
     np.cumsum([len(t) for t in test_items], out=indptr[1:])
-    indices = (np.concatenate([np.asarray(t, dtype=np.int32).ravel() for t in test_items])
-               if indptr[-1] > 0 else np.zeros(0, np.int32))
+    # rows may be arrays, lists or Python sets (BERT4Rec passes `set(items[-1:])`, bert4rec_utils.py:25; the
+    # reference converts them through Cython's cset[int], pyx_eval_matrix.pyx:27)
+    indices = (np.concatenate([_as_i32(t) for t in test_items]) if indptr[-1] > 0 else np.zeros(0, np.int32))
     ctx = _context(dev)
     ctx.set_train_csr(None, None, s.shape[1])
     ctx.set_test_csr(indptr, indices, s.shape[1])

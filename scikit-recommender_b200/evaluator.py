@@ -28,8 +28,39 @@ import numpy as np
 
 from .report import EarlyStopping, MetricReport, colour_join
 
+class _nvtx(object):
+    """NVTX range around a phase of an evaluate (visible in Nsight Systems / ncu --nvtx); nothing without CUDA."""
+
+    def __init__(self, name):
+        self.name, self.on = name, False
+
+    def __enter__(self):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.nvtx.range_push(self.name)
+                self.on = True
+        except Exception:  # pragma: no cover - NVTX is best effort
+            self.on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 _metric2id = {"Precision": 1, "Recall": 2, "MAP": 3, "NDCG": 4, "MRR": 5}
 _id2metric = {value: key for key, value in _metric2id.items()}
+
+
+def _as_i32(items):
+    """One user's items -> flat int32 array.  The reference accepts arrays, lists and (through Cython's `cset[int]`
+    conversion, pyx_eval_matrix.pyx:27; BERT4Rec passes `set(items[-1:])`, bert4rec_utils.py:25) Python sets."""
+    if isinstance(items, (set, frozenset)):
+        return np.fromiter(items, dtype=np.int32, count=len(items))
+    return np.asarray(items, dtype=np.int32).ravel()
 
 
 def _dict_to_csr(users, d, col_range=None):
@@ -41,7 +72,7 @@ def _dict_to_csr(users, d, col_range=None):
     np.cumsum(counts, out=indptr[1:])
     if indptr[-1] == 0:
         return indptr, np.zeros(0, np.int32)
-    indices = np.concatenate([np.asarray(d[u], dtype=np.int32).ravel() for u in users if u in d and len(d[u]) > 0])
+    indices = np.concatenate([_as_i32(d[u]) for u in users if u in d and len(d[u]) > 0])
     if col_range is not None:
         lo, hi = col_range
         keep = (indices >= lo) & (indices < hi)
@@ -139,8 +170,11 @@ class _Plan(object):
     def __init__(self, users, n_items, train, test, device, item_range=None):
         """item_range=(lo, hi): this rank scores only item rows [lo, hi) (item-sharded evaluation): the
         train CSR becomes that column partition with shard-local ids; the test CSR keeps global ids."""
+        import time
         from . import _native
+        t0 = time.perf_counter()
         self.users = users
+        self.users_arr = np.asarray(users, dtype=np.int64)
         self.n_items = n_items
         self.item_range = item_range
         self.ctx = _native.Context(device)
@@ -152,6 +186,13 @@ class _Plan(object):
             self.ctx.set_train_csr(rp, ri, n_local)
         else:
             self.ctx.set_train_csr(None, None, n_local)
+        self.build_ms = (time.perf_counter() - t0) * 1e3  # CSR slicing + normalisation + mask keys + upload
+
+    def close(self):
+        """Free the native context (device CSRs and workspace) now rather than when the object is collected."""
+        if self.ctx is not None:
+            self.ctx.close()
+            self.ctx = None
 
 
 class RankingEvaluator(object):
@@ -168,8 +209,10 @@ class RankingEvaluator(object):
         mean: "f64" (float64 sums, rounded once to float32) or "numpy_f32" (the reference's
             float32 row-order accumulation of np.mean, evaluator.py:208, bit for bit;
             single-process only).
-        shard_users: with torch.distributed initialised, each rank evaluates a contiguous slice
-            of the users and the metric sums are all-reduced (default True).
+        shard_users: opt-in.  With torch.distributed initialised, each rank evaluates a contiguous slice
+            of the users and the metric sums are all-reduced: `evaluate` becomes a COLLECTIVE that every
+            rank of `process_group` must call.  The default (False) keeps reference-style call sites such
+            as `if rank == 0: evaluator.evaluate(model)` working unchanged under DDP.
         shard: "users" (default; the item table is replicated) or "items" (catalogue beyond one HBM:
             every rank holds a contiguous range of item rows, computes every user's top-K over its
             range, the per-rank lists are all-gathered and merged, then the sums all-reduced).  With
@@ -184,7 +227,7 @@ class RankingEvaluator(object):
                  top_k: Union[int, List[int], Tuple[int]] = 50,
                  batch_size: int = 256, num_thread: int = 8, *,
                  device: Optional[int] = None, precision: str = "auto", mean: str = "f64",
-                 shard_users: bool = True, shard: str = "users", process_group=None):
+                 shard_users: bool = False, shard: str = "users", process_group=None):
         super(RankingEvaluator, self).__init__()
         if metric is None:
             metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
@@ -201,6 +244,7 @@ class RankingEvaluator(object):
         self.user_pos_train = dict()
         self.user_pos_test = dict()
         self._plans = OrderedDict()
+        self._slices = {}
         self.set_train_data(user_train_dict)
         self.set_test_data(user_test_dict)
 
@@ -225,6 +269,7 @@ class RankingEvaluator(object):
         self.mean = mean
         self.shard_users = shard_users
         self.process_group = process_group
+        self.item_chunk_rows = 1 << 18  # shard='items': users per top-K / all-gather / merge round
         self.last_stats = {}
 
     @classmethod
@@ -282,14 +327,16 @@ class RankingEvaluator(object):
         return cls.from_pairs(tr, _read_pairs(test_file, sep), num_users=num_users, num_items=num_items, **kwargs)
 
     def set_train_data(self, user_train_dict: Optional[Dict[int, np.ndarray]] = None):
+        """Replace the train interactions.  The device copies are rebuilt on the next evaluate; editing the dict's
+        arrays in place afterwards is not seen (the reference re-reads the dicts every call) -- call this again."""
         self.user_pos_train = user_train_dict if user_train_dict is not None else dict()
-        self._plans = OrderedDict()
+        self._drop_plans()
 
     def set_test_data(self, user_test_dict: Dict[int, np.ndarray]):
         assert len(user_test_dict) > 0, "'user_test_dict' can be empty."
         self.user_pos_test = user_test_dict
         self._all_users = list(user_test_dict.keys())  # evaluation order of evaluate(model) (evaluator.py:184)
-        self._plans = OrderedDict()
+        self._drop_plans()
 
     @property
     def metrics_list(self) -> List[str]:
@@ -307,25 +354,121 @@ class RankingEvaluator(object):
             raise RuntimeError("RankingEvaluator needs a CUDA device (sm_100a); there is no CPU fallback")
         return torch.cuda.current_device() if self.device is None else int(self.device)
 
+    _MAX_PLANS = 3  # every plan owns a native context (device CSRs + grow-only workspace: GBs at 10^6 users)
+
+    def _drop_plans(self):
+        for plan in getattr(self, "_plans", {}).values():
+            plan.close()
+        self._plans = OrderedDict()
+        self._slices = {}
+
     def _plan(self, users, n_items, key, item_range=None):
+        """Device state for this user list.  A cached plan is reused only if it was built for exactly these users
+        (the key of a `test_users` subset is a hash: equality is checked, not assumed)."""
         plan = self._plans.get(key)
-        if plan is not None and plan.n_items == n_items and plan.item_range == item_range:
+        if plan is not None and plan.n_items == n_items and plan.item_range == item_range and \
+                (plan.users is users or np.array_equal(plan.users_arr, np.asarray(users, dtype=np.int64))):
             self._plans.move_to_end(key)
             return plan
-        plan = _Plan(users, n_items, self.user_pos_train, self.user_pos_test, self._device_index(), item_range)
+        if plan is not None:
+            del self._plans[key]
+            plan.close()
+        with _nvtx("skrec:plan (CSR upload)"):
+            plan = _Plan(users, n_items, self.user_pos_train, self.user_pos_test, self._device_index(), item_range)
         self._plans[key] = plan
-        while len(self._plans) > 6:
-            self._plans.popitem(last=False)
+        while len(self._plans) > self._MAX_PLANS:
+            _, old = self._plans.popitem(last=False)
+            old.close()
         return plan
 
     def _shard(self, n):
         """(rank, world, lo, hi): this rank's contiguous slice of n evaluated users."""
         from . import dist
-        if not self.shard_users:
+        if not self.shard_users and self.shard != "items":
             return 0, 1, 0, n
         rank, world = dist.rank_world(self.process_group)
         lo, hi = dist.shard_range(n, rank, world)
         return rank, world, lo, hi
+
+    def _resolve_users(self, test_users):
+        """-> (evaluated users in order, cache key).  evaluator.py:181-184: all test users in dict order, or
+        `test_users` filtered to those with test items, in the caller's order."""
+        if test_users is not None:
+            assert isinstance(test_users, Iterable), "'test_user' must be iterable."
+            test_users = [u for u in test_users if u in self.user_pos_test]
+            arr = np.asarray(test_users, dtype=np.int64)
+            return test_users, ("subset", len(test_users), hash(arr.tobytes()))
+        if len(self._all_users) != len(self.user_pos_test):  # the dict was mutated behind our back
+            self._all_users = list(self.user_pos_test.keys())
+            self._drop_plans()
+        return self._all_users, ("all",)
+
+    def _evaluate_packed(self, model, test_users, host_fast):
+        """The evaluation up to the exchanged vector.  -> dict(packed, host_sums, n_users, per_user, key, path, world, MK)
+
+        packed: float64 device tensor [M*K + 1] = [column sums | user count], summed over the ranks when sharded --
+        everything stays on the device and on the current stream (kernels, then one NCCL all-reduce); nothing is
+        synchronised.  host_fast: single-process evaluation of HOST tables may instead run as one native call that
+        does its own copies and returns `host_sums` (float64 numpy [M*K]); `packed` is then None."""
+        import torch
+        from . import dist
+
+        assert hasattr(model, "predict") or hasattr(model, "eval_embeddings"), "the model must have attribute 'predict'."
+        users_all, key_all = self._resolve_users(test_users)
+        rank, world, lo, hi = self._shard(len(users_all))
+        item_sharded = self.shard == "items" and world > 1
+        # argument combinations are checked before any work or communication
+        if self.mean == "numpy_f32" and world > 1:
+            raise RuntimeError("mean='numpy_f32' reproduces a sequential sum and is single-process only")
+        if item_sharded:
+            assert hasattr(model, "eval_embeddings"), "shard='items' needs a model with eval_embeddings"
+            assert self.mean == "f64", "shard='items' supports mean='f64' only"
+            lo, hi = 0, len(users_all)  # every rank sees every user; the items are what is split
+        key = key_all + (rank, world, self.shard)
+        if world > 1 and not item_sharded:
+            users = self._slices.get(key) if key_all == ("all",) else None
+            if users is None:
+                users = users_all[lo:hi]
+                if key_all == ("all",):
+                    self._slices[key] = users
+        else:
+            users = users_all
+        dev = torch.device("cuda", self._device_index())
+        K, M = self.max_top, self.metrics_num
+        MK = M * K
+        want_pu = self.mean == "numpy_f32"
+        out = dict(packed=None, host_sums=None, n_users=len(users), per_user=None, key=key, path="none", world=world,
+                   MK=MK, dev=dev)
+        with torch.cuda.device(dev):
+            packed = torch.zeros(MK + 1, dtype=torch.float64, device=dev)
+            sums = packed[:MK]
+            if len(users) > 0:
+                if item_sharded:
+                    out["path"], out["n_users"] = self._evaluate_item_sharded(model, users, key, dev, rank, world, sums)
+                elif hasattr(model, "eval_embeddings"):
+                    out["path"], out["host_sums"], out["per_user"] = self._evaluate_fused(
+                        model, users, key, dev, want_pu, sums, host_fast and world == 1)
+                else:
+                    out["path"], out["per_user"] = self._evaluate_predict(model, users, key, dev, want_pu, sums)
+            if out["host_sums"] is None:
+                packed[MK:].fill_(float(out["n_users"]))
+                if world > 1:
+                    with _nvtx("skrec:allreduce [sums | count]"):
+                        dist.allreduce_sums(packed, self.process_group)
+                out["packed"] = packed
+        return out
+
+    def last_context(self):
+        """The native context of the most recently used plan (instrumentation: launch counts, kernel timings), or None."""
+        if not self._plans:
+            return None
+        return next(reversed(self._plans.values())).ctx
+
+    def evaluate_device(self, model, test_users: Optional[Iterable[int]] = None):
+        """`evaluate` without its final device-to-host copy: -> float64 CUDA tensor [n_metrics * max_top + 1] holding
+        [column sums over all evaluated users | number of users] (already all-reduced when sharded), produced
+        asynchronously on the current stream.  `evaluate` is this plus one copy to the host and the division."""
+        return self._evaluate_packed(model, test_users, host_fast=False)["packed"]
 
     def evaluate(self, model, test_users: Optional[Iterable[int]] = None) -> MetricReport:
         """Evaluate `model` (reference evaluator.py:163-214).
@@ -336,61 +479,24 @@ class RankingEvaluator(object):
         import torch
         from . import dist
 
-        assert hasattr(model, "predict") or hasattr(model, "eval_embeddings"), "the model must have attribute 'predict'."
-        if test_users is not None:
-            test_users = [u for u in test_users if u in self.user_pos_test]
-            key_all = ("subset", hash(tuple(test_users)), len(test_users))
-        else:
-            if len(self._all_users) != len(self.user_pos_test):  # the dict was mutated behind our back
-                self._all_users = list(self.user_pos_test.keys())
-                self._plans = OrderedDict()
-            test_users = self._all_users
-            key_all = ("all",)
-        assert isinstance(test_users, Iterable), "'test_user' must be iterable."
-
-        rank, world, lo, hi = self._shard(len(test_users))
-        item_sharded = self.shard == "items" and world > 1
-        if item_sharded:
-            assert hasattr(model, "eval_embeddings"), "shard='items' needs a model with eval_embeddings"
-            assert self.mean == "f64", "shard='items' supports mean='f64' only"
-            lo, hi = 0, len(test_users)  # every rank sees every user; the items are what is split
-        users = test_users[lo:hi] if world > 1 else test_users
-        key = key_all + (rank, world, self.shard)
-        dev = torch.device("cuda", self._device_index())
-        K, M = self.max_top, self.metrics_num
-        MK = M * K
-        per_user = None
-        path = "none"
-        n_mine = 0
-        col_sums = np.zeros(MK, dtype=np.float64)  # this rank's float64 column sums
-        want_pu = self.mean == "numpy_f32"
-
-        if len(users) > 0:
-            with torch.cuda.device(dev):
-                if item_sharded:
-                    path, col_sums, n_mine = self._evaluate_item_sharded(model, users, key, dev, rank, world)
-                elif hasattr(model, "eval_embeddings"):
-                    path, col_sums, per_user = self._evaluate_fused(model, users, key, dev, want_pu)
-                else:
-                    path, col_sums, per_user = self._evaluate_predict(model, users, key, dev, want_pu)
-
+        r = self._evaluate_packed(model, test_users, host_fast=True)
+        MK = r["MK"]
         if self.mean == "numpy_f32":
-            if world > 1:
-                raise RuntimeError("mean='numpy_f32' reproduces a sequential sum and is single-process only")
-            plan = self._plans[key]
-            acc = torch.zeros(MK, dtype=torch.float32, device=dev)
-            plan.ctx.colsum_f32_seq(per_user, acc)
-            final_results = (acc / torch.tensor(float(len(users)), dtype=torch.float32, device=dev)).cpu().numpy()
+            if r["per_user"] is None:  # nobody to evaluate
+                final_results = np.zeros(MK, np.float32)
+            else:
+                plan = self._plans[r["key"]]
+                with torch.cuda.device(r["dev"]):
+                    acc = torch.zeros(MK, dtype=torch.float32, device=r["dev"])
+                    plan.ctx.colsum_f32_seq(r["per_user"], acc)
+                    final_results = (acc / torch.tensor(float(r["n_users"]), dtype=torch.float32, device=r["dev"])).cpu().numpy()
+        elif r["host_sums"] is not None:
+            final_results = dist.finalize_means(r["host_sums"], r["n_users"])
         else:
-            n_users = float(n_mine) if item_sharded else float(len(users))
-            if world > 1:
-                packed = torch.from_numpy(np.concatenate([col_sums, [n_users]])).to(dev)  # [column sums | user count]
-                dist.allreduce_sums(packed, self.process_group)
-                host = packed.cpu().numpy()
-                col_sums, n_users = host[:MK], host[MK]
-            final_results = dist.finalize_means(col_sums, n_users)
+            host = r["packed"].cpu().numpy()  # the one device-to-host copy (and synchronisation) of an evaluate
+            final_results = dist.finalize_means(host[:MK], host[MK])
 
-        self.last_stats = {"path": path, "users": len(users), "world": world}
+        self.last_stats = {"path": r["path"], "users": r["n_users"], "world": r["world"]}
         final_results = np.reshape(final_results, [self.metrics_num, self.max_top])
         final_results = final_results[:, self.top_show - 1]
         final_results = np.reshape(final_results, [-1])
@@ -415,12 +521,13 @@ class RankingEvaluator(object):
         if not union:
             return [MetricReport(self.metrics_list, np.zeros(M * len(self.top_show), np.float32)) for _ in groups]
         dev = torch.device("cuda", self._device_index())
-        key = ("subset", hash(tuple(union)), len(union), 0, 1, "groups")
+        key = ("subset", len(union), hash(np.asarray(union, dtype=np.int64).tobytes()), 0, 1, "groups")
         with torch.cuda.device(dev):
+            scratch = torch.zeros(MK, dtype=torch.float64, device=dev)
             if hasattr(model, "eval_embeddings"):
-                _, _, per_user = self._evaluate_fused(model, union, key, dev, True)
+                _, _, per_user = self._evaluate_fused(model, union, key, dev, True, scratch, False)
             else:
-                _, _, per_user = self._evaluate_predict(model, union, key, dev, True)
+                _, per_user = self._evaluate_predict(model, union, key, dev, True, scratch)
             plan = self._plans[key]
             sums = torch.zeros((len(groups), MK), dtype=torch.float64, device=dev)
             for gi, g in enumerate(groups):
@@ -474,18 +581,19 @@ class RankingEvaluator(object):
             return False
         if self.precision in ("3xtf32", "tf32r", "1xtf32"):
             return True  # an explicit tensor-core request fails loudly in the library if the shape is out of range
+        if self.precision == "fp32":  # the FP32 FMA kernel reads float4: d and the row pitch are multiples of 4
+            return d % 4 == 0 and d <= 1024
         if self.precision == "auto" and n_items is not None and n_items < max(3072, 160 * self.max_top):
             return False
         return d <= 128 or (d % 4 == 0 and d <= 1024)
 
-    def _evaluate_by_blocks(self, uv, iv, b, users, key, dev, want_pu):
+    def _evaluate_by_blocks(self, uv, iv, b, users, key, dev, want_pu, sums):
         """Shapes outside the fused kernels (top-K > 128, odd wide d): score blocks of `batch_size` users on the
         device (`U_b @ I^T + b`, FP32 -- the one place a library GEMM is used) and feed them to the
         score-matrix kernels, like the `predict` path but without the host round trip."""
         import torch
         MK = self.metrics_num * self.max_top
         plan = self._plan(users, int(iv.shape[0]), key)
-        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
         per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
         step = max(1, min(int(self.batch_size), 4096))
         for b0 in range(0, len(users), step):
@@ -494,43 +602,51 @@ class RankingEvaluator(object):
                 s = s + b
             plan.ctx.eval_scores(s.contiguous(), b0, self.metrics, self.max_top,
                                  per_user=None if per_user is None else per_user[b0:b0 + s.shape[0]], sums=sums)
-        return "scores:device_blocks", sums.cpu().numpy(), per_user
+        return "scores:device_blocks", None, per_user
 
-    def _evaluate_fused(self, model, users, key, dev, want_pu):
-        """-> (path, float64 column sums [M*K] on the host, per-user block on the device or None)"""
+    def _evaluate_fused(self, model, users, key, dev, want_pu, sums, host_fast):
+        """Column sums are ADDED into `sums` (float64 device tensor [M*K]) -- unless host tables took the one-call
+        native path (`host_fast`), which returns them on the host.
+        -> (path, float64 host sums or None, per-user block on the device or None)"""
         import torch
-        user_vecs, item_vecs, bias = model.eval_embeddings(users)
+        with _nvtx("skrec:model.eval_embeddings"):
+            user_vecs, item_vecs, bias = model.eval_embeddings(users)
         MK = self.metrics_num * self.max_top
         if not self._fused_can_take(int(item_vecs.shape[1]), int(item_vecs.shape[0])):
             uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
             assert uv.shape[0] == len(users) and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
-            return self._evaluate_by_blocks(uv, iv, b, users, key, dev, want_pu)
+            return self._evaluate_by_blocks(uv, iv, b, users, key, dev, want_pu, sums)
         on_host = not (isinstance(user_vecs, torch.Tensor) and user_vecs.is_cuda) and \
             not (isinstance(item_vecs, torch.Tensor) and item_vecs.is_cuda)
-        if on_host and not want_pu:
+        if on_host and host_fast and not want_pu:
             # host tables (numpy / CPU tensors, pinned or not): one native call does H2D, the whole
             # pipeline and the D2H of the sums, with a single synchronisation at the end
             uv, iv, b = self._host_f32(user_vecs), self._host_f32(item_vecs), self._host_f32(bias)
             assert uv.ndim == 2 and iv.ndim == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
             assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
             plan = self._plan(users, int(iv.shape[0]), key)
-            _, _, sums = plan.ctx.eval_fused_host(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision)
-            return "fused:" + plan.ctx.last_fused_kernel, sums, None
-        uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
+            with _nvtx("skrec:fused (host tables: H2D + kernels + D2H)"):
+                _, _, host_sums = plan.ctx.eval_fused_host(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision)
+            return "fused:" + plan.ctx.last_fused_kernel, host_sums, None
+        with _nvtx("skrec:H2D embedding tables"):
+            uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
         assert uv.dim() == 2 and iv.dim() == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
         assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
         plan = self._plan(users, int(iv.shape[0]), key)
-        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
         per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
-        plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision, per_user=per_user, sums=sums)
-        return "fused:" + plan.ctx.last_fused_kernel, sums.cpu().numpy(), per_user
+        with _nvtx("skrec:fused (split + SAMPLE + COLLECT + select + metrics)"):
+            plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision, per_user=per_user, sums=sums)
+        return "fused:" + plan.ctx.last_fused_kernel, None, per_user
 
-    def _evaluate_item_sharded(self, model, users, key, dev, rank, world, chunk_rows=1 << 18):
+    def _evaluate_item_sharded(self, model, users, key, dev, rank, world, sums):
         """Item-sharded evaluation.  Per user chunk: local top-K over this rank's item rows
         (fused kernels) -> all-gather of the [n, K] rank keys -> this rank merges and evaluates its slice
-        of the chunk's users.  -> (path, float64 column sums of my slices, number of users in them)"""
+        of the chunk's users; column sums are ADDED into `sums`.  The all-gather of chunk n is issued from a side
+        stream and overlaps the top-K of chunk n + 1 (double-buffered lists); every library call stays on the
+        current stream.  -> (path, number of users in my slices)"""
         import inspect
         import torch
+        import torch.distributed as td
         from . import dist
         try:
             takes_shard = "item_shard" in inspect.signature(model.eval_embeddings).parameters
@@ -548,42 +664,103 @@ class RankingEvaluator(object):
         uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_rows, dev), self._to_dev(bias_rows, dev)
         assert iv.shape[0] == ihi - ilo, "eval_embeddings(item_shard=...) must return exactly this rank's item rows"
         assert uv.shape[0] == len(users) and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
-        K, MK = self.max_top, self.metrics_num * self.max_top
+        K = self.max_top
         assert world * K <= 1024, "shard='items': world_size * max(top_k) must not exceed 1024"
         plan = self._plan(users, int(n_items), key, (ilo, ihi))
-        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
         n_mine = 0
-        chunk_rows = max(128, (int(chunk_rows) // 128) * 128)  # row offsets of the fused kernels are multiples of 128
-        for c0 in range(0, len(users), chunk_rows):
-            n = min(chunk_rows, len(users) - c0)
-            keys = torch.empty((n, K), dtype=torch.int64, device=dev)
-            plan.ctx.topk_fused(uv[c0:c0 + n], iv, b, c0, ilo, K, keys, precision=self.precision)
-            keys_all = dist.allgather_keys(keys, self.process_group)  # [world, n, K]
+        chunk_rows = max(128, (int(self.item_chunk_rows) // 128) * 128)  # row offsets of the fused kernels are multiples of 128
+        chunks = [(c0, min(chunk_rows, len(users) - c0)) for c0 in range(0, len(users), chunk_rows)]
+        n_max = chunks[0][1]
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        keys = [torch.empty((n_max, K), dtype=torch.int64, device=dev) for _ in range(min(2, len(chunks)))]
+        gathered = [torch.empty((world, n_max, K), dtype=torch.int64, device=dev) for _ in range(min(2, len(chunks)))]
+        self.last_gather_bytes = 0
+
+        def merge(j, work):
+            nonlocal n_mine
+            c0, n = chunks[j]
+            work.wait()  # the current stream waits for the all-gather of chunk j
             lo, hi = dist.shard_range(n, rank, world)
             if hi > lo:
-                plan.ctx.eval_merged_topk(keys_all, lo, hi - lo, c0 + lo, self.metrics, K, sums=sums)
+                with _nvtx("skrec:merge + metrics of my slice"):
+                    plan.ctx.eval_merged_topk(gathered[j % 2][:, :n] if n == n_max else gathered[j % 2][:, :n].contiguous(),
+                                              lo, hi - lo, c0 + lo, self.metrics, K, sums=sums)
                 n_mine += hi - lo
-        return "items:" + plan.ctx.last_fused_kernel, sums.cpu().numpy(), n_mine
 
-    def _evaluate_predict(self, model, users, key, dev, want_pu):
+        pending = None
+        for j, (c0, n) in enumerate(chunks):
+            kj = keys[j % 2][:n]
+            with _nvtx("skrec:topk_fused (my item rows)"):
+                plan.ctx.topk_fused(uv[c0:c0 + n], iv, b, c0, ilo, K, kj, precision=self.precision)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(side), _nvtx("skrec:all-gather rank keys"):
+                side.wait_event(done)
+                if n == n_max:
+                    out = gathered[j % 2]
+                    work = td.all_gather_into_tensor(out, kj, group=self.process_group, async_op=True)
+                else:  # short last chunk: gather into a dense [world, n, K] view of the buffer
+                    out = gathered[j % 2].view(-1)[:world * n * K].view(world, n, K)
+                    work = td.all_gather_into_tensor(out, kj, group=self.process_group, async_op=True)
+                    gathered[j % 2] = out
+            self.last_gather_bytes += int(world * n * K * 8)
+            if pending is not None:
+                merge(*pending)
+            pending = (j, work)
+        merge(*pending)
+        return "items:" + plan.ctx.last_fused_kernel, n_mine
+
+    def _side_stream(self, dev):
+        import torch
+        st = getattr(self, "_side", None)
+        if st is None or st.device != dev:
+            st = self._side = torch.cuda.Stream(device=dev)
+        return st
+
+    def _evaluate_predict(self, model, users, key, dev, want_pu, sums):
+        """The reference protocol: `predict(batch)` blocks (evaluator.py:188-202), column sums ADDED into `sums`.
+        Host blocks go through two pinned staging buffers and a copy stream: the upload of block n + 1 overlaps the
+        masking / top-K / metric kernels of block n (the model's own `predict` of block n + 1 overlaps both)."""
         import torch
         plan = None
         MK = self.metrics_num * self.max_top
-        sums = torch.zeros(MK, dtype=torch.float64, device=dev)
         per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        stage = getattr(self, "_stage", None)
+        slot = 0
         for b0 in range(0, len(users), self.batch_size):  # sequential, last batch short (batch_iterator.py:98-106)
             batch_users = users[b0:b0 + self.batch_size]
-            ranking_score = model.predict(batch_users)  # (B,N)
+            with _nvtx("skrec:model.predict"):
+                ranking_score = model.predict(batch_users)  # (B,N)
             if isinstance(ranking_score, torch.Tensor):
                 s = ranking_score.detach().to(device=dev, dtype=torch.float32)
+                if s.stride(1) != 1:
+                    s = s.contiguous()
             else:
                 assert isinstance(ranking_score, np.ndarray), "'ranking_score' must be an np.ndarray"
-                s = torch.from_numpy(np.ascontiguousarray(ranking_score, dtype=np.float32)).to(dev)
-            if s.stride(1) != 1:
-                s = s.contiguous()
+                h = np.ascontiguousarray(ranking_score, dtype=np.float32)
+                if stage is None or stage[0][0].numel() < h.size:
+                    n_el = max(h.size, int(self.batch_size) * h.shape[1])
+                    stage = self._stage = [(torch.empty(n_el, dtype=torch.float32).pin_memory(),
+                                            torch.empty(n_el, dtype=torch.float32, device=dev), torch.cuda.Event()) for _ in range(2)]
+                pin, dbuf, free = stage[slot]
+                slot ^= 1
+                free.synchronize()  # the kernels that read this slot two blocks ago are done (host may overwrite `pin`)
+                pin[:h.size].view(h.shape).numpy()[...] = h
+                with torch.cuda.stream(side), _nvtx("skrec:H2D score block"):
+                    s = dbuf[:h.size].view(h.shape)
+                    s.copy_(pin[:h.size].view(h.shape), non_blocking=True)
+                    up = torch.cuda.Event()
+                    up.record(side)
+                main.wait_event(up)
             if plan is None:
                 plan = self._plan(users, int(s.shape[1]), key)
-            plan.ctx.eval_scores(s, b0, self.metrics, self.max_top,
-                                 per_user=None if per_user is None else per_user[b0:b0 + len(batch_users)],
-                                 sums=sums)
-        return "scores", sums.cpu().numpy(), per_user
+            with _nvtx("skrec:eval_scores (mask + top-K + metrics)"):
+                plan.ctx.eval_scores(s, b0, self.metrics, self.max_top,
+                                     per_user=None if per_user is None else per_user[b0:b0 + len(batch_users)],
+                                     sums=sums)
+            if not isinstance(ranking_score, torch.Tensor):
+                free.record(main)
+        return "scores", per_user

@@ -155,6 +155,105 @@ def make(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_pool=200,
                 users=U, items=I, d=d)
 
 
+def make_large(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_pool=200, device="cuda", item_seed=None,
+               user_range=None, **_unused):
+    """The recipe of `make` for the 10^6-user configs, vectorised with torch on `device` (a GPU): no Python loop over users,
+    no dicts.  Same distributions -- N(0, 0.1^2) embeddings, log-normal degrees, Zipf-like item popularity without
+    replacement per user, train and test disjoint, half of every user's test items planted among the items the user
+    scores highest -- but not the same random streams as `make`.  Planting: an item is a candidate when its score
+    (one bf16 tensor-core pass, this is data synthesis) exceeds the user's expected top-`plant_pool` cut sigma_u * z,
+    sigma_u = 0.1 ||u||, z = Phi^-1(1 - plant_pool / items); planted items are drawn uniformly from the candidates.
+    Returns the dict of `make` without `train` / `test` dicts (use RankingEvaluator.from_csr); embeddings come as CUDA
+    tensors (`user_emb`, `item_emb`, `bias`)."""
+    import math
+    import torch
+
+    dev = torch.device(device)
+    U, I = int(users), int(items)
+    g = torch.Generator(device=dev).manual_seed(int(seed))
+    gi = g if item_seed is None else torch.Generator(device=dev).manual_seed(int(item_seed))
+    user_emb = torch.randn((U, d), generator=g, device=dev) * 0.1
+    item_emb = torch.randn((I, d), generator=gi, device=dev) * 0.1
+    b = torch.randn(I, generator=gi, device=dev) * 0.01 if bias else None
+
+    gn = np.random.default_rng(seed)
+    deg_train = _degrees(gn, U, nnz_train, 1, max(1, I // 4))
+    deg_test = _degrees(gn, U, nnz_test, 1, max(1, I // 8))
+    n_plant = deg_test // 2
+    n_rand = deg_test - n_plant
+    need = torch.from_numpy(deg_train + n_rand).to(dev)
+    perm = torch.randperm(I, generator=g, device=dev).double()
+    p = 1.0 / (perm + 10.0) ** 0.8
+    cdf = torch.cumsum(p / p.sum(), 0)
+
+    # draws: 1.3x + 4 per user, first occurrences of every (user, item), a random `need[u]` of them kept
+    draws = (need.double() * 1.3).long() + 4
+    owner = torch.repeat_interleave(torch.arange(U, device=dev), draws)
+    item = torch.searchsorted(cdf, torch.rand(owner.numel(), generator=g, device=dev, dtype=torch.float64), right=True).clamp_(max=I - 1)
+    key = torch.unique(owner * I + item)  # sorted, distinct
+    del owner, item
+    owner = key // I
+    # random order inside every user: sort by (user, random priority)
+    order = torch.argsort(owner.double() + torch.rand(key.numel(), generator=g, device=dev, dtype=torch.float64))
+    key = key[order]
+    owner = owner[order]
+    del order
+    start = torch.searchsorted(owner, torch.arange(U + 1, device=dev))
+    have = torch.minimum(start[1:] - start[:-1], need)
+    rank_in = torch.arange(key.numel(), device=dev) - start[owner]
+    keep = rank_in < have[owner]
+    key, owner, rank_in = key[keep], owner[keep], rank_in[keep]
+    drawn_sorted = torch.sort(key).values  # for the "already drawn" test while planting
+    # first deg_train[u] of a user's kept draws are train items, the rest random test items (short users: train first)
+    dtr = torch.minimum(torch.from_numpy(deg_train).to(dev), have)
+    is_train = rank_in < dtr[owner]
+    tr_idx = (key[is_train] % I).int()
+    tr_ptr = torch.zeros(U + 1, dtype=torch.int64, device=dev)
+    tr_ptr[1:] = torch.cumsum(dtr, 0)
+    te_rand_owner = owner[~is_train]
+    te_rand_item = (key[~is_train] % I).int()
+    del key, owner, rank_in, keep, is_train
+
+    # planted half
+    z = math.sqrt(2.0) * float(torch.erfinv(torch.tensor(1.0 - 2.0 * min(plant_pool, I // 4) / I, dtype=torch.float64)))
+    sig = 0.1 * user_emb.norm(dim=1)
+    it16 = item_emb.to(torch.bfloat16)
+    npl = torch.from_numpy(n_plant).to(dev)
+    pl_owner, pl_item = [], []
+    chunk = max(1, min(U, (6 << 30) // max(2 * I, 1)))
+    for u0 in range(0, U, chunk):
+        u1 = min(U, u0 + chunk)
+        sc = user_emb[u0:u1].to(torch.bfloat16) @ it16.T
+        if b is not None:
+            sc += b.to(torch.bfloat16)
+        hit = (sc.float() > (sig[u0:u1] * z).unsqueeze(1)).nonzero()
+        del sc
+        ck = (hit[:, 0] + u0) * I + hit[:, 1]
+        pos = torch.searchsorted(drawn_sorted, ck).clamp_(max=drawn_sorted.numel() - 1)
+        ck = ck[drawn_sorted[pos] != ck]  # not among the user's drawn items
+        co = ck // I
+        order = torch.argsort(co.double() + torch.rand(ck.numel(), generator=g, device=dev, dtype=torch.float64))
+        ck, co = ck[order], co[order]
+        st = torch.searchsorted(co, torch.arange(u0, u1 + 1, device=dev))
+        r_in = torch.arange(ck.numel(), device=dev) - st[co - u0]
+        keep = r_in < npl[co]
+        pl_owner.append(co[keep])
+        pl_item.append((ck[keep] % I).int())
+    pl_owner, pl_item = torch.cat(pl_owner), torch.cat(pl_item)
+    te_owner = torch.cat([te_rand_owner, pl_owner])
+    te_item = torch.cat([te_rand_item, pl_item])
+    order = torch.argsort(te_owner, stable=True)  # random items first, then the planted ones, like `make`
+    te_owner, te_idx = te_owner[order], te_item[order]
+    te_ptr = torch.searchsorted(te_owner, torch.arange(U + 1, device=dev))
+    # users whose draws all went to train keep one test item: their best-scoring candidate is not guaranteed, so give them item 0..
+    empty = (te_ptr[1:] - te_ptr[:-1]) == 0
+    if bool(empty.any()):  # (does not happen with the recipe's degrees: n_rand >= 1 and draws exceed the need)
+        raise RuntimeError("synthetic workload: a user without test items")
+    return dict(user_emb=user_emb, item_emb=item_emb, bias=b,
+                train_indptr=tr_ptr.cpu().numpy(), train_indices=tr_idx.cpu().numpy(),
+                test_indptr=te_ptr.cpu().numpy(), test_indices=te_idx.cpu().numpy(), users=U, items=I, d=d)
+
+
 def make_config(name, scale=1.0, device=None):
     """Workload of a named config; `scale` < 1 shrinks users, items and interactions together."""
     cfg = dict(CONFIGS[name])

@@ -523,8 +523,12 @@ def _items_worker(rank, world, port, out_path):
     out = {}
     for shard in ("users", "items"):
         ev = RankingEvaluator(data["train"], data["test"], metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], top_k=[10, 50],
-                              device=rank, shard=shard)
+                              device=rank, shard=shard, shard_users=True)
+        ev.item_chunk_rows = 512  # 1,500 users: three rounds, the last one short -- the overlapped all-gather path
         rep = ev.evaluate(model)
+        dev_vec = ev.evaluate_device(model).cpu().numpy()  # [sums | count], already reduced over the ranks
+        assert dev_vec[-1] == 1500 and np.max(np.abs((dev_vec[:-1] / dev_vec[-1]).astype(np.float32).reshape(5, 50)[:, [9, 49]].ravel()
+                                                     - np.array(list(rep.values()), np.float32))) == 0.0
         out[shard] = np.array(list(rep.values()), np.float32)
         out[shard + "_path"] = ev.last_stats["path"]
     if rank == 0:
@@ -533,17 +537,18 @@ def _items_worker(rank, world, port, out_path):
 
 
 def test_item_sharded_evaluator_two_gpus_nccl(torch_cuda, tmp_path):
-    """Two ranks, NCCL: shard='items' (all-gather + merge) == shard='users' (all-reduce only) == oracle."""
+    """All GPUs of the box (2..8 ranks), NCCL: shard='items' (all-gather + merge) == shard='users' (all-reduce only) == oracle."""
     import socket
     import torch.multiprocessing as mp
     from skrec_b200 import synth
-    if torch_cuda.cuda.device_count() < 2:
+    world = min(torch_cuda.cuda.device_count(), 8)
+    if world < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     out = str(tmp_path / "rep.npz")
-    mp.spawn(_items_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_items_worker, args=(world, port, out), nprocs=world, join=True)
     got = np.load(out)
     assert str(got["path"]).startswith("items:tcgen05")
     assert np.max(np.abs(got["users"] - got["items"])) <= 1e-7

@@ -103,21 +103,41 @@ def test_evaluate_requires_predict_and_a_gpu():
             ev.evaluate(M())
 
 
-def test_bench_rank_config_c4_is_one_eighth_of_the_users():
-    """bench.py --config c4: a rank holds 125,000 of the 1M users against the full item table, interactions scaled
-    with the users; c1-c3 stay whole; --users-per-gpu slices any config."""
+def test_bench_workload_configs():
+    """bench.py: both arms print the same `config` object; the default workload is c4 at full size, strong-scaled; the
+    reference arm's sample of a large config keeps the catalogue and scales the interactions with the users."""
     import importlib.util
     import os
     spec = importlib.util.spec_from_file_location("skr_bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     from skrec_b200 import synth
-    c4 = bench.rank_config("c4")
-    assert (c4["users"], c4["items"], c4["d"]) == (125_000, 1_000_000, 128)
-    assert c4["nnz_train"] == 6_250_000 and c4["nnz_test"] == 1_250_000
-    assert c4["top_k"] == [10, 20, 50, 100] and len(c4["metric"]) == 5
-    assert bench.rank_config("c2") == synth.CONFIGS["c2"]
-    half = bench.rank_config("c2", users=1000)
-    assert half["users"] == 1000 and half["items"] == synth.CONFIGS["c2"]["items"]
-    assert abs(half["nnz_train"] - 810_128 * 1000 / 29858) <= 1
+    c4 = bench.workload_config("c4", "strong")
+    assert (c4["users"], c4["items"], c4["d"], c4["scaling"]) == (1_000_000, 1_000_000, 128, "strong")
+    assert c4["top_k"] == [10, 20, 50, 100] and len(c4["metrics"]) == 5 and c4["workload"].startswith("c4")
+    s = bench.sample_config("c4")
+    assert (s["users"], s["items"], s["d"]) == (2048, 1_000_000, 128)
+    assert s["nnz_train"] == 102_400 and s["nnz_test"] == 20_480 and s["item_seed"] == synth.CONFIGS["c4"]["seed"] + 7
     assert synth.CONFIGS["c4"]["users"] == 1_000_000  # the table itself is not touched
+    assert "c4" in bench.STRONG and "c3b" in bench.STRONG and "c2" not in bench.STRONG
+    assert bench._span([5, 6, 7, 8]) == (5, 4) and bench._span([5, 7, 8]) is None and bench._span([]) is None
+
+
+def test_set_valued_rows_are_accepted_like_the_reference():
+    """BERT4Rec hands `eval_score_matrix` Python sets (bert4rec_utils.py:25); the reference converts them through
+    Cython's cset[int].  Same for set-valued evaluator dicts."""
+    from skrec_b200.evaluator import _as_i32, _dict_to_csr
+    assert sorted(_as_i32({3, 1, 2}).tolist()) == [1, 2, 3] and _as_i32({3, 1, 2}).dtype == np.int32
+    assert _as_i32([4, 5]).tolist() == [4, 5] and _as_i32(np.array([[7], [8]])).tolist() == [7, 8]
+    ptr, idx = _dict_to_csr([0, 1, 2], {0: {9}, 1: frozenset(), 2: [1, 2]})
+    assert ptr.tolist() == [0, 1, 1, 3] and idx.tolist() == [9, 1, 2]
+
+
+def test_sharding_is_opt_in_and_arguments_are_checked_before_work():
+    """`evaluate` must not become a collective just because torch.distributed is initialised."""
+    ev = RankingEvaluator({0: np.array([1])}, {0: np.array([2])})
+    assert ev.shard_users is False
+    assert ev._shard(10) == (0, 1, 0, 10)
+    users, key = ev._resolve_users([0, 5, 0])
+    assert users == [0, 0] and key[0] == "subset" and key[1] == 2
+    assert ev._resolve_users(None) == ([0], ("all",))

@@ -56,7 +56,7 @@ class Model(object):
 
 
 def run(shard, reps):
-    ev = RankingEvaluator.from_csr(tr, te, metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], top_k=[K], device=local, shard=shard)
+    ev = RankingEvaluator.from_csr(tr, te, metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], top_k=[K], device=local, shard=shard, shard_users=True)
     model, times = Model(), []
     for r in range(reps + 1):  # first call: CSR upload, workspace, work plan
         torch.cuda.synchronize()
