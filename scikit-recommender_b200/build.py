@@ -25,8 +25,14 @@ def build(force=False, verbose=False):
             return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("SKR_NVCC_EXTRA", "").split()  # e.g. -DSKR_TC_TRACE=1 for tools/trace_tiles.py
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "skrec_b200.cu")]
-    subprocess.run(cmd, check=True)
+    tmp = LIB + ".tmp.%d" % os.getpid()  # built next to the target and renamed: a snapshot never sees a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "skrec_b200.cu")]
+    try:
+        subprocess.run(cmd, check=True)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 

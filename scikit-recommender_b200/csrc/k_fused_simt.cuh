@@ -17,6 +17,7 @@ constexpr int SIMT_KC = 32;   // k chunk
 constexpr int SIMT_LD = 36;   // padded smem row (floats): conflict-free LDS.128
 constexpr int SIMT_CAP = 16;  // staged survivors per row per column step (16 columns per step)
 
+// K = 0: the score-block variant (no heaps; the other small arrays are laid out but unused)
 __host__ __device__ inline size_t simt_smem_bytes(int K)
 {
     return (size_t)(2 * 2 * TM * SIMT_LD) * 4   // As[2], Bs[2]
@@ -51,8 +52,14 @@ __device__ __forceinline__ void simt_load_chunk(float *dst, const float *__restr
     }
 }
 
+// SCORES = true: the same FP32 tile main loop, but the tile (+ bias) is written to a score block
+// scores_out[row, item] (row pitch ld_out) instead of going through the heaps -- the library's own GEMM for the
+// shapes the selection epilogues do not take (top-K > 128): the block is consumed by k_topk_scores, which masks the
+// train items itself, so no bitmap is built here.  One CTA per (user tile, item tile range).
+template <bool SCORES>
 __global__ void __launch_bounds__(SIMT_THREADS, 1)
-k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict__ V, int64_t ld_v, FusedParams P)
+k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict__ V, int64_t ld_v, FusedParams P,
+             float *__restrict__ scores_out, int64_t ld_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *As = reinterpret_cast<float *>(smem_raw);
@@ -81,11 +88,11 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
     const int64_t my_row = row_base + tid;
     const bool owner = tid < TM;
     const bool my_valid = owner && my_row < P.n_rows;
-    if (owner) { scnt[tid] = 0; thr_row[tid] = my_valid ? NINF : -NINF; }  // rows beyond n_rows collect nothing
+    if (!SCORES && owner) { scnt[tid] = 0; thr_row[tid] = my_valid ? NINF : -NINF; }  // rows beyond n_rows collect nothing
 
     // cursor into this user tile's mask keys
     int64_t mcur = 0, mend = 0;
-    if (P.mask_keys != nullptr) {
+    if (!SCORES && P.mask_keys != nullptr) {
         const int64_t rt_abs = (P.row0 / TM) + rt;
         if (tid == 0) {
             int64_t lo = P.mask_tile_ptr[rt_abs], hi = P.mask_tile_ptr[rt_abs + 1];
@@ -94,7 +101,7 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
         mend = P.mask_tile_ptr[rt_abs + 1];
     }
     __syncthreads();
-    if (P.mask_keys != nullptr) mcur = s_mcur;
+    if (!SCORES && P.mask_keys != nullptr) mcur = s_mcur;
 
     const int n_kc = (P.d + SIMT_KC - 1) / SIMT_KC;
 
@@ -106,7 +113,7 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
         cp_async_commit();
 
         // thresholds published by other CTAs for these rows
-        if (my_valid) {
+        if (!SCORES && my_valid) {
             uint32_t g = P.thr_g[my_row];
             if (g != 0) {
                 float gf = unord_f32(g);
@@ -115,9 +122,9 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
             thr_row[tid] = thr;
         }
         // bitmap: out-of-range columns, then this tile's train items
-        for (int i = tid; i < 4 * TM; i += SIMT_THREADS) bitmap[i] = oob_bits(col0, i / TM, P.n_items);
+        if (!SCORES) for (int i = tid; i < 4 * TM; i += SIMT_THREADS) bitmap[i] = oob_bits(col0, i / TM, P.n_items);
         __syncthreads();
-        if (P.mask_keys != nullptr) {
+        if (!SCORES && P.mask_keys != nullptr) {
             const uint32_t lim = ((uint32_t)(col0 + TN)) << 7;
             for (;;) {
                 int64_t p = mcur + tid;
@@ -172,6 +179,20 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
             __syncthreads();
         }
 
+        if (SCORES) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int gcol = col0 + tx + 16 * j;
+                if (gcol >= P.n_items) continue;
+                const float b = (P.bias != nullptr) ? __ldg(P.bias + gcol) : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t row = row_base + ty + 16 * i;
+                    if (row < P.n_rows) scores_out[row * ld_out + gcol] = acc[i][j] + b;
+                }
+            }
+            continue;
+        }
         // epilogue: 8 steps of 16 columns; survivors are staged, owners fold them into the heaps
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -214,6 +235,7 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
         }
     }
 
+    if (SCORES) return;
     // partial lists out: [row, c, K], coalesced along K
     if (owner) hcnt[tid] = hn;
     __syncthreads();

@@ -67,7 +67,7 @@ struct skr_ctx {
     float *d_idcg = nullptr;  // iDCG after n terms (metric.h:82), host-accumulated
     int disc_n = 0;
     // workspace, grow-only
-    Buf trace, stats, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
+    Buf trace, stats, stage_s, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
     int *d_err = nullptr;
     double *h_pin = nullptr;  // pinned host staging for the small results ([sums | watchdog flag]), SKR_PIN_DOUBLES doubles
     int64_t launches = 0;
@@ -631,7 +631,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
-                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt};
+                   &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->stage_s, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt};
     for (Buf *b : bufs) free_dev(b->p);
     for (auto &w : ctx->work_cache) free_dev(w.buf.p);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
@@ -923,6 +923,65 @@ int skr_eval_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64
 
 // The fused pipeline.  keys_only == null: metrics of the rows (skr_eval_fused).  keys_only != null: the rows'
 // sorted top-K rank keys over this item table with item ids shifted by item_offset, no metrics (skr_topk_fused).
+// Shapes outside the selection epilogues of the fused kernels (top-K > 128): score blocks of rows with the library's
+// own FP32 tile kernel (k_fused_simt<true>: same FMA chain as the exact path) into a workspace block sized to stay in
+// L2 between producer and consumer, then the score-matrix kernels (train masking, top-K <= 512, metrics).  The U x I
+// matrix still never exists: one block of at most 96 MB is live at a time.
+static int fused_by_blocks(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev, int64_t n_items,
+                           int64_t ld_i, int d, const float *bias_dev, int64_t row0, const MetricIds &m, int top_k, int32_t *topk_idx_dev,
+                           float *topk_val_dev, float *per_user_dev, double *sums_dev, void *stream)
+{
+    int rc;
+    if ((d & 3) || (ld_u & 3) || (ld_i & 3) || ((uintptr_t)user_vecs_dev & 15) || ((uintptr_t)item_vecs_dev & 15))
+        return fail(ctx, SKR_ERR_UNSUPPORTED, "top_k > 128 runs on the FP32 tile kernel: d, ld_u, ld_i must be multiples of 4 and the tables 16-byte aligned");
+    if (n_items > 0x7fffffffll - K2_CHUNK) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_items=%lld too large", (long long)n_items);
+    if (ctx->has_train && (row0 < 0 || row0 + n_rows > ctx->tr_rows))
+        return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the train CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->tr_rows);
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ld_s = (n_items + 3) & ~(int64_t)3;
+    int64_t blk = std::max<int64_t>(TM, ((96ll << 20) / (ld_s * 4)) / TM * TM);
+    blk = std::min<int64_t>(blk, ((n_rows + TM - 1) / TM) * TM);
+    if ((rc = ensure(ctx, ctx->stage_s, (size_t)blk * ld_s * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->keys, (size_t)blk * top_k * sizeof(u64)))) return rc;
+    FusedParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_items = (int)n_items;
+    P.d = d;
+    P.K = top_k;
+    P.n_ct = (int)((n_items + TN - 1) / TN);
+    P.bias = bias_dev;  // read only below n_items
+    const size_t smem = simt_smem_bytes(0);
+    SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int MK = m.n * top_k;
+    const size_t slot = (size_t)(ctx->ev_calls % (int64_t)ctx->ev0.size());
+    SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
+    SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
+    for (int64_t b0 = 0; b0 < n_rows; b0 += blk) {
+        const int64_t nb = std::min(blk, n_rows - b0);
+        P.n_rows = nb;
+        P.row0 = 0;
+        P.n_rt = (int)((nb + TM - 1) / TM);
+        // item tile ranges per user tile: enough CTAs to fill the GPU
+        P.S = (int)std::max<int64_t>(1, std::min<int64_t>(P.n_ct, (2 * ctx->n_sm + P.n_rt - 1) / P.n_rt));
+        P.tiles_per_chunk = (P.n_ct + P.S - 1) / P.S;
+        P.S = (P.n_ct + P.tiles_per_chunk - 1) / P.tiles_per_chunk;
+        k_fused_simt<true><<<(unsigned)(P.n_rt * P.S), SIMT_THREADS, smem, st>>>(user_vecs_dev + b0 * ld_u, ld_u, item_vecs_dev, ld_i, P, (float *)ctx->stage_s.p, ld_s);
+        k_topk_scores<<<(unsigned)nb, K2_THREADS, 0, st>>>((const float *)ctx->stage_s.p, ld_s, (int)n_items, row0 + b0, ctx->has_train ? ctx->d_tr_indptr : nullptr,
+                                                          ctx->has_train ? ctx->d_tr_idx : nullptr, top_k, (u64 *)ctx->keys.p);
+        ctx->launches += 2;
+        SKR_CUDA(ctx, cudaGetLastError());
+        if ((rc = run_metrics(ctx, (const u64 *)ctx->keys.p, nullptr, nb, row0 + b0, m, top_k, topk_idx_dev ? topk_idx_dev + b0 * top_k : nullptr,
+                              topk_val_dev ? topk_val_dev + b0 * top_k : nullptr, per_user_dev ? per_user_dev + b0 * MK : nullptr, sums_dev, st)))
+            return rc;
+    }
+    SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
+    ctx->ev_calls++;
+    ctx->last_fused = "simt_fp32_blocks";
+    ctx->last_plan = {0, 0, 0, 0, 0, 0};
+    return SKR_OK;
+}
+
 // One row chunk of the fused pipeline.  first_chunk: the item-side preparation (bias padding, TF32 split, item
 // statistics) runs; later chunks of the same evaluate reuse it.
 static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows, int64_t ld_u, const float *item_vecs_dev,
@@ -935,7 +994,12 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
     if (ld_u < d || ld_i < d) return fail(ctx, SKR_ERR_INVALID, "ld_u=%lld / ld_i=%lld < d=%d", (long long)ld_u, (long long)ld_i, d);
     if (n_items < top_k) return fail(ctx, SKR_ERR_INVALID, "n_items=%lld < top_k=%d (evaluate.h:45 would read out of bounds)", (long long)n_items, top_k);
     if (n_items >= (1ll << 25)) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_items=%lld >= 2^25", (long long)n_items);
-    if (top_k > 128) return fail(ctx, SKR_ERR_UNSUPPORTED, "fused path supports top_k <= 128 (got %d)", top_k);
+    if (top_k > K2_MAX_K) return fail(ctx, SKR_ERR_UNSUPPORTED, "top_k=%d > %d", top_k, K2_MAX_K);
+    if (top_k > 128) {
+        if (keys_only != nullptr) return fail(ctx, SKR_ERR_UNSUPPORTED, "per-shard lists (skr_topk_fused) support top_k <= 128 (got %d)", top_k);
+        return fused_by_blocks(ctx, user_vecs_dev, n_rows, ld_u, item_vecs_dev, n_items, ld_i, d, bias_dev, row0, m, top_k, topk_idx_dev, topk_val_dev,
+                               per_user_dev, sums_dev, stream);
+    }
     if (row0 % TM != 0) return fail(ctx, SKR_ERR_INVALID, "row0=%lld must be a multiple of %d", (long long)row0, TM);
     if (ctx->has_train && (row0 < 0 || row0 + n_rows > ctx->tr_rows))
         return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the train CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->tr_rows);
@@ -949,6 +1013,12 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
     const int nkb = (d + TC_KB - 1) / TC_KB;
     const bool tc_ok = (nkb <= 4) && (tc_smem_bytes() <= ctx->max_smem);
     bool use_tc = (precision != SKR_PREC_FP32) && tc_ok;
+    // AUTO, catalogue too small for sampled thresholds (about 160 items per requested rank: ml-1m at top-50 or
+    // top-100): the tensor-core pipeline would settle every row through its exact per-row fallback.  The FP32 FMA
+    // kernel with running per-row heaps is one launch and exact; the whole job is a few GFLOP.
+    const bool simt_ok = !((d & 3) || (ld_u & 3) || (ld_i & 3) || ((uintptr_t)user_vecs_dev & 15) || ((uintptr_t)item_vecs_dev & 15)) &&
+                         simt_smem_bytes(top_k) <= ctx->max_smem;
+    if (precision == SKR_PREC_AUTO && simt_ok && n_items < std::max<int64_t>(3072, 160 * (int64_t)top_k)) use_tc = false;
     if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32 || precision == SKR_PREC_TF32R))
         return fail(ctx, SKR_ERR_UNSUPPORTED, "tcgen05 path needs d <= 128 (d=%d)", d);
     if (!use_tc) {
@@ -1139,10 +1209,10 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         P.part = (u64 *)ctx->part.p;
         SKR_CUDA(ctx, cudaMemsetAsync(P.thr_g, 0, (size_t)n_rows * sizeof(uint32_t), st));
         const size_t smem = simt_smem_bytes(K);
-        SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
-        k_fused_simt<<<grid, SIMT_THREADS, smem, st>>>(user_vecs_dev, ld_u, item_vecs_dev, ld_i, P);
+        k_fused_simt<false><<<grid, SIMT_THREADS, smem, st>>>(user_vecs_dev, ld_u, item_vecs_dev, ld_i, P, nullptr, 0);
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches++;
         ctx->last_fused = "simt_fp32";

@@ -456,6 +456,7 @@ class RankingEvaluator(object):
                     with _nvtx("skrec:allreduce [sums | count]"):
                         dist.allreduce_sums(packed, self.process_group)
                 out["packed"] = packed
+        self.last_stats = {"path": out["path"], "users": out["n_users"], "world": world}
         return out
 
     def last_context(self):
@@ -496,7 +497,6 @@ class RankingEvaluator(object):
             host = r["packed"].cpu().numpy()  # the one device-to-host copy (and synchronisation) of an evaluate
             final_results = dist.finalize_means(host[:MK], host[MK])
 
-        self.last_stats = {"path": r["path"], "users": r["n_users"], "world": r["world"]}
         final_results = np.reshape(final_results, [self.metrics_num, self.max_top])
         final_results = final_results[:, self.top_show - 1]
         final_results = np.reshape(final_results, [-1])
@@ -572,38 +572,6 @@ class RankingEvaluator(object):
             x = np.ascontiguousarray(x)
         return x
 
-    def _fused_can_take(self, d, n_items=None):
-        """Shapes the fused kernels cover: top-K <= 128; d <= 128 on tensor cores, else FP32 FMA with d % 4 == 0.
-        With precision "auto" a catalogue too small for sampled thresholds (about 160 items per requested rank:
-        ml-1m at top-50) goes to the score-block path as well -- the fused kernels would still be exact there, but
-        through their per-row fallback, which is slower than a GEMM plus the HBM-bound top-K kernel."""
-        if self.max_top > 128:
-            return False
-        if self.precision in ("3xtf32", "tf32r", "1xtf32"):
-            return True  # an explicit tensor-core request fails loudly in the library if the shape is out of range
-        if self.precision == "fp32":  # the FP32 FMA kernel reads float4: d and the row pitch are multiples of 4
-            return d % 4 == 0 and d <= 1024
-        if self.precision == "auto" and n_items is not None and n_items < max(3072, 160 * self.max_top):
-            return False
-        return d <= 128 or (d % 4 == 0 and d <= 1024)
-
-    def _evaluate_by_blocks(self, uv, iv, b, users, key, dev, want_pu, sums):
-        """Shapes outside the fused kernels (top-K > 128, odd wide d): score blocks of `batch_size` users on the
-        device (`U_b @ I^T + b`, FP32 -- the one place a library GEMM is used) and feed them to the
-        score-matrix kernels, like the `predict` path but without the host round trip."""
-        import torch
-        MK = self.metrics_num * self.max_top
-        plan = self._plan(users, int(iv.shape[0]), key)
-        per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
-        step = max(1, min(int(self.batch_size), 4096))
-        for b0 in range(0, len(users), step):
-            s = torch.matmul(uv[b0:b0 + step].float(), iv.float().T)
-            if b is not None:
-                s = s + b
-            plan.ctx.eval_scores(s.contiguous(), b0, self.metrics, self.max_top,
-                                 per_user=None if per_user is None else per_user[b0:b0 + s.shape[0]], sums=sums)
-        return "scores:device_blocks", None, per_user
-
     def _evaluate_fused(self, model, users, key, dev, want_pu, sums, host_fast):
         """Column sums are ADDED into `sums` (float64 device tensor [M*K]) -- unless host tables took the one-call
         native path (`host_fast`), which returns them on the host.
@@ -612,10 +580,6 @@ class RankingEvaluator(object):
         with _nvtx("skrec:model.eval_embeddings"):
             user_vecs, item_vecs, bias = model.eval_embeddings(users)
         MK = self.metrics_num * self.max_top
-        if not self._fused_can_take(int(item_vecs.shape[1]), int(item_vecs.shape[0])):
-            uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
-            assert uv.shape[0] == len(users) and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
-            return self._evaluate_by_blocks(uv, iv, b, users, key, dev, want_pu, sums)
         on_host = not (isinstance(user_vecs, torch.Tensor) and user_vecs.is_cuda) and \
             not (isinstance(item_vecs, torch.Tensor) and item_vecs.is_cuda)
         if on_host and host_fast and not want_pu:
@@ -632,6 +596,12 @@ class RankingEvaluator(object):
             uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
         assert uv.dim() == 2 and iv.dim() == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
         assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
+        d = int(iv.shape[1])
+        if d % 4 != 0 and (d > 128 or self.max_top > 128 or self.precision == "fp32"):
+            # the FP32 tile kernels (wide d, top-K > 128, precision="fp32") read float4: zero-pad the rows to a
+            # multiple of four columns -- zeros add nothing to a dot product (the host entry pads the same way)
+            uv = torch.nn.functional.pad(uv, (0, 4 - d % 4))
+            iv = torch.nn.functional.pad(iv, (0, 4 - d % 4))
         plan = self._plan(users, int(iv.shape[0]), key)
         per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
         with _nvtx("skrec:fused (split + SAMPLE + COLLECT + select + metrics)"):

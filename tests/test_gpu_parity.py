@@ -847,16 +847,23 @@ def test_fused_special_values_and_limits(torch_cuda, ctx):
 
 
 def test_evaluator_routes_shapes_outside_the_fused_kernels(torch_cuda):
-    """top-K > 128 or a wide d that is not a multiple of 4: device score blocks + score-matrix kernels, same numbers."""
+    """top-K > 128 or a wide d that is not a multiple of 4: the library's own FP32 tile kernels (score blocks + the
+    score-matrix kernels for top-K > 128; padded rows + the fused FP32 kernel for the odd width) -- no library GEMM."""
     from skrec_b200 import RankingEvaluator, adapters, synth
-    for d, top_k in ((64, [10, 200]), (130, [5, 20])):
+    import torch
+    for d, top_k, path, on_dev in ((64, [10, 200], "fused:simt_fp32_blocks", False), (130, [5, 20], "fused:simt_fp32", True),
+                                   (50, [3, 300], "fused:simt_fp32_blocks", True), (64, [10, 200], "fused:simt_fp32_blocks", True)):
         data = synth.make(users=300, items=1500, d=d, nnz_train=6000, nnz_test=1500, seed=51 + d, bias=True)
         metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
         ids = [synth.METRIC_IDS[m] for m in metric]
-        model = adapters.dot_product(data["user_emb"], data["item_emb"], data["bias"])
+        if on_dev:
+            model = adapters.dot_product(torch.from_numpy(data["user_emb"]).cuda(), torch.from_numpy(data["item_emb"]).cuda(),
+                                         torch.from_numpy(data["bias"]).cuda())
+        else:
+            model = adapters.dot_product(data["user_emb"], data["item_emb"], data["bias"])
         ev = RankingEvaluator(data["train"], data["test"], metric=metric, top_k=top_k, device=0, batch_size=128)
         got = np.array(list(ev.evaluate(model).values()), np.float32)
-        assert ev.last_stats["path"] == "scores:device_blocks"
+        assert ev.last_stats["path"] == path, ev.last_stats["path"]
         per, _ = oracle.evaluate_dicts(synth.PredictOnlyModel(data["user_emb"], data["item_emb"], data["bias"]).predict,
                                        data["train"], data["test"], ids, max(top_k))
         expect = oracle.mean_f32(per).reshape(len(ids), max(top_k))[:, np.array(top_k) - 1].ravel()
@@ -864,13 +871,14 @@ def test_evaluator_routes_shapes_outside_the_fused_kernels(torch_cuda):
 
 
 def test_evaluator_routes_small_catalogues_by_requested_rank(torch_cuda):
-    """ml-1m-sized catalogue: top-20 fits the sampled-threshold plan (fused), top-50 does not (score blocks); same numbers."""
+    """ml-1m-sized catalogue: top-20 fits the sampled-threshold plan (tensor cores); top-50 and the reference's default
+    top-100 (run_config.py:16) do not: the exact FP32 fused kernel takes them -- a `fused:` path, no library GEMM."""
     from skrec_b200 import RankingEvaluator, adapters, synth
     data = synth.make(users=500, items=3706, d=64, nnz_train=20000, nnz_test=2500, seed=77, bias=True)
     metric = ["Precision", "Recall", "NDCG"]
     ids = [synth.METRIC_IDS[m] for m in metric]
     model = adapters.dot_product(data["user_emb"], data["item_emb"], data["bias"])
-    for top_k, path in (([10, 20], "fused:"), ([20, 50], "scores:device_blocks")):
+    for top_k, path in (([10, 20], "fused:tcgen05"), ([20, 50], "fused:simt_fp32"), (list(range(10, 101, 10)), "fused:simt_fp32")):
         ev = RankingEvaluator(data["train"], data["test"], metric=metric, top_k=top_k, device=0)
         got = np.array(list(ev.evaluate(model).values()), np.float32)
         assert ev.last_stats["path"].startswith(path), ev.last_stats["path"]
@@ -912,3 +920,63 @@ def test_exact_fallback_when_thresholds_are_useless(torch_cuda, U, I, seg_rows):
                          d["user_emb"], d["item_emb"], None, (d["train_indptr"], d["train_indices"]),
                          (d["test_indptr"], d["test_indices"]), metric, K)
     c.close()
+
+
+def test_eval_score_matrix_accepts_sets_like_bert4rec(torch_cuda):
+    """bert4rec_utils.py:25,78: test_items is a list of Python sets; same numbers as arrays."""
+    from skrec_b200 import eval_score_matrix
+    g = np.random.default_rng(12)
+    s = g.standard_normal((40, 300)).astype(np.float32)
+    items = [g.choice(300, size=int(g.integers(1, 6)), replace=False).astype(np.int32) for _ in range(40)]
+    a = eval_score_matrix(s.copy(), items, [1, 2, 3, 4, 5], 10, 4)
+    b = eval_score_matrix(s.copy(), [set(int(x) for x in it) for it in items], [1, 2, 3, 4, 5], 10, 4)
+    assert np.array_equal(a, b)
+
+
+def test_plan_cache_never_mixes_up_two_subsets_of_the_same_length(torch_cuda):
+    """a cache hit is trusted only after comparing the users."""
+    from skrec_b200 import RankingEvaluator, synth
+    data = synth.make(users=400, items=2000, d=32, nnz_train=8000, nnz_test=2000, seed=5, bias=False)
+    model = synth.EmbeddingModel(data["user_emb"], data["item_emb"], None)
+    ev = RankingEvaluator(data["train"], data["test"], metric=["Recall", "NDCG"], top_k=[5, 10], device=0, precision="fp32")
+    a, b = list(range(0, 200)), list(range(200, 400))
+    ra = np.array(list(ev.evaluate(model, a).values()))
+    rb = np.array(list(ev.evaluate(model, b).values()))
+    # force a key collision: whatever the hash, the second lookup must notice the users differ
+    ka = ev._resolve_users(a)[1] + (0, 1, "users")
+    plan_b = ev._plans[ev._resolve_users(b)[1] + (0, 1, "users")]
+    ev._plans[ka] = plan_b
+    ra2 = np.array(list(ev.evaluate(model, a).values()))
+    assert np.array_equal(ra, ra2) and not np.array_equal(ra, rb)
+    ev2 = RankingEvaluator(data["train"], data["test"], metric=["Recall", "NDCG"], top_k=[5, 10], device=0, precision="fp32")
+    assert np.array_equal(np.array(list(ev2.evaluate(model, b).values())), rb)
+    for i in range(6):  # the cache is bounded and evicted contexts are closed
+        ev.evaluate(model, list(range(i, i + 50)))
+    assert len(ev._plans) <= ev._MAX_PLANS
+
+
+def test_row_chunked_fused_equals_one_call(torch_cuda, ctx):
+    """skr_eval_fused cuts large row counts into chunks (item-side preparation once): same per-user block, same sums."""
+    from skrec_b200 import _native, synth
+    torch = torch_cuda
+    d = synth.make(users=1000, items=9000, d=64, nnz_train=30000, nnz_test=6000, seed=21, bias=True, device="cuda")
+    ue, ie, b = (torch.from_numpy(d[k]).cuda() for k in ("user_emb", "item_emb", "bias"))
+    metric, K = [1, 2, 3, 4, 5], 20
+    out = {}
+    for rows in (0, 256):
+        c = _native.Context(0)
+        c.set_train_csr(d["train_indptr"], d["train_indices"], 9000)
+        c.set_test_csr(d["test_indptr"], d["test_indices"], 9000)
+        c.set_option("chunk_rows", rows)
+        for prec in ("tf32r", "3xtf32", "fp32"):
+            idx = torch.empty((1000, K), dtype=torch.int32, device="cuda")
+            per = torch.empty((1000, len(metric) * K), dtype=torch.float32, device="cuda")
+            sums = torch.zeros(len(metric) * K, dtype=torch.float64, device="cuda")
+            c.eval_fused(ue, ie, b, 0, metric, K, precision=prec, topk_idx=idx, per_user=per, sums=sums)
+            torch.cuda.synchronize()
+            out[(rows, prec)] = (idx.cpu().numpy(), per.cpu().numpy(), sums.cpu().numpy())
+        c.close()
+    for prec in ("tf32r", "3xtf32", "fp32"):
+        a, bb = out[(0, prec)], out[(256, prec)]
+        assert np.array_equal(a[0], bb[0]) and np.array_equal(a[1], bb[1])
+        assert np.max(np.abs(a[2] - bb[2])) < 1e-9
