@@ -13,7 +13,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def sources():
     out = [os.path.join(HERE, "..", "include", "skrec_b200.h")]
     for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".cu", ".cuh")):
+        if f.endswith((".cu", ".cuh", ".h")):
             out.append(os.path.join(CSRC, f))
     return out
 
@@ -26,13 +26,21 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("SKR_NVCC_EXTRA", "").split()  # e.g. -DSKR_TC_TRACE=1 for tools/trace_tiles.py
     tmp = LIB + ".tmp.%d" % os.getpid()  # built next to the target and renamed: a snapshot never sees a half-written library
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "skrec_b200.cu")]
+    units = [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+    objs = [os.path.join(CSRC, "." + f[:-3] + ".%d.o" % os.getpid()) for f in units]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
     try:
-        subprocess.run(cmd, check=True)
+        # translation units compile concurrently (the kernels; the CUB-based ingestion), then one device link
+        procs = [subprocess.Popen([nvcc] + compile_flags + ["-c", "-o", o, os.path.join(CSRC, f)]) for f, o in zip(units, objs)]
+        rcs = [p.wait() for p in procs]
+        if any(rcs):
+            raise subprocess.CalledProcessError(max(rcs), "nvcc -c")
+        subprocess.run([nvcc] + [f for f in NVCC_FLAGS if f not in ("-lineinfo", "-O3", "-std=c++17")] + ["-o", tmp] + objs, check=True)
         os.replace(tmp, LIB)
     finally:
-        if os.path.exists(tmp):
-            os.remove(tmp)
+        for f in objs + [tmp]:
+            if os.path.exists(f):
+                os.remove(f)
     return LIB
 
 

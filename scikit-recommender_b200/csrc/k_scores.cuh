@@ -30,22 +30,6 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float *p)
     return r;
 }
 
-// score source: a row of a score matrix
-struct RowLoad {
-    const float *row;
-    bool vec_ok;
-    __device__ __forceinline__ void get4(int j0, int n_items, float (&v)[4]) const
-    {
-        if (vec_ok && j0 + 3 < n_items) {
-            const float4 t = ldg_stream_f4(row + j0);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = (j0 + q < n_items) ? __ldg(row + j0 + q) : 0.0f;
-        }
-    }
-};
-
 // score source: FP32 dot products of one user vector (shared memory) with item rows, k ascending
 struct RowDot {
     const float *u;  // shared memory, d floats
@@ -179,21 +163,166 @@ __device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int6
     for (int i = tid; i < K; i += K2_THREADS) out[i] = (i < base) ? keys[i] : 0ull;
 }
 
+// Streaming form for a score-matrix row with 16-byte aligned float4 access (the HBM-bound kernel of the `predict`
+// path: 4 I bytes per user is all it must read).  The generic routine above meets 2-3 block barriers per 1,024
+// scores and keeps one float4 per thread in flight -- measured 0.77 TB/s at c2.  Here:
+//   * the first pieces of 1,024 scores establish the K-th key (threshold) exactly as before;
+//   * after that a "super-chunk" is 8 float4 per thread (8,192 scores, 32 KB per block in flight), issued before the
+//     first compare; a score is dropped after ONE compare against the threshold; the rare survivor is checked against
+//     the row's sorted train items by binary search (masked: -inf, still a candidate, like evaluator.py:195-200),
+//     turned into a rank key and appended to the shared buffer with one atomic -- no barrier, no bitmap;
+//   * one barrier per super-chunk reads the buffer level: the buffer is folded into the sorted top-K (block bitonic)
+//     only when it is half full or at the end of the row (random order: ~K ln(I / 1024) survivors in total), and a
+//     super-chunk that overflowed it (adversarial ascending rows) is discarded and redone in pieces.
+constexpr int K2_SUPER = 8;  // float4 per thread and super-chunk
+
+__device__ __forceinline__ void k2_fold(u64 *keys, int *s_cnt, int &base, int K, u64 &thr_key, float &thr_f, int tid)
+{
+    // callers have passed a barrier since the last append; every thread reads the same count
+    const int room = K2_P - base;
+    const int cnt = min(*s_cnt, room);
+    __syncthreads();
+    const int tot = base + cnt;
+    int n_sort = next_pow2(tot);
+    if (n_sort < 2) n_sort = 2;
+    for (int i = tot + tid; i < n_sort; i += K2_THREADS) keys[i] = 0;
+    __syncthreads();
+    block_bitonic_desc(keys, n_sort, tid, K2_THREADS);
+    base = tot < K ? tot : K;
+    if (base == K) {
+        thr_key = keys[K - 1];
+        thr_f = key_score(thr_key);
+    }
+    __syncthreads();
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void k2_offer(float s, int j, float thr_f, u64 thr_key, int64_t tb, int64_t te, const int32_t *__restrict__ tr_idx,
+                                         u64 *keys, int base, int *s_cnt)
+{
+    if (!(s < thr_f)) {  // also NaN: ranked like -inf by make_key
+        if (te > tb && sorted_contains(tr_idx + tb, (int)(te - tb), (int32_t)j)) s = -__int_as_float(0x7f800000);
+        const u64 key = make_key(s, (uint32_t)j);
+        if (key > thr_key) {
+            const int pos = atomicAdd(s_cnt, 1);
+            if (pos < K2_P - base) keys[base + pos] = key;
+        }
+    }
+}
+
+__device__ __forceinline__ void topk_row_stream(const float *__restrict__ row, int n_items, int64_t tb, int64_t te,
+                                                const int32_t *__restrict__ tr_idx, int K, u64 *__restrict__ out, u64 *keys, int *s_cnt)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    int base = 0;
+    u64 thr_key = 0;
+    float thr_f = -__int_as_float(0x7f800000);
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+    // rows of a matrix whose pitch is not a multiple of 4 floats start at any 4-byte offset: up to 3 head scores are
+    // offered one by one, the float4 stream starts at the first 16-byte boundary (element a0 of the row)
+    const int a0 = (int)((4u - (unsigned)((reinterpret_cast<uintptr_t>(row) >> 2) & 3u)) & 3u);
+    const float *rowa = row + a0;
+    const int n_body = n_items - a0;  // n_items >= K >= 1 and a0 <= 3; a row shorter than a0 has n_body <= 0
+    if (tid < a0 && tid < n_items) k2_offer(__ldg(row + tid), tid, thr_f, thr_key, tb, te, tr_idx, keys, base, s_cnt);
+    // 4 body scores per thread starting at body element c0 (guarded at the end of the row)
+    auto load4 = [&](int jj, float (&v)[4]) {
+        if (jj + 3 < n_body) {
+            const float4 t = ldg_stream_f4(rowa + jj);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = (jj + q < n_body) ? __ldg(rowa + jj + q) : 0.0f;
+        }
+    };
+    // one piece: 1,024 scores, appended with one atomic per warp and step (in the first piece every score passes), then a fold
+    auto piece = [&](int c0) {
+        const int jj = c0 + tid * 4;
+        float v[4];
+        load4(jj, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float sc = v[q];
+            bool pass = (jj + q < n_body) && !(sc < thr_f);
+            u64 key = 0;
+            if (pass) {
+                const int j = a0 + jj + q;
+                if (te > tb && sorted_contains(tr_idx + tb, (int)(te - tb), (int32_t)j)) sc = -__int_as_float(0x7f800000);
+                key = make_key(sc, (uint32_t)j);
+                pass = key > thr_key;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+                const int leader = __ffs(bal) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(s_cnt, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(bal & ((1u << lane) - 1u));
+                if (pass && pos < K2_P - base) keys[base + pos] = key;
+            }
+        }
+        __syncthreads();
+        k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
+    };
+    int c0 = 0;
+    // threshold first: pieces until K keys are known (K <= 512 <= 1,024: one piece unless the row is shorter)
+    do { piece(c0); c0 += K2_CHUNK; } while (c0 < n_body && base < K);
+    constexpr int SUPER = K2_SUPER * K2_CHUNK;
+    int pending = 0;  // survivors in the buffer that are not folded yet (block-uniform)
+    while (c0 < n_body) {
+        float v[K2_SUPER][4];
+        if (c0 + SUPER <= n_body) {
+#pragma unroll
+            for (int q = 0; q < K2_SUPER; ++q) {
+                const float4 t = ldg_stream_f4(rowa + c0 + q * K2_CHUNK + tid * 4);
+                v[q][0] = t.x; v[q][1] = t.y; v[q][2] = t.z; v[q][3] = t.w;
+            }
+        } else {  // the last, partial super-chunk: guarded loads, missing scores are never offered
+#pragma unroll
+            for (int q = 0; q < K2_SUPER; ++q) load4(c0 + q * K2_CHUNK + tid * 4, v[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < K2_SUPER; ++q) {
+            const int jj = c0 + q * K2_CHUNK + tid * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (jj + e < n_body) k2_offer(v[q][e], a0 + jj + e, thr_f, thr_key, tb, te, tr_idx, keys, base, s_cnt);
+        }
+        __syncthreads();
+        const int cnt = *s_cnt;
+        const int room = K2_P - base;
+        __syncthreads();  // everyone has the count before anyone appends again or resets it
+        if (cnt > room) {
+            // overflow: positions are handed out in order, so everything at or beyond `pending` (the level before this
+            // super-chunk) is this super-chunk's: drop it, fold the older survivors, redo the super-chunk in pieces
+            if (tid == 0) *s_cnt = pending;
+            __syncthreads();
+            k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
+            for (int p = 0; p < K2_SUPER && c0 + p * K2_CHUNK < n_body; ++p) piece(c0 + p * K2_CHUNK);
+            pending = 0;
+        } else if (2 * cnt > room) {  // half full: fold (also tightens the threshold)
+            k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
+            pending = 0;
+        } else {
+            pending = cnt;
+        }
+        c0 += SUPER;
+    }
+    if (pending > 0) k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
+    for (int i = tid; i < K; i += K2_THREADS) out[i] = (i < base) ? keys[i] : 0ull;
+}
+
 __global__ void __launch_bounds__(K2_THREADS)
 k_topk_scores(const float *__restrict__ scores, int64_t ld, int n_items, int64_t row0,
               const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K,
               u64 *__restrict__ out_keys)
 {
     __shared__ u64 keys[K2_P];
-    __shared__ uint32_t bitmap[K2_CHUNK / 32];
     __shared__ int s_cnt;
     const int64_t r = blockIdx.x;
-    RowLoad src;
-    src.row = scores + r * ld;
-    src.vec_ok = ((reinterpret_cast<uintptr_t>(src.row) & 15) == 0);
     int64_t tb = 0, te = 0;
     if (tr_indptr != nullptr) { tb = __ldg(tr_indptr + row0 + r); te = __ldg(tr_indptr + row0 + r + 1); }
-    topk_row_block(src, n_items, tb, te, tr_idx, K, out_keys + r * K, keys, bitmap, &s_cnt);
+    topk_row_stream(scores + r * ld, n_items, tb, te, tr_idx, K, out_keys + r * K, keys, &s_cnt);
 }
 
 // Rows on the fail list of k_select_cands: exact FP32 scores on the fly, same selection.  A work item is

@@ -21,6 +21,7 @@
 #include "../../include/skrec_b200.h"
 #include "common.cuh"
 #include "fused_common.cuh"
+#include "ingest.h"
 #include "k_fused_simt.cuh"
 #include "k_fused_tc.cuh"
 #include "k_metrics.cuh"
@@ -164,46 +165,6 @@ int ensure(skr_ctx *ctx, Buf &b, size_t bytes)
 void free_dev(void *p)
 {
     if (p) cudaFree(p);
-}
-
-// rows -> sorted unique, validated
-int normalise_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indices, int64_t n_rows, int64_t n_items,
-                  std::vector<int64_t> &optr, std::vector<int32_t> &oidx)
-{
-    if (n_rows < 0 || n_items <= 0) return fail(ctx, SKR_ERR_INVALID, "csr: n_rows=%lld n_items=%lld", (long long)n_rows, (long long)n_items);
-    if (indptr[0] < 0) return fail(ctx, SKR_ERR_INVALID, "csr: indptr[0] < 0");
-    optr.assign((size_t)n_rows + 1, 0);
-    oidx.clear();
-    oidx.reserve((size_t)(indptr[n_rows] - indptr[0]));
-    std::vector<int32_t> tmp;
-    for (int64_t r = 0; r < n_rows; ++r) {
-        if (indptr[r + 1] < indptr[r]) return fail(ctx, SKR_ERR_INVALID, "csr: indptr not monotone at row %lld", (long long)r);
-        tmp.assign(indices + indptr[r], indices + indptr[r + 1]);
-        bool sorted = true;
-        for (size_t i = 0; i < tmp.size(); ++i) {
-            if (tmp[i] < 0 || tmp[i] >= n_items)
-                return fail(ctx, SKR_ERR_INVALID, "csr: item %d out of [0,%lld) in row %lld", tmp[i], (long long)n_items, (long long)r);
-            if (i && tmp[i] <= tmp[i - 1]) sorted = false;
-        }
-        if (!sorted) {
-            std::sort(tmp.begin(), tmp.end());
-            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        }
-        oidx.insert(oidx.end(), tmp.begin(), tmp.end());
-        optr[(size_t)r + 1] = (int64_t)oidx.size();
-    }
-    return SKR_OK;
-}
-
-template <typename T>
-int upload(skr_ctx *ctx, T **dst, const std::vector<T> &src)
-{
-    free_dev(*dst);
-    *dst = nullptr;
-    size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
-    SKR_CUDA(ctx, cudaMalloc((void **)dst, bytes));
-    if (!src.empty()) SKR_CUDA(ctx, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return SKR_OK;
 }
 
 int check_metrics(skr_ctx *ctx, const int32_t *metric_ids, int n_metrics, int top_k, MetricIds &m)
@@ -754,39 +715,21 @@ int skr_set_train_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indice
         return SKR_OK;
     }
     if (n_items >= (1ll << 25)) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_items=%lld >= 2^25 (mask key packing)", (long long)n_items);
-    std::vector<int64_t> optr;
-    std::vector<int32_t> oidx;
-    int rc = normalise_csr(ctx, indptr, indices, n_rows, n_items, optr, oidx);
-    if (rc) return rc;
-    // fused-path mask keys: per 128-row user tile, ascending (item << 7 | row_in_tile)
-    const int64_t n_rt = (n_rows + TM - 1) / TM;
-    std::vector<int64_t> tile_ptr((size_t)n_rt + 1, 0);
-    std::vector<uint32_t> keys(oidx.size());
-    const int64_t n_ct = (n_items + TN - 1) / TN;
-    std::vector<uint32_t> tile_off((size_t)n_rt * (size_t)(n_ct + 1), 0);
-    for (int64_t rt = 0; rt < n_rt; ++rt) {
-        const int64_t r0 = rt * TM, r1 = std::min<int64_t>(r0 + TM, n_rows);
-        const int64_t b = optr[(size_t)r0], e = optr[(size_t)r1];
-        tile_ptr[(size_t)rt] = b;
-        for (int64_t r = r0; r < r1; ++r)
-            for (int64_t p = optr[(size_t)r]; p < optr[(size_t)r + 1]; ++p)
-                keys[(size_t)p] = ((uint32_t)oidx[(size_t)p] << 7) | (uint32_t)(r - r0);
-        std::sort(keys.begin() + b, keys.begin() + e);
-        // where each 128-item tile starts inside this user tile's keys
-        uint32_t *off = tile_off.data() + (size_t)rt * (size_t)(n_ct + 1);
-        int64_t p = b;
-        for (int64_t ct = 0; ct <= n_ct; ++ct) {
-            const uint32_t lim = (uint32_t)std::min<int64_t>(ct * TN, n_items) << 7;
-            while (p < e && keys[(size_t)p] < lim) ++p;
-            off[ct] = (uint32_t)(p - b);
-        }
+    // rows -> sorted unique, plus the fused path's mask keys (per 128-row user tile, ascending (item << 7 | row_in_tile),
+    // with the offset of every 128-item tile): built on the device (ingest.cu)
+    IngestOut o;
+    char msg[256] = "";
+    const int rc = ingest_csr(indptr, indices, n_rows, n_items, true, TM, TN, &o, msg, sizeof(msg), nullptr);
+    if (rc) {
+        ingest_free(&o);
+        return fail(ctx, rc, "%s", msg);
     }
-    tile_ptr[(size_t)n_rt] = (int64_t)oidx.size();
-    if ((rc = upload(ctx, &ctx->d_tr_indptr, optr))) return rc;
-    if ((rc = upload(ctx, &ctx->d_tr_idx, oidx))) return rc;
-    if ((rc = upload(ctx, &ctx->d_mask_keys, keys))) return rc;
-    if ((rc = upload(ctx, &ctx->d_mask_tile_ptr, tile_ptr))) return rc;
-    if ((rc = upload(ctx, &ctx->d_mask_tile_off, tile_off))) return rc;
+    free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr); free_dev(ctx->d_mask_tile_off);
+    ctx->d_tr_indptr = o.indptr;
+    ctx->d_tr_idx = o.idx;
+    ctx->d_mask_keys = o.mask_keys;
+    ctx->d_mask_tile_ptr = o.tile_ptr;
+    ctx->d_mask_tile_off = o.tile_off;
     ctx->tr_rows = n_rows;
     ctx->tr_items = n_items;
     ctx->has_train = true;
@@ -798,12 +741,16 @@ int skr_set_test_csr(skr_ctx *ctx, const int64_t *indptr, const int32_t *indices
     if (!ctx) return SKR_ERR_INVALID;
     if (!indptr || n_rows <= 0) return fail(ctx, SKR_ERR_INVALID, "test CSR must not be empty (evaluator.py:144)");
     SKR_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::vector<int64_t> optr;
-    std::vector<int32_t> oidx;
-    int rc = normalise_csr(ctx, indptr, indices, n_rows, n_items, optr, oidx);
-    if (rc) return rc;
-    if ((rc = upload(ctx, &ctx->d_te_indptr, optr))) return rc;
-    if ((rc = upload(ctx, &ctx->d_te_idx, oidx))) return rc;
+    IngestOut o;
+    char msg[256] = "";
+    const int rc = ingest_csr(indptr, indices, n_rows, n_items, false, TM, TN, &o, msg, sizeof(msg), nullptr);
+    if (rc) {
+        ingest_free(&o);
+        return fail(ctx, rc, "%s", msg);
+    }
+    free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx);
+    ctx->d_te_indptr = o.indptr;
+    ctx->d_te_idx = o.idx;
     ctx->te_rows = n_rows;
     ctx->te_items = n_items;
     ctx->has_test = true;

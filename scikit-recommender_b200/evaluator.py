@@ -117,6 +117,11 @@ class _LazyRows(object):
 def _csr_rows(indptr, indices, rows, col_range=None):
     """rows of a CSR, in the given order -> (indptr int64, indices int32), vectorised"""
     rows = np.asarray(rows, dtype=np.int64)
+    if col_range is None and rows.size > 0 and int(rows[-1]) - int(rows[0]) + 1 == rows.size and \
+            (rows.size < 3 or bool(np.all(np.diff(rows) == 1))):
+        # a run of consecutive rows (every user of a from_csr evaluator, or a rank's contiguous slice): views, no gather
+        lo, hi = int(rows[0]), int(rows[-1]) + 1
+        return indptr[lo:hi + 1] - indptr[lo], indices[indptr[lo]:indptr[hi]]
     cnt = indptr[rows + 1] - indptr[rows]
     optr = np.zeros(rows.size + 1, dtype=np.int64)
     np.cumsum(cnt, out=optr[1:])
