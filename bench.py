@@ -195,10 +195,10 @@ class Problem(object):
     """One global evaluation problem, identical on every rank: host CSRs of all users, the item table (and bias)
     on the device, the user table on the device and -- for the end-to-end arm -- in pinned host memory."""
 
-    def __init__(self, name, scaling, world, rank, dev):
+    def __init__(self, name, scaling, world, rank, dev, norms="iid"):
         import torch
         from skrec_b200 import synth
-        cfg = dict(synth.CONFIGS[name])
+        cfg = dict(synth.CONFIGS[name], norms=norms)
         self.name, self.cfg, self.scaling = name, cfg, scaling
         t0 = time.time()
         if name in LARGE:
@@ -306,7 +306,7 @@ def measure(args, name, scaling, steps, warmup, e2e_cap, dev, rank, world, local
     import torch.distributed as td
     from skrec_b200 import RankingEvaluator, dist
 
-    prob = Problem(name, scaling, world, rank, dev)
+    prob = Problem(name, scaling, world, rank, dev, norms=args.norms if headline else "iid")
     cfg = prob.cfg
     K = max(cfg["top_k"])
     M = len(cfg["metric"])
@@ -558,7 +558,7 @@ def run_ours(args):
                     "traffic": traffic, "traffic_note": "per launch (one row chunk of <= 131,072 users) from profiles/traffic.json; null = no ncu capture of this kernel at this config in this round",
                     "kernel_ms": r["kernel_ms"], "kernel_launches_per_step": r["chunks_per_step"],
                     "kernel_share_of_step": r["kernel_ms"] / r["ms_per_step"], "prepass_kernel_ms": r["prepass_ms"], "plan": r["plan"],
-                    "exact_rows_last_chunk": r["plan"].get("exact_rows"),
+                    "exact_rows_last_chunk": r["plan"].get("exact_rows"), "retried_rows_last_chunk": r["plan"].get("retried_rows"),
                     "algorithmic_flops_per_step_rank0": flops, "mma_passes": passes,
                     "tensor_pipe_utilisation_est": passes * achieved / peak, "peak_note": peak_note,
                     "rank0_rows": rows_rank0, "rank0_items": items_rank0}
@@ -575,7 +575,7 @@ def run_ours(args):
                                     else "user-sharded x%d, item table replicated, metric-sum all-reduce") % world,
                     "path": r["path"], "users_counted": r["users_counted"], "precision": args.precision,
                     "l2": "256 MB buffer written between steps, outside the event pairs",
-                    "clock_ramp_steps": r["n_ramp"], "prep_ms": r["prep_ms"], "data_generation_s": r["gen_s"]},
+                    "item_norms": args.norms, "clock_ramp_steps": r["n_ramp"], "prep_ms": r["prep_ms"], "data_generation_s": r["gen_s"]},
             "clocks": clocks, "e2e": r["e2e"], "gpu_launches": r["launches"], "roofline": roofline, "cpu_baseline": cpu,
             "metrics_at_top_k": {n_: float(v) for n_, v in zip(r["names"], r["means"])},
             "also": also}
@@ -596,6 +596,7 @@ def main():
     ap.add_argument("--path", default="fused", choices=["fused", "predict"], help="predict: the model only offers the reference's predict()")
     ap.add_argument("--batch-size", type=int, default=256, help="user batch of the predict path (reference default 256)")
     ap.add_argument("--precision", default="auto", choices=["auto", "3xtf32", "fp32", "tf32r"])
+    ap.add_argument("--norms", default="iid", choices=["iid", "heavy"], help="heavy: heavy-tailed item norms, outliers, norm-correlated bias (c1-c3 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()

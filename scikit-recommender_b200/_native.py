@@ -167,9 +167,10 @@ class Context(object):
         return float(ms.value)
 
     def fused_stats(self):
-        out = (_i64 * 8)()
-        self._check(self._L.skr_fused_stats(self._h, out, 8))
-        return dict(zip(("sample_tiles", "stride", "rank", "cap", "chunks", "stages", "exact_rows", "timed_launches"), [int(x) for x in out]))
+        out = (_i64 * 9)()
+        self._check(self._L.skr_fused_stats(self._h, out, 9))
+        return dict(zip(("sample_tiles", "stride", "rank", "cap", "chunks", "stages", "exact_rows", "timed_launches", "retried_rows"),
+                        [int(x) for x in out]))
 
     def fused_trace(self, n_tiles):
         """[n_tiles, 16] SM-clock timestamps of the traced CTA (set_option("trace_cta", c) first)."""

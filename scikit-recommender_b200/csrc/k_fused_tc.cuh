@@ -230,6 +230,9 @@ struct TcArgs {
     // built on the host with unequal chunk counts per user tile and ordered largest first, so that the hardware's
     // in-order block scheduler packs the SMs evenly (LPT) instead of leaving a quarter of them idle in the last wave
     const int4 *work;        // {rt, t0, n, slot}
+    // second attempt of precision "tf32r" (see run_select_metrics): only rows whose retry_cnt[row] == 0 (not settled by
+    // the first attempt) collect, with the threshold in `thr`; CTAs whose user tile has no such row exit at once
+    const int *retry_cnt;    // [n_rows] or null
     // development aid: per-tile clock64 timestamps of one CTA (null = off), [tile][TC_TRACE_SLOTS]
     long long *trace;
     int trace_cta;
@@ -402,6 +405,11 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     const int rt = wk.x, t0 = wk.y, n_tiles = wk.z, c = wk.w;
     const int t_step = SAMPLE ? A.stride : 1;
     const int64_t row_base = (int64_t)rt * TM;
+    if (!SAMPLE && A.retry_cnt != nullptr) {  // kernel argument: the branch is uniform over the grid
+        pdl_wait();                           // the flags are the previous kernel's output
+        const bool mine = tid < TM && row_base + tid < P.n_rows && __ldg(A.retry_cnt + row_base + tid) == 0;
+        if (!__syncthreads_or(mine)) return;  // nothing to redo in this user tile (the usual case)
+    }
 
     if (tid == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -661,14 +669,14 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         float v[TC_R];  // SAMPLE: largest group maxima so far, descending
 #pragma unroll
         for (int q = 0; q < TC_R; ++q) v[q] = NINF;
-        if (!SAMPLE && my_valid) {
+        if (!SAMPLE && my_valid && (A.retry_cnt == nullptr || __ldg(A.retry_cnt + my_row) == 0)) {
             thr = __ldg(A.thr + my_row);
             if (PRESUB) {
                 thr_hi = __ldg(A.thr_hi + my_row);
                 thr_lo = __ldg(A.thr_lo + my_row);
             }
-            wbase = A.cand + ((my_row * P.S + c) * 4 + cq) * (int64_t)A.cap;
         }
+        if (!SAMPLE && my_valid) wbase = A.cand + ((my_row * P.S + c) * 4 + cq) * (int64_t)A.cap;
         if (PRESUB && cq == 3) {  // A': -T0 as TF32 hi + lo (k_sample_thr), 16 columns reserved, 8 read
             uint32_t x[16];
 #pragma unroll
@@ -759,7 +767,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 __global__ void __launch_bounds__(256)
 k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
              int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
-             float *__restrict__ thr_lo_out)
+             float *__restrict__ thr_lo_out, float eps3_coef, float *__restrict__ eps2_3_out, float *__restrict__ thr3_out)
 {
     pdl_wait();
     pdl_trigger();
@@ -790,6 +798,17 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
         float e2 = 2.0f * eps;
         const float INF = __int_as_float(0x7f800000);
         if (!(e2 < INF)) e2 = INF;  // overflow / NaN operands: collect everything, the exact kernel settles the row
+        if (thr3_out != nullptr) {
+            // the retry of rows this band was too wide for scores in three passes (3xTF32): operands are then exact to
+            // 2^-22 each and the dropped lo*lo term is 2^-22 |u_k i_k|, the accumulator takes 3 d terms:
+            // eps3 = 1.25 [(3.25 d + 11) 2^-22 ||u|| N_max + 2^-22 B_max] -- 10 to 20 times narrower than eps
+            float e3 = 2.0f * 1.25f * (eps3_coef * sqrtf(ss) * sqrtf(__ldg(stats)) + 2.384185791015625e-07f * __ldg(stats + 1));
+            if (!(e3 < INF)) e3 = INF;
+            if (lane == 0) {
+                eps2_3_out[row] = e3;
+                thr3_out[row] = (e3 < INF) ? __fsub_rd(t0, e3) : -INF;
+            }
+        }
         t0 = (e2 < INF) ? __fsub_rd(t0, e2) : -INF;
         if (lane == 0) eps2_out[row] = e2;
     }
@@ -833,7 +852,7 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (zero_a != nullptr) *zero_a = 0;
+        if (zero_a != nullptr) { zero_a[0] = 0; zero_a[1] = 0; }  // fail counters of the first attempt and of the retry
         if (stats_next != nullptr) { stats_next[0] = 0u; stats_next[1] = 0u; }
     }
     float best = 0.0f, bb = 0.0f;
@@ -873,6 +892,28 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
     if (lane == 0 && stats_cur != nullptr) {
         atomicMax(stats_cur, __float_as_uint(best));
         if (bias != nullptr) atomicMax(stats_cur + 1, __float_as_uint(bb));
+    }
+}
+
+// The lo table of the three-pass retry, built only when the first attempt left rows unsettled (*need != 0): the
+// common case costs one block-wide early exit per CTA.
+__global__ void __launch_bounds__(256)
+k_split_lo_if(const int *__restrict__ need, const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, float *__restrict__ lo)
+{
+    pdl_wait();
+    pdl_trigger();
+    if (*need == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = lane + 32 * q;
+            if (k < d_pad) {
+                const float x = (k < d) ? __ldg(X + row * ld + k) : 0.0f;
+                const uint32_t h = to_tf32(x);
+                lo[row * d_pad + k] = __uint_as_float(to_tf32(x - __uint_as_float(h)));
+            }
+        }
     }
 }
 

@@ -163,18 +163,25 @@ __device__ __forceinline__ void topk_row_block(const Src &src, int n_items, int6
     for (int i = tid; i < K; i += K2_THREADS) out[i] = (i < base) ? keys[i] : 0ull;
 }
 
-// Streaming form for a score-matrix row with 16-byte aligned float4 access (the HBM-bound kernel of the `predict`
-// path: 4 I bytes per user is all it must read).  The generic routine above meets 2-3 block barriers per 1,024
-// scores and keeps one float4 per thread in flight -- measured 0.77 TB/s at c2.  Here:
-//   * the first pieces of 1,024 scores establish the K-th key (threshold) exactly as before;
-//   * after that a "super-chunk" is 8 float4 per thread (8,192 scores, 32 KB per block in flight), issued before the
-//     first compare; a score is dropped after ONE compare against the threshold; the rare survivor is checked against
-//     the row's sorted train items by binary search (masked: -inf, still a candidate, like evaluator.py:195-200),
-//     turned into a rank key and appended to the shared buffer with one atomic -- no barrier, no bitmap;
-//   * one barrier per super-chunk reads the buffer level: the buffer is folded into the sorted top-K (block bitonic)
-//     only when it is half full or at the end of the row (random order: ~K ln(I / 1024) survivors in total), and a
-//     super-chunk that overflowed it (adversarial ascending rows) is discarded and redone in pieces.
-constexpr int K2_SUPER = 8;  // float4 per thread and super-chunk
+// Streaming form for a row of a score matrix (the HBM-bound kernel of the `predict` path: 4 I bytes per user is all
+// it must read).  The generic routine above meets 2-3 block barriers per 1,024 scores and keeps one float4 per
+// thread in flight -- measured 0.77 TB/s at c2.  Here a chunk is 1, 2, 4, then 8 float4 per thread (8,192 scores,
+// 32 KB per block in flight), all loads issued before the first compare, and the work is split in two so that no
+// warp ever walks a slow path for the sake of one lane:
+//   filter   one compare per score against the threshold; survivors are appended RAW (score bits, item) to the shared
+//            buffer with one atomic per warp and score position (ballot + popc);
+//   fix-up   after the chunk's barrier all threads share the new entries: train items (binary search in the row's
+//            sorted CSR; evaluator.py:195-200) become -inf and stay candidates, the entry becomes a rank key and is
+//            kept only if it beats the K-th key.  (Doing this inside the filter cost ~2,000 cycles per score position
+//            whenever ANY lane of the warp had a survivor -- 80 % of the positions of a young row.)
+//   fold     block bitonic of [sorted top-K | buffer].  A threshold taken from the first m scores lets K / m of
+//            everything after it through until it is tightened, so chunks grow geometrically and are folded right away
+//            while the row is young (about K survivors per doubling); after 65,536 scores a chunk yields a handful and
+//            the buffer is folded only when half full.  A chunk that overflows the buffer (adversarial ascending rows)
+//            is dropped and redone 1,024 scores at a time.
+// Rows of a matrix whose pitch is not a multiple of 4 floats start at any 4-byte offset: up to 3 head scores are
+// offered one by one and the float4 stream starts at the first 16-byte boundary.
+constexpr int K2_SUPER = 8;  // float4 per thread in a full chunk
 
 __device__ __forceinline__ void k2_fold(u64 *keys, int *s_cnt, int &base, int K, u64 &thr_key, float &thr_f, int tid)
 {
@@ -189,7 +196,7 @@ __device__ __forceinline__ void k2_fold(u64 *keys, int *s_cnt, int &base, int K,
     __syncthreads();
     block_bitonic_desc(keys, n_sort, tid, K2_THREADS);
     base = tot < K ? tot : K;
-    if (base == K) {
+    if (base == K && keys[K - 1] != 0ull) {
         thr_key = keys[K - 1];
         thr_f = key_score(thr_key);
     }
@@ -198,117 +205,121 @@ __device__ __forceinline__ void k2_fold(u64 *keys, int *s_cnt, int &base, int K,
     __syncthreads();
 }
 
-__device__ __forceinline__ void k2_offer(float s, int j, float thr_f, u64 thr_key, int64_t tb, int64_t te, const int32_t *__restrict__ tr_idx,
-                                         u64 *keys, int base, int *s_cnt)
-{
-    if (!(s < thr_f)) {  // also NaN: ranked like -inf by make_key
-        if (te > tb && sorted_contains(tr_idx + tb, (int)(te - tb), (int32_t)j)) s = -__int_as_float(0x7f800000);
-        const u64 key = make_key(s, (uint32_t)j);
-        if (key > thr_key) {
-            const int pos = atomicAdd(s_cnt, 1);
-            if (pos < K2_P - base) keys[base + pos] = key;
-        }
-    }
-}
-
 __device__ __forceinline__ void topk_row_stream(const float *__restrict__ row, int n_items, int64_t tb, int64_t te,
                                                 const int32_t *__restrict__ tr_idx, int K, u64 *__restrict__ out, u64 *keys, int *s_cnt)
 {
     const int tid = threadIdx.x, lane = tid & 31;
-    int base = 0;
-    u64 thr_key = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int base = 0;          // keys[0 .. base) sorted best-so-far; the buffer starts at keys[base]
+    u64 thr_key = 0;       // K-th key once K are known
     float thr_f = -__int_as_float(0x7f800000);
     if (tid == 0) *s_cnt = 0;
     __syncthreads();
-    // rows of a matrix whose pitch is not a multiple of 4 floats start at any 4-byte offset: up to 3 head scores are
-    // offered one by one, the float4 stream starts at the first 16-byte boundary (element a0 of the row)
     const int a0 = (int)((4u - (unsigned)((reinterpret_cast<uintptr_t>(row) >> 2) & 3u)) & 3u);
-    const float *rowa = row + a0;
-    const int n_body = n_items - a0;  // n_items >= K >= 1 and a0 <= 3; a row shorter than a0 has n_body <= 0
-    if (tid < a0 && tid < n_items) k2_offer(__ldg(row + tid), tid, thr_f, thr_key, tb, te, tr_idx, keys, base, s_cnt);
-    // 4 body scores per thread starting at body element c0 (guarded at the end of the row)
-    auto load4 = [&](int jj, float (&v)[4]) {
-        if (jj + 3 < n_body) {
-            const float4 t = ldg_stream_f4(rowa + jj);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = (jj + q < n_body) ? __ldg(rowa + jj + q) : 0.0f;
+    const float *rowa = row + a0;       // 16-byte aligned
+    const int n_body = n_items - a0;    // scores from the first aligned one on (<= 0 for a row of 1-3 scores)
+
+    // raw append of one score position across the warp (every lane calls this, `pass` says who has a survivor)
+    auto offer = [&](bool pass, float sc, int j) {
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+            int pos = 0;
+            if (lane == __ffs(bal) - 1) pos = atomicAdd(s_cnt, __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs(bal) - 1) + __popc(bal & lt_mask);
+            if (pass && pos < K2_P - base) keys[base + pos] = ((u64)__float_as_uint(sc) << 32) | (u64)(uint32_t)j;
         }
     };
-    // one piece: 1,024 scores, appended with one atomic per warp and step (in the first piece every score passes), then a fold
-    auto piece = [&](int c0) {
-        const int jj = c0 + tid * 4;
-        float v[4];
-        load4(jj, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float sc = v[q];
-            bool pass = (jj + q < n_body) && !(sc < thr_f);
-            u64 key = 0;
-            if (pass) {
-                const int j = a0 + jj + q;
-                if (te > tb && sorted_contains(tr_idx + tb, (int)(te - tb), (int32_t)j)) sc = -__int_as_float(0x7f800000);
-                key = make_key(sc, (uint32_t)j);
-                pass = key > thr_key;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
-                const int leader = __ffs(bal) - 1;
-                int pos = 0;
-                if (lane == leader) pos = atomicAdd(s_cnt, __popc(bal));
-                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(bal & ((1u << lane) - 1u));
-                if (pass && pos < K2_P - base) keys[base + pos] = key;
-            }
+    // raw entries [from, to) of the buffer -> rank keys (0 = rejected); all threads
+    auto fixup = [&](int from, int to) {
+        for (int i = from + tid; i < to; i += K2_THREADS) {
+            const u64 raw = keys[base + i];
+            float sc = __uint_as_float((uint32_t)(raw >> 32));
+            const int j = (int)(uint32_t)raw;
+            if (te > tb && sorted_contains(tr_idx + tb, (int)(te - tb), (int32_t)j)) sc = -__int_as_float(0x7f800000);
+            const u64 key = make_key(sc, (uint32_t)j);
+            keys[base + i] = (key > thr_key) ? key : 0ull;
         }
-        __syncthreads();
-        k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
     };
-    int c0 = 0;
-    // threshold first: pieces until K keys are known (K <= 512 <= 1,024: one piece unless the row is shorter)
-    do { piece(c0); c0 += K2_CHUNK; } while (c0 < n_body && base < K);
-    constexpr int SUPER = K2_SUPER * K2_CHUNK;
-    int pending = 0;  // survivors in the buffer that are not folded yet (block-uniform)
-    while (c0 < n_body) {
+    // one chunk of nf4 float4 per thread starting at body score c0; force_fold: fold whatever it appended.
+    // -> false when the chunk overflowed the buffer (nothing of it was kept; the caller redoes it in pieces)
+    int pending = 0;  // entries in the buffer (already fixed up) that are not folded yet; block-uniform
+    auto chunk = [&](int c0, int nf4, bool force_fold, bool head) -> bool {
         float v[K2_SUPER][4];
-        if (c0 + SUPER <= n_body) {
+        if (c0 + nf4 * K2_CHUNK <= n_body) {
 #pragma unroll
-            for (int q = 0; q < K2_SUPER; ++q) {
-                const float4 t = ldg_stream_f4(rowa + c0 + q * K2_CHUNK + tid * 4);
-                v[q][0] = t.x; v[q][1] = t.y; v[q][2] = t.z; v[q][3] = t.w;
+            for (int q = 0; q < K2_SUPER; ++q)
+                if (q < nf4) {
+                    const float4 t = ldg_stream_f4(rowa + c0 + q * K2_CHUNK + tid * 4);
+                    v[q][0] = t.x; v[q][1] = t.y; v[q][2] = t.z; v[q][3] = t.w;
+                }
+        } else {  // the last, partial chunk: guarded loads, missing scores are never offered
+#pragma unroll
+            for (int q = 0; q < K2_SUPER; ++q)
+                if (q < nf4) {
+                    const int jj = c0 + q * K2_CHUNK + tid * 4;
+                    if (jj + 3 < n_body) {
+                        const float4 t = ldg_stream_f4(rowa + jj);
+                        v[q][0] = t.x; v[q][1] = t.y; v[q][2] = t.z; v[q][3] = t.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[q][e] = (jj + e < n_body) ? __ldg(rowa + jj + e) : 0.0f;
+                    }
+                }
+        }
+        if (head) {  // the up to 3 scores before the first 16-byte boundary (first chunk only; warp 0 holds lanes 0-2)
+            if (tid < 32) {
+                const bool have = tid < a0 && tid < n_items;
+                offer(have, have ? __ldg(row + tid) : 0.0f, tid);
             }
-        } else {  // the last, partial super-chunk: guarded loads, missing scores are never offered
-#pragma unroll
-            for (int q = 0; q < K2_SUPER; ++q) load4(c0 + q * K2_CHUNK + tid * 4, v[q]);
         }
 #pragma unroll
         for (int q = 0; q < K2_SUPER; ++q) {
-            const int jj = c0 + q * K2_CHUNK + tid * 4;
+            if (q < nf4) {
+                const int jj = c0 + q * K2_CHUNK + tid * 4;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (jj + e < n_body) k2_offer(v[q][e], a0 + jj + e, thr_f, thr_key, tb, te, tr_idx, keys, base, s_cnt);
+                for (int e = 0; e < 4; ++e) offer(jj + e < n_body && !(v[q][e] < thr_f), v[q][e], a0 + jj + e);
+            }
         }
         __syncthreads();
         const int cnt = *s_cnt;
         const int room = K2_P - base;
         __syncthreads();  // everyone has the count before anyone appends again or resets it
         if (cnt > room) {
-            // overflow: positions are handed out in order, so everything at or beyond `pending` (the level before this
-            // super-chunk) is this super-chunk's: drop it, fold the older survivors, redo the super-chunk in pieces
+            // positions are handed out in order: everything at or beyond `pending` is this chunk's -- drop it, fold the rest
             if (tid == 0) *s_cnt = pending;
             __syncthreads();
             k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
-            for (int p = 0; p < K2_SUPER && c0 + p * K2_CHUNK < n_body; ++p) piece(c0 + p * K2_CHUNK);
             pending = 0;
-        } else if (2 * cnt > room) {  // half full: fold (also tightens the threshold)
+            return false;
+        }
+        fixup(pending, cnt);
+        if (cnt > pending && (force_fold || 2 * cnt > room)) {
+            __syncthreads();
             k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
             pending = 0;
         } else {
             pending = cnt;
         }
-        c0 += SUPER;
+        return true;
+    };
+
+    int c0 = 0, nf4 = 1;
+    bool first = true;
+    do {  // threshold first: chunks of 1,024 until K keys are known (one, unless the row is shorter or full of train items)
+        chunk(c0, 1, true, first);  // cannot overflow: the buffer is empty and takes 1,024 + 3
+        first = false;
+        c0 += K2_CHUNK;
+    } while (c0 < n_body && thr_key == 0ull);
+    while (c0 < n_body) {
+        if (!chunk(c0, nf4, c0 < 65536, false))
+            for (int p = 0; p < nf4 && c0 + p * K2_CHUNK < n_body; ++p) chunk(c0 + p * K2_CHUNK, 1, true, false);
+        c0 += nf4 * K2_CHUNK;
+        if (nf4 < K2_SUPER) nf4 *= 2;
     }
-    if (pending > 0) k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
+    if (pending > 0) {
+        __syncthreads();
+        k2_fold(keys, s_cnt, base, K, thr_key, thr_f, tid);
+    }
     for (int i = tid; i < K; i += K2_THREADS) out[i] = (i < base) ? keys[i] : 0ull;
 }
 

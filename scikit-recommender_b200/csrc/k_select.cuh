@@ -122,7 +122,8 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count,
                const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
                const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
-               float *__restrict__ topk_val_out, double *__restrict__ acc_out, RescoreArgs R, const float *__restrict__ add_back)
+               float *__restrict__ topk_val_out, double *__restrict__ acc_out, RescoreArgs R, const float *__restrict__ add_back,
+               int retry_only)
 {
     pdl_wait();
     pdl_trigger();
@@ -149,6 +150,8 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
     const int64_t n_warps = (int64_t)gridDim.x * SEL_WARPS;
     for (int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp; row < n_rows; row += n_warps) {
         __syncwarp();
+        // second attempt (RESCORE): only the rows the first one left unsettled (rs_cnt == 0) are looked at
+        if (RESCORE && retry_only && R.rs_cnt[row] != 0) continue;
         // ---- 1. sub-list sizes (n_sub <= 32: one per lane), exclusive scan, gather -----------------
         const int c_mine = (lane < n_sub) ? (int)__ldg(cand_cnt + row * n_sub + lane) : 0;
         int incl = c_mine;

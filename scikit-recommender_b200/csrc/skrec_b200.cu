@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -286,15 +287,30 @@ int run_row_exact(skr_ctx *ctx, const ExactArgs &E, int32_t *fail_list, int *fai
     return SKR_OK;
 }
 
+// Second attempt of precision "tf32r" for the rows the first one left unsettled (sub-list overflow, band below the
+// collection threshold, too many candidates inside the band -- what a few high-norm items or heavy-tailed tables do to
+// the single-pass error band): the same pipeline in THREE TF32 passes, whose band is 10-20 times narrower, restricted to
+// those rows.  collect() launches the lo-table build and the 3-pass COLLECT kernel (both return at once when nothing
+// failed); the second selection looks only at rows with rs_cnt == 0 and puts what it cannot settle on fail list 2,
+// which alone goes to the exact per-row kernel.
+struct RetryPlan {
+    const std::function<int()> *collect;  // null: no retry (3xTF32 / 1xTF32 requested explicitly)
+    const float *eps2_3;                  // [n_rows] 2 eps of the three-pass scores
+    const float *thr3;                    // [n_rows] threshold the retry collects with
+    int32_t *fail_list2;
+    int *fail_count2;
+};
+
 int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
                        const MetricIds &m, int K, const ExactArgs &E, int32_t *fail_list, int *fail_count, int32_t *topk_idx,
-                       float *topk_val, float *per_user, double *sums, u64 *keys_only, RescoreArgs RA, const float *add_back, cudaStream_t st)
+                       float *topk_val, float *per_user, double *sums, u64 *keys_only, RescoreArgs RA, const float *add_back,
+                       const RetryPlan &RP, cudaStream_t st)
 {
     const bool rescore = RA.U != nullptr;
     // kernel instantiations: the sort capacity is 64 / 128 keys (K <= 64 / 128); re-scoring doubles it (error band) and
     // splits the job in two kernels: candidates -> exact keys of the survivors, then sort + metrics
     typedef void (*SelKernel)(const uint2 *, const uint32_t *, int, int, int, int, int64_t, int64_t, u64 *, int32_t *, int *, const int64_t *,
-                              const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs, const float *);
+                              const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs, const float *, int);
     typedef void (*SortKernel)(const u64 *, const int *, int, int64_t, int64_t, u64 *, const int64_t *, const int32_t *, MetricIds, const double *,
                                const float *, float *, int32_t *, float *, double *);
     const int per = rescore ? (K <= 64 ? 4 : 8) : (K <= 64 ? 2 : 4);
@@ -311,7 +327,18 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     const int g_sel = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
     if (keys_only != nullptr) {  // per-shard lists: sorted keys out, no metrics
         SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back));
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back, 0));
+        if (rescore && RP.collect != nullptr) {
+            if ((rc = (*RP.collect)())) return rc;
+            RescoreArgs R2 = RA;
+            R2.eps2 = RP.eps2_3;
+            R2.thr_c = RP.thr3;
+            SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, RP.fail_list2, RP.fail_count2,
+                                                  nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R2, nullptr, 1));
+            ctx->launches += 3;
+            fail_list = RP.fail_list2;
+            fail_count = RP.fail_count2;
+        }
         if (rescore) {
             SKR_CUDA(ctx, launch_pdl(srt, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, RA.rs_keys, RA.rs_cnt, K, n_rows, row0, keys_only, nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr,
                                                   nullptr, nullptr));
@@ -354,13 +381,24 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     }
     if (rescore) {
         SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, nullptr, nullptr, m, nullptr,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back));
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back, 0));
+        if (RP.collect != nullptr) {
+            if ((rc = (*RP.collect)())) return rc;
+            RescoreArgs R2 = RA;
+            R2.eps2 = RP.eps2_3;
+            R2.thr_c = RP.thr3;
+            SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, RP.fail_list2, RP.fail_count2,
+                                                  nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R2, nullptr, 1));
+            ctx->launches += 3;
+            fail_list = RP.fail_list2;
+            fail_count = RP.fail_count2;
+        }
         SKR_CUDA(ctx, launch_pdl(srt, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(dyn_sel), st, RA.rs_keys, RA.rs_cnt, K, n_rows, row0, nullptr, ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc,
                                                     ctx->d_idcg, pu, topk_idx, topk_val, acc));
         ctx->launches++;
     } else {
         SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(dyn_sel), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
-                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA, add_back));
+                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA, add_back, 0));
     }
     SKR_AFTER(ctx, st, "k_select_cands / k_sort_metrics");
     if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys, st))) return rc;
@@ -679,9 +717,14 @@ int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out)
 {
     if (!ctx || !out || n_out < 7) return SKR_ERR_INVALID;
     if (n_out >= 8) out[7] = ctx->ev_calls;  // timed scoring launches since the last "event_ring" option (one per row chunk)
-    int n_fail = 0;
+    int n_fails[2] = {0, 0};
     SKR_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->fail_list.p) SKR_CUDA(ctx, cudaMemcpy(&n_fail, ctx->fail_list.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ctx->fail_list.p) SKR_CUDA(ctx, cudaMemcpy(n_fails, ctx->fail_list.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    // tf32r: [0] rows the single-pass attempt left to the three-pass retry, [1] rows the retry left to the exact kernel;
+    // other precisions have one attempt
+    const bool two = !strcmp(ctx->last_fused, "tcgen05_tf32r");
+    const int n_fail = two ? n_fails[1] : n_fails[0];
+    if (n_out >= 9) out[8] = two ? n_fails[0] : 0;
     out[0] = ctx->last_plan.n_samp;
     out[1] = ctx->last_plan.stride;
     out[2] = ctx->last_plan.r;
@@ -1020,8 +1063,8 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         const int d_pad = nkb * TC_KB;
         const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
         if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;
-        if (passes == 3 && (rc = ensure(ctx, ctx->blo, tbytes))) return rc;
-        if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
+        if ((passes == 3 || rescore) && (rc = ensure(ctx, ctx->blo, tbytes))) return rc;  // tf32r: filled on demand by the retry
+        if ((rc = ensure(ctx, ctx->fail_list, (size_t)(2 * n_rows + 2) * sizeof(int32_t)))) return rc;
         if (ctx->stats.cap == 0) {  // two slots of {max ||item||^2, max |bias|}, alternating between evaluates
             if ((rc = ensure(ctx, ctx->stats, 4 * sizeof(uint32_t)))) return rc;
             SKR_CUDA(ctx, cudaMemsetAsync(ctx->stats.p, 0, 4 * sizeof(uint32_t), st));
@@ -1036,12 +1079,12 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
                                                                                                       stats_next));
             ctx->launches++;
         } else {
-            SKR_CUDA(ctx, cudaMemsetAsync(ctx->fail_list.p, 0, sizeof(int), st));  // the split kernel's other job: empty fail list
+            SKR_CUDA(ctx, cudaMemsetAsync(ctx->fail_list.p, 0, 2 * sizeof(int), st));  // the split kernel's other job: empty fail lists
         }
         uint32_t *stats_cur = ctx->stats_cur_ptr;
         CUtensorMap mhi, mlo;
         if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
-        if (passes == 3) { if ((rc = make_tmap(ctx, &mlo, (const float *)ctx->blo.p, n_items, d_pad))) return rc; }
+        if (passes == 3 || rescore) { if ((rc = make_tmap(ctx, &mlo, (const float *)ctx->blo.p, n_items, d_pad))) return rc; }
         else mlo = mhi;  // single-pass kernels never touch the lo table: it is not even built
 
         // sampling plan (k_fused_tc.cuh header): fraction f ~ 6/K of the item tiles, threshold = r-th largest
@@ -1085,11 +1128,12 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
 
         if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 4 * TC_R * sizeof(float)))) return rc;
         if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * cap * sizeof(uint2)))) return rc;
-        if ((rc = ensure(ctx, ctx->thr, (size_t)3 * n_rows * sizeof(float)))) return rc;  // thr | TF32 hi | TF32 lo (threshold MMA)
+        if ((rc = ensure(ctx, ctx->thr, (size_t)4 * n_rows * sizeof(float)))) return rc;  // thr | TF32 hi | TF32 lo (threshold MMA) | retry threshold
         if ((rc = ensure(ctx, ctx->cand_cnt, (size_t)n_rows * n_sub * sizeof(uint32_t)))) return rc;
-        if ((rc = ensure(ctx, ctx->fail_list, (size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
-        int *fail_count = (int *)ctx->fail_list.p;             // [0] = count, [1..] = rows
-        int32_t *fail_list = (int32_t *)ctx->fail_list.p + 1;
+        int *fail_count = (int *)ctx->fail_list.p;             // [0] = count of the first attempt, [1] = count after the retry
+        int32_t *fail_list = (int32_t *)ctx->fail_list.p + 2;  // [2 ..) rows of the first attempt, [2 + n_rows ..) rows left after the retry
+        int *fail_count2 = fail_count + 1;
+        int32_t *fail_list2 = fail_list + n_rows;
 
         TcArgs A;
         A.U = user_vecs_dev;
@@ -1109,13 +1153,18 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         A.trace = nullptr;
         A.trace_cta = -1;
         A.trace_tiles = 0;
+        A.retry_cnt = nullptr;
         const bool presub = (passes == 1);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
         A.thr_hi = presub ? A.thr + n_rows : nullptr;
         A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
-        float eps_coef = 0.0f;
+        float eps_coef = 0.0f, eps3_coef = 0.0f;
+        float *thr3 = nullptr, *eps2_3 = nullptr;
         if (rescore) {
-            if ((rc = ensure(ctx, ctx->eps2, (size_t)n_rows * sizeof(float)))) return rc;
+            if ((rc = ensure(ctx, ctx->eps2, (size_t)2 * n_rows * sizeof(float)))) return rc;  // 2 eps | 2 eps of the 3-pass retry
             eps_coef = (float)(ldexp(1.0, -10) + (2.5 * d + 8.0) * ldexp(1.0, -22));
+            eps3_coef = (float)((3.25 * d + 11.0) * ldexp(1.0, -22));
+            thr3 = (float *)ctx->thr.p + 3 * n_rows;
+            eps2_3 = (float *)ctx->eps2.p + n_rows;
         }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
@@ -1123,7 +1172,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
         SKR_CUDA(ctx, launch_pdl(k_sample_thr, dim3((unsigned)((unsigned)((n_rows + 7) / 8))), dim3((unsigned)(256)), (size_t)(0), st, (const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
                                                                    (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr,
-                                                                   (float *)A.thr_hi, (float *)A.thr_lo));
+                                                                   (float *)A.thr_hi, (float *)A.thr_lo, eps3_coef, eps2_3, thr3));
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
             A.trace_tiles = wc->max_tiles;
@@ -1146,8 +1195,25 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         const ExactArgs E = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (int)n_items, tp, ti};
         RescoreArgs RA = {nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (rescore) RA = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (const float *)ctx->thr.p, (const float *)ctx->eps2.p, nullptr, nullptr};
+        // the retry of unsettled rows (tf32r only): lo table on demand, then the three-pass kernel over the same work list
+        const std::function<int()> retry_collect = [&]() -> int {
+            SKR_CUDA(ctx, launch_pdl(k_split_lo_if, dim3((unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm)), dim3(256u), (size_t)0, st, (const int *)fail_count, item_vecs_dev, ld_i, n_items, d,
+                                     d_pad, (float *)ctx->blo.p));
+            TcArgs A2 = A;
+            A2.thr = thr3;
+            A2.thr_hi = nullptr;
+            A2.thr_lo = nullptr;
+            A2.retry_cnt = (const int *)ctx->rs_cnt.p;
+            A2.trace = nullptr;
+            A2.trace_cta = -1;
+            int rc2 = launch_tc(ctx, nkb, 3, TC_MODE_COLLECT, grid_tc, st, mhi, mlo, A2, P);
+            if (rc2) return rc2;
+            SKR_AFTER(ctx, st, "k_fused_tc COLLECT (retry)");
+            return SKR_OK;
+        };
+        const RetryPlan RP = {rescore ? &retry_collect : nullptr, eps2_3, thr3, fail_list2, fail_count2};
         rc = run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
-                                per_user_dev, sums_dev, keys_only, RA, presub ? A.thr : nullptr, st);
+                                per_user_dev, sums_dev, keys_only, RA, presub ? A.thr : nullptr, RP, st);
         if (rc || keys_only == nullptr) return rc;
     } else {
         if ((rc = ensure(ctx, ctx->thr, (size_t)n_rows * sizeof(uint32_t)))) return rc;

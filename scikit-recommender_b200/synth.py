@@ -91,10 +91,28 @@ def _draw_distinct(g, cdf, need, n_items):
     return indptr, out
 
 
-def make(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_pool=200, device=None, item_seed=None, **_unused):
+def heavy_tailed(item_emb, bias, seed):
+    """What trained tables look like rather than i.i.d. N(0, 0.1^2): item norms log-normal (sigma 0.5), a handful of
+    items (0.05 %, at least 3) at ten times the typical norm, and -- when there is a bias -- a bias that grows with
+    the norm (popular items), spread over ~0.3.  In place on copies; -> (item_emb, bias)."""
+    g = np.random.default_rng(seed + 99)
+    n = item_emb.shape[0]
+    f = np.exp(0.5 * g.standard_normal(n)).astype(np.float32)
+    out = g.choice(n, size=max(3, n // 2000), replace=False)
+    f[out] = 10.0
+    emb = (item_emb * f[:, None]).astype(np.float32)
+    b = None
+    if bias is not None:
+        b = (bias + 0.1 * np.log(f)).astype(np.float32)
+    return emb, b
+
+
+def make(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_pool=200, device=None, item_seed=None, norms="iid",
+         **_unused):
     """Generate one workload.  Returns a dict: user_emb [U,d] f32, item_emb [I,d] f32, bias [I] f32 or
     None, train/test OrderedDict {user: int32 array} (keys ascending), and the CSR forms
     train_indptr/train_indices/test_indptr/test_indices (rows = users 0..U-1).
+    norms="heavy": heavy-tailed item norms, a few outliers and a norm-correlated bias (`heavy_tailed`).
     item_seed: draw the item table (and bias) from their own generator -- ranks of a user-sharded run pass
     the same item_seed and different `seed`s: one replicated catalogue, different user slices."""
     import torch
@@ -105,6 +123,8 @@ def make(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_pool=200,
     gi = g if item_seed is None else np.random.default_rng(item_seed)
     item_emb = (gi.standard_normal((I, d)) * 0.1).astype(np.float32)
     b = (gi.standard_normal(I) * 0.01).astype(np.float32) if bias else None
+    if norms == "heavy":
+        item_emb, b = heavy_tailed(item_emb, b, seed if item_seed is None else item_seed)
 
     deg_train = _degrees(g, U, nnz_train, 1, max(1, I // 4))
     deg_test = _degrees(g, U, nnz_test, 1, max(1, I // 8))

@@ -980,3 +980,54 @@ def test_row_chunked_fused_equals_one_call(torch_cuda, ctx):
         a, bb = out[(0, prec)], out[(256, prec)]
         assert np.array_equal(a[0], bb[0]) and np.array_equal(a[1], bb[1])
         assert np.max(np.abs(a[2] - bb[2])) < 1e-9
+
+
+@pytest.mark.parametrize("U,I,d,bias,K", [(1500, 20000, 64, True, 50), (900, 30000, 128, False, 100), (700, 9000, 32, True, 20)])
+def test_tf32r_on_heavy_tailed_tables_equals_fp32_and_retries_instead_of_walking_rows(torch_cuda, U, I, d, bias, K):
+    """trained tables have heavy-tailed item norms and a few outliers; the single-pass error band
+    (proportional to max ||item||) then leaves rows unsettled.  They are retried in three TF32 passes (band 10-20x
+    narrower) instead of being walked one by one; results stay bit-identical to the exact FP32 path."""
+    from skrec_b200 import _native, synth
+    torch = torch_cuda
+    dta = synth.make(users=U, items=I, d=d, nnz_train=U * 30, nnz_test=U * 6, seed=100 + d, bias=bias, norms="heavy", device="cuda")
+    norms = np.linalg.norm(dta["item_emb"], axis=1)
+    assert norms.max() > 6 * np.median(norms)
+    c = _native.Context(0)
+    c.set_train_csr(dta["train_indptr"], dta["train_indices"], I)
+    c.set_test_csr(dta["test_indptr"], dta["test_indices"], I)
+    ue, ie = torch.from_numpy(dta["user_emb"]).cuda(), torch.from_numpy(dta["item_emb"]).cuda()
+    b = None if dta["bias"] is None else torch.from_numpy(dta["bias"]).cuda()
+    metric = [1, 2, 3, 4, 5]
+    out = {}
+    for prec in ("tf32r", "fp32"):
+        idx = torch.empty((U, K), dtype=torch.int32, device="cuda")
+        val = torch.empty((U, K), dtype=torch.float32, device="cuda")
+        per = torch.empty((U, len(metric) * K), dtype=torch.float32, device="cuda")
+        sums = torch.zeros(len(metric) * K, dtype=torch.float64, device="cuda")
+        c.eval_fused(ue, ie, b, 0, metric, K, precision=prec, topk_idx=idx, topk_val=val, per_user=per, sums=sums)
+        torch.cuda.synchronize()
+        out[prec] = (idx.cpu().numpy(), val.cpu().numpy(), per.cpu().numpy(), sums.cpu().numpy())
+        if prec == "tf32r":
+            st = c.fused_stats()
+    a, f = out["tf32r"], out["fp32"]
+    assert np.array_equal(a[0], f[0]) and np.array_equal(a[1], f[1]) and np.array_equal(a[2], f[2])
+    assert np.max(np.abs(a[3] - f[3])) < 1e-9
+    _check_fused(*a, dta["user_emb"], dta["item_emb"], dta["bias"], (dta["train_indptr"], dta["train_indices"]),
+                 (dta["test_indptr"], dta["test_indices"]), metric, K)
+    # the retry settles (nearly) everything the first attempt could not: the per-row exact kernel is the exception
+    assert st["exact_rows"] <= max(8, st["retried_rows"] // 4), st
+    c.close()
+
+
+def test_three_pass_error_stays_inside_the_band_the_retry_assumes(torch_cuda, ctx):
+    """eps3 = 1.25 [(3.25 d + 11) 2^-22 ||u|| max||i|| + 2^-22 max|b|] must bound |s_3xtf32 - s_fp32| with room to spare."""
+    g = np.random.default_rng(8)
+    for d in (32, 64, 128):
+        U, I, K = 256, 4096, 64
+        ue = (g.standard_normal((U, d)) * g.lognormal(0, 1, (U, 1))).astype(np.float32)
+        ie = (g.standard_normal((I, d)) * g.lognormal(0, 1, (I, 1))).astype(np.float32)
+        te = _rand_csr(g, U, I, 3, min_n=1)
+        idx3, val3, _, _ = _run_fused(torch_cuda, ctx, ue, ie, None, None, te, [1], K, "3xtf32")
+        exact = np.take_along_axis(oracle.scores(ue, ie, None), idx3.astype(np.int64), 1)
+        eps3 = 1.25 * (3.25 * d + 11) * 2.0 ** -22 * np.linalg.norm(ue, axis=1, keepdims=True) * np.linalg.norm(ie, axis=1).max()
+        assert np.all(np.abs(val3 - exact) <= 0.5 * eps3), d
