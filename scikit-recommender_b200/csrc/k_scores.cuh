@@ -336,6 +336,257 @@ k_topk_scores(const float *__restrict__ scores, int64_t ld, int n_items, int64_t
     topk_row_stream(scores + r * ld, n_items, tb, te, tr_idx, K, out_keys + r * K, keys, &s_cnt);
 }
 
+// ---- one WARP per row, top-K <= 128: the form the common evaluations (K <= 100, run_config.py:16) take -------------
+// ncu on the block-per-row kernel (c1: 6,040 rows of 3,706 scores, 0.50 ms; c2: 8,192 rows of 40,981, 1.34 ms): issue
+// slots 61 % busy, DRAM 2 % -- it is bound by the INSTRUCTIONS of its block-wide bitonic sorts, not by memory.  A first
+// warp-per-row version that kept a sorted best-128 in registers and merged every batch of survivors through a 256-key
+// bitonic network still executed 40,000 warp instructions per 41 K-item row (ncu, 1.03 ms).  Sorting is not needed to
+// stream: only the K-th best matters.  Now a warp owns a row and
+//   * full steps of 1,024 scores arrive through a per-warp ring of four 4 KB bulk copies (cp.async.bulk + mbarrier:
+//     16 KB in flight per warp, no stream data in registers);
+//   * a float4 position costs a NaN-propagating max of four, one compare and one vote when nothing passes; survivors are
+//     appended RAW (score bits, item) to the warp's staging area in shared memory (positions from ballot + popc);
+//   * PRUNE (when the area may overflow, and after 256, 1,024, 4,096, 16,384, 65,536 scores -- a threshold from m scores
+//     lets K / m of what follows through): new entries are fixed up by all lanes (train items -> -inf by binary search in
+//     the row's sorted CSR, evaluator.py:195-200; rank keys), then the K-th largest score is found by a 32-step bit
+//     search over the monotone integer image of the scores (one compare per entry and step, one REDUX per step), the
+//     entries at or above it are compacted to the front and it becomes the threshold.  No sort.  Only when more than 32
+//     entries tie at the cut (constant rows) a 64-step search over the full keys (score, then lower item id) runs;
+//   * at the end of the row the survivors are cut to exactly K by that exact search and sorted once.
+constexpr int KW_WARPS = 8;
+constexpr int KW_STEP = 512;              // scores per step and warp: one 2 KB bulk copy
+constexpr int KW_RING = 2;                // steps in flight per warp: 4 KB (occupancy matters more than depth: the row loop is latency-bound)
+__host__ __device__ constexpr size_t kw_smem(int capq) { return (size_t)KW_WARPS * (KW_RING * KW_STEP * 4 + capq * 32 * 8 + KW_RING * 8) + 16; }
+
+__device__ __forceinline__ float max_nan(float a, float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void kw_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool kw_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// stage[0 .. n_keep) rank keys kept by the last prune, stage[n_keep .. cnt) raw entries.  Afterwards stage[0 .. cnt)
+// holds the survivors' rank keys: every key that can still be among the row's best K (exactly the best K when `exact`).
+template <int CAPQ>
+__device__ __forceinline__ void kw_prune(u64 *stage, int &cnt, int &n_keep, const int32_t *__restrict__ tr, int n_tr, int K, int lane,
+                                         uint32_t lt_mask, u64 &thr_key, float &thr_f, bool exact)
+{
+    __syncwarp();
+    for (int i = n_keep + lane; i < cnt; i += 32) {  // fix-up of the new entries
+        const u64 raw = stage[i];
+        float sc = __uint_as_float((uint32_t)(raw >> 32));
+        const uint32_t j = (uint32_t)raw;
+        if (n_tr > 0 && sorted_contains(tr, n_tr, (int32_t)j)) sc = -__int_as_float(0x7f800000);
+        const u64 key = make_key(sc, j);
+        stage[i] = (key > thr_key) ? key : 0ull;
+    }
+    __syncwarp();
+    uint32_t hi[CAPQ];  // ord(score) of my entries (0: empty / rejected; a valid key has ord >= 0x007fffff > 0)
+    int nv = 0;
+#pragma unroll
+    for (int q = 0; q < CAPQ; ++q) {
+        const int i = q * 32 + lane;
+        hi[q] = (i < cnt) ? (uint32_t)(stage[i] >> 32) : 0u;
+        nv += hi[q] != 0u;
+    }
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    uint32_t T = 1u;        // keep everything valid
+    u64 T64 = 0ull;
+    bool use64 = false;
+    if (nv > K) {
+        T = 0u;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = T | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int q = 0; q < CAPQ; ++q) c += hi[q] >= cand;
+            if (__reduce_add_sync(0xffffffffu, c) >= K) T = cand;
+        }
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < CAPQ; ++q) c += hi[q] >= T;
+        const int n_ge = __reduce_add_sync(0xffffffffu, c);
+        if (exact ? n_ge > K : n_ge > K + 32) {
+            // ties at the cut: the K-th largest full key (score desc, item id asc); 64 steps, rare
+            use64 = true;
+#pragma unroll 1
+            for (int bit = 63; bit >= 0; --bit) {
+                const u64 cand = T64 | (1ull << bit);
+                int c2 = 0;
+#pragma unroll
+                for (int q = 0; q < CAPQ; ++q) {
+                    const int i = q * 32 + lane;
+                    c2 += (i < cnt) && stage[i] >= cand;
+                }
+                if (__reduce_add_sync(0xffffffffu, c2) >= K) T64 = cand;
+            }
+        }
+        // the new threshold: nothing below the K-th best score (or key) can enter the best K any more
+        if (use64) { thr_key = T64 - 1ull; thr_f = key_score(T64); }
+        else { thr_key = ((u64)T << 32) - 1ull; thr_f = unord_f32(T); }
+    }
+    // compaction (stable): survivors to the front
+    int base = 0;
+#pragma unroll
+    for (int q = 0; q < CAPQ; ++q) {
+        const int i = q * 32 + lane;
+        const u64 k = (i < cnt) ? stage[i] : 0ull;
+        const bool keep = use64 ? (k >= T64 && k != 0ull) : (hi[q] >= T && hi[q] != 0u);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();  // all lanes have read position q before anyone overwrites entries (base + ... <= i always)
+        if (keep) stage[base + __popc(bal & lt_mask)] = k;
+        base += __popc(bal);
+    }
+    __syncwarp();
+    cnt = n_keep = base;
+}
+
+template <int CAPQ>
+__global__ void __launch_bounds__(KW_WARPS * 32, CAPQ <= 8 ? 4 : 3)
+k_topk_rows(const float *__restrict__ scores, int64_t ld, int n_items, int64_t n_rows, int64_t row0,
+            const int64_t *__restrict__ tr_indptr, const int32_t *__restrict__ tr_idx, int K, u64 *__restrict__ out_keys, int *err_flag)
+{
+    constexpr int CAP = CAPQ * 32;
+    extern __shared__ __align__(128) unsigned char kw_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *ring = reinterpret_cast<float *>(kw_smem_raw) + (size_t)warp * KW_RING * KW_STEP;
+    u64 *stage = reinterpret_cast<u64 *>(kw_smem_raw + (size_t)KW_WARPS * KW_RING * KW_STEP * 4) + (size_t)warp * CAP;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(kw_smem_raw + (size_t)KW_WARPS * (KW_RING * KW_STEP * 4 + CAP * 8)) + warp * KW_RING;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t r = (int64_t)blockIdx.x * KW_WARPS + warp;
+    if (r >= n_rows) return;  // warps are independent: no block-wide barrier below
+    const float *row = scores + r * ld;
+    int64_t tb = 0, te = 0;
+    if (tr_indptr != nullptr) { tb = __ldg(tr_indptr + row0 + r); te = __ldg(tr_indptr + row0 + r + 1); }
+    const int n_tr = (int)(te - tb);
+    const int32_t *tr = tr_idx + tb;
+    const int a0 = (int)((4u - (unsigned)((reinterpret_cast<uintptr_t>(row) >> 2) & 3u)) & 3u);
+    const float *rowa = row + a0;     // 16-byte aligned
+    const int n_body = n_items - a0;
+    const int n_steps = n_body > 0 ? n_body / KW_STEP : 0;  // full steps
+
+    if (lane == 0) {
+        for (int s = 0; s < KW_RING; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + s)));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < KW_RING && s < n_steps; ++s) kw_bulk_load(ring + s * KW_STEP, rowa + (size_t)s * KW_STEP, KW_STEP * 4, bars + s);
+    }
+    __syncwarp();
+
+    u64 thr_key = 0;   // a key must be strictly larger to matter
+    float thr_f = -__int_as_float(0x7f800000);
+    int cnt = 0, n_keep = 0;  // warp-uniform
+
+    // one score position across the warp
+    auto offer = [&](bool pass, float sc, int j) {
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+            if (pass) stage[cnt + __popc(bal & lt_mask)] = ((u64)__float_as_uint(sc) << 32) | (u64)(uint32_t)j;
+            cnt += __popc(bal);
+        }
+    };
+    // one float4 position: 4 x 32 scores, item ids jj .. jj + 3 per lane
+    auto offer4 = [&](float x0, float x1, float x2, float x3, int jj) {
+        const bool p0 = jj < n_items && !(x0 < thr_f), p1 = jj + 1 < n_items && !(x1 < thr_f);
+        const bool p2 = jj + 2 < n_items && !(x2 < thr_f), p3 = jj + 3 < n_items && !(x3 < thr_f);
+        if (__any_sync(0xffffffffu, p0 | p1 | p2 | p3)) {
+            if (cnt > CAP - 128) kw_prune<CAPQ>(stage, cnt, n_keep, tr, n_tr, K, lane, lt_mask, thr_key, thr_f, false);
+            offer(p0, x0, jj);
+            offer(p1, x1, jj + 1);
+            offer(p2, x2, jj + 2);
+            offer(p3, x3, jj + 3);
+        }
+    };
+    {   // head scores before the first 16-byte boundary
+        const bool have = lane < a0 && lane < n_items;
+        offer(have, have ? __ldg(row + lane) : 0.0f, lane);
+    }
+    int next_prune = 256;
+    for (int st = 0; st < n_steps; ++st) {
+        const int slot = st % KW_RING;
+        const uint32_t parity = (uint32_t)((st / KW_RING) & 1);
+        if (!kw_try_wait(bars + slot, parity)) {
+            const long long t0 = clock64();
+            while (!kw_try_wait(bars + slot, parity)) {
+                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a lost copy must not hang the GPU
+                    if (err_flag != nullptr) atomicExch(err_flag, 21);
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+        }
+        const float4 *buf = reinterpret_cast<const float4 *>(ring + slot * KW_STEP);
+        const int c0 = st * KW_STEP;
+#pragma unroll
+        for (int q = 0; q < KW_STEP / 128; ++q) {
+            const float4 v = buf[q * 32 + lane];
+            const float m = max_nan(max_nan(v.x, v.y), max_nan(v.z, v.w));
+            if (__any_sync(0xffffffffu, !(m < thr_f))) offer4(v.x, v.y, v.z, v.w, a0 + c0 + q * 128 + lane * 4);
+            if (c0 + (q + 1) * 128 >= next_prune && next_prune <= 65536) {
+                if (cnt > n_keep) kw_prune<CAPQ>(stage, cnt, n_keep, tr, n_tr, K, lane, lt_mask, thr_key, thr_f, false);
+                next_prune *= 4;
+            }
+        }
+        __syncwarp();  // every lane has read the slot: it may be refilled
+        if (lane == 0 && st + KW_RING < n_steps)
+            kw_bulk_load(ring + slot * KW_STEP, rowa + (size_t)(st + KW_RING) * KW_STEP, KW_STEP * 4, bars + slot);
+    }
+    // tail: guarded positions read directly
+    for (int c0 = n_steps * KW_STEP; c0 < n_body; c0 += 128) {
+        const int jj = c0 + lane * 4;
+        float x[4];
+        if (jj + 3 < n_body) {
+            const float4 t = ldg_stream_f4(rowa + jj);
+            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = (jj + e < n_body) ? __ldg(rowa + jj + e) : 0.0f;
+        }
+        offer4(x[0], x[1], x[2], x[3], a0 + jj);
+        if (c0 + 128 >= next_prune && next_prune <= 65536) {
+            if (cnt > n_keep) kw_prune<CAPQ>(stage, cnt, n_keep, tr, n_tr, K, lane, lt_mask, thr_key, thr_f, false);
+            next_prune *= 4;
+        }
+    }
+    // exactly the best K, sorted once
+    kw_prune<CAPQ>(stage, cnt, n_keep, tr, n_tr, K, lane, lt_mask, thr_key, thr_f, true);
+    constexpr int PER = CAPQ / 4;  // K <= 64: 64 keys, K <= 128: 128 keys
+    u64 v[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int i = e * 32 + lane;
+        v[e] = (i < cnt) ? stage[i] : 0ull;
+    }
+    warp_bitonic_desc<PER>(v, lane);
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int i = e * 32 + lane;
+        if (i < K) out_keys[r * (int64_t)K + i] = v[e];
+    }
+}
+
 // Rows on the fail list of k_select_cands: exact FP32 scores on the fly, same selection.  A work item is
 // (failed row, one of n_seg item ranges): a handful of failed rows then spreads over the whole GPU instead of
 // occupying one CTA each for the time it takes to walk the catalogue (0.6 ms per row at 92 K items).  The n_seg

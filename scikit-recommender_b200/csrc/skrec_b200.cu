@@ -168,6 +168,25 @@ void free_dev(void *p)
     if (p) cudaFree(p);
 }
 
+// score-matrix rows -> sorted top-K rank keys: one warp per row for top-K <= 128, one block per row above
+void launch_topk_scores(const float *scores, int64_t ld, int n_items, int64_t n_rows, int64_t row0, const int64_t *tr_indptr,
+                               const int32_t *tr_idx, int K, u64 *keys, int *err_flag, cudaStream_t st)
+{
+    if (K <= 128) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_topk_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem(8));
+            cudaFuncSetAttribute(k_topk_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem(16));
+            attr_set = true;
+        }
+        const unsigned g = (unsigned)((n_rows + KW_WARPS - 1) / KW_WARPS);
+        // staging area of 256 entries for K <= 64, 512 for K <= 128 (room for 128 new survivors next to the K kept ones)
+        if (K <= 64) k_topk_rows<8><<<g, KW_WARPS * 32, kw_smem(8), st>>>(scores, ld, n_items, n_rows, row0, tr_indptr, tr_idx, K, keys, err_flag);
+        else k_topk_rows<16><<<g, KW_WARPS * 32, kw_smem(16), st>>>(scores, ld, n_items, n_rows, row0, tr_indptr, tr_idx, K, keys, err_flag);
+    } else
+        k_topk_scores<<<(unsigned)n_rows, K2_THREADS, 0, st>>>(scores, ld, n_items, row0, tr_indptr, tr_idx, K, keys);
+}
+
 int check_metrics(skr_ctx *ctx, const int32_t *metric_ids, int n_metrics, int top_k, MetricIds &m)
 {
     if (!metric_ids || n_metrics < 1 || n_metrics > 8) return fail(ctx, SKR_ERR_INVALID, "n_metrics=%d not in [1,8]", n_metrics);
@@ -855,7 +874,7 @@ int skr_topk_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure(ctx, ctx->keys, (size_t)n_rows * top_k * sizeof(u64));
     if (rc) return rc;
-    k_topk_scores<<<(unsigned)n_rows, K2_THREADS, 0, st>>>(scores_dev, ld, (int)n_items, 0, nullptr, nullptr, top_k, (u64 *)ctx->keys.p);
+    launch_topk_scores(scores_dev, ld, (int)n_items, n_rows, 0, nullptr, nullptr, top_k, (u64 *)ctx->keys.p, ctx->d_err, st);
     const int64_t nk = n_rows * top_k;
     k_unpack_keys<<<(unsigned)((nk + 255) / 256), 256, 0, st>>>((const u64 *)ctx->keys.p, nk, topk_idx_dev, topk_val_dev);
     ctx->launches += 2;
@@ -904,8 +923,8 @@ int skr_eval_scores(skr_ctx *ctx, const float *scores_dev, int64_t n_rows, int64
     cudaStream_t st = (cudaStream_t)stream;
     rc = ensure(ctx, ctx->keys, (size_t)n_rows * top_k * sizeof(u64));
     if (rc) return rc;
-    k_topk_scores<<<(unsigned)n_rows, K2_THREADS, 0, st>>>(scores_dev, ld, (int)n_items, row0, ctx->has_train ? ctx->d_tr_indptr : nullptr,
-                                                          ctx->has_train ? ctx->d_tr_idx : nullptr, top_k, (u64 *)ctx->keys.p);
+    launch_topk_scores(scores_dev, ld, (int)n_items, n_rows, row0, ctx->has_train ? ctx->d_tr_indptr : nullptr, ctx->has_train ? ctx->d_tr_idx : nullptr,
+                       top_k, (u64 *)ctx->keys.p, ctx->d_err, st);
     ctx->launches++;
     SKR_CUDA(ctx, cudaGetLastError());
     return run_metrics(ctx, (const u64 *)ctx->keys.p, nullptr, n_rows, row0, m, top_k, topk_idx_dev, topk_val_dev, per_user_dev, sums_dev, st);
