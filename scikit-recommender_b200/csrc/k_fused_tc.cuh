@@ -233,6 +233,8 @@ struct TcArgs {
     // second attempt of precision "tf32r" (see run_select_metrics): only rows whose retry_cnt[row] == 0 (not settled by
     // the first attempt) collect, with the threshold in `thr`; CTAs whose user tile has no such row exit at once
     const int *retry_cnt;    // [n_rows] or null
+    const int *retry_total;  // number of unsettled rows; below retry_min the retry does not pay (see fused_chunk) and every CTA exits
+    int retry_min;
     // development aid: per-tile clock64 timestamps of one CTA (null = off), [tile][TC_TRACE_SLOTS]
     long long *trace;
     int trace_cta;
@@ -407,6 +409,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     const int64_t row_base = (int64_t)rt * TM;
     if (!SAMPLE && A.retry_cnt != nullptr) {  // kernel argument: the branch is uniform over the grid
         pdl_wait();                           // the flags are the previous kernel's output
+        if (__ldg(A.retry_total) < A.retry_min) return;  // a handful of rows: the per-row exact kernel is cheaper than a tile sweep
         const bool mine = tid < TM && row_base + tid < P.n_rows && __ldg(A.retry_cnt + row_base + tid) == 0;
         if (!__syncthreads_or(mine)) return;  // nothing to redo in this user tile (the usual case)
     }
@@ -898,11 +901,11 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
 // The lo table of the three-pass retry, built only when the first attempt left rows unsettled (*need != 0): the
 // common case costs one block-wide early exit per CTA.
 __global__ void __launch_bounds__(256)
-k_split_lo_if(const int *__restrict__ need, const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, float *__restrict__ lo)
+k_split_lo_if(const int *__restrict__ need, int need_min, const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, float *__restrict__ lo)
 {
     pdl_wait();
     pdl_trigger();
-    if (*need == 0) return;
+    if (*need < need_min) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
 #pragma unroll

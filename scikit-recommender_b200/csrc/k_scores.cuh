@@ -40,26 +40,42 @@ struct RowDot {
     bool vec_ok;
     __device__ __forceinline__ void get4(int j0, int n_items, float (&v)[4]) const
     {
+        // four items at once: four independent FMA chains (each still k ascending, the reference order of the exact
+        // path) with their loads in flight together -- one chain at a time left this kernel waiting on every load
+        // (4 ms to walk one 1M-item row at d = 128)
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float *it[4];
+        bool ok[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int j = j0 + q;
-            float acc = 0.0f;
-            if (j < n_items) {
-                const float *it = V + (int64_t)j * ld_v;
-                int k = 0;
-                if (vec_ok) {
-                    for (; k + 4 <= d; k += 4) {
-                        const float4 x = __ldg(reinterpret_cast<const float4 *>(it + k));
-                        acc = fmaf(u[k], x.x, acc);
-                        acc = fmaf(u[k + 1], x.y, acc);
-                        acc = fmaf(u[k + 2], x.z, acc);
-                        acc = fmaf(u[k + 3], x.w, acc);
-                    }
+            ok[q] = j0 + q < n_items;
+            it[q] = V + (int64_t)(ok[q] ? j0 + q : 0) * ld_v;
+        }
+        int k = 0;
+        if (vec_ok) {
+            for (; k + 4 <= d; k += 4) {
+                float4 x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const float4 *>(it[q] + k));
+                const float u0 = u[k], u1 = u[k + 1], u2 = u[k + 2], u3 = u[k + 3];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[q] = fmaf(u0, x[q].x, acc[q]);
+                    acc[q] = fmaf(u1, x[q].y, acc[q]);
+                    acc[q] = fmaf(u2, x[q].z, acc[q]);
+                    acc[q] = fmaf(u3, x[q].w, acc[q]);
                 }
-                for (; k < d; ++k) acc = fmaf(u[k], __ldg(it + k), acc);
-                if (bias != nullptr) acc += __ldg(bias + j);
             }
-            v[q] = acc;
+        }
+        for (; k < d; ++k) {
+            const float uk = u[k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fmaf(uk, __ldg(it[q] + k), acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (bias != nullptr && ok[q]) acc[q] += __ldg(bias + j0 + q);
+            v[q] = ok[q] ? acc[q] : 0.0f;
         }
     }
 };
@@ -638,7 +654,9 @@ k_row_exact(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_
     }
 }
 
-// n_seg partial lists of every failed row -> its sorted top-K in out_keys[row]
+// n_seg partial lists of every failed row -> its sorted top-K in out_keys[row].  One block per row at a time: the
+// lists (<= 1,024 keys) are sorted by the block bitonic network in shared memory (a 1,024-key network in one warp's
+// registers -- the round-1 version -- took 111 us for a handful of rows).
 template <int PER>
 __global__ void __launch_bounds__(128)
 k_merge_fail(const int32_t *__restrict__ fail_list, const int *__restrict__ fail_count, const u64 *__restrict__ part, int n_seg, int K,
@@ -646,24 +664,18 @@ k_merge_fail(const int32_t *__restrict__ fail_list, const int *__restrict__ fail
 {
     pdl_wait();
     pdl_trigger();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ u64 s_keys[32 * PER];
     const int n_fail = min(*fail_count, max_seg_rows);
     const int n = n_seg * K;
-    for (int i = blockIdx.x * 4 + warp; i < n_fail; i += gridDim.x * 4) {
+    const int n_sort = next_pow2(n < 2 ? 2 : n);
+    for (int i = blockIdx.x; i < n_fail; i += gridDim.x) {
         const u64 *src = part + (int64_t)i * n;
-        u64 v[PER];
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int j = e * 32 + lane;
-            v[e] = (j < n) ? src[j] : 0ull;
-        }
-        warp_bitonic_desc<PER>(v, lane);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_sort; j += 128) s_keys[j] = (j < n) ? src[j] : 0ull;
+        __syncthreads();
+        block_bitonic_desc(s_keys, n_sort, threadIdx.x, 128);
         u64 *dst = out_keys + (int64_t)fail_list[i] * K;
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int j = e * 32 + lane;
-            if (j < K) dst[j] = v[e];
-        }
+        for (int j = threadIdx.x; j < K; j += 128) dst[j] = s_keys[j];
     }
 }
 

@@ -123,7 +123,7 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                const int64_t *__restrict__ te_indptr, const int32_t *__restrict__ te_idx, MetricIds mids, const double *__restrict__ disc,
                const float *__restrict__ idcg, float *__restrict__ per_user, int32_t *__restrict__ topk_idx_out,
                float *__restrict__ topk_val_out, double *__restrict__ acc_out, RescoreArgs R, const float *__restrict__ add_back,
-               int retry_only)
+               int retry_only, const int *__restrict__ retry_total, int retry_min)
 {
     pdl_wait();
     pdl_trigger();
@@ -151,7 +151,13 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
     for (int64_t row = (int64_t)blockIdx.x * SEL_WARPS + warp; row < n_rows; row += n_warps) {
         __syncwarp();
         // second attempt (RESCORE): only the rows the first one left unsettled (rs_cnt == 0) are looked at
-        if (RESCORE && retry_only && R.rs_cnt[row] != 0) continue;
+        if (RESCORE && retry_only) {
+            if (R.rs_cnt[row] != 0) continue;
+            if (*retry_total < retry_min) {  // no retry pass ran (too few rows to pay for a tile sweep): straight to the exact kernel
+                if (lane == 0) fail_list[atomicAdd(fail_count, 1)] = (int32_t)row;
+                continue;
+            }
+        }
         // ---- 1. sub-list sizes (n_sub <= 32: one per lane), exclusive scan, gather -----------------
         const int c_mine = (lane < n_sub) ? (int)__ldg(cand_cnt + row * n_sub + lane) : 0;
         int incl = c_mine;

@@ -80,6 +80,7 @@ struct skr_ctx {
     int64_t opt_rank = 0;
     int64_t opt_dbg = 0;
     int64_t opt_chunk_rows = 0;      // rows per chunk of the fused pipeline (0 = default)
+    int64_t opt_retry_min = -1;      // tf32r: unsettled rows from which the three-pass retry runs (-1 = cost model)
     int64_t opt_exact_seg_rows = -1;  // development: how many failed rows are cut in segments (-1 = default)
     bool debug_sync = false;  // SKR_DEBUG_SYNC=1: synchronise and check after every kernel, naming the one that failed
     int64_t opt_trace_cta = -1;  // >= 0: record the tile timeline of that CTA of the main pass (development aid)
@@ -282,7 +283,9 @@ struct ExactArgs {
 int run_row_exact(skr_ctx *ctx, const ExactArgs &E, int32_t *fail_list, int *fail_count, int64_t n_rows, int64_t row0, int K, u64 *keys_out,
                   cudaStream_t st)
 {
-    int n_seg = std::max(1, std::min(16, 1024 / K));
+    // as many item segments per row as the merge takes (4,096 keys): a segment is walked by ONE block, and a walk is
+    // latency-bound (3.6 ms for a tenth of a 1M-item catalogue at d = 128)
+    int n_seg = std::max(1, std::min(64, 4096 / K));
     int seg_items = (int)(((int64_t)E.n_items + n_seg - 1) / n_seg);
     seg_items = ((seg_items + K2_CHUNK - 1) / K2_CHUNK) * K2_CHUNK;  // ranges start on chunk boundaries (vector loads)
     n_seg = (E.n_items + seg_items - 1) / seg_items;
@@ -299,7 +302,9 @@ int run_row_exact(skr_ctx *ctx, const ExactArgs &E, int32_t *fail_list, int *fai
     else if (n <= 128) SKR_CUDA(ctx, launch_pdl(k_merge_fail<4>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
     else if (n <= 256) SKR_CUDA(ctx, launch_pdl(k_merge_fail<8>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
     else if (n <= 512) SKR_CUDA(ctx, launch_pdl(k_merge_fail<16>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
-    else SKR_CUDA(ctx, launch_pdl(k_merge_fail<32>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
+    else if (n <= 1024) SKR_CUDA(ctx, launch_pdl(k_merge_fail<32>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
+    else if (n <= 2048) SKR_CUDA(ctx, launch_pdl(k_merge_fail<64>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
+    else SKR_CUDA(ctx, launch_pdl(k_merge_fail<128>, dim3((unsigned)(g)), dim3((unsigned)(128)), (size_t)(0), st, fail_list, fail_count, (const u64 *)ctx->part.p, n_seg, K, (int)max_fail, keys_out));
     ctx->launches += 2;
     SKR_AFTER(ctx, st, "k_merge_fail");
     SKR_CUDA(ctx, cudaGetLastError());
@@ -318,6 +323,7 @@ struct RetryPlan {
     const float *thr3;                    // [n_rows] threshold the retry collects with
     int32_t *fail_list2;
     int *fail_count2;
+    int retry_min;                        // fewest unsettled rows for which the tile-wise retry beats the per-row exact kernel
 };
 
 int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt, int n_sub, int cap, int64_t n_rows, int64_t row0,
@@ -326,10 +332,12 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
                        const RetryPlan &RP, cudaStream_t st)
 {
     const bool rescore = RA.U != nullptr;
+    const int *fail_count_first = fail_count;
     // kernel instantiations: the sort capacity is 64 / 128 keys (K <= 64 / 128); re-scoring doubles it (error band) and
     // splits the job in two kernels: candidates -> exact keys of the survivors, then sort + metrics
     typedef void (*SelKernel)(const uint2 *, const uint32_t *, int, int, int, int, int64_t, int64_t, u64 *, int32_t *, int *, const int64_t *,
-                              const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs, const float *, int);
+                              const int32_t *, MetricIds, const double *, const float *, float *, int32_t *, float *, double *, RescoreArgs, const float *, int,
+                              const int *, int);
     typedef void (*SortKernel)(const u64 *, const int *, int, int64_t, int64_t, u64 *, const int64_t *, const int32_t *, MetricIds, const double *,
                                const float *, float *, int32_t *, float *, double *);
     const int per = rescore ? (K <= 64 ? 4 : 8) : (K <= 64 ? 2 : 4);
@@ -346,14 +354,14 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     const int g_sel = (int)std::min<int64_t>((n_rows + SEL_WARPS - 1) / SEL_WARPS, 8 * ctx->n_sm);
     if (keys_only != nullptr) {  // per-shard lists: sorted keys out, no metrics
         SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, fail_list, fail_count, nullptr, nullptr, m,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back, 0));
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back, 0, (const int *)nullptr, 0));
         if (rescore && RP.collect != nullptr) {
             if ((rc = (*RP.collect)())) return rc;
             RescoreArgs R2 = RA;
             R2.eps2 = RP.eps2_3;
             R2.thr_c = RP.thr3;
             SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, keys_only, RP.fail_list2, RP.fail_count2,
-                                                  nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R2, nullptr, 1));
+                                                  nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R2, nullptr, 1, (const int *)fail_count_first, RP.retry_min));
             ctx->launches += 3;
             fail_list = RP.fail_list2;
             fail_count = RP.fail_count2;
@@ -400,14 +408,14 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     }
     if (rescore) {
         SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, nullptr, nullptr, m, nullptr,
-                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back, 0));
+                                              nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back, 0, (const int *)nullptr, 0));
         if (RP.collect != nullptr) {
             if ((rc = (*RP.collect)())) return rc;
             RescoreArgs R2 = RA;
             R2.eps2 = RP.eps2_3;
             R2.thr_c = RP.thr3;
             SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, RP.fail_list2, RP.fail_count2,
-                                                  nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R2, nullptr, 1));
+                                                  nullptr, nullptr, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, R2, nullptr, 1, (const int *)fail_count_first, RP.retry_min));
             ctx->launches += 3;
             fail_list = RP.fail_list2;
             fail_count = RP.fail_count2;
@@ -417,7 +425,7 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
         ctx->launches++;
     } else {
         SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(dyn_sel), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
-                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA, add_back, 0));
+                                                    ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val, acc, RA, add_back, 0, (const int *)nullptr, 0));
     }
     SKR_AFTER(ctx, st, "k_select_cands / k_sort_metrics");
     if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys, st))) return rc;
@@ -506,6 +514,13 @@ static WorkPlan plan_work(int n_sm, int64_t opt_chunks, int n_rt, int n_ct, int 
         if (s_lo + 1 > smax) break;
         WorkPlan w = make_work(n_rt, n_ct, s_lo, n_plus, n_sm, overhead);
         if (w.makespan < best.makespan) best = w;
+    }
+    // Many user tiles (>= the SM count): every split fills the GPU and the makespans differ by a per cent.  More chunks mean
+    // more and shorter candidate sub-lists per row, which the selection stage reads faster (measured at c4, 1,024 user
+    // tiles: 8 chunks instead of 1 take k_select_cands from 5.6 to 2.7 ms and the main pass from 45.4 to 44.1 ms).
+    if (best.slots < smax) {
+        WorkPlan w = make_work(n_rt, n_ct, smax, 0, n_sm, overhead);
+        if (w.makespan * 100 <= best.makespan * 103) best = w;
     }
     return best;
 }
@@ -667,6 +682,7 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "sample_tiles")) { ctx->opt_sample_tiles = value; return SKR_OK; }
     if (!strcmp(name, "rank")) { ctx->opt_rank = value; return SKR_OK; }
     if (!strcmp(name, "dbg")) { ctx->opt_dbg = value; return SKR_OK; }
+    if (!strcmp(name, "retry_min")) { ctx->opt_retry_min = value; return SKR_OK; }
     if (!strcmp(name, "chunk_rows")) { ctx->opt_chunk_rows = value < 0 ? 0 : value; return SKR_OK; }
     if (!strcmp(name, "exact_seg_rows")) { ctx->opt_exact_seg_rows = value; return SKR_OK; }
     if (!strcmp(name, "trace_cta")) { ctx->opt_trace_cta = value; return SKR_OK; }
@@ -1173,6 +1189,8 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         A.trace_cta = -1;
         A.trace_tiles = 0;
         A.retry_cnt = nullptr;
+        A.retry_total = nullptr;
+        A.retry_min = 0;
         const bool presub = (passes == 1);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
         A.thr_hi = presub ? A.thr + n_rows : nullptr;
         A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
@@ -1214,15 +1232,25 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         const ExactArgs E = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (int)n_items, tp, ti};
         RescoreArgs RA = {nullptr, 0, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
         if (rescore) RA = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (const float *)ctx->thr.p, (const float *)ctx->eps2.p, nullptr, nullptr};
+        // The retry sweeps the item tiles of a user tile's work items in three passes on ONE SM each: a latency of
+        // max_tiles x ~0.4 us per k-block and pass (c2: ~80 us, c4: 13 ms) however few rows it serves.  The per-row exact
+        // kernel spreads a row over the GPU and costs ~10 us + 0.14 us per 10^6 item-table floats per row (measured: 11 us
+        // at c2, ~28 us at c4).  The retry runs only when more rows than the ratio of the two are unsettled.
+        const double sweep_us = (double)wc->max_tiles * (0.25 + 0.37 * nkb);
+        const double exact_row_us = 10.0 + 1.4e-7 * (double)n_items * d;
+        const int retry_min = ctx->opt_retry_min >= 0 ? (int)std::min<int64_t>(ctx->opt_retry_min, 1 << 30)
+                                                      : (int)std::max(4.0, std::min(1.0e9, sweep_us / exact_row_us));
         // the retry of unsettled rows (tf32r only): lo table on demand, then the three-pass kernel over the same work list
         const std::function<int()> retry_collect = [&]() -> int {
-            SKR_CUDA(ctx, launch_pdl(k_split_lo_if, dim3((unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm)), dim3(256u), (size_t)0, st, (const int *)fail_count, item_vecs_dev, ld_i, n_items, d,
-                                     d_pad, (float *)ctx->blo.p));
+            SKR_CUDA(ctx, launch_pdl(k_split_lo_if, dim3((unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm)), dim3(256u), (size_t)0, st, (const int *)fail_count, retry_min, item_vecs_dev, ld_i,
+                                     n_items, d, d_pad, (float *)ctx->blo.p));
             TcArgs A2 = A;
             A2.thr = thr3;
             A2.thr_hi = nullptr;
             A2.thr_lo = nullptr;
             A2.retry_cnt = (const int *)ctx->rs_cnt.p;
+            A2.retry_total = (const int *)fail_count;
+            A2.retry_min = retry_min;
             A2.trace = nullptr;
             A2.trace_cta = -1;
             int rc2 = launch_tc(ctx, nkb, 3, TC_MODE_COLLECT, grid_tc, st, mhi, mlo, A2, P);
@@ -1230,7 +1258,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
             SKR_AFTER(ctx, st, "k_fused_tc COLLECT (retry)");
             return SKR_OK;
         };
-        const RetryPlan RP = {rescore ? &retry_collect : nullptr, eps2_3, thr3, fail_list2, fail_count2};
+        const RetryPlan RP = {rescore ? &retry_collect : nullptr, eps2_3, thr3, fail_list2, fail_count2, retry_min};
         rc = run_select_metrics(ctx, A.cand, A.cand_cnt, n_sub, cap, n_rows, row0, m, K, E, fail_list, fail_count, topk_idx_dev, topk_val_dev,
                                 per_user_dev, sums_dev, keys_only, RA, presub ? A.thr : nullptr, RP, st);
         if (rc || keys_only == nullptr) return rc;

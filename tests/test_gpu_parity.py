@@ -999,19 +999,27 @@ def test_tf32r_on_heavy_tailed_tables_equals_fp32_and_retries_instead_of_walking
     b = None if dta["bias"] is None else torch.from_numpy(dta["bias"]).cuda()
     metric = [1, 2, 3, 4, 5]
     out = {}
-    for prec in ("tf32r", "fp32"):
+    c.set_option("retry_min", 1)  # always retry (the cost model would hand a handful of rows straight to the exact kernel)
+    for prec in ("tf32r", "fp32", "tf32r_model"):
+        if prec == "tf32r_model":
+            c.set_option("retry_min", -1)
+            prec = "tf32r"
+            key = "tf32r_model"
+        else:
+            key = prec
         idx = torch.empty((U, K), dtype=torch.int32, device="cuda")
         val = torch.empty((U, K), dtype=torch.float32, device="cuda")
         per = torch.empty((U, len(metric) * K), dtype=torch.float32, device="cuda")
         sums = torch.zeros(len(metric) * K, dtype=torch.float64, device="cuda")
         c.eval_fused(ue, ie, b, 0, metric, K, precision=prec, topk_idx=idx, topk_val=val, per_user=per, sums=sums)
         torch.cuda.synchronize()
-        out[prec] = (idx.cpu().numpy(), val.cpu().numpy(), per.cpu().numpy(), sums.cpu().numpy())
-        if prec == "tf32r":
+        out[key] = (idx.cpu().numpy(), val.cpu().numpy(), per.cpu().numpy(), sums.cpu().numpy())
+        if key == "tf32r":
             st = c.fused_stats()
-    a, f = out["tf32r"], out["fp32"]
+    a, f, am = out["tf32r"], out["fp32"], out["tf32r_model"]
     assert np.array_equal(a[0], f[0]) and np.array_equal(a[1], f[1]) and np.array_equal(a[2], f[2])
-    assert np.max(np.abs(a[3] - f[3])) < 1e-9
+    assert np.array_equal(am[0], f[0]) and np.array_equal(am[1], f[1]) and np.array_equal(am[2], f[2])
+    assert np.max(np.abs(a[3] - f[3])) < 1e-9 and np.max(np.abs(am[3] - f[3])) < 1e-9
     _check_fused(*a, dta["user_emb"], dta["item_emb"], dta["bias"], (dta["train_indptr"], dta["train_indices"]),
                  (dta["test_indptr"], dta["test_indices"]), metric, K)
     # the retry settles (nearly) everything the first attempt could not: the per-row exact kernel is the exception

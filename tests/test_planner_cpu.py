@@ -41,7 +41,9 @@ def test_work_list_partitions_every_user_tile(n_sm, overhead):
         total = int(n.sum()) + overhead * items.shape[0]
         assert n.sum() == n_rt * n_ct and info["makespan"] >= -(-total // n_sm)
         single = -(-n_rt // n_sm) * (n_ct + overhead)
-        assert info["makespan"] <= single
+        # (up to 3 % may be given away for more, shorter candidate sub-lists when there are many user tiles: the selection
+        # stage gains more than the main pass loses)
+        assert info["makespan"] * 100 <= single * 103
 
 
 def test_c2_plan_fills_whole_waves():

@@ -11,15 +11,20 @@ from skrec_b200 import _native, synth  # noqa: E402
 prec = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfgname = sys.argv[3] if len(sys.argv) > 3 else "c2"
-if cfgname == "c4":  # one GPU's share of the 8-way user sharding, like bench.py --config c4
-    import bench  # noqa: E402
-    cfg = bench.rank_config("c4")
-    cfg["item_seed"] = cfg["seed"] + 7
-    d = synth.make(device="cuda", **cfg)
+if cfgname in ("c4", "c5"):  # one row chunk (131,072 users) of the large configs against the full catalogue, generated on the GPU
+    cfg = dict(synth.CONFIGS[cfgname])
+    f = 131072.0 / cfg["users"]
+    cfg.update(users=131072, nnz_train=int(cfg["nnz_train"] * f), nnz_test=int(cfg["nnz_test"] * f))
+    if cfgname == "c5":
+        cfg["items"] = cfg["items"] // 8  # one rank's item shard of the 8-way item sharding
+    d = synth.make_large(device="cuda", item_seed=cfg["seed"] + 7, **cfg)
+    d["user_emb"], d["item_emb"] = d["user_emb"].cpu().numpy(), d["item_emb"].cpu().numpy()
+    d["bias"] = None if d["bias"] is None else d["bias"].cpu().numpy()
 else:
     d = synth.make_config(cfgname, device="cuda")
     cfg = d["config"]
 ctx = _native.Context(0)
+ctx.set_option("chunks", int(os.environ.get("SKR_CHUNKS", "0")))  # item-range chunks per user tile (0 = planner)
 ctx.set_train_csr(d["train_indptr"], d["train_indices"], d["items"])
 ctx.set_test_csr(d["test_indptr"], d["test_indices"], d["items"])
 ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"]).cuda()
