@@ -161,8 +161,8 @@ int skr_colsum_f32_seq(skr_ctx *ctx, const float *per_user_dev, int64_t n_rows, 
 /* Number of kernels this library has launched on `ctx` since creation (bench.py's gpu_launches). */
 int64_t skr_launch_count(const skr_ctx *ctx);
 
-/* Name of the scoring kernel the last skr_eval_fused* call on ctx used: "tcgen05_3xtf32",
- * "tcgen05_1xtf32" or "simt_fp32". */
+/* Name of the scoring kernel the last skr_eval_fused* call on ctx used: "tcgen05_3xtf32", "tcgen05_tf32r",
+ * "tcgen05_1xtf32", "simt_fp32" or "simt_fp32_blocks" (top_k > 128: score blocks + the score-matrix kernels). */
 const char *skr_last_fused_kernel(const skr_ctx *ctx);
 
 /* Device time, in milliseconds, of the scoring kernel launched by a recent skr_eval_fused* call on
@@ -171,9 +171,10 @@ const char *skr_last_fused_kernel(const skr_ctx *ctx);
 int skr_fused_kernel_ms(skr_ctx *ctx, int back, float *ms_out);
 /* Same for the sampled threshold pre-pass that precedes the main scoring kernel (0 for the FP32 path). */
 int skr_fused_prepass_ms(skr_ctx *ctx, int back, float *ms_out);
-/* Plan and outcome of the last tcgen05 skr_eval_fused* call: out[0..7) = sample tiles, sample stride,
- * threshold rank r, sub-list capacity, item chunks, TMA stages, rows re-done by the exact kernel.
- * Synchronises the device. */
+/* Plan and outcome of the last tcgen05 skr_eval_fused* call (its last row chunk): out[0..7) = sample tiles, sample
+ * stride, threshold rank r, sub-list capacity, item chunks, TMA stages, rows re-done by the exact kernel; with n_out >= 8
+ * out[7] = scoring launches timed since the last "event_ring" option; with n_out >= 9 out[8] = rows the single-pass
+ * attempt of tf32r left unsettled (retried in three passes or handed to the exact kernel).  Synchronises the device. */
 int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out);
 /* Host only -- no CUDA call, usable without a GPU: the work list the tcgen05 main pass runs for n_user_tiles x
  * n_item_tiles tiles (128 users x 128 items each) on n_sm SMs.  A work item is (user tile, first item tile, number of
@@ -192,8 +193,29 @@ int skr_fused_trace(skr_ctx *ctx, int64_t *out, int64_t n_out);
 /* Tunables: "chunks" (item-range chunks per user tile of the fused path, 0 = automatic), "stages"
  * (ignored: the ring depth is fixed by the kernel instantiation), "sample_tiles" / "rank" (pre-pass size and threshold rank, 0 =
  * automatic), "event_ring" (see skr_fused_kernel_ms), "trace_cta"
- * (see skr_fused_trace; -1 = off), "dbg" (timing ablations, results invalid). */
+ * (see skr_fused_trace; -1 = off), "dbg" (timing ablations, results invalid), "chunk_rows" (rows per internal chunk of the
+ * fused pipeline, 0 = 131,072), "retry_min" (tf32r: unsettled rows from which the three-pass retry runs, -1 = cost model). */
 int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
+
+/* ---- one-shot all-reduce of the metric sums over NVLink peer memory ------------------------------------------------
+ * User-sharded evaluation exchanges n_metrics * top_k + 1 doubles per evaluate; the reference has no
+ * counterpart (its mean runs over one process's users, evaluator.py:206-208).  One process per GPU of ONE node:
+ *   skr_comm_create   allocates this rank's inbox on `device`;
+ *   skr_comm_handle   -> 64 bytes (a cudaIpcMemHandle_t) to hand to the other ranks by any host channel
+ *                        (torch.distributed all_gather_object in the Python host);
+ *   skr_comm_connect  maps the peers' inboxes (handles: world x 64 bytes in rank order);
+ *   skr_comm_allreduce in-place SUM over the ranks of vec_dev[0 .. n), n <= 4096, asynchronous on `stream`: one kernel
+ *                        that writes the vector into every peer's inbox, publishes a flag, waits (bounded, ~3 s) for the
+ *                        peers' flags and adds the vectors in rank order -- every rank ends with identical bits;
+ *   skr_comm_status   0 unless a rank failed to arrive inside the time limit in some earlier call. */
+typedef struct skr_comm skr_comm;
+int skr_comm_create(int device, int rank, int world, skr_comm **out);
+int skr_comm_handle(skr_comm *comm, void *handle_out64);
+int skr_comm_connect(skr_comm *comm, const void *handles);
+int skr_comm_allreduce(skr_comm *comm, double *vec_dev, int n, void *stream);
+int skr_comm_status(skr_comm *comm);
+const char *skr_comm_last_error(const skr_comm *comm);
+int skr_comm_destroy(skr_comm *comm);
 
 #ifdef __cplusplus
 }

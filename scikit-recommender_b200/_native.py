@@ -19,7 +19,8 @@ SYMBOLS = (
     "skr_abi_version", "skr_ctx_create", "skr_ctx_destroy", "skr_last_error", "skr_set_train_csr",
     "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
     "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace", "skr_topk_fused", "skr_eval_merged_topk", "skr_topk_scores", "skr_topk_scores_host", "skr_colsum_rows",
-    "skr_plan_work_host",
+    "skr_plan_work_host", "skr_comm_create", "skr_comm_handle", "skr_comm_connect", "skr_comm_allreduce", "skr_comm_status",
+    "skr_comm_last_error", "skr_comm_destroy",
 )
 
 _lib = None
@@ -74,6 +75,14 @@ def lib():
     L.skr_fused_trace.argtypes = [_vp, ctypes.POINTER(_i64), _i64]
     L.skr_plan_work_host.argtypes = [_int, _int, _int, _int, _int, _vp, _i64, ctypes.POINTER(_i64)]
     L.skr_plan_work_host.restype = _i64
+    L.skr_comm_create.argtypes = [_int, _int, _int, ctypes.POINTER(_vp)]
+    L.skr_comm_handle.argtypes = [_vp, _vp]
+    L.skr_comm_connect.argtypes = [_vp, _vp]
+    L.skr_comm_allreduce.argtypes = [_vp, _vp, _int, _vp]
+    L.skr_comm_status.argtypes = [_vp]
+    L.skr_comm_last_error.argtypes = [_vp]
+    L.skr_comm_last_error.restype = ctypes.c_char_p
+    L.skr_comm_destroy.argtypes = [_vp]
     for name in SYMBOLS:
         getattr(L, name)
     if L.skr_abi_version() != 1:
@@ -281,6 +290,52 @@ class Context(object):
                                                 int(m.size), int(top_k), PREC[precision], _np_ptr(idx), _np_ptr(pu),
                                                 _np_ptr(sums), None))
         return pu, idx, sums
+
+
+class Comm(object):
+    """One-shot all-reduce over NVLink peer memory (skr_comm_* of the C ABI): one per (device, process group)."""
+    MAX_N = 4096
+
+    def __init__(self, device, rank, world):
+        self._L = lib()
+        h = _vp()
+        rc = self._L.skr_comm_create(int(device), int(rank), int(world), ctypes.byref(h))
+        if rc != SKR_OK:
+            raise NativeError(rc, (self._L.skr_last_error(None) or b"").decode())
+        self._h, self.rank, self.world = h, int(rank), int(world)
+
+    def _check(self, rc):
+        if rc != SKR_OK:
+            raise NativeError(rc, (self._L.skr_comm_last_error(self._h) or b"").decode())
+
+    def handle(self):
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._L.skr_comm_handle(self._h, ctypes.cast(buf, _vp)))
+        return buf.raw
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        self._check(self._L.skr_comm_connect(self._h, ctypes.cast(ctypes.create_string_buffer(blob, len(blob)), _vp)))
+
+    def allreduce(self, vec, stream=None):
+        """in-place SUM over the ranks of a float64 CUDA vector (<= 4096 elements), asynchronous on the stream"""
+        assert vec.is_cuda and vec.is_contiguous() and vec.element_size() == 8 and vec.numel() <= self.MAX_N
+        self._check(self._L.skr_comm_allreduce(self._h, _dev_ptr(vec), int(vec.numel()), _stream_ptr(stream)))
+
+    def status(self):
+        self._check(self._L.skr_comm_status(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.skr_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _stream_ptr(stream):

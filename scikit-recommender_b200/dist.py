@@ -31,9 +31,59 @@ def shard_range(n, rank, world):
     return lo, hi
 
 
-def allreduce_sums(sums, group=None):
-    """In-place SUM all-reduce of the float64 [n_metrics*max_top + 1] vector (sums | user count)."""
+_comms = {}  # (group id, device index) -> _native.Comm, or False when the one-shot path is not available there
+
+
+def nvlink_comm(device, group=None):
+    """The one-shot NVLink all-reduce communicator of (device, group), set up on first use: every rank exports its inbox
+    with cudaIpc, the 64-byte handles travel through `all_gather_object`, every rank maps its peers' inboxes.  COLLECTIVE
+    on first use.  -> _native.Comm, or None when the group is not NCCL, spans more than 16 ranks, or the peers' memory
+    cannot be mapped (different nodes, no peer access) -- the caller then uses `torch.distributed.all_reduce`."""
+    import os
     import torch.distributed as td
+    key = (id(group) if group is not None else 0, int(device))
+    c = _comms.get(key)
+    if c is not None:
+        return c or None
+    c = False
+    rank, world = td.get_rank(group), td.get_world_size(group)
+    usable = td.get_backend(group) == "nccl" and 1 < world <= 16 and os.environ.get("SKR_NVLINK_ALLREDUCE", "1") != "0"
+    if usable:
+        from . import _native
+        comm, handle = None, b""
+        try:
+            comm = _native.Comm(device, rank, world)
+            handle = comm.handle()
+        except _native.NativeError:
+            comm = None
+        handles = [None] * world
+        td.all_gather_object(handles, handle, group=group)
+        ok = comm is not None and all(isinstance(h, (bytes, bytearray)) and len(h) == 64 for h in handles)
+        if ok:
+            try:
+                comm.connect([bytes(h) for h in handles])
+            except _native.NativeError:
+                ok = False
+        flags = [None] * world
+        td.all_gather_object(flags, bool(ok), group=group)  # all or nobody: a mixed choice would deadlock
+        if all(flags):
+            c = comm
+        elif comm is not None:
+            comm.close()
+    _comms[key] = c
+    return c or None
+
+
+def allreduce_sums(sums, group=None):
+    """In-place SUM all-reduce of the float64 [n_metrics*max_top + 1] vector (sums | user count): on CUDA tensors of
+    an NCCL group inside one node, one kernel over NVLink peer memory (`nvlink_comm`), ranks added in rank order --
+    identical bits on every rank; otherwise `torch.distributed.all_reduce` (NCCL across nodes, gloo in the CPU tests)."""
+    import torch.distributed as td
+    if sums.is_cuda and sums.numel() <= 4096:
+        comm = nvlink_comm(sums.device.index, group)
+        if comm is not None:
+            comm.allreduce(sums)
+            return sums
     td.all_reduce(sums, op=td.ReduceOp.SUM, group=group)
     return sums
 

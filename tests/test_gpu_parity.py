@@ -531,8 +531,24 @@ def _items_worker(rank, world, port, out_path):
                                                      - np.array(list(rep.values()), np.float32))) == 0.0
         out[shard] = np.array(list(rep.values()), np.float32)
         out[shard + "_path"] = ev.last_stats["path"]
+    # one-shot NVLink all-reduce against NCCL: same bits (two ranks: a + b either way), repeated calls (parity, sequence)
+    from skrec_b200 import dist
+    comm = dist.nvlink_comm(rank, None)
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    nv_ok = comm is not None
+    worst = 0.0
+    if nv_ok:
+        for it in range(50):
+            v = torch.randn(501, generator=g, device="cuda", dtype=torch.float64)
+            a, b = v.clone(), v.clone()
+            comm.allreduce(a)
+            td.all_reduce(b)
+            if world == 2:
+                assert torch.equal(a, b), it
+            worst = max(worst, float((a - b).abs().max()))
+        comm.status()
     if rank == 0:
-        np.savez(out_path, users=out["users"], items=out["items"], path=out["items_path"])
+        np.savez(out_path, users=out["users"], items=out["items"], path=out["items_path"], nvlink=nv_ok, nvlink_err=worst)
     td.destroy_process_group()
 
 
@@ -550,6 +566,7 @@ def test_item_sharded_evaluator_two_gpus_nccl(torch_cuda, tmp_path):
     out = str(tmp_path / "rep.npz")
     mp.spawn(_items_worker, args=(world, port, out), nprocs=world, join=True)
     got = np.load(out)
+    assert bool(got["nvlink"]) and float(got["nvlink_err"]) < 1e-12  # GPUs of one box: the one-shot path must come up
     assert str(got["path"]).startswith("items:")  # 6,000 / world item rows per shard: below 3,072 the exact FP32 kernel takes them
     assert np.max(np.abs(got["users"] - got["items"])) <= 1e-7
     data = synth.make(users=1500, items=6000, d=64, nnz_train=60000, nnz_test=12000, seed=11, bias=True)
