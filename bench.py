@@ -335,11 +335,7 @@ def measure(args, name, scaling, steps, warmup, e2e_cap, dev, rank, world, local
     torch.cuda.synchronize()
     # short steps: keep the GPU busy for about a second so the clocks ramp (same count on every rank: each step
     # holds a collective).  Reported separately; --warmup is honoured as given.
-    t_probe = time.time()
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    per = (time.time() - t_probe) / 3
+    per = (time.time() - t_w0) / max(warmup, 3)
     extra = torch.tensor([int(min(3000, max(0.0, (1.0 - (time.time() - t_w0)) / max(per, 1e-5))))], dtype=torch.int64, device=dev)
     if world > 1:
         td.broadcast(extra, 0)
@@ -367,7 +363,7 @@ def measure(args, name, scaling, steps, warmup, e2e_cap, dev, rank, world, local
     torch.cuda.synchronize()
     launches = (ctx.launch_count - launches0) if ctx is not None else 0
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    res = dict(prob=prob, evaluator=evaluator, U=U, K=K, M=M, I=prob.I, d=prob.d, prep_ms=prep_ms, n_ramp=n_ramp + 3,
+    res = dict(prob=prob, evaluator=evaluator, U=U, K=K, M=M, I=prob.I, d=prob.d, prep_ms=prep_ms, n_ramp=n_ramp,
                path=evaluator.last_stats.get("path"), gen_s=prob.gen_s, names=list(evaluator.metrics_list))
     fused = ctx is not None and not predict_path and ctx.last_fused_kernel != "none"
     if fused:
