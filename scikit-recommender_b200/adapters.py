@@ -24,11 +24,22 @@ transform of it per user, which leaves every rank list and therefore every metri
 | MultVAE, CDAE                                        | h(x_u).W^T + c       (MultVAE.py:138-141)            | decoder_layer(H, W, c) |
 | CML                                                  | -||u - i||           (CML.py:152)                    | neg_euclidean(U, I)  (monotone: 2u.i - ||i||^2) |
 | Pop                                                  | popularity count     (Pop.py:41-44)                  | item_scores(counts) |
-| TransRec                                             | -||u + g + last - i|| + b_i (TransRec.py:86-93)      | none: the square root next to a per-item bias is not a monotone image of a dot product; use `predict` (score-block path) |
+| TransRec                                             | -||u + g + last - i|| + b_i (TransRec.py:86-93)      | transrec(U, g, I, b, last_items): neg_l2_plus_bias on the translated queries |
+| SGAT                                                 | -||head + u - i|| + b_i     (SGAT.py:300)            | neg_l2_plus_bias(head + u, I, b) |
+
+`neg_l2_plus_bias` is not a contraction: the square root next to a per-item bias is not a monotone image of a dot
+product.  The scorer carries `score_fn = "neg_l2"`; the evaluator then runs the FP32 tile kernels with a distance
+inner loop (sum of (q_k - i_k)^2, k ascending, -sqrt in the epilogue, + bias) -- still fused, nothing is materialised.
+
+Activations: "monotone final activation dropped" holds for strictly increasing ones (linear, leaky_relu, tanh, sigmoid
+up to float saturation).  GRU4Rec's `final_act` may be relu (GRU4Rec.py:274-276), which is only weakly monotone: all
+negative scores collapse to 0 and tie, so a user with fewer than K positive scores gets a different tail of the rank
+list than the reference (which orders the tied zeros by its heap).  For relu keep the model's own `predict`.
 """
 import numpy as np
 
-__all__ = ["EmbeddingScorer", "dot_product", "two_tower_sum", "summed_query", "decoder_layer", "neg_euclidean", "item_scores"]
+__all__ = ["EmbeddingScorer", "dot_product", "two_tower_sum", "summed_query", "decoder_layer", "neg_euclidean", "item_scores",
+           "neg_l2_plus_bias", "transrec"]
 
 
 def _t(x):
@@ -55,6 +66,7 @@ class EmbeddingScorer(object):
             assert self.bias.shape[0] == self.item_table.shape[0]
         self.user_index = user_index
         self.note = note
+        self.score_fn = "dot"  # "neg_l2": score = -||u - i|| + b (read by RankingEvaluator)
         self._torch = torch
 
     def _rows(self, users):
@@ -78,7 +90,11 @@ class EmbeddingScorer(object):
         return self._rows(users), self.item_table[lo:hi], None if self.bias is None else self.bias[lo:hi], n_items
 
     def predict(self, users):
-        s = self._rows(users).float() @ self.item_table.float().T
+        if self.score_fn == "neg_l2":  # TransRec.py:90: -torch.norm(q.unsqueeze(1) - I, dim=-1)
+            q = self._rows(users).float()
+            s = -self._torch.norm(q.unsqueeze(1) - self.item_table.float().unsqueeze(0), p=None, dim=-1)
+        else:
+            s = self._rows(users).float() @ self.item_table.float().T
         if self.bias is not None:
             s = s + self.bias
         return s.cpu().numpy()
@@ -125,6 +141,23 @@ def neg_euclidean(user_table, item_table, user_index=None):
     except where float rounding makes two distances equal.)"""
     u, i = _t(user_table).float(), _t(item_table).float()
     return EmbeddingScorer(2.0 * u, i, -(i * i).sum(1), user_index, "neg_euclidean(monotone)")
+
+
+def neg_l2_plus_bias(query_table, item_table, item_bias=None, user_index=None):
+    """score(u, i) = -||q_u - i|| + b_i (TransRec.py:86-93, SGAT.py:300).  `query_table[B, d]` holds the translated
+    query of every evaluated user.  Scored by the FP32 tile kernels with a distance inner loop (see the module text)."""
+    sc = EmbeddingScorer(query_table, item_table, item_bias, user_index, "neg_l2_plus_bias")
+    sc.score_fn = "neg_l2"
+    return sc
+
+
+def transrec(user_table, global_transition, item_table, item_bias, last_items, user_index=None):
+    """TransRec.py:86-93: q_u = U[u] + g + I[last_item(u)], score = -||q_u - i|| + b_i.  `last_items[u]` is the item the
+    user interacted with last (`user_pos_dict[u][-1]`, TransRec.py:154), one per row of `user_table`."""
+    import torch
+    u, g, it = _t(user_table).float(), _t(global_transition).float().reshape(1, -1), _t(item_table).float()
+    last = torch.as_tensor(np.asarray(last_items, dtype=np.int64), device=it.device)
+    return neg_l2_plus_bias(u + g + it.index_select(0, last), it, item_bias, user_index)
 
 
 def item_scores(scores, num_users, user_index=None):

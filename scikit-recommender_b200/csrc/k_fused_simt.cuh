@@ -56,7 +56,12 @@ __device__ __forceinline__ void simt_load_chunk(float *dst, const float *__restr
 // scores_out[row, item] (row pitch ld_out) instead of going through the heaps -- the library's own GEMM for the
 // shapes the selection epilogues do not take (top-K > 128): the block is consumed by k_topk_scores, which masks the
 // train items itself, so no bitmap is built here.  One CTA per (user tile, item tile range).
-template <bool SCORES>
+// SMODE = 1: score = -||u - i|| (+ bias) instead of u . i (+ bias): the translation scorers of the reference
+// (TransRec.py:86-93 `-l2_distance(u + g + last, I) + b`, SGAT.py:300) -- a square root next to a per-item bias is not
+// a monotone image of a dot product, so it cannot go through the tensor-core contraction.  The tile loop accumulates
+// (u_k - i_k)^2, k ascending (the reference's torch.norm(a - b): no ||u||^2 - 2 u.i + ||i||^2 cancellation), the epilogue
+// takes -sqrt.
+template <bool SCORES, int SMODE>
 __global__ void __launch_bounds__(SIMT_THREADS, 1)
 k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict__ V, int64_t ld_v, FusedParams P,
              float *__restrict__ scores_out, int64_t ld_out)
@@ -170,10 +175,18 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        acc[i][j] = fmaf(a4[i].x, b4[j].x, acc[i][j]);
-                        acc[i][j] = fmaf(a4[i].y, b4[j].y, acc[i][j]);
-                        acc[i][j] = fmaf(a4[i].z, b4[j].z, acc[i][j]);
-                        acc[i][j] = fmaf(a4[i].w, b4[j].w, acc[i][j]);
+                        if (SMODE == 0) {
+                            acc[i][j] = fmaf(a4[i].x, b4[j].x, acc[i][j]);
+                            acc[i][j] = fmaf(a4[i].y, b4[j].y, acc[i][j]);
+                            acc[i][j] = fmaf(a4[i].z, b4[j].z, acc[i][j]);
+                            acc[i][j] = fmaf(a4[i].w, b4[j].w, acc[i][j]);
+                        } else {
+                            const float t0 = a4[i].x - b4[j].x, t1 = a4[i].y - b4[j].y, t2 = a4[i].z - b4[j].z, t3 = a4[i].w - b4[j].w;
+                            acc[i][j] = fmaf(t0, t0, acc[i][j]);
+                            acc[i][j] = fmaf(t1, t1, acc[i][j]);
+                            acc[i][j] = fmaf(t2, t2, acc[i][j]);
+                            acc[i][j] = fmaf(t3, t3, acc[i][j]);
+                        }
                     }
             }
             __syncthreads();
@@ -188,7 +201,7 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int64_t row = row_base + ty + 16 * i;
-                    if (row < P.n_rows) scores_out[row * ld_out + gcol] = acc[i][j] + b;
+                    if (row < P.n_rows) scores_out[row * ld_out + gcol] = (SMODE == 0 ? acc[i][j] : -sqrtf(acc[i][j])) + b;
                 }
             }
             continue;
@@ -203,7 +216,7 @@ k_fused_simt(const float *__restrict__ U, int64_t ld_u, const float *__restrict_
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = ty + 16 * i;
-                const float s = acc[i][j] + b;
+                const float s = (SMODE == 0 ? acc[i][j] : -sqrtf(acc[i][j])) + b;
                 if (s >= thr_row[r]) {
                     if (((bitmap[(cc >> 5) * TM + r] >> (cc & 31)) & 1u) == 0u) {
                         int slot = atomicAdd(&scnt[r], 1);

@@ -80,6 +80,7 @@ struct skr_ctx {
     int64_t opt_rank = 0;
     int64_t opt_dbg = 0;
     int64_t opt_chunk_rows = 0;      // rows per chunk of the fused pipeline (0 = default)
+    int64_t opt_score_fn = 0;        // 0: u . i + b   1: -||u - i|| + b (FP32 tile kernels only)
     int64_t opt_retry_min = -1;      // tf32r: unsettled rows from which the three-pass retry runs (-1 = cost model)
     int64_t opt_exact_seg_rows = -1;  // development: how many failed rows are cut in segments (-1 = default)
     bool debug_sync = false;  // SKR_DEBUG_SYNC=1: synchronise and check after every kernel, naming the one that failed
@@ -683,6 +684,11 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "sample_tiles")) { ctx->opt_sample_tiles = value; return SKR_OK; }
     if (!strcmp(name, "rank")) { ctx->opt_rank = value; return SKR_OK; }
     if (!strcmp(name, "dbg")) { ctx->opt_dbg = value; return SKR_OK; }
+    if (!strcmp(name, "score_fn")) {
+        if (value != 0 && value != 1) return fail(ctx, SKR_ERR_INVALID, "score_fn=%lld not in {0, 1}", (long long)value);
+        ctx->opt_score_fn = value;
+        return SKR_OK;
+    }
     if (!strcmp(name, "retry_min")) { ctx->opt_retry_min = value; return SKR_OK; }
     if (!strcmp(name, "chunk_rows")) { ctx->opt_chunk_rows = value < 0 ? 0 : value; return SKR_OK; }
     if (!strcmp(name, "exact_seg_rows")) { ctx->opt_exact_seg_rows = value; return SKR_OK; }
@@ -978,7 +984,9 @@ static int fused_by_blocks(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_r
     P.n_ct = (int)((n_items + TN - 1) / TN);
     P.bias = bias_dev;  // read only below n_items
     const size_t smem = simt_smem_bytes(0);
-    SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    typedef void (*SimtKernel)(const float *, int64_t, const float *, int64_t, FusedParams, float *, int64_t);
+    SimtKernel simt = ctx->opt_score_fn == 1 ? (SimtKernel)k_fused_simt<true, 1> : (SimtKernel)k_fused_simt<true, 0>;
+    SKR_CUDA(ctx, cudaFuncSetAttribute(simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int MK = m.n * top_k;
     const size_t slot = (size_t)(ctx->ev_calls % (int64_t)ctx->ev0.size());
     SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
@@ -992,7 +1000,7 @@ static int fused_by_blocks(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_r
         P.S = (int)std::max<int64_t>(1, std::min<int64_t>(P.n_ct, (2 * ctx->n_sm + P.n_rt - 1) / P.n_rt));
         P.tiles_per_chunk = (P.n_ct + P.S - 1) / P.S;
         P.S = (P.n_ct + P.tiles_per_chunk - 1) / P.tiles_per_chunk;
-        k_fused_simt<true><<<(unsigned)(P.n_rt * P.S), SIMT_THREADS, smem, st>>>(user_vecs_dev + b0 * ld_u, ld_u, item_vecs_dev, ld_i, P, (float *)ctx->stage_s.p, ld_s);
+        simt<<<(unsigned)(P.n_rt * P.S), SIMT_THREADS, smem, st>>>(user_vecs_dev + b0 * ld_u, ld_u, item_vecs_dev, ld_i, P, (float *)ctx->stage_s.p, ld_s);
         k_topk_scores<<<(unsigned)nb, K2_THREADS, 0, st>>>((const float *)ctx->stage_s.p, ld_s, (int)n_items, row0 + b0, ctx->has_train ? ctx->d_tr_indptr : nullptr,
                                                           ctx->has_train ? ctx->d_tr_idx : nullptr, top_k, (u64 *)ctx->keys.p);
         ctx->launches += 2;
@@ -1003,7 +1011,7 @@ static int fused_by_blocks(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_r
     }
     SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
     ctx->ev_calls++;
-    ctx->last_fused = "simt_fp32_blocks";
+    ctx->last_fused = ctx->opt_score_fn == 1 ? "simt_fp32_blocks_negl2" : "simt_fp32_blocks";
     ctx->last_plan = {0, 0, 0, 0, 0, 0};
     return SKR_OK;
 }
@@ -1039,6 +1047,11 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
     const int nkb = (d + TC_KB - 1) / TC_KB;
     const bool tc_ok = (nkb <= 4) && (tc_smem_bytes() <= ctx->max_smem);
     bool use_tc = (precision != SKR_PREC_FP32) && tc_ok;
+    if (ctx->opt_score_fn == 1) {  // -||u - i|| + b: FP32 tile kernel only
+        if (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32 || precision == SKR_PREC_TF32R)
+            return fail(ctx, SKR_ERR_UNSUPPORTED, "score_fn = -||u - i|| + b runs on the FP32 tile kernel: precision must be auto or fp32");
+        use_tc = false;
+    }
     // AUTO, catalogue too small for sampled thresholds (about 160 items per requested rank: ml-1m at top-50 or
     // top-100): the tensor-core pipeline would settle every row through its exact per-row fallback.  The FP32 FMA
     // kernel with running per-row heaps is one launch and exact; the whole job is a few GFLOP.
@@ -1270,13 +1283,15 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         P.part = (u64 *)ctx->part.p;
         SKR_CUDA(ctx, cudaMemsetAsync(P.thr_g, 0, (size_t)n_rows * sizeof(uint32_t), st));
         const size_t smem = simt_smem_bytes(K);
-        SKR_CUDA(ctx, cudaFuncSetAttribute(k_fused_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        typedef void (*SimtKernel)(const float *, int64_t, const float *, int64_t, FusedParams, float *, int64_t);
+        SimtKernel simt = ctx->opt_score_fn == 1 ? (SimtKernel)k_fused_simt<false, 1> : (SimtKernel)k_fused_simt<false, 0>;
+        SKR_CUDA(ctx, cudaFuncSetAttribute(simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
-        k_fused_simt<false><<<grid, SIMT_THREADS, smem, st>>>(user_vecs_dev, ld_u, item_vecs_dev, ld_i, P, nullptr, 0);
+        simt<<<grid, SIMT_THREADS, smem, st>>>(user_vecs_dev, ld_u, item_vecs_dev, ld_i, P, nullptr, 0);
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches++;
-        ctx->last_fused = "simt_fp32";
+        ctx->last_fused = ctx->opt_score_fn == 1 ? "simt_fp32_negl2" : "simt_fp32";
         SKR_CUDA(ctx, cudaGetLastError());
         // merge the S partial lists per row
         if ((rc = merge_lists(ctx, P.part, P.S, K, n_rows, row0, (int64_t)P.S * K, K, tp, ti, keys_only ? keys_only : keys, st))) return rc;

@@ -585,6 +585,13 @@ class RankingEvaluator(object):
         with _nvtx("skrec:model.eval_embeddings"):
             user_vecs, item_vecs, bias = model.eval_embeddings(users)
         MK = self.metrics_num * self.max_top
+        score_fn = getattr(model, "score_fn", "dot")
+        assert score_fn in ("dot", "neg_l2"), "score_fn must be 'dot' or 'neg_l2'"
+        neg_l2 = score_fn == "neg_l2"
+        prec = self.precision
+        if neg_l2:
+            assert prec in ("auto", "fp32"), "score_fn='neg_l2' (-||u - i|| + b) runs on the FP32 tile kernels: precision auto|fp32"
+            prec = "fp32"
         on_host = not (isinstance(user_vecs, torch.Tensor) and user_vecs.is_cuda) and \
             not (isinstance(item_vecs, torch.Tensor) and item_vecs.is_cuda)
         if on_host and host_fast and not want_pu:
@@ -594,23 +601,25 @@ class RankingEvaluator(object):
             assert uv.ndim == 2 and iv.ndim == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
             assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
             plan = self._plan(users, int(iv.shape[0]), key)
+            plan.ctx.set_option("score_fn", 1 if neg_l2 else 0)
             with _nvtx("skrec:fused (host tables: H2D + kernels + D2H)"):
-                _, _, host_sums = plan.ctx.eval_fused_host(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision)
+                _, _, host_sums = plan.ctx.eval_fused_host(uv, iv, b, 0, self.metrics, self.max_top, precision=prec)
             return "fused:" + plan.ctx.last_fused_kernel, host_sums, None
         with _nvtx("skrec:H2D embedding tables"):
             uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
         assert uv.dim() == 2 and iv.dim() == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
         assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
         d = int(iv.shape[1])
-        if d % 4 != 0 and (d > 128 or self.max_top > 128 or self.precision == "fp32"):
+        if d % 4 != 0 and (d > 128 or self.max_top > 128 or prec == "fp32"):
             # the FP32 tile kernels (wide d, top-K > 128, precision="fp32") read float4: zero-pad the rows to a
             # multiple of four columns -- zeros add nothing to a dot product (the host entry pads the same way)
             uv = torch.nn.functional.pad(uv, (0, 4 - d % 4))
             iv = torch.nn.functional.pad(iv, (0, 4 - d % 4))
         plan = self._plan(users, int(iv.shape[0]), key)
         per_user = torch.empty((len(users), MK), dtype=torch.float32, device=dev) if want_pu else None
+        plan.ctx.set_option("score_fn", 1 if neg_l2 else 0)
         with _nvtx("skrec:fused (split + SAMPLE + COLLECT + select + metrics)"):
-            plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=self.precision, per_user=per_user, sums=sums)
+            plan.ctx.eval_fused(uv, iv, b, 0, self.metrics, self.max_top, precision=prec, per_user=per_user, sums=sums)
         return "fused:" + plan.ctx.last_fused_kernel, None, per_user
 
     def _evaluate_item_sharded(self, model, users, key, dev, rank, world, sums):

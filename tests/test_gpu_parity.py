@@ -1056,3 +1056,47 @@ def test_three_pass_error_stays_inside_the_band_the_retry_assumes(torch_cuda, ct
         exact = np.take_along_axis(oracle.scores(ue, ie, None), idx3.astype(np.int64), 1)
         eps3 = 1.25 * (3.25 * d + 11) * 2.0 ** -22 * np.linalg.norm(ue, axis=1, keepdims=True) * np.linalg.norm(ie, axis=1).max()
         assert np.all(np.abs(val3 - exact) <= 0.5 * eps3), d
+
+
+def test_translation_scorers_neg_l2_plus_bias(torch_cuda):
+    """f1 remainder (TransRec.py:86-93, SGAT.py:300): score = -||q - i|| + b_i through the fused FP32 tile kernel with a
+    distance inner loop, against the reference expression evaluated in float64 and ranked by the oracle."""
+    import torch
+    from skrec_b200 import RankingEvaluator, adapters
+    g = np.random.default_rng(41)
+    for U, I, d, top_k in ((600, 5000, 32, [5, 20]), (300, 2000, 50, [10, 50]), (257, 3000, 64, [10, 200])):
+        ue = (g.standard_normal((U, d)) * 0.3).astype(np.float32)
+        ie = (g.standard_normal((I, d)) * 0.3).astype(np.float32)
+        gt = (g.standard_normal(d) * 0.1).astype(np.float32)
+        b = (g.standard_normal(I) * 0.2).astype(np.float32)
+        tr = _rand_csr(g, U, I, 25, min_n=1)
+        te = _rand_csr(g, U, I, 8, min_n=1)
+        train = {u: tr[1][tr[0][u]:tr[0][u + 1]] for u in range(U)}
+        test = {u: te[1][te[0][u]:te[0][u + 1]] for u in range(U)}
+        last = np.array([train[u][-1] for u in range(U)], np.int64)
+        metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
+        model = adapters.transrec(ue, gt, ie, b, last)
+        assert model.score_fn == "neg_l2"
+        # the reference expression (TransRec.py:89-92), float64
+        q = ue.astype(np.float64) + gt.astype(np.float64) + ie[last].astype(np.float64)
+        S = -np.sqrt(((q[:, None, :] - ie[None, :, :].astype(np.float64)) ** 2).sum(-1)) + b.astype(np.float64)
+        S = S.astype(np.float32)
+        assert np.max(np.abs(model.predict(list(range(U))) - S)) < 1e-5   # the scorer's own predict is that expression
+        oracle.mask_rows(S, tr[0], tr[1])
+        K = max(top_k)
+        per = oracle.eval_scores(S, te[0], te[1], [1, 2, 3, 4, 5], K)
+        expect = oracle.mean_f32(per).reshape(5, K)[:, np.array(top_k) - 1].ravel()
+        for on_dev in (False, True):
+            m = model
+            if on_dev:
+                m = adapters.neg_l2_plus_bias(torch.from_numpy((ue + gt + ie[last]).astype(np.float32)).cuda(), torch.from_numpy(ie).cuda(),
+                                              torch.from_numpy(b).cuda())
+            ev = RankingEvaluator(train, test, metric=metric, top_k=top_k, device=0)
+            got = np.array(list(ev.evaluate(m).values()), np.float32)
+            assert "negl2" in ev.last_stats["path"], ev.last_stats["path"]
+            assert np.max(np.abs(got - expect)) <= TOL_METRIC, (U, I, d, on_dev, float(np.max(np.abs(got - expect))))
+        # a dot-product model afterwards on the same evaluator: the option does not stick
+        ev2 = RankingEvaluator(train, test, metric=metric, top_k=[5], device=0, precision="fp32")
+        ev2.evaluate(model)
+        ev2.evaluate(adapters.dot_product(ue, ie, b))
+        assert ev2.last_stats["path"] == "fused:simt_fp32"

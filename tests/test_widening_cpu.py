@@ -272,3 +272,22 @@ def test_monotone_activations_leave_every_rank_list_unchanged():
         keep = np.abs(np.diff(np.sort(ref, 1), axis=1)).min() > 0  # no two scores collapse in the activation's float image
         if keep:
             assert np.array_equal(np.argsort(-ref, 1, kind="stable"), np.argsort(-raw.astype(np.float64), 1, kind="stable"))
+
+
+def test_transrec_scorer_is_the_reference_expression():
+    """TransRec.py:86-93: ratings = -l2_distance((u + g + last).unsqueeze(1), I) + b with l2_distance = torch.norm(a - b)
+    (utils/torch.py:24-29).  The adapter's own `predict` is that expression; the fused path is checked on the GPU."""
+    import torch
+    from skrec_b200 import adapters
+    g = torch.Generator().manual_seed(3)
+    U, I, d = 7, 23, 12
+    ue, ie = torch.randn(U, d, generator=g), torch.randn(I, d, generator=g)
+    gt, b = torch.randn(1, d, generator=g), torch.randn(I, generator=g)
+    last = torch.randint(0, I, (U,), generator=g)
+    sc = adapters.transrec(ue, gt, ie, b, last.numpy())
+    transed = ue + gt + ie[last]
+    ref = -torch.norm(transed.unsqueeze(1) - ie, p=None, dim=-1) + b
+    assert sc.score_fn == "neg_l2" and sc.note == "neg_l2_plus_bias"
+    assert np.allclose(sc.predict(list(range(U))), ref.numpy(), atol=1e-6)
+    uv, iv, bb = sc.eval_embeddings([2, 5])
+    assert torch.equal(uv, transed[[2, 5]]) and iv.shape == (I, d) and torch.equal(bb, b)
