@@ -240,13 +240,14 @@ def make_large(users, items, d, nnz_train, nnz_test, seed, bias=False, plant_poo
     it16 = item_emb.to(torch.bfloat16)
     npl = torch.from_numpy(n_plant).to(dev)
     pl_owner, pl_item = [], []
-    chunk = max(1, min(U, (6 << 30) // max(2 * I, 1)))
+    b16 = None if b is None else b.to(torch.bfloat16)
+    chunk = max(1, min(U, (16 << 30) // max(2 * I, 1)))  # 16 GB of bf16 scores per step: few, large steps
     for u0 in range(0, U, chunk):
         u1 = min(U, u0 + chunk)
         sc = user_emb[u0:u1].to(torch.bfloat16) @ it16.T
-        if b is not None:
-            sc += b.to(torch.bfloat16)
-        hit = (sc.float() > (sig[u0:u1] * z).unsqueeze(1)).nonzero()
+        if b16 is not None:
+            sc += b16
+        hit = (sc > (sig[u0:u1] * z).to(torch.bfloat16).unsqueeze(1)).nonzero()  # compared in bf16: a third of the traffic
         del sc
         ck = (hit[:, 0] + u0) * I + hit[:, 1]
         pos = torch.searchsorted(drawn_sorted, ck).clamp_(max=drawn_sorted.numel() - 1)
