@@ -197,6 +197,20 @@ int skr_fused_trace(skr_ctx *ctx, int64_t *out, int64_t n_out);
  * fused pipeline, 0 = 131,072), "retry_min" (tf32r: unsettled rows from which the three-pass retry runs, -1 = cost model). */
 int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
 
+/* ---- negative sampler ----------------------------------------------------------------------------------------------
+ * GPU form of c_batch_randint_choice (skrec/utils/py/cython/include/randint.h:97-128; pyx_random.pyx:79-150): element b
+ * of the batch gets out[out_indptr[b] .. out_indptr[b + 1]) integers from [0, high): uniform (cdf_dev == NULL) or by
+ * probabilities given as inclusive prefix sums (`cdf_dev` float [high], or [n_batch, high] with cdf_per_row != 0), with
+ * (replace != 0) or without replacement, never a member of row b of the exclusion CSR (rows sorted and unique; NULL = none).
+ * Every draw is a function of (seed, position, attempt) through Philox4x32-10: reproducible, independent of the launch
+ * geometry; NOT the reference's mt19937 stream (sequential by construction).  All pointers are device memory; n_out =
+ * out_indptr[n_batch].  Asynchronous on `stream`; a row that cannot be filled is reported by skr_check. */
+int skr_batch_randint(skr_ctx *ctx, int64_t high, const int64_t *out_indptr_dev, int64_t n_batch, int64_t n_out, int replace,
+                      const float *cdf_dev, int cdf_per_row, const int64_t *excl_indptr_dev, const int32_t *excl_idx_dev,
+                      uint64_t seed, int32_t *out_dev, void *stream);
+/* 0, or SKR_ERR_CUDA once a kernel of ctx reported a condition it could not handle; synchronises, clears the flag. */
+int skr_check(skr_ctx *ctx);
+
 /* ---- one-shot all-reduce of the metric sums over NVLink peer memory ------------------------------------------------
  * User-sharded evaluation exchanges n_metrics * top_k + 1 doubles per evaluate; the reference has no
  * counterpart (its mean runs over one process's users, evaluator.py:206-208).  One process per GPU of ONE node:

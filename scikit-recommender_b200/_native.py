@@ -20,7 +20,7 @@ SYMBOLS = (
     "skr_set_test_csr", "skr_eval_scores", "skr_eval_scores_host", "skr_eval_fused", "skr_eval_fused_host",
     "skr_metrics_from_topk", "skr_colsum_f32_seq", "skr_launch_count", "skr_last_fused_kernel", "skr_set_option", "skr_fused_kernel_ms", "skr_fused_prepass_ms", "skr_fused_stats", "skr_fused_trace", "skr_topk_fused", "skr_eval_merged_topk", "skr_topk_scores", "skr_topk_scores_host", "skr_colsum_rows",
     "skr_plan_work_host", "skr_comm_create", "skr_comm_handle", "skr_comm_connect", "skr_comm_allreduce", "skr_comm_status",
-    "skr_comm_last_error", "skr_comm_destroy",
+    "skr_comm_last_error", "skr_comm_destroy", "skr_batch_randint", "skr_check",
 )
 
 _lib = None
@@ -75,6 +75,8 @@ def lib():
     L.skr_fused_trace.argtypes = [_vp, ctypes.POINTER(_i64), _i64]
     L.skr_plan_work_host.argtypes = [_int, _int, _int, _int, _int, _vp, _i64, ctypes.POINTER(_i64)]
     L.skr_plan_work_host.restype = _i64
+    L.skr_batch_randint.argtypes = [_vp, _i64, _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, ctypes.c_uint64, _vp, _vp]
+    L.skr_check.argtypes = [_vp]
     L.skr_comm_create.argtypes = [_int, _int, _int, ctypes.POINTER(_vp)]
     L.skr_comm_handle.argtypes = [_vp, _vp]
     L.skr_comm_connect.argtypes = [_vp, _vp]
@@ -257,6 +259,18 @@ class Context(object):
     def colsum_f32_seq(self, per_user, acc, stream=None):
         self._check(self._L.skr_colsum_f32_seq(self._h, _dev_ptr(per_user), per_user.shape[0], per_user.shape[1],
                                                _dev_ptr(acc), _stream_ptr(stream)))
+
+    def batch_randint(self, high, out_indptr, out, replace=True, cdf=None, excl_indptr=None, excl_idx=None, seed=0, stream=None):
+        """Device tensors: out_indptr int64 [n + 1], out int32 [out_indptr[-1]], cdf float32 [high] | [n, high] | None,
+        exclusion CSR (int64 / int32, rows sorted unique) | None."""
+        n = int(out_indptr.numel()) - 1
+        per_row = int(cdf is not None and cdf.dim() == 2)
+        self._check(self._L.skr_batch_randint(self._h, int(high), _dev_ptr(out_indptr), n, int(out.numel()), int(bool(replace)), _dev_ptr(cdf),
+                                              per_row, _dev_ptr(excl_indptr), _dev_ptr(excl_idx), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                              _dev_ptr(out), _stream_ptr(stream)))
+
+    def check(self):
+        self._check(self._L.skr_check(self._h))
 
     # -- host entry points (numpy arrays; copies inside the call) -------------------------------
     def eval_scores_host(self, scores, row0, metric_ids, top_k, want_topk=False, want_per_user=True):

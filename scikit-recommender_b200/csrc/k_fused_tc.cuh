@@ -218,6 +218,8 @@ struct TcArgs {
     // SAMPLE: item tiles 0, stride, 2*stride, ...; out: samp[row][4][TC_R] group maxima, descending
     int stride;
     int n_samp;
+    int samp_chunks;  // CTAs per user tile in SAMPLE mode: each scores a contiguous share of the sample tiles (fills the GPU when
+                      // there are fewer user tiles than SMs: a rank's share of a strong-scaled run) and writes its own 4 x TC_R maxima
     float *samp;
     // COLLECT: per-row thresholds (k_sample_thr) and candidate lists
     const float *thr;        // [n_rows]
@@ -402,8 +404,14 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = warp - TC_EPI_WARPS;  // 0 TMA producer, 1 MMA issuer (even tiles) + TMEM allocator, 2 mask builder (even), 3 MMA issuer (odd tiles), 4 mask builder (odd)
     // tiles of this work item: COLLECT t0 + i (work list), SAMPLE i * stride
-    int4 wk = make_int4((int)blockIdx.x, 0, A.n_samp, 0);
-    if (!SAMPLE) wk = __ldg(A.work + blockIdx.x);
+    int4 wk;
+    if (SAMPLE) {
+        const int C = A.samp_chunks, rt_ = (int)blockIdx.x / C, c_ = (int)blockIdx.x % C;
+        const int s0 = (int)((long)A.n_samp * c_ / C), s1 = (int)((long)A.n_samp * (c_ + 1) / C);
+        wk = make_int4(rt_, s0 * A.stride, s1 - s0, c_);
+    } else {
+        wk = __ldg(A.work + blockIdx.x);
+    }
     const int rt = wk.x, t0 = wk.y, n_tiles = wk.z, c = wk.w;
     const int t_step = SAMPLE ? A.stride : 1;
     const int64_t row_base = (int64_t)rt * TM;
@@ -700,6 +708,10 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         uint32_t bph = 0;  // buffer and its phase for tile i
         for (int i = 0; i < n_tiles; ++i) {
             const int col0 = (t0 + i * t_step) * TN + cq * 32;
+            // the 128 bytes of bias this warp adds two tiles from now: into L1 while the tensor core works (ncu, c4: 57 % of the
+            // kernel's stall samples were long-scoreboard waits, the epilogue's bias loads being its only global reads per tile)
+            if (P.bias != nullptr && lane == 0 && i + 2 < n_tiles)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(P.bias + col0 + 2 * t_step * TN));
             mbar_wait(tile_full + b, bph, A.err_flag, 6);
             tc_fence_after();
             const int tslot = (warp == 0) ? 7 : 10;
@@ -730,7 +742,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 
         if (my_valid) {
             if (SAMPLE) {
-                float4 *dst = reinterpret_cast<float4 *>(A.samp + (my_row * 4 + cq) * TC_R);
+                float4 *dst = reinterpret_cast<float4 *>(A.samp + ((my_row * A.samp_chunks + c) * 4 + cq) * TC_R);
 #pragma unroll
                 for (int q = 0; q < TC_R / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             } else {
@@ -768,7 +780,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 // the norms and leaves slack (tests assert the observed error stays below eps / 2).  eps_coef carries the
 // bracket's first factor, stats = {N_max^2, B_max} from k_split_tf32.
 __global__ void __launch_bounds__(256)
-k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
+k_sample_thr(const float *__restrict__ samp, int n_vals, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
              int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
              float *__restrict__ thr_lo_out, float eps3_coef, float *__restrict__ eps2_3_out, float *__restrict__ thr3_out)
 {
@@ -777,16 +789,28 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= n_rows) return;
-    const float2 x = __ldg(reinterpret_cast<const float2 *>(samp + row * (4 * TC_R)) + lane);
-    const uint32_t a = ord_f32(x.x), b = ord_f32(x.y);
-    const uint32_t lo = __reduce_min_sync(0xffffffffu, min(a, b)), hi = __reduce_max_sync(0xffffffffu, max(a, b));
+    // n_vals = 64 per sampling chunk of the row (at most 4 chunks): 2 values per lane and chunk
+    uint32_t v[8];
+    uint32_t vlo = 0xffffffffu, vhi = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 x = make_float2(-__int_as_float(0x7f800000), -__int_as_float(0x7f800000));
+        if (q * 64 < n_vals) x = __ldg(reinterpret_cast<const float2 *>(samp + row * n_vals + q * 64) + lane);
+        v[2 * q] = ord_f32(x.x);
+        v[2 * q + 1] = ord_f32(x.y);
+        vlo = min(vlo, min(v[2 * q], v[2 * q + 1]));
+        vhi = max(vhi, max(v[2 * q], v[2 * q + 1]));
+    }
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, vlo), hi = __reduce_max_sync(0xffffffffu, vhi);
     // bits above the highest bit in which min and max differ are common to every value
     const int nb = 32 - __clz((lo ^ hi) | 1u);
     uint32_t T = (nb >= 32) ? 0u : (hi >> nb) << nb;
     for (int bit = nb - 1; bit >= 0; --bit) {
         const uint32_t cand = T | (1u << bit);
-        const int cnt = __reduce_add_sync(0xffffffffu, (int)(a >= cand) + (int)(b >= cand));
-        if (cnt >= r) T = cand;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c += (int)(v[q] >= cand);
+        if (__reduce_add_sync(0xffffffffu, c) >= r) T = cand;
     }
     float t0 = unord_f32(T);
     if (eps2_out != nullptr) {

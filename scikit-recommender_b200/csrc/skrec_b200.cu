@@ -26,6 +26,7 @@
 #include "k_fused_simt.cuh"
 #include "k_fused_tc.cuh"
 #include "k_metrics.cuh"
+#include "k_sampler.cuh"
 #include "k_scores.cuh"
 #include "k_select.cuh"
 
@@ -1175,7 +1176,9 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         int cap = next_pow2((int)(2.0 * expect / (4 * wc->min_slots)) + 16);
         cap = std::max(16, std::min(cap, 512));
 
-        if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * 4 * TC_R * sizeof(float)))) return rc;
+        // SAMPLE CTAs per user tile: enough to fill the GPU when there are few user tiles, at least 8 sample tiles each
+        const int samp_chunks = std::max(1, std::min(std::min(4, n_samp / 8), (2 * ctx->n_sm) / std::max(1, P.n_rt)));
+        if ((rc = ensure(ctx, ctx->samp, (size_t)n_rows * samp_chunks * 4 * TC_R * sizeof(float)))) return rc;
         if ((rc = ensure(ctx, ctx->cand, (size_t)n_rows * n_sub * cap * sizeof(uint2)))) return rc;
         if ((rc = ensure(ctx, ctx->thr, (size_t)4 * n_rows * sizeof(float)))) return rc;  // thr | TF32 hi | TF32 lo (threshold MMA) | retry threshold
         if ((rc = ensure(ctx, ctx->cand_cnt, (size_t)n_rows * n_sub * sizeof(uint32_t)))) return rc;
@@ -1191,6 +1194,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         A.dbg = (int)ctx->opt_dbg;
         A.stride = stride;
         A.n_samp = n_samp;
+        A.samp_chunks = samp_chunks;
         A.samp = (float *)ctx->samp.p;
         A.thr = (const float *)ctx->thr.p;
         A.cap = cap;
@@ -1219,9 +1223,9 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
-        if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)P.n_rt, st, mhi, mlo, A, P))) return rc;
+        if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, mhi, mlo, A, P))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
-        SKR_CUDA(ctx, launch_pdl(k_sample_thr, dim3((unsigned)((unsigned)((n_rows + 7) / 8))), dim3((unsigned)(256)), (size_t)(0), st, (const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
+        SKR_CUDA(ctx, launch_pdl(k_sample_thr, dim3((unsigned)((unsigned)((n_rows + 7) / 8))), dim3((unsigned)(256)), (size_t)(0), st, (const float *)ctx->samp.p, samp_chunks * 4 * TC_R, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
                                                                    (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr,
                                                                    (float *)A.thr_hi, (float *)A.thr_lo, eps3_coef, eps2_3, thr3));
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
@@ -1475,6 +1479,40 @@ int skr_eval_fused_host(skr_ctx *ctx, const float *user_vecs_host, int64_t n_row
 }
 
 }  // extern "C"
+
+extern "C" int skr_batch_randint(skr_ctx *ctx, int64_t high, const int64_t *out_indptr_dev, int64_t n_batch, int64_t n_out, int replace,
+                                 const float *cdf_dev, int cdf_per_row, const int64_t *excl_indptr_dev, const int32_t *excl_idx_dev,
+                                 uint64_t seed, int32_t *out_dev, void *stream)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    if (high <= 1 || high > 0x7fffffffll) return fail(ctx, SKR_ERR_INVALID, "'high' must be larger than 1 (and fit int32): %lld", (long long)high);
+    if (!out_indptr_dev || !out_dev || n_batch <= 0 || n_out < 0) return fail(ctx, SKR_ERR_INVALID, "batch_randint: bad arguments");
+    if ((excl_indptr_dev == nullptr) != (excl_idx_dev == nullptr)) return fail(ctx, SKR_ERR_INVALID, "batch_randint: exclusion CSR needs both arrays");
+    if (n_out == 0) return SKR_OK;
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SamplerArgs A = {high, out_indptr_dev, n_batch, cdf_dev, cdf_per_row, excl_indptr_dev, excl_idx_dev, (uint32_t)seed, (uint32_t)(seed >> 32), out_dev, ctx->d_err};
+    if (replace) k_sample_with_replacement<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(A, n_out);
+    else k_sample_without_replacement<<<(unsigned)((n_batch + 3) / 4), 128, 0, st>>>(A);
+    ctx->launches++;
+    SKR_CUDA(ctx, cudaGetLastError());
+    return SKR_OK;
+}
+
+/* 0, or SKR_ERR_CUDA once a kernel of this ctx has reported a condition it could not handle (a watchdog, a sampler row
+ * that cannot be filled); synchronises the device and clears the flag. */
+extern "C" int skr_check(skr_ctx *ctx)
+{
+    if (!ctx) return SKR_ERR_INVALID;
+    int v = 0;
+    SKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    SKR_CUDA(ctx, cudaMemcpy(&v, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (v) {
+        cudaMemset(ctx->d_err, 0, sizeof(int));
+        return fail(ctx, SKR_ERR_CUDA, v == 41 ? "sampler: a row asks for more values than exist outside its exclusion set (code 41)" : "a kernel reported error code %d", v);
+    }
+    return SKR_OK;
+}
 
 // ---- one-shot all-reduce of the metric sums over NVLink (user-sharded evaluation exchanges M*K + 1 doubles) ----
 // Every rank owns an inbox [2 parities][world][SKR_COMM_MAX doubles] + flags in its own HBM, exported with cudaIpc and

@@ -1100,3 +1100,55 @@ def test_translation_scorers_neg_l2_plus_bias(torch_cuda):
         ev2.evaluate(model)
         ev2.evaluate(adapters.dot_product(ue, ie, b))
         assert ev2.last_stats["path"] == "fused:simt_fp32"
+
+
+def test_negative_sampler_like_randint_h(torch_cuda):
+    """f-5 (randint.h:22-128, random.py:9-41): range, exclusion, distinctness without replacement, uniformity,
+    probabilities, reproducibility from the seed, the reference's argument errors and return types."""
+    from skrec_b200 import batch_randint_choice, randint_choice
+    g = np.random.default_rng(0)
+    high = 5000
+    excl = [np.unique(g.integers(0, high, size=int(n))) for n in g.integers(1, 400, size=300)]
+    size = g.integers(1, 200, size=300)
+    a = batch_randint_choice(high, size, replace=True, exclusion=excl, thread_num=4, seed=7)
+    b = batch_randint_choice(high, size, replace=True, exclusion=excl, seed=7)
+    c = batch_randint_choice(high, size, replace=True, exclusion=excl, seed=8)
+    assert isinstance(a, list) and len(a) == 300
+    assert all(x.dtype == np.int32 and x.shape == (s,) for x, s in zip(a, size))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and any(not np.array_equal(x, y) for x, y in zip(a, c))
+    for x, e in zip(a, excl):
+        assert x.min() >= 0 and x.max() < high and not np.isin(x, e).any()
+    d = batch_randint_choice(high, size, replace=False, exclusion=excl, seed=9)
+    for x, e, s in zip(d, excl, size):
+        assert x.shape == (s,) and np.unique(x).size == s and not np.isin(x, e).any() and x.min() >= 0 and x.max() < high
+    # nearly exhaustive draw without replacement: 90 of the 100 values left after excluding 28
+    ex = np.arange(0, 128, 1)[:28]
+    x = randint_choice(128, size=90, replace=False, exclusion=ex, seed=3)
+    assert np.unique(x).size == 90 and not np.isin(x, ex).any()
+    # uniformity: chi-square of 2*10^6 draws over 1,000 values minus 100 excluded (900 cells, expected 2,222 each)
+    ex = np.arange(0, 1000, 10)
+    x = randint_choice(1000, size=2_000_000, exclusion=ex, seed=11)
+    cnt = np.bincount(x, minlength=1000)
+    assert cnt[ex].sum() == 0
+    cells = np.delete(cnt, ex)
+    chi2 = float(((cells - cells.mean()) ** 2 / cells.mean()).sum())
+    assert 700 < chi2 < 1100, chi2   # 899 degrees of freedom: mean 899, sd 42
+    # probabilities (one row per element; zero-probability values never come out)
+    p = np.zeros((2, 10), np.float32)
+    p[0, [1, 3]] = [1.0, 3.0]
+    p[1, :] = 1.0
+    y = batch_randint_choice(10, [40000, 10], p=p, seed=5)
+    assert set(np.unique(y[0])) == {1, 3} and abs((y[0] == 3).mean() - 0.75) < 0.01
+    # scalar form: int for size 1, array otherwise; the reference's errors
+    assert isinstance(randint_choice(50, seed=1), (int, np.integer))
+    assert randint_choice(50, size=7, seed=1).shape == (7,)
+    for bad in (lambda: randint_choice(1), lambda: randint_choice(10, size=0), lambda: randint_choice(10, replace=1),
+                lambda: randint_choice(10, size=10, replace=False), lambda: randint_choice(10, p=[0.5, 0.5]),
+                lambda: batch_randint_choice(10, [[1, 2]]), lambda: batch_randint_choice(10, [3, 0]),
+                lambda: batch_randint_choice(10, [3, 3], exclusion=[[1]]),
+                lambda: batch_randint_choice(10, [9], replace=False, exclusion=[[1, 2]])):
+        with pytest.raises((ValueError, TypeError)):
+            bad()
+    # the training-side use (data_iterator.py:81-94): negatives of every user against its positives, on the device
+    out, ptr = batch_randint_choice(high, size, exclusion=excl, seed=12, as_tensor=True)
+    assert out.is_cuda and out.dtype == torch_cuda.int32 and int(ptr[-1]) == int(size.sum())

@@ -27,16 +27,22 @@ ctx = _native.Context(0)
 ctx.set_option("chunks", int(os.environ.get("SKR_CHUNKS", "0")))  # item-range chunks per user tile (0 = planner)
 ctx.set_train_csr(d["train_indptr"], d["train_indices"], d["items"])
 ctx.set_test_csr(d["test_indptr"], d["test_indices"], d["items"])
-ue, ie = torch.from_numpy(d["user_emb"]).cuda(), torch.from_numpy(d["item_emb"]).cuda()
+n_use = int(os.environ.get("SKR_USERS", "0")) or d["users"]  # evaluate only the first rows (a rank's share of a strong-scaled run)
+ue, ie = torch.from_numpy(d["user_emb"][:n_use]).cuda(), torch.from_numpy(d["item_emb"]).cuda()
 b = None if d["bias"] is None else torch.from_numpy(d["bias"]).cuda()
 ids = [synth.METRIC_IDS[m] for m in cfg["metric"]]
 K = max(cfg["top_k"])
 sums = torch.zeros(len(ids) * K, dtype=torch.float64, device="cuda")
 ms = []
+import time
+wall = []
 for _ in range(n):
     sums.zero_()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     ctx.eval_fused(ue, ie, b, 0, ids, K, precision=prec, sums=sums)
     torch.cuda.synchronize()
+    wall.append((time.perf_counter() - t0) * 1e3)
     ms.append(ctx.fused_kernel_ms(0))
-print("%s %s kernel ms:" % (cfgname, prec), ["%.3f" % m for m in ms], "prepass %.3f" % ctx.fused_prepass_ms(0),
+print("%s %s rows %d wall ms:" % (cfgname, prec, n_use), ["%.3f" % m for m in wall], "kernel ms:", ["%.3f" % m for m in ms], "prepass %.3f" % ctx.fused_prepass_ms(0),
       "NDCG@%d=%.6f" % (K, float(sums[-1]) / d["users"]), ctx.fused_stats())
