@@ -208,7 +208,7 @@ class RankingEvaluator(object):
         grid replaces the thread pool.  `batch_size` is the user batch of the `predict` path.
     Keyword-only additions:
         device: CUDA device index (default: current torch device).
-        precision: "auto" | "3xtf32" | "fp32" | "tf32r" | "1xtf32" -- arithmetic of the fused scoring
+        precision: "auto" | "3xtf32" | "fp32" | "tf32r" -- arithmetic of the fused scoring
             ("tf32r": one TF32 pass finds candidates inside a rigorous error band, the survivors are
             re-scored in exact FP32; same results as "fp32").
         mean: "f64" (float64 sums, rounded once to float32) or "numpy_f32" (the reference's
@@ -265,7 +265,11 @@ class RankingEvaluator(object):
             self.max_top = max(top_k)
             self.top_show = np.sort(top_k)
 
-        assert precision in ("auto", "3xtf32", "fp32", "1xtf32", "tf32r"), "precision must be auto|3xtf32|fp32|1xtf32|tf32r"
+        import os
+        allowed = ("auto", "3xtf32", "fp32", "tf32r") + (("1xtf32",) if os.environ.get("SKR_ALLOW_1XTF32") == "1" else ())
+        # "1xtf32" (one TF32 pass, no re-scoring) misses the 1e-5 metric contract: measurement only,
+        # reachable only with SKR_ALLOW_1XTF32=1
+        assert precision in allowed, "precision must be auto|3xtf32|fp32|tf32r"
         assert mean in ("f64", "numpy_f32"), "mean must be f64|numpy_f32"
         assert shard in ("users", "items"), "shard must be users|items"
         self.shard = shard
