@@ -615,11 +615,28 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             }
             __syncwarp();
             if (lane == 0) tc_trace(A, i, 14);
-            for (uint32_t p = kb0; p < ke0; p += 32) {
-                if (p != kb0) key = (p + lane < ke0) ? __ldg(keys + p + lane) : 0xffffffffu;
-                if (p + lane < ke0) {
+            // 256 keys per step, their loads issued together: dense interaction data (ml-1m: ~580 train items per
+            // 128-user x 128-item tile) otherwise pays one L2 round trip per 32 keys -- 7 us per tile, which made this warp
+            // the pace of the whole kernel at c1 (77 us for a 10-tile sample pass)
+            if (ke0 - kb0 <= 32u) {  // the usual case (c2: ~11 keys per tile): the prefetched keys are all there is
+                if (kb0 + lane < ke0) {
                     const int cc = (int)(key >> 7) - col0;
                     atomicOr(&bm[(cc >> 5) * TM + (int)(key & 127u)], 1u << (cc & 31));
+                }
+            } else
+            for (uint32_t p = kb0; p < ke0; p += 256) {
+                uint32_t k4[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t idx = p + 32u * q + lane;
+                    k4[q] = (q == 0 && p == kb0) ? key : ((idx < ke0) ? __ldg(keys + idx) : 0xffffffffu);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (p + 32u * q + lane < ke0) {
+                        const int cc = (int)(k4[q] >> 7) - col0;
+                        atomicOr(&bm[(cc >> 5) * TM + (int)(k4[q] & 127u)], 1u << (cc & 31));
+                    }
                 }
             }
             __syncwarp();
@@ -779,8 +796,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 // eps = 1.25 [(2^-10 + (2.5 d + 8) 2^-22) ||u|| N_max + 2^-22 B_max]: the 1.25 covers the FP32 evaluation of
 // the norms and leaves slack (tests assert the observed error stays below eps / 2).  eps_coef carries the
 // bracket's first factor, stats = {N_max^2, B_max} from k_split_tf32.
+template <int NQ>  // sampling chunks per row (1..4): 64 NQ values per row, 2 NQ per lane
 __global__ void __launch_bounds__(256)
-k_sample_thr(const float *__restrict__ samp, int n_vals, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
+k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
              int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
              float *__restrict__ thr_lo_out, float eps3_coef, float *__restrict__ eps2_3_out, float *__restrict__ thr3_out)
 {
@@ -789,13 +807,13 @@ k_sample_thr(const float *__restrict__ samp, int n_vals, int64_t n_rows, int r, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= n_rows) return;
-    // n_vals = 64 per sampling chunk of the row (at most 4 chunks): 2 values per lane and chunk
-    uint32_t v[8];
+    // 64 values per sampling chunk of the row: 2 per lane and chunk
+    constexpr int n_vals = 64 * NQ;
+    uint32_t v[2 * NQ];
     uint32_t vlo = 0xffffffffu, vhi = 0u;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float2 x = make_float2(-__int_as_float(0x7f800000), -__int_as_float(0x7f800000));
-        if (q * 64 < n_vals) x = __ldg(reinterpret_cast<const float2 *>(samp + row * n_vals + q * 64) + lane);
+    for (int q = 0; q < NQ; ++q) {
+        const float2 x = __ldg(reinterpret_cast<const float2 *>(samp + row * n_vals + q * 64) + lane);
         v[2 * q] = ord_f32(x.x);
         v[2 * q + 1] = ord_f32(x.y);
         vlo = min(vlo, min(v[2 * q], v[2 * q + 1]));
@@ -809,7 +827,7 @@ k_sample_thr(const float *__restrict__ samp, int n_vals, int64_t n_rows, int r, 
         const uint32_t cand = T | (1u << bit);
         int c = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) c += (int)(v[q] >= cand);
+        for (int q = 0; q < 2 * NQ; ++q) c += (int)(v[q] >= cand);
         if (__reduce_add_sync(0xffffffffu, c) >= r) T = cand;
     }
     float t0 = unord_f32(T);

@@ -1225,9 +1225,15 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
         if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, mhi, mlo, A, P))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
-        SKR_CUDA(ctx, launch_pdl(k_sample_thr, dim3((unsigned)((unsigned)((n_rows + 7) / 8))), dim3((unsigned)(256)), (size_t)(0), st, (const float *)ctx->samp.p, samp_chunks * 4 * TC_R, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
-                                                                   (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : nullptr,
-                                                                   (float *)A.thr_hi, (float *)A.thr_lo, eps3_coef, eps2_3, thr3));
+        {
+            typedef void (*ThrKernel)(const float *, int64_t, int, float *, const float *, int64_t, int, const float *, float, float *, float *, float *, float,
+                                      float *, float *);
+            const ThrKernel thr_k = samp_chunks == 1 ? (ThrKernel)k_sample_thr<1> : samp_chunks == 2 ? (ThrKernel)k_sample_thr<2>
+                                    : samp_chunks == 3 ? (ThrKernel)k_sample_thr<3> : (ThrKernel)k_sample_thr<4>;
+            SKR_CUDA(ctx, launch_pdl(thr_k, dim3((unsigned)((n_rows + 7) / 8)), dim3(256u), (size_t)0, st, (const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
+                                     (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : (float *)nullptr, (float *)A.thr_hi, (float *)A.thr_lo, eps3_coef, eps2_3,
+                                     thr3));
+        }
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
             A.trace_tiles = wc->max_tiles;
