@@ -483,6 +483,11 @@ static WorkPlan make_work(int n_rt, int n_ct, int s_lo, int n_plus, int n_sm, in
     wp.slots = s_lo + (n_plus > 0 ? 1 : 0);
     wp.min_slots = (n_plus >= n_rt) ? s_lo + 1 : s_lo;
     wp.mixed = n_plus > 0 && n_plus < n_rt;
+    // Generated user-tile-major, which the stable sort below keeps among equal sizes: at c4 the 148 CTAs of a wave then
+    // sweep 8 different item ranges.  Tried and not kept: chunk-major order (a wave sweeps ONE 62 MB range, L2-resident):
+    // DRAM reads per 131,072-user chunk fall from 16.0 to 4.7 GB (L2 hit 87 -> 96 %), but 148 SMs asking the same L2 lines
+    // at the same time cost more than the HBM traffic saves -- tensor pipe active 77 -> 70 %, kernel 45.5 -> 49 ms.
+    // Sharing a panel between SMs wants TMA multicast inside a cluster, not coincidence in L2.
     for (int rt = 0; rt < n_rt; ++rt) {
         const int s = s_lo + (rt < n_plus ? 1 : 0);
         for (int c = 0; c < s; ++c) {
