@@ -1152,3 +1152,149 @@ def test_negative_sampler_like_randint_h(torch_cuda):
     # the training-side use (data_iterator.py:81-94): negatives of every user against its positives, on the device
     out, ptr = batch_randint_choice(high, size, exclusion=excl, seed=12, as_tensor=True)
     assert out.is_cuda and out.dtype == torch_cuda.int32 and int(ptr[-1]) == int(size.sum())
+
+
+# ---- the remaining BASELINE.json configs at full size ---------------------------------------------
+def _oracle_sample_check(d, bias, a, sample, metric, K, min_hit):
+    """oracle on `sample` users of workload d against the fused outputs a = (idx, val, per, sums)"""
+    S = oracle.scores(d["user_emb"][sample], d["item_emb"], bias)
+    sp, si = oracle.dicts_to_csr(sample.tolist(), d["train"])
+    oracle.mask_rows(S, sp, si)
+    ep, ei = oracle.dicts_to_csr(sample.tolist(), d["test"], dedup_sort=True)
+    eper, etop = oracle.eval_scores(S, ep, ei, metric, K, return_topk=True)
+    got = a[0][sample]
+    diff = got != etop
+    if diff.any():
+        gs = np.take_along_axis(S, got.astype(np.int64), 1)
+        es = np.take_along_axis(S, etop.astype(np.int64), 1)
+        assert np.max(np.abs(gs[diff] - es[diff])) < TOL_NEAR_TIE
+    assert diff.mean() < 0.02
+    assert np.max(np.abs(a[2][sample].astype(np.float64).mean(0) - eper.astype(np.float64).mean(0))) <= TOL_METRIC
+    same = ~diff.any(axis=1)
+    assert np.array_equal(a[2][sample][same], eper[same])  # per-user metric vectors bit for bit where the lists agree
+    assert eper[:, K - 1].mean() > min_hit                 # planted test items: the check is not vacuous
+
+
+def test_c1_full_size_every_user_against_the_oracle(torch_cuda, ctx):
+    """BASELINE.json configs[0] (ml-1m shape, bias, top-20) whole: every one of the 6,040 users against the oracle, through
+    the tensor-core path the evaluator picks at this size (3xTF32) and the exact FP32 path; dense train rows (132 per user)
+    exercise the batched mask builder."""
+    from skrec_b200 import synth
+    d = synth.make_config("c1", device="cuda")
+    tr, te = (d["train_indptr"], d["train_indices"]), (d["test_indptr"], d["test_indices"])
+    metric, K = [1, 2, 4], 20
+    a = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], d["bias"], tr, te, metric, K, "auto")
+    assert ctx.last_fused_kernel == "tcgen05_3xtf32"
+    b = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], d["bias"], tr, te, metric, K, "fp32")
+    assert np.max(np.abs(a[3] - b[3])) / d["users"] <= TOL_METRIC
+    _oracle_sample_check(d, d["bias"], b, np.arange(d["users"]), metric, K, 0.005)
+    _oracle_sample_check(d, d["bias"], a, np.arange(d["users"]), metric, K, 0.005)
+
+
+@pytest.mark.parametrize("name", ["c3a", "c3b"])
+def test_c3_full_size_tf32r_vs_fp32_slice_and_oracle_sample(torch_cuda, ctx, name):
+    """BASELINE.json configs[2] at full size: the default path (TF32 candidates + exact re-scoring) on every user; the
+    exact FP32 kernel on a 4,096-user slice gives the same items, scores and metric vectors bit for bit; the oracle on a
+    256-user sample; every list ordered and free of train items."""
+    from skrec_b200 import synth
+    d = synth.make_config(name, device="cuda")
+    U, I = d["users"], d["items"]
+    tr, te = (d["train_indptr"], d["train_indices"]), (d["test_indptr"], d["test_indices"])
+    metric, K = [1, 2, 4], 50
+    a = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], None, tr, te, metric, K, "auto")
+    assert ctx.last_fused_kernel == "tcgen05_tf32r" and ctx.fused_stats()["exact_rows"] < 0.01 * U
+    n = 4096
+    trs, tes = (tr[0][:n + 1], tr[1][:tr[0][n]]), (te[0][:n + 1], te[1][:te[0][n]])
+    b = _run_fused(torch_cuda, ctx, d["user_emb"][:n], d["item_emb"], None, trs, tes, metric, K, "fp32")
+    assert np.array_equal(a[0][:n], b[0]) and np.array_equal(a[1][:n], b[1]) and np.array_equal(a[2][:n], b[2])
+    assert np.all((a[1][:, :-1] > a[1][:, 1:]) | ((a[1][:, :-1] == a[1][:, 1:]) & (a[0][:, :-1] < a[0][:, 1:])))
+    rows = np.repeat(np.arange(U), np.diff(tr[0]))
+    assert not np.isin((np.arange(U, dtype=np.int64)[:, None] * I + a[0]).ravel(), rows.astype(np.int64) * I + tr[1]).any()
+    _oracle_sample_check(d, None, a, np.arange(0, U, U // 256)[:256], metric, K, 0.005)
+
+
+def test_c5_catalogue_size_item_shards_merge_to_the_unsharded_lists(torch_cuda):
+    """BASELINE.json configs[4] at the full catalogue size (10^7 items, d = 128, top-100) on 1,024 users: the catalogue cut in
+    8 item shards of 1.25M rows (what each of 8 ranks holds), per-shard top-100 rank keys, merge -- bit-identical to the
+    unsharded evaluation; the oracle's exact scores on 8 users."""
+    from skrec_b200 import _native, dist
+    torch = torch_cuda
+    U, I, d, K, W = 1024, 10_000_000, 128, 100, 8
+    g = torch.Generator(device="cuda").manual_seed(2026)
+    ue = torch.randn((U, d), generator=g, device="cuda") * 0.1
+    ie = torch.randn((I, d), generator=g, device="cuda") * 0.1
+    rng = np.random.default_rng(5)
+    tr = (np.arange(U + 1, dtype=np.int64) * 50, rng.integers(0, I, size=U * 50, dtype=np.int32))
+    te = (np.arange(U + 1, dtype=np.int64) * 10, rng.integers(0, I, size=U * 10, dtype=np.int32))
+    metric = [1, 2, 3, 4, 5]
+    ref_ctx = _native.Context(0)
+    ref_ctx.set_train_csr(tr[0], tr[1], I)
+    ref_ctx.set_test_csr(te[0], te[1], I)
+    idx = torch.empty((U, K), dtype=torch.int32, device="cuda")
+    val = torch.empty((U, K), dtype=torch.float32, device="cuda")
+    per = torch.empty((U, 5 * K), dtype=torch.float32, device="cuda")
+    sums = torch.zeros(5 * K, dtype=torch.float64, device="cuda")
+    ref_ctx.eval_fused(ue, ie, None, 0, metric, K, topk_idx=idx, topk_val=val, per_user=per, sums=sums)
+    torch.cuda.synchronize()
+    keys = torch.empty((W, U, K), dtype=torch.int64, device="cuda")
+    sh = _native.Context(0)
+    for r in range(W):
+        lo, hi = dist.shard_range(I, r, W)
+        ptr, ind = _col_partition(tr, lo, hi)
+        sh.set_train_csr(ptr, ind, hi - lo)
+        sh.topk_fused(ue, ie[lo:hi], None, 0, lo, K, keys[r])
+    idx2 = torch.empty_like(idx); val2 = torch.empty_like(val); per2 = torch.empty_like(per)
+    sums2 = torch.zeros_like(sums)
+    ref_ctx.eval_merged_topk(keys, 0, U, 0, metric, K, topk_idx=idx2, topk_val=val2, per_user=per2, sums=sums2)
+    torch.cuda.synchronize()
+    assert torch.equal(idx, idx2) and torch.equal(val, val2) and torch.equal(per, per2)
+    assert float((sums - sums2).abs().max()) < 1e-9
+    # exact scores of 8 users (float64 on the device, then the oracle's selection on the host)
+    sample = np.arange(0, U, U // 8)[:8]
+    S = (ue[sample].double() @ ie.double().T).float().cpu().numpy()
+    sp = np.arange(9, dtype=np.int64) * 50
+    si = np.concatenate([tr[1][tr[0][u]:tr[0][u + 1]] for u in sample])
+    oracle.mask_rows(S, sp, si)
+    ep = np.arange(9, dtype=np.int64) * 10
+    ei = np.concatenate([np.unique(te[1][te[0][u]:te[0][u + 1]]) for u in sample])
+    ep = np.concatenate([[0], np.cumsum([np.unique(te[1][te[0][u]:te[0][u + 1]]).size for u in sample])]).astype(np.int64)
+    eper, etop = oracle.eval_scores(S, ep, ei, metric, K, return_topk=True)
+    got = idx.cpu().numpy()[sample]
+    diff = got != etop
+    if diff.any():
+        gs = np.take_along_axis(S, got.astype(np.int64), 1)
+        es = np.take_along_axis(S, etop.astype(np.int64), 1)
+        assert np.max(np.abs(gs[diff] - es[diff])) < TOL_NEAR_TIE
+    assert diff.mean() < 0.02
+    ref_ctx.close(); sh.close()
+
+
+def test_million_row_call_is_chunked_and_counts_every_user_once(torch_cuda):
+    """c4's user count through ONE native call (8 row chunks of 131,072 inside skr_eval_fused) on a small catalogue: size-
+    independent properties -- every user is evaluated exactly once (Recall@K of a user whose only test item is its own best
+    item is 1), the sums equal the sum of per-user rows, and a second call reproduces them bit for bit."""
+    from skrec_b200 import _native
+    torch = torch_cuda
+    U, I, d, K = 1_000_000, 4096, 32, 10
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ue = torch.randn((U, d), generator=g, device="cuda")
+    ie = torch.randn((I, d), generator=g, device="cuda")
+    best = torch.empty(U, dtype=torch.int64, device="cuda")
+    for u0 in range(0, U, 65536):
+        best[u0:u0 + 65536] = (ue[u0:u0 + 65536].double() @ ie.double().T).argmax(1)
+    c = _native.Context(0)
+    c.set_train_csr(None, None, I)
+    c.set_test_csr(np.arange(U + 1, dtype=np.int64), best.cpu().numpy().astype(np.int32), I)
+    out = []
+    for _ in range(2):
+        per = torch.empty((U, 2 * K), dtype=torch.float32, device="cuda")
+        sums = torch.zeros(2 * K, dtype=torch.float64, device="cuda")
+        c.eval_fused(ue, ie, None, 0, [2, 5], K, precision="tf32r", per_user=per, sums=sums)
+        torch.cuda.synchronize()
+        out.append((per, sums))
+    per, sums = out[0]
+    assert torch.equal(per, out[1][0]) and torch.equal(sums, out[1][1])
+    assert float(per[:, K - 1].min()) == 1.0                                       # Recall@10 of EVERY user: nobody was skipped
+    assert float(per[:, 0].double().mean()) > 0.99999 and float(per[:, K:].min()) >= 0.5   # first, bar float64-vs-float32 near-ties
+    assert float((sums - per.double().sum(0)).abs().max()) < 1e-6 and abs(float(sums[0]) - U) < 1e-6
+    c.close()
