@@ -415,12 +415,18 @@ def measure(args, name, scaling, steps, warmup, e2e_cap, dev, rank, world, local
     elif shard == "items":
         h2d = 4 * (world * U * prob.d + prob.I * prob.d + (prob.I if prob.bias is not None else 0))
     else:
-        h2d = 4 * (U * prob.d + world * (prob.I * prob.d + (prob.I if prob.bias is not None else 0)))
+        # every rank uploads its users; the item table once in total when sharded (1/world per rank, all-gathered over
+        # NVLink: RankingEvaluator(upload="sharded"), the default), the bias vector whole
+        tables = 1 if (world > 1 and evaluator.upload == "sharded") else world
+        h2d = 4 * (U * prob.d + tables * prob.I * prob.d + world * (prob.I if prob.bias is not None else 0))
     res["e2e"] = {"value": U / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(h2d),
                   "d2h_bytes_per_step": int(8 * (MK + 1) * world),
                   "api": ("RankingEvaluator.evaluate(model), model.predict -> host score blocks" if predict_path else
-                          "RankingEvaluator(shard_users=True%s).evaluate(model) with pinned host embedding tables"
-                          % (", shard='items'" if shard == "items" else "")) + "; bytes summed over the %d rank(s)" % world,
+                          "RankingEvaluator(shard_users=True%s).evaluate(model) with pinned host embedding tables%s"
+                          % (", shard='items'" if shard == "items" else "",
+                             " (item table: 1/%d uploaded per rank, all-gathered over NVLink)" % world
+                             if (world > 1 and shard == "users" and evaluator.upload == "sharded") else ""))
+                         + "; bytes summed over the %d rank(s)" % world,
                   "timing": "wall clock, best of %d blocks of %d evaluate() calls, max over ranks; blocks on rank %d (ms/step): %s"
                             % (len(blocks), e2e_steps, rank, ", ".join("%.3f" % (x * 1e3) for x in blocks))}
     res["report"] = rep

@@ -103,6 +103,37 @@ def allgather_keys(keys, group=None):
     return out
 
 
+def gather_host_table(host, dev, rank, world, group=None):
+    """A float32 table [n, d] (or vector [n]) that every rank holds in HOST memory (the replicated item table of
+    user-sharded evaluation) -> the whole table on this rank's device.  Instead of `world` identical uploads competing
+    for the host's memory and PCIe links, each rank uploads only rows [rank * per, (rank + 1) * per), per = ceil(n /
+    world), and the slices are all-gathered in place (NCCL over NVLink / NVSwitch on GPUs, gloo on CPU tensors in the
+    tests).  COLLECTIVE.  The all-gather runs asynchronously: -> (table view [n, ...], work handle or None); the caller
+    issues whatever else it has to upload, then `work.wait()`s (the current stream waits, not the host)."""
+    import torch
+    import torch.distributed as td
+    if isinstance(host, np.ndarray):
+        host = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32))
+    host = host.detach()
+    if host.dtype != torch.float32:
+        host = host.float()
+    if not host.is_contiguous():
+        host = host.contiguous()
+    n = int(host.shape[0])
+    per = -(-n // world)
+    full = torch.empty((per * world,) + tuple(host.shape[1:]), dtype=torch.float32, device=dev)
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    mine = full[rank * per:(rank + 1) * per]
+    if hi > lo:
+        mine[:hi - lo].copy_(host[lo:hi])  # blocking for the host: the caller may change its table as soon as we return
+    try:
+        work = td.all_gather_into_tensor(full, mine, group=group, async_op=True)
+    except (RuntimeError, NotImplementedError):  # backends without the fused form
+        parts = [full[r * per:(r + 1) * per] for r in range(world)]
+        work = td.all_gather(parts, mine.clone(), group=group, async_op=True)
+    return full[:n], work
+
+
 def finalize_means(col_sums, n_users):
     """float64 column sums / user count, rounded once to float32 (what MetricReport carries)."""
     n = float(n_users)

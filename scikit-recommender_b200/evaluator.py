@@ -224,6 +224,9 @@ class RankingEvaluator(object):
             "items" the model's `eval_embeddings` may take `item_shard=(rank, world)` and return just
             its rows plus the catalogue size, `(user_vecs, item_rows, bias_rows | None, n_items)`.
         process_group: the group to reduce over (default: WORLD).
+        upload: how user-sharded ranks bring a HOST item table to their GPUs.  "sharded" (default): the table is
+            taken to be identical on every rank (it is the replicated model); each rank uploads 1/world of its rows
+            over PCIe and the slices are all-gathered over NVLink.  "replicated": every rank uploads the whole table.
     """
 
     def __init__(self, user_train_dict: Optional[Dict[int, np.ndarray]],
@@ -232,7 +235,7 @@ class RankingEvaluator(object):
                  top_k: Union[int, List[int], Tuple[int]] = 50,
                  batch_size: int = 256, num_thread: int = 8, *,
                  device: Optional[int] = None, precision: str = "auto", mean: str = "f64",
-                 shard_users: bool = False, shard: str = "users", process_group=None):
+                 shard_users: bool = False, shard: str = "users", process_group=None, upload: str = "sharded"):
         super(RankingEvaluator, self).__init__()
         if metric is None:
             metric = ["Precision", "Recall", "MAP", "NDCG", "MRR"]
@@ -272,6 +275,8 @@ class RankingEvaluator(object):
         assert precision in allowed, "precision must be auto|3xtf32|fp32|tf32r"
         assert mean in ("f64", "numpy_f32"), "mean must be f64|numpy_f32"
         assert shard in ("users", "items"), "shard must be users|items"
+        assert upload in ("sharded", "replicated"), "upload must be sharded|replicated"
+        self.upload = upload
         self.shard = shard
         self.device = device
         self.precision = precision
@@ -451,12 +456,15 @@ class RankingEvaluator(object):
         with torch.cuda.device(dev):
             packed = torch.zeros(MK + 1, dtype=torch.float64, device=dev)
             sums = packed[:MK]
-            if len(users) > 0:
+            # a rank left without users (fewer users than ranks) still takes part in the item table's all-gather
+            gather_only = len(users) == 0 and world > 1 and not item_sharded and self.upload == "sharded" and \
+                hasattr(model, "eval_embeddings")
+            if len(users) > 0 or gather_only:
                 if item_sharded:
                     out["path"], out["n_users"] = self._evaluate_item_sharded(model, users, key, dev, rank, world, sums)
                 elif hasattr(model, "eval_embeddings"):
                     out["path"], out["host_sums"], out["per_user"] = self._evaluate_fused(
-                        model, users, key, dev, want_pu, sums, host_fast and world == 1)
+                        model, users, key, dev, want_pu, sums, host_fast and world == 1, rank, world)
                 else:
                     out["path"], out["per_user"] = self._evaluate_predict(model, users, key, dev, want_pu, sums)
             if out["host_sums"] is None:
@@ -581,7 +589,7 @@ class RankingEvaluator(object):
             x = np.ascontiguousarray(x)
         return x
 
-    def _evaluate_fused(self, model, users, key, dev, want_pu, sums, host_fast):
+    def _evaluate_fused(self, model, users, key, dev, want_pu, sums, host_fast, rank=0, world=1):
         """Column sums are ADDED into `sums` (float64 device tensor [M*K]) -- unless host tables took the one-call
         native path (`host_fast`), which returns them on the host.
         -> (path, float64 host sums or None, per-user block on the device or None)"""
@@ -610,7 +618,19 @@ class RankingEvaluator(object):
                 _, _, host_sums = plan.ctx.eval_fused_host(uv, iv, b, 0, self.metrics, self.max_top, precision=prec)
             return "fused:" + plan.ctx.last_fused_kernel, host_sums, None
         with _nvtx("skrec:H2D embedding tables"):
-            uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
+            items_on_host = not (isinstance(item_vecs, torch.Tensor) and item_vecs.is_cuda)
+            if items_on_host and world > 1 and self.upload == "sharded" and getattr(item_vecs, "ndim", 0) == 2:
+                # user-sharded ranks all hold the same item table on the host: each uploads 1/world of its rows and
+                # the slices are all-gathered over NVLink, while the PCIe links carry this rank's user rows
+                from . import dist
+                iv, work = dist.gather_host_table(item_vecs, dev, rank, world, self.process_group)
+                uv, b = self._to_dev(user_vecs, dev), self._to_dev(bias, dev)
+                if work is not None:
+                    work.wait()
+            else:
+                uv, iv, b = self._to_dev(user_vecs, dev), self._to_dev(item_vecs, dev), self._to_dev(bias, dev)
+        if len(users) == 0:
+            return "none", None, None
         assert uv.dim() == 2 and iv.dim() == 2 and uv.shape[1] == iv.shape[1], "eval_embeddings: shapes"
         assert uv.shape[0] == len(users), "eval_embeddings must return one row per requested user"
         d = int(iv.shape[1])

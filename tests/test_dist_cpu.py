@@ -125,3 +125,29 @@ def test_column_partition_of_interactions():
     assert ptr.tolist() == [0, 1, 3, 3, 3] and idx.tolist() == [3, 0, 2]
     ptr, idx = ev._dict_to_csr(users, d, (100, 200))
     assert ptr.tolist() == [0, 0, 0, 0, 0] and idx.size == 0
+
+
+# ---- replicated host item table: 1/world uploaded per rank + all-gather (gloo here, NCCL over NVLink on GPUs) -----
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for n, d in ((7, 5), (1, 3), (64, 4), (0, 4), (9, None)):  # ragged last slice, fewer rows than ranks, even, empty, vector
+        g = np.random.default_rng(n)
+        table = g.standard_normal((n, d) if d is not None else (n,)).astype(np.float32)  # identical on every rank
+        host = table if (n % 2) else torch.from_numpy(table)
+        full, work = dist.gather_host_table(host, torch.device("cpu"), rank, world)
+        if work is not None:
+            work.wait()
+        ok = ok and tuple(full.shape) == table.shape and np.array_equal(full.numpy(), table)
+    np.save(os.path.join(out_dir, "ok%d.npy" % rank), np.array([ok]))
+    td.destroy_process_group()
+
+
+def test_two_rank_gloo_host_table_is_uploaded_in_slices_and_gathered(tmp_path):
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(bool(np.load(str(tmp_path / ("ok%d.npy" % r)))[0]) for r in range(2))

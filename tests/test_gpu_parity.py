@@ -531,6 +531,16 @@ def _items_worker(rank, world, port, out_path):
                                                      - np.array(list(rep.values()), np.float32))) == 0.0
         out[shard] = np.array(list(rep.values()), np.float32)
         out[shard + "_path"] = ev.last_stats["path"]
+    # host item table: 1/world uploaded per rank + NVLink all-gather (the default above) == every rank uploading all of it;
+    # a single evaluated user leaves every rank but one without users -- they still take part in the all-gather
+    ev_r = RankingEvaluator(data["train"], data["test"], metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], top_k=[10, 50],
+                            device=rank, shard_users=True, upload="replicated")
+    out["users_replicated"] = np.array(list(ev_r.evaluate(model).values()), np.float32)
+    one = [next(iter(data["test"].keys()))]
+    ev_s = RankingEvaluator(data["train"], data["test"], metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], top_k=[10, 50],
+                            device=rank, shard_users=True)
+    out["one_sharded"] = np.array(list(ev_s.evaluate(model, test_users=one).values()), np.float32)
+    out["one_replicated"] = np.array(list(ev_r.evaluate(model, test_users=one).values()), np.float32)
     # one-shot NVLink all-reduce against NCCL: same bits (two ranks: a + b either way), repeated calls (parity, sequence)
     from skrec_b200 import dist
     comm = dist.nvlink_comm(rank, None)
@@ -548,7 +558,8 @@ def _items_worker(rank, world, port, out_path):
             worst = max(worst, float((a - b).abs().max()))
         comm.status()
     if rank == 0:
-        np.savez(out_path, users=out["users"], items=out["items"], path=out["items_path"], nvlink=nv_ok, nvlink_err=worst)
+        np.savez(out_path, users=out["users"], items=out["items"], path=out["items_path"], nvlink=nv_ok, nvlink_err=worst,
+                 users_replicated=out["users_replicated"], one_sharded=out["one_sharded"], one_replicated=out["one_replicated"])
     td.destroy_process_group()
 
 
@@ -569,6 +580,8 @@ def test_item_sharded_evaluator_two_gpus_nccl(torch_cuda, tmp_path):
     assert bool(got["nvlink"]) and float(got["nvlink_err"]) < 1e-12  # GPUs of one box: the one-shot path must come up
     assert str(got["path"]).startswith("items:")  # 6,000 / world item rows per shard: below 3,072 the exact FP32 kernel takes them
     assert np.max(np.abs(got["users"] - got["items"])) <= 1e-7
+    assert np.array_equal(got["users"], got["users_replicated"])  # same table on the device either way: same bits
+    assert np.array_equal(got["one_sharded"], got["one_replicated"]) and np.all(np.isfinite(got["one_sharded"]))
     data = synth.make(users=1500, items=6000, d=64, nnz_train=60000, nnz_test=12000, seed=11, bias=True)
     plain = synth.PredictOnlyModel(data["user_emb"], data["item_emb"], data["bias"])
     per, _ = oracle.evaluate_dicts(plain.predict, data["train"], data["test"], [1, 2, 3, 4, 5], 50)
