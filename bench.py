@@ -520,7 +520,8 @@ def run_ours(args):
                 "value": a["value"], "unit": UNIT, "ms_per_step": a["ms_per_step"], "steps": 200,
                 "e2e_value": a["e2e"]["value"], "e2e_ms_per_step": a["e2e"]["ms_per_step"], "gpu_launches": a["launches"],
                 "kernel": a.get("kernel"), "kernel_ms": a.get("kernel_ms"),
-                "roofline_frac": (2.0 * a["U"] / world * a["I"] * a["d"] / (a["kernel_ms"] * 1e-3) / 1e12 / (pk["bf16"] / 2.0)) if a.get("kernel_ms") else None,
+                "roofline_frac": (2.0 * a["U"] / world * a["I"] * a["d"] / (a["kernel_ms"] * 1e-3) / 1e12 /
+                                  (pk["bf16"] if a.get("kernel") == "tcgen05_f16r" else pk["bf16"] / 2.0)) if a.get("kernel_ms") else None,
                 "exact_rows": a.get("plan", {}).get("exact_rows"), "path": a["path"]}
 
     if rank != 0:
@@ -546,7 +547,11 @@ def run_ours(args):
         achieved = flops / (r["kernel_ms"] * 1e-3) / 1e12
         kern = r["kernel"]
         passes = {"tcgen05_3xtf32": 3}.get(kern, 1)
-        if kern.startswith("tcgen05"):
+        if kern == "tcgen05_f16r":
+            peak = pk["bf16"]
+            peak_note = ("FP16 operands (tcgen05 kind::f16, FP32 accumulate): dense 16-bit peak = the %s cuBLAS bf16 burst peak (%.1f TFLOP/s) in "
+                         "MEASURED_PEAKS.json; against the TF32 peak used for the tf32r kernel (half of it) the same throughput reads frac x 2" % (pk["src"], pk["bf16"]))
+        elif kern.startswith("tcgen05"):
             peak = pk["bf16"] / 2.0
             peak_note = "TF32 dense = 1/2 of the %s cuBLAS bf16 burst peak (%.1f TFLOP/s) in MEASURED_PEAKS.json" % (pk["src"], pk["bf16"])
         else:
@@ -567,6 +572,7 @@ def run_ours(args):
 
     kern = r.get("kernel", "score blocks")
     dtype = {"tcgen05_3xtf32": "tf32x3 (fp32-grade)", "tcgen05_tf32r": "tf32 candidates + f32 re-scoring (fp32-exact)",
+             "tcgen05_f16r": "scaled fp16 candidates (f32 accumulate) + f32 re-scoring (fp32-exact)",
              "tcgen05_1xtf32": "tf32", "simt_fp32": "f32"}.get(kern, "f32")
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -597,7 +603,7 @@ def main():
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="default: strong (c3a, c3b, c4, c5), weak (c1, c2)")
     ap.add_argument("--path", default="fused", choices=["fused", "predict"], help="predict: the model only offers the reference's predict()")
     ap.add_argument("--batch-size", type=int, default=256, help="user batch of the predict path (reference default 256)")
-    ap.add_argument("--precision", default="auto", choices=["auto", "3xtf32", "fp32", "tf32r"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "3xtf32", "fp32", "tf32r", "f16r"])
     ap.add_argument("--norms", default="iid", choices=["iid", "heavy"], help="heavy: heavy-tailed item norms, outliers, norm-correlated bias (c1-c3 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")

@@ -64,6 +64,9 @@ extern "C" {
 #define SKR_PREC_1XTF32 3 /* single TF32 pass; NOT reference-grade, for measurement only */
 #define SKR_PREC_TF32R 4  /* single TF32 pass to find candidates inside a rigorous error band, then exact FP32
                            * re-scoring of the survivors: results equal SKR_PREC_FP32 bit for bit */
+#define SKR_PREC_F16R 5   /* the same with FP16 operands (tcgen05 kind::f16, twice the TF32 rate, half the item-panel bytes):
+                           * tables scaled by powers of two into fp16's range, the same 2^-11 operand rounding as TF32,
+                           * exact FP32 re-scoring of the survivors: results equal SKR_PREC_FP32 bit for bit */
 
 typedef struct skr_ctx skr_ctx;
 
@@ -161,7 +164,7 @@ int skr_colsum_f32_seq(skr_ctx *ctx, const float *per_user_dev, int64_t n_rows, 
 /* Number of kernels this library has launched on `ctx` since creation (bench.py's gpu_launches). */
 int64_t skr_launch_count(const skr_ctx *ctx);
 
-/* Name of the scoring kernel the last skr_eval_fused* call on ctx used: "tcgen05_3xtf32", "tcgen05_tf32r",
+/* Name of the scoring kernel the last skr_eval_fused* call on ctx used: "tcgen05_3xtf32", "tcgen05_tf32r", "tcgen05_f16r",
  * "tcgen05_1xtf32", "simt_fp32" or "simt_fp32_blocks" (top_k > 128: score blocks + the score-matrix kernels). */
 const char *skr_last_fused_kernel(const skr_ctx *ctx);
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libskrec_b200.so")
 
 SKR_OK = 0
-PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "1xtf32": 3, "tf32r": 4}
+PREC = {"auto": 0, "fp32": 1, "3xtf32": 2, "1xtf32": 3, "tf32r": 4, "f16r": 5}
 
 # every symbol include/skrec_b200.h declares (tests check the library exports all of them)
 SYMBOLS = (

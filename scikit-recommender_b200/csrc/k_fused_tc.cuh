@@ -57,6 +57,7 @@
 // buffer lets the issuers run a tile further ahead of the epilogue.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "fused_common.cuh"
 
 namespace skr {
@@ -69,6 +70,10 @@ constexpr int TC_TILE_BYTES = TN * TC_KB * 4;         // 16 KB: one operand tile
 constexpr int TC_RING_BYTES = 8 * TC_TILE_BYTES;      // 4 stages of hi+lo (3xTF32) or 8 stages of hi (1xTF32)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_BUF = 3;                         // accumulator / bitmap buffers
+// bias tiles live one slot longer than accumulators: the epilogue hands an accumulator back BEFORE it works on the scores
+// (and reads the bias), so the builder of tile i + 4, which has waited for every epilogue warp to take tile i + 4 - NBUF >= i + 1
+// (a warp takes tile i + 1 only after it is done with tile i), may overwrite the bias of tile i
+constexpr int TC_BIAS_RING = 4;
 constexpr int TC_R = 16;                              // group maxima kept per row and column quarter (SAMPLE)
 constexpr int TC_MAX_RANK = 32;                       // largest threshold rank the 4 x TC_R lists support
 constexpr long long TC_TIMEOUT_CYCLES = 4000000000ll; // watchdog: ~2 s
@@ -82,6 +87,7 @@ __host__ __device__ inline size_t tc_smem_bytes()
            + (size_t)TC_MAX_BUF * 4 * TM * 4     // train-mask bitmaps, one per accumulator buffer
            + (size_t)8 * TC_EPI_THREADS * 16     // score staging: one 32-float row per epilogue thread, [8][512] float4
            + (size_t)TC_TILE_BYTES               // constant B tile of the threshold MMA (single-pass COLLECT)
+           + (size_t)TC_BIAS_RING * TN * 4       // bias of the last tiles (staged by the mask builders)
            + 256;                                // barriers + tmem pointer
 }
 
@@ -167,6 +173,16 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with FP16 operands (kind::f16: K = 16 per instruction, twice the TF32 rate), FP32 accumulation
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t to_tf32(float x)
 {
     uint32_t r;
@@ -209,6 +225,38 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr)
 // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format TF32 (2) [7,10) | b_format TF32 (2)
 // [10,13) | a/b K-major | N>>3 [17,23) | M>>4 [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// a_format / b_format F16 (0)
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// ---- FP16 operands (precision "f16r") -------------------------------------------------------------------------------
+// fp16 keeps 11 significant bits like TF32 but only 5 exponent bits, so both tables are scaled by powers of two (exact)
+// before the conversion: the item table by one factor s_i for the whole catalogue, every user row by its own s_u, each
+// chosen so that the largest magnitude lands in [2^9, 2^10).  Elements down to 2^-23 of the largest keep a relative error
+// of 2^-11 (fp16 normals reach down to 2^-14); smaller ones are off by at most 2^-25 in scaled units, which the error
+// band accounts for (k_sample_thr).  Scaled scores stay below d 2^20 <= 2^27.  The threshold operand of the threshold
+// MMA is (hi + lo) x C with C = 2^12 in the constant B' tile, hi and lo fp16 values of magnitude < 2^15.
+constexpr int TC_F16_TARGET = 9;     // floor(log2(scaled maximum))
+constexpr int TC_F16_THR_SHIFT = 12;  // log2 C
+__host__ __device__ inline int f16_scale_exp(float amax)
+{
+    // exponent e with amax 2^e in [2^9, 2^10); 0 for an all-zero, infinite or NaN maximum (garbage in: the rows fail over to the exact kernel)
+    if (!(amax > 0.0f) || !(amax < 3.0e38f)) return 0;
+#ifdef __CUDA_ARCH__
+    const int ex = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;
+#else
+    int ex;
+    frexpf(amax, &ex);
+    ex -= 1;
+#endif
+    int e = TC_F16_TARGET - ex;
+    return e < -60 ? -60 : (e > 60 ? 60 : e);
+}
+__device__ __forceinline__ float exp2i(int e) { return __int_as_float((uint32_t)(e + 127) << 23); }  // 2^e, -126 <= e <= 127
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi)  // (lo, hi) -> fp16 pair, lo in bits 0-15 (the lower k index)
+{
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
 
 struct TcArgs {
     const float *U;   // user vectors [n_rows, ld_u]
@@ -225,6 +273,10 @@ struct TcArgs {
     const float *thr;        // [n_rows]
     const float *thr_hi;     // [n_rows] single-pass COLLECT: thr = fl(hi + lo), hi and lo TF32 values (k_sample_thr)
     const float *thr_lo;
+    // FP16 operands: s_i of the item table (k_split_f16); COLLECT: per-row s_u s_i from k_sample_thr, 0 = the row collects
+    // nothing (no usable threshold); SAMPLE derives s_u from the row itself
+    const float *item_scale;
+    const float *scale;
     int cap;                 // entries per (row, chunk, column quarter) sub-list
     uint2 *cand;             // [n_rows, S*4, cap] (score bits, item); PRESUB kernels store score - thr[row]
     uint32_t *cand_cnt;      // [n_rows, S*4] entries offered (> cap means overflow)
@@ -285,20 +337,31 @@ __device__ __forceinline__ void sorted_insert(float (&v)[TC_R], float x)
 
 // One thread's share of a tile: 32 scores of its row.  SAMPLE: fold the group maximum into the sorted
 // list v.  COLLECT: survivor mask against the row threshold, survivors appended to the sub-list.
-template <bool SAMPLE, bool BIAS, bool PRESUB>
+// HALF (FP16 operands): the accumulator is in scaled units, inv = 1 / (s_u s_i) brings it back (a power of two: exact);
+// with a bias that is the multiplier of the FMA that adds the bias, without one only survivors / sampled maxima are
+// rescaled.  dead: all ones for a row that must not collect (no usable threshold), else 0.
+template <bool SAMPLE, bool BIAS, bool PRESUB, bool HALF>
 __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const float *__restrict__ bias32, uint32_t mword, float thr, int col0,
-                                           bool my_valid, int cap, int dbg, float4 *my_stage, uint2 *wbase, int &wn, float (&v)[TC_R])
+                                           bool my_valid, int cap, int dbg, float4 *my_stage, uint2 *wbase, int &wn, float (&v)[TC_R],
+                                           float inv, uint32_t dead)
 {
     float s[32];
     if (BIAS) {
-        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);  // shared memory: this tile's bias, my 32 columns
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 x = __ldg(b4 + q);
-            s[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + x.x;
-            s[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + x.y;
-            s[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + x.z;
-            s[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + x.w;
+            const float4 x = b4[q];
+            if (HALF) {
+                s[4 * q + 0] = fmaf(__uint_as_float(raw[4 * q + 0]), inv, x.x);
+                s[4 * q + 1] = fmaf(__uint_as_float(raw[4 * q + 1]), inv, x.y);
+                s[4 * q + 2] = fmaf(__uint_as_float(raw[4 * q + 2]), inv, x.z);
+                s[4 * q + 3] = fmaf(__uint_as_float(raw[4 * q + 3]), inv, x.w);
+            } else {
+                s[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + x.x;
+                s[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + x.y;
+                s[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + x.z;
+                s[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + x.w;
+            }
         }
     } else {
 #pragma unroll
@@ -336,7 +399,7 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
         // chain j holds items 8j..8j+7 with item 8j in bit 7: assemble so that item 0 lands in bit 31,
         // then reverse
         const uint32_t m = (m0 << 24) | (m1 << 16) | (m2 << 8) | m3;
-        uint32_t pass = ~__brev(m) & ~mword;
+        uint32_t pass = ~__brev(m) & ~mword & ~dead;  // one LOP3
         if (TC_DBG(dbg, 32)) pass &= (uint32_t)(wn >> 30);  // timing experiment: detection only
         if (pass != 0u) {
             // rare per lane: park my 32 scores in shared memory so they can be indexed, then append
@@ -353,7 +416,8 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
                 const int q = 31 - __clz(pass);  // highest first: one FLO instead of BREV + FLO; the lists are unordered
                 pass ^= 1u << q;
                 // PRESUB: the sub-lists hold margins (score - T0); k_select_cands adds T0 back
-                const float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
+                float sc = row_f[(q >> 2) * (TC_EPI_THREADS * 4) + (q & 3)];
+                if (HALF && !BIAS) sc *= inv;
                 if (wn < cap && !TC_DBG(dbg, 64)) wbase[wn] = make_uint2(__float_as_uint(sc), (uint32_t)(col0 + q));
                 if (TC_DBG(dbg, 64)) wn += (int)(__float_as_uint(sc) >> 31);  // timing experiment: no global store
                 ++wn;
@@ -362,12 +426,16 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
     }
 }
 
-template <int NKB, int PASSES, int MODE>
+// HALF: FP16 operands (tm_bhi describes the scaled fp16 item table; a k-block is 64 elements = the same 128-byte swizzle
+// row, 32 TMEM columns of packed pairs and four K = 16 MMAs, so the pipeline below is unchanged), single pass only.
+template <int NKB, int PASSES, int MODE, bool HALF = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, TcArgs A, FusedParams P)
 {
     pdl_trigger();  // the wait comes after the prologue, which touches nothing an earlier kernel wrote
     constexpr bool SAMPLE = (MODE == TC_MODE_SAMPLE);
+    constexpr int KB_ELEMS = HALF ? 2 * TC_KB : TC_KB;  // operand elements per k-block
+    static_assert(!HALF || PASSES == 1, "FP16 operands: single pass");
     constexpr int STAGES = (PASSES == 3) ? 4 : 8;
     constexpr int STAGE_BYTES = (PASSES == 3) ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
     static_assert(NKB >= 1 && NKB <= 4 && (PASSES == 1 || PASSES == 3), "tile shape");
@@ -391,7 +459,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(smem + TC_RING_BYTES);        // [NBUF][4][TM]
     float4 *stage_buf = reinterpret_cast<float4 *>(bitmap + TC_MAX_BUF * 4 * TM);  // [8][TC_EPI_THREADS]
     unsigned char *thr_tile = reinterpret_cast<unsigned char *>(stage_buf + 8 * TC_EPI_THREADS);  // [TN][128 B], SWIZZLE_128B, 1024-aligned
-    uint64_t *bars = reinterpret_cast<uint64_t *>(thr_tile + TC_TILE_BYTES);
+    float *bias_buf = reinterpret_cast<float *>(thr_tile + TC_TILE_BYTES);                        // [TC_BIAS_RING][TN]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_buf + TC_BIAS_RING * TN);
     uint64_t *full = bars;                            // [TC_MAX_STAGES] TMA landed
     uint64_t *empty = bars + TC_MAX_STAGES;           // [TC_MAX_STAGES] MMAs that read the stage are done
     uint64_t *tile_full = bars + 2 * TC_MAX_STAGES;   // [NBUF] accumulator complete (MMA commit) + bitmap built (mask warp)
@@ -437,7 +506,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         uint4 *t4 = reinterpret_cast<uint4 *>(thr_tile);
         for (int j = tid; j < TC_TILE_BYTES / 16; j += TC_THREADS) {
             const int r8 = (j >> 3) & 7, pos = j & 7;
-            t4[j] = ((pos ^ r8) == 0) ? make_uint4(0x3f800000u, 0x3f800000u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+            // TF32: k = 0, 1 are 1.0f; FP16: k = 0, 1 are C = 2^12 (0x6c00), one packed pair
+            const uint4 one = HALF ? make_uint4(0x6c006c00u, 0u, 0u, 0u) : make_uint4(0x3f800000u, 0x3f800000u, 0u, 0u);
+            t4[j] = ((pos ^ r8) == 0) ? one : make_uint4(0u, 0u, 0u, 0u);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
     }
@@ -475,7 +546,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     } else {
                         mbar_expect_tx(full + s, STAGE_BYTES);
                         unsigned char *dst = b_tiles + (size_t)s * STAGE_BYTES;
-                        tma_load_2d(dst, &tm_bhi, kb * TC_KB, t * TN, full + s);
+                        tma_load_2d(dst, &tm_bhi, kb * KB_ELEMS, t * TN, full + s);
                         if (PASSES == 3) tma_load_2d(dst + TC_TILE_BYTES, &tm_blo, kb * TC_KB, t * TN, full + s);
                     }
                     if (kb == NKB - 1) tc_trace(A, i, 1);
@@ -515,9 +586,12 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 if (elect_one()) {
                     if (kb == 0) tc_trace(A, i, 3);
                     if (do_mma) {
-                        if (PRESUB && kb == 0) tc_mma_ts(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC, 0u);  // acc = -T0[row]
+                        if (PRESUB && kb == 0) {  // acc = -T0[row]
+                            if (HALF) tc_mma_ts_f16(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC_F16, 0u);
+                            else tc_mma_ts(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC, 0u);
+                        }
 #pragma unroll
-                        for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 = 32 bytes
+                        for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 / 16 fp16 = 32 bytes of B, 8 TMEM columns of A
                             const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
                             const uint64_t dhi = ds + (uint64_t)(k8 * 2);
                             const uint32_t acc = (PRESUB || (kb | k8)) ? 1u : 0u;
@@ -526,6 +600,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                                 tc_mma_ts(d_tmem, a_lo0 + acol, dhi, TC_IDESC, acc);
                                 tc_mma_ts(d_tmem, a_hi0 + acol, dlo, TC_IDESC, 1u);
                                 tc_mma_ts(d_tmem, a_hi0 + acol, dhi, TC_IDESC, 1u);
+                            } else if (HALF) {
+                                tc_mma_ts_f16(d_tmem, a_hi0 + acol, dhi, TC_IDESC_F16, acc);
                             } else {
                                 tc_mma_ts(d_tmem, a_hi0 + acol, dhi, TC_IDESC, acc);
                             }
@@ -582,6 +658,16 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         uint32_t nk[TC_MASK_PF];
 #pragma unroll
         for (int j = 0; j < TC_MASK_PF; ++j) nk[j] = fetch(mp + 2 * j, 0);
+        // The tile's 128 bias values travel the same way: fetched TC_MASK_PF own tiles ahead (one float4 per lane), stored
+        // next to the bitmap, published by the same arrive.  The epilogue then reads them with shared-memory latency (its
+        // per-tile global loads were the long-scoreboard stalls of the c4 profile: 57 % of the kernel's samples).
+        auto fetch_bias = [&](int x) -> float4 {
+            if (P.bias == nullptr || x >= n_tiles) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            return __ldg(reinterpret_cast<const float4 *>(P.bias + (size_t)(t0 + x * t_step) * TN) + lane);
+        };
+        float4 nb4[TC_MASK_PF];
+#pragma unroll
+        for (int j = 0; j < TC_MASK_PF; ++j) nb4[j] = fetch_bias(mp + 2 * j);
         for (int i0 = mp; i0 < n_tiles; i0 += 2 * TC_MASK_PF) {
 #pragma unroll
           for (int j = 0; j < TC_MASK_PF; ++j) {
@@ -598,7 +684,10 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             const uint32_t kb0 = __shfl_sync(0xffffffffu, off_b, i & 31), ke0 = __shfl_sync(0xffffffffu, off_e, i & 31);
             uint32_t key = nk[j];
             nk[j] = fetch(i + 2 * TC_MASK_PF, i);
+            const float4 bias4 = nb4[j];
+            nb4[j] = fetch_bias(i + 2 * TC_MASK_PF);
             mbar_wait(tile_empty + b, (uint32_t)(((i / NBUF) & 1) ^ 1), A.err_flag, 5);
+            if (P.bias != nullptr) reinterpret_cast<float4 *>(bias_buf + (i & (TC_BIAS_RING - 1)) * TN)[lane] = bias4;
             if (lane == 0) tc_trace(A, i, 5);
             uint32_t *bm = bitmap + b * 4 * TM;
             if (TC_DBG(A.dbg, 16)) {  // timing ablation: no bitmap work at all
@@ -654,7 +743,70 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         const float NINF = -__int_as_float(0x7f800000);
         const float PINF = __int_as_float(0x7f800000);
 
-        if (cq < NKB) {  // A: k-block cq of my user's vector -> hi/lo TF32 -> TMEM
+        // FP16 operands: scale of my row.  su: what the row is multiplied by before the conversion; inv = 1 / (su s_i)
+        // brings accumulator values back to true units; dead: the row has no usable threshold and collects nothing.
+        float su = 1.0f, inv = 1.0f;
+        uint32_t dead = 0u;
+        if (HALF) {
+            const float si = __ldg(A.item_scale);
+            if (SAMPLE) {
+                float amax = 0.0f;  // fmaxf drops NaNs: a NaN element poisons its own products only
+                if (my_valid) {
+                    const float *urow = A.U + my_row * A.ld_u;
+                    if (((A.ld_u & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.U) & 15) == 0) && (P.d & 3) == 0) {
+                        for (int k = 0; k < P.d; k += 4) {
+                            const float4 f = __ldg(reinterpret_cast<const float4 *>(urow + k));
+                            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y))), fmaxf(fabsf(f.z), fabsf(f.w)));
+                        }
+                    } else {
+                        for (int k = 0; k < P.d; ++k) amax = fmaxf(amax, fabsf(__ldg(urow + k)));
+                    }
+                }
+                su = exp2i(f16_scale_exp(amax));
+                inv = 1.0f / (su * si);  // powers of two with exponents within +-60 each: exact
+            } else {
+                const float S = my_valid ? __ldg(A.scale + my_row) : 0.0f;
+                if (S > 0.0f) {
+                    su = S / si;
+                    inv = 1.0f / S;
+                } else {
+                    dead = 0xffffffffu;
+                }
+            }
+        }
+        if (HALF && cq < NKB) {  // A: k-block cq (64 elements) of my user's vector -> scaled fp16 pairs -> 32 TMEM columns
+            const int kb = cq;
+            const float *urow = A.U + (my_valid ? my_row : 0) * A.ld_u;
+            const bool vec = ((A.ld_u & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.U) & 15) == 0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = kb * KB_ELEMS + h * 32;
+                uint32_t pk[16];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    const int k = k0 + 4 * q;
+                    if (my_valid) {
+                        if (vec && k + 4 <= P.d) {
+                            f = __ldg(reinterpret_cast<const float4 *>(urow + k));
+                        } else {
+                            if (k + 0 < P.d) f.x = __ldg(urow + k + 0);
+                            if (k + 1 < P.d) f.y = __ldg(urow + k + 1);
+                            if (k + 2 < P.d) f.z = __ldg(urow + k + 2);
+                            if (k + 3 < P.d) f.w = __ldg(urow + k + 3);
+                        }
+                    }
+                    pk[2 * q + 0] = pack_h2(f.x * su, f.y * su);
+                    pk[2 * q + 1] = pack_h2(f.z * su, f.w * su);
+                }
+                tmem_st16(lane_addr + (uint32_t)(kb * TC_KB + h * 16), pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        }
+        if (!HALF && cq < NKB) {  // A: k-block cq of my user's vector -> hi/lo TF32 -> TMEM
             const int kb = cq;
             const float *urow = A.U + (my_valid ? my_row : 0) * A.ld_u;
             const bool vec = ((A.ld_u & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.U) & 15) == 0);
@@ -709,8 +861,12 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             uint32_t x[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) x[q] = 0u;
-            x[0] = __float_as_uint(-thr_hi);
-            x[1] = __float_as_uint(-thr_lo);
+            if (HALF) {  // k_sample_thr wrote hi, lo as fp16 values of T0 su s_i / C; a dead row's operand is irrelevant
+                x[0] = dead ? 0u : pack_h2(-thr_hi, -thr_lo);
+            } else {
+                x[0] = __float_as_uint(-thr_hi);
+                x[1] = __float_as_uint(-thr_lo);
+            }
             tmem_st16(lane_addr + (uint32_t)A_THR_COL, x);
             tmem_wait_st();
             tc_fence_before();
@@ -725,10 +881,6 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         uint32_t bph = 0;  // buffer and its phase for tile i
         for (int i = 0; i < n_tiles; ++i) {
             const int col0 = (t0 + i * t_step) * TN + cq * 32;
-            // the 128 bytes of bias this warp adds two tiles from now: into L1 while the tensor core works (ncu, c4: 57 % of the
-            // kernel's stall samples were long-scoreboard waits, the epilogue's bias loads being its only global reads per tile)
-            if (P.bias != nullptr && lane == 0 && i + 2 < n_tiles)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(P.bias + col0 + 2 * t_step * TN));
             mbar_wait(tile_full + b, bph, A.err_flag, 6);
             tc_fence_after();
             const int tslot = (warp == 0) ? 7 : 10;
@@ -751,15 +903,20 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             // two copies of the per-tile work, so that without a bias the scores are consumed in the very
             // registers tcgen05.ld wrote (one shared copy costs 32 register moves per tile)
             if (P.bias != nullptr)
-                tc_process<SAMPLE, true, PRESUB>(raw, P.bias + col0, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
+                tc_process<SAMPLE, true, PRESUB, HALF>(raw, bias_buf + (i & (TC_BIAS_RING - 1)) * TN + cq * 32, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage,
+                                                       wbase, wn, v, inv, dead);
             else
-                tc_process<SAMPLE, false, PRESUB>(raw, nullptr, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v);
+                tc_process<SAMPLE, false, PRESUB, HALF>(raw, nullptr, mword, thr, col0, my_valid, A.cap, A.dbg, my_stage, wbase, wn, v, inv, dead);
             if (tr_me) tc_trace(A, i, tslot + 2);
         }
 
         if (my_valid) {
             if (SAMPLE) {
                 float4 *dst = reinterpret_cast<float4 *>(A.samp + ((my_row * A.samp_chunks + c) * 4 + cq) * TC_R);
+                if (HALF && P.bias == nullptr) {  // the maxima were kept in scaled units
+#pragma unroll
+                    for (int q = 0; q < TC_R; ++q) v[q] *= inv;
+                }
 #pragma unroll
                 for (int q = 0; q < TC_R / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             } else {
@@ -800,8 +957,17 @@ template <int NQ>  // sampling chunks per row (1..4): 64 NQ values per row, 2 NQ
 __global__ void __launch_bounds__(256)
 k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
              int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
-             float *__restrict__ thr_lo_out, float eps3_coef, float *__restrict__ eps2_3_out, float *__restrict__ thr3_out)
+             float *__restrict__ thr_lo_out, float eps3_coef, float *__restrict__ eps2_3_out, float *__restrict__ thr3_out,
+             const float *__restrict__ item_scale, float *__restrict__ scale_out)
 {
+    // item_scale != null: FP16 operands (precision "f16r").  The band gets one more term -- elements too small for an fp16
+    // normal are off by up to 2^-25 in scaled units instead of 2^-11 relative: sum_k |du'_k i'_k| + |u'_k di'_k| <=
+    // 2^-25 sqrt(d) (N'_max + ||u'||), i.e. 2^-25 sqrt(d) (N_max / s_u + ||u|| / s_i) in true units (fp16 round-to-nearest
+    // has the same 2^-11 relative bound as TF32's rna, and products of two fp16 values are exact in FP32) -- and the
+    // row's scale s_u is chosen here: largest magnitude to [2^9, 2^10), lowered if need be until the threshold operand
+    // T0 s_u s_i / C fits fp16 (|.| < 2^15; only when |T0| exceeds ~256 max|u| max|i|, i.e. the bias dominates).  Rows
+    // whose scale would fall more than 14 binades short, or without a usable threshold, are marked dead (scale 0):
+    // they collect nothing and the exact kernel settles them.
     pdl_wait();
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -831,15 +997,35 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
         if (__reduce_add_sync(0xffffffffu, c) >= r) T = cand;
     }
     float t0 = unord_f32(T);
+    int eu = 0, ei = 0;  // FP16 operands: exponents of s_u, s_i
+    bool half_dead = false;
     if (eps2_out != nullptr) {
-        float ss = 0.0f;
+        float ss = 0.0f, amax = 0.0f;
         for (int k = lane; k < d; k += 32) {
             const float v = __ldg(U + row * ld_u + k);
             ss = fmaf(v, v, ss);
+            amax = fmaxf(amax, fabsf(v));
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float eps = 1.25f * (eps_coef * sqrtf(ss) * sqrtf(__ldg(stats)) + 2.384185791015625e-07f * __ldg(stats + 1));
+        for (int o = 16; o > 0; o >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        }
+        float eps = 1.25f * (eps_coef * sqrtf(ss) * sqrtf(__ldg(stats)) + 2.384185791015625e-07f * __ldg(stats + 1));
+        if (item_scale != nullptr) {
+            ei = (int)((__float_as_uint(__ldg(item_scale)) >> 23) & 0xffu) - 127;
+            const int eu0 = f16_scale_exp(amax);
+            eu = eu0;
+            // |T0 - 2 eps| 2^(eu + ei - 12) < 2^14 (one binade of headroom for the terms added below)
+            const float tmag = fabsf(t0) + 2.0f * eps;
+            if (tmag < 3.0e38f && tmag > 0.0f) {
+                const int et = (int)((__float_as_uint(tmag) >> 23) & 0xffu) - 127 + 1;  // tmag < 2^et
+                eu = min(eu, 14 + TC_F16_THR_SHIFT - ei - et);
+            }
+            half_dead = !(tmag < 3.0e38f) || eu < eu0 - 14 || eu + ei < -100 || eu + ei > 100;
+            if (!half_dead)
+                eps += 1.25f * 2.98023223876953125e-08f * sqrtf((float)d) * (sqrtf(__ldg(stats)) * exp2i(-eu) + sqrtf(ss) * exp2i(-ei));
+        }
         float e2 = 2.0f * eps;
         const float INF = __int_as_float(0x7f800000);
         if (!(e2 < INF)) e2 = INF;  // overflow / NaN operands: collect everything, the exact kernel settles the row
@@ -864,6 +1050,29 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
         // what k_select_cands compares against.  Without a usable threshold (-inf: fewer than r finite samples;
         // NaN) the row collects nothing and k_select_cands hands it to the exact kernel.
         float hi = __int_as_float(0x7e800000), lo = 0.0f;  // 2^126
+        if (item_scale != nullptr) {
+            // FP16: T0 s_u s_i / C = hi + lo, fp16 values, lo rounded towards -inf; hi + lo spans at most 22 bits, so
+            // thr = (hi + lo) C / (s_u s_i) is exact in FP32 -- the same construction as the TF32 one below
+            float S = 0.0f;
+            hi = 0.0f;
+            if (!half_dead && fabsf(t0) < 1.0e37f) {
+                const float t = t0 * exp2i(eu + ei - TC_F16_THR_SHIFT);
+                if (fabsf(t) < 32000.0f) {
+                    hi = __half2float(__float2half_rn(t));
+                    lo = __half2float(__float2half_rd(t - hi));
+                    S = exp2i(eu + ei);
+                    t0 = (hi + lo) * exp2i(TC_F16_THR_SHIFT - eu - ei);
+                }
+            }
+            if (S == 0.0f) { hi = 0.0f; lo = 0.0f; t0 = __int_as_float(0x7e800000); }
+            if (lane == 0) {
+                scale_out[row] = S;
+                thr_hi_out[row] = hi;
+                thr_lo_out[row] = lo;
+                thr[row] = t0;
+            }
+            return;
+        }
         if (fabsf(t0) < 1.0e37f) {
             hi = __uint_as_float(to_tf32(t0));
             const float rem = t0 - hi;
@@ -937,6 +1146,105 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
     if (lane == 0 && stats_cur != nullptr) {
         atomicMax(stats_cur, __float_as_uint(best));
         if (bias != nullptr) atomicMax(stats_cur + 1, __float_as_uint(bb));
+    }
+}
+
+// ---- FP16 operands: largest item magnitude, then the scaled fp16 item table ---------------------------------------------
+// amax_bits: zeroed by the host before the launch; non-negative floats order like their bit patterns.
+__global__ void __launch_bounds__(256)
+k_item_absmax(const float *__restrict__ X, int64_t ld, int64_t n, int d, uint32_t *__restrict__ amax_bits)
+{
+    pdl_wait();
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float best = 0.0f;
+    for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 4; row0 < n; row0 += (int64_t)gridDim.x * 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (row0 + r < n)
+                for (int k = lane; k < d; k += 32) best = fmaxf(best, fabsf(__ldg(X + (row0 + r) * ld + k)));  // NaNs are skipped
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0 && best > 0.0f) atomicMax(amax_bits, __float_as_uint(best));
+}
+
+// item table -> fp16 table [n, d_pad] (d_pad = 64 or 128, zero padded in k), every element multiplied by s_i = 2^e with
+// e = f16_scale_exp(max |item element|) first (exact); s_i is published in *si_out for the kernels that follow.  Same
+// side jobs as k_split_tf32: max ||item||^2 and max |bias| of the UNscaled table for the error band, counters reset.
+__global__ void __launch_bounds__(256)
+k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, __half *__restrict__ out, const float *__restrict__ bias,
+            int *__restrict__ zero_a, uint32_t *__restrict__ stats_cur, uint32_t *__restrict__ stats_next, const uint32_t *__restrict__ amax_bits,
+            float *__restrict__ si_out)
+{
+    pdl_wait();
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float si = exp2i(f16_scale_exp(__uint_as_float(__ldg(amax_bits))));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (zero_a != nullptr) { zero_a[0] = 0; zero_a[1] = 0; }
+        if (stats_next != nullptr) { stats_next[0] = 0u; stats_next[1] = 0u; }
+        *si_out = si;
+    }
+    float best = 0.0f, bb = 0.0f;
+    // four rows per warp and step; lane l owns the element pairs (2 l, 2 l + 1) and (64 + 2 l, 65 + 2 l) of a row
+    for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 4; row0 < n; row0 += (int64_t)gridDim.x * 32) {
+        float x[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = 2 * lane + 64 * (q >> 1) + (q & 1);
+                x[r][q] = (row0 + r < n && k < d) ? __ldg(X + (row0 + r) * ld + k) : 0.0f;
+            }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (row0 + r >= n) break;
+            float ss = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; q += 2) {
+                const int k = 2 * lane + 64 * (q >> 1);
+                if (k < d_pad) {
+                    *reinterpret_cast<uint32_t *>(out + (row0 + r) * d_pad + k) = pack_h2(x[r][q] * si, x[r][q + 1] * si);
+                    ss = fmaf(x[r][q], x[r][q], ss);
+                    ss = fmaf(x[r][q + 1], x[r][q + 1], ss);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            best = fmaxf(best, (ss == ss) ? ss : __int_as_float(0x7f800000));
+            if (bias != nullptr && lane == 0) {
+                const float v = fabsf(__ldg(bias + row0 + r));
+                bb = fmaxf(bb, (v == v) ? v : __int_as_float(0x7f800000));
+            }
+        }
+    }
+    if (lane == 0 && stats_cur != nullptr) {
+        atomicMax(stats_cur, __float_as_uint(best));
+        if (bias != nullptr) atomicMax(stats_cur + 1, __float_as_uint(bb));
+    }
+}
+
+// hi AND lo TF32 tables for the three-pass retry of an "f16r" evaluate (the first attempt built neither), on demand
+__global__ void __launch_bounds__(256)
+k_split_hilo_if(const int *__restrict__ need, int need_min, const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad,
+                float *__restrict__ hi, float *__restrict__ lo)
+{
+    pdl_wait();
+    pdl_trigger();
+    if (*need < need_min) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += (int64_t)gridDim.x * 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = lane + 32 * q;
+            if (k < d_pad) {
+                const float x = (k < d) ? __ldg(X + row * ld + k) : 0.0f;
+                const uint32_t h = to_tf32(x);
+                hi[row * d_pad + k] = __uint_as_float(h);
+                lo[row * d_pad + k] = __uint_as_float(to_tf32(x - __uint_as_float(h)));
+            }
+        }
     }
 }
 

@@ -71,6 +71,7 @@ struct skr_ctx {
     int disc_n = 0;
     // workspace, grow-only
     Buf trace, stats, stage_s, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
+    Buf bh16, f16s, rscale;  // precision "f16r": scaled fp16 item table; {max |item| bits, s_i}; per-row scale s_u s_i
     int *d_err = nullptr;
     double *h_pin = nullptr;  // pinned host staging for the small results ([sums | watchdog flag]), SKR_PIN_DOUBLES doubles
     int64_t launches = 0;
@@ -564,6 +565,21 @@ int make_tmap(skr_ctx *ctx, CUtensorMap *map, const float *base, int64_t n_rows,
 }
 
 
+// scaled fp16 item table [n_rows, d_pad] (d_pad = 64 or 128 elements): boxes of 64 elements x 128 rows, the same 128-byte
+// swizzle rows and 16 KB tiles as the TF32 tables
+int make_tmap_f16(skr_ctx *ctx, CUtensorMap *map, const void *base, int64_t n_rows, int d_pad)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)(2 * TC_KB), (cuuint32_t)TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SKR_ERR_CUDA, "cuTensorMapEncodeTiled (fp16) failed (%d)", (int)r);
+    return SKR_OK;
+}
+
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, TcArgs, FusedParams);
 
 template <int NKB>
@@ -573,11 +589,16 @@ TcKernel tc_kernel_for(int passes, int mode)
     return passes == 3 ? k_fused_tc<NKB, 3, TC_MODE_COLLECT> : k_fused_tc<NKB, 1, TC_MODE_COLLECT>;
 }
 
+// half: FP16 operands (nkb counts 64-element k-blocks: 1 or 2; single pass)
 int launch_tc(skr_ctx *ctx, int nkb, int passes, int mode, unsigned grid, cudaStream_t st, const CUtensorMap &mhi, const CUtensorMap &mlo,
-              const TcArgs &A, const FusedParams &P)
+              const TcArgs &A, const FusedParams &P, bool half = false)
 {
     TcKernel k = nkb == 1 ? tc_kernel_for<1>(passes, mode) : nkb == 2 ? tc_kernel_for<2>(passes, mode)
                : nkb == 3 ? tc_kernel_for<3>(passes, mode) : tc_kernel_for<4>(passes, mode);
+    if (half) {
+        if (mode == TC_MODE_SAMPLE) k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_SAMPLE, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_SAMPLE, true>;
+        else k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_COLLECT, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_COLLECT, true>;
+    }
     const size_t smem = tc_smem_bytes();
     SKR_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SKR_CUDA(ctx, launch_pdl(k, dim3((unsigned)(grid)), dim3((unsigned)(TC_THREADS)), (size_t)(smem), st, mhi, mlo, A, P));
@@ -670,7 +691,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr); free_dev(ctx->d_mask_tile_off);
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    Buf *bufs[] = {&ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
+    Buf *bufs[] = {&ctx->bh16, &ctx->f16s, &ctx->rscale, &ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
                    &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->stage_s, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt};
     for (Buf *b : bufs) free_dev(b->p);
@@ -770,7 +791,7 @@ int skr_fused_stats(skr_ctx *ctx, int64_t *out, int n_out)
     if (ctx->fail_list.p) SKR_CUDA(ctx, cudaMemcpy(n_fails, ctx->fail_list.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     // tf32r: [0] rows the single-pass attempt left to the three-pass retry, [1] rows the retry left to the exact kernel;
     // other precisions have one attempt
-    const bool two = !strcmp(ctx->last_fused, "tcgen05_tf32r");
+    const bool two = !strcmp(ctx->last_fused, "tcgen05_tf32r") || !strcmp(ctx->last_fused, "tcgen05_f16r");
     const int n_fail = two ? n_fails[1] : n_fails[0];
     if (n_out >= 9) out[8] = two ? n_fails[0] : 0;
     out[0] = ctx->last_plan.n_samp;
@@ -1044,7 +1065,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
     if (ctx->has_train && (row0 < 0 || row0 + n_rows > ctx->tr_rows))
         return fail(ctx, SKR_ERR_INVALID, "rows [%lld,%lld) outside the train CSR (%lld rows)", (long long)row0, (long long)(row0 + n_rows), (long long)ctx->tr_rows);
     if (ctx->has_train && ctx->tr_items != n_items) return fail(ctx, SKR_ERR_INVALID, "train CSR was built for %lld items, item table has %lld", (long long)ctx->tr_items, (long long)n_items);
-    if (precision < SKR_PREC_AUTO || precision > SKR_PREC_TF32R) return fail(ctx, SKR_ERR_INVALID, "precision=%d", precision);
+    if (precision < SKR_PREC_AUTO || precision > SKR_PREC_F16R) return fail(ctx, SKR_ERR_INVALID, "precision=%d", precision);
     SKR_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int K = top_k;
@@ -1054,7 +1075,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
     const bool tc_ok = (nkb <= 4) && (tc_smem_bytes() <= ctx->max_smem);
     bool use_tc = (precision != SKR_PREC_FP32) && tc_ok;
     if (ctx->opt_score_fn == 1) {  // -||u - i|| + b: FP32 tile kernel only
-        if (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32 || precision == SKR_PREC_TF32R)
+        if (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32 || precision == SKR_PREC_TF32R || precision == SKR_PREC_F16R)
             return fail(ctx, SKR_ERR_UNSUPPORTED, "score_fn = -||u - i|| + b runs on the FP32 tile kernel: precision must be auto or fp32");
         use_tc = false;
     }
@@ -1064,7 +1085,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
     const bool simt_ok = !((d & 3) || (ld_u & 3) || (ld_i & 3) || ((uintptr_t)user_vecs_dev & 15) || ((uintptr_t)item_vecs_dev & 15)) &&
                          simt_smem_bytes(top_k) <= ctx->max_smem;
     if (precision == SKR_PREC_AUTO && simt_ok && n_items < std::max<int64_t>(3072, 160 * (int64_t)top_k)) use_tc = false;
-    if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32 || precision == SKR_PREC_TF32R))
+    if (!use_tc && (precision == SKR_PREC_3XTF32 || precision == SKR_PREC_1XTF32 || precision == SKR_PREC_TF32R || precision == SKR_PREC_F16R))
         return fail(ctx, SKR_ERR_UNSUPPORTED, "tcgen05 path needs d <= 128 (d=%d)", d);
     if (!use_tc) {
         if ((d & 3) || (ld_u & 3) || (ld_i & 3) || ((uintptr_t)user_vecs_dev & 15) || ((uintptr_t)item_vecs_dev & 15))
@@ -1112,13 +1133,21 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         // the catalogue: measured on one B200, tf32r is 5 % faster at c2 (I d = 2.6 M) and 22 % at c3b (5.9 M); below
         // ~1 M the sampled thresholds stop working for either and the choice does not matter
         if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 2.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
-        const bool rescore = (precision == SKR_PREC_TF32R);
+        const bool half = (precision == SKR_PREC_F16R);  // FP16 operands for the first attempt; the retry stays 3xTF32
+        const bool rescore = (precision == SKR_PREC_TF32R) || half;
         const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
         // operand prep: item table -> hi (and, for three passes, lo) TF32 tables, TMA descriptors
         const int d_pad = nkb * TC_KB;
+        const int nkb_h = (d + 2 * TC_KB - 1) / (2 * TC_KB), d_pad_h = nkb_h * 2 * TC_KB;  // FP16: 64-element k-blocks
+        const int nkb_1 = half ? nkb_h : nkb;  // k-blocks of the first attempt's kernels
         const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
-        if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;
+        if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;  // f16r: filled on demand by the retry, like blo
         if ((passes == 3 || rescore) && (rc = ensure(ctx, ctx->blo, tbytes))) return rc;  // tf32r: filled on demand by the retry
+        if (half) {
+            if ((rc = ensure(ctx, ctx->bh16, (size_t)n_items * d_pad_h * 2))) return rc;
+            if ((rc = ensure(ctx, ctx->f16s, 2 * sizeof(uint32_t)))) return rc;
+            if ((rc = ensure(ctx, ctx->rscale, (size_t)n_rows * sizeof(float)))) return rc;
+        }
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(2 * n_rows + 2) * sizeof(int32_t)))) return rc;
         if (ctx->stats.cap == 0) {  // two slots of {max ||item||^2, max |bias|}, alternating between evaluates
             if ((rc = ensure(ctx, ctx->stats, 4 * sizeof(uint32_t)))) return rc;
@@ -1129,18 +1158,29 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
             uint32_t *stats_next = (uint32_t *)ctx->stats.p + 2 * (ctx->stats_slot ^ 1);
             ctx->stats_slot ^= 1;
             ctx->stats_cur_ptr = stats_cur;
-            SKR_CUDA(ctx, launch_pdl(k_split_tf32, dim3((unsigned)((unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm))), dim3((unsigned)(256)), (size_t)(0), st, item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
-                                                                                                      passes == 3 ? (float *)ctx->blo.p : (float *)nullptr, bias_dev, (int *)ctx->fail_list.p, stats_cur,
-                                                                                                      stats_next));
+            const dim3 sgrid((unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm));
+            if (half) {
+                SKR_CUDA(ctx, cudaMemsetAsync(ctx->f16s.p, 0, 2 * sizeof(uint32_t), st));
+                SKR_CUDA(ctx, launch_pdl(k_item_absmax, sgrid, dim3(256u), (size_t)0, st, item_vecs_dev, ld_i, n_items, d, (uint32_t *)ctx->f16s.p));
+                SKR_CUDA(ctx, launch_pdl(k_split_f16, sgrid, dim3(256u), (size_t)0, st, item_vecs_dev, ld_i, n_items, d, d_pad_h, (__half *)ctx->bh16.p, bias_dev,
+                                         (int *)ctx->fail_list.p, stats_cur, stats_next, (const uint32_t *)ctx->f16s.p, (float *)ctx->f16s.p + 1));
+                ctx->launches++;
+            } else {
+                SKR_CUDA(ctx, launch_pdl(k_split_tf32, sgrid, dim3((unsigned)(256)), (size_t)(0), st, item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
+                                         passes == 3 ? (float *)ctx->blo.p : (float *)nullptr, bias_dev, (int *)ctx->fail_list.p, stats_cur, stats_next));
+            }
             ctx->launches++;
         } else {
             SKR_CUDA(ctx, cudaMemsetAsync(ctx->fail_list.p, 0, 2 * sizeof(int), st));  // the split kernel's other job: empty fail lists
         }
         uint32_t *stats_cur = ctx->stats_cur_ptr;
-        CUtensorMap mhi, mlo;
+        CUtensorMap mhi, mlo, mh16;
         if ((rc = make_tmap(ctx, &mhi, (const float *)ctx->bhi.p, n_items, d_pad))) return rc;
         if (passes == 3 || rescore) { if ((rc = make_tmap(ctx, &mlo, (const float *)ctx->blo.p, n_items, d_pad))) return rc; }
         else mlo = mhi;  // single-pass kernels never touch the lo table: it is not even built
+        if (half) { if ((rc = make_tmap_f16(ctx, &mh16, ctx->bh16.p, n_items, d_pad_h))) return rc; }
+        else mh16 = mhi;
+        const CUtensorMap &m1 = half ? mh16 : mhi;  // what the first attempt's kernels stream
 
         // sampling plan (k_fused_tc.cuh header): fraction f ~ 6/K of the item tiles, threshold = r-th largest
         // sampled group maximum with r = K f + 4.5 sqrt(K f) + 8 (a ~4-sigma margin against fewer than K survivors)
@@ -1217,27 +1257,29 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         const bool presub = (passes == 1);  // k_fused_tc's PRESUB: the threshold is subtracted by an extra MMA
         A.thr_hi = presub ? A.thr + n_rows : nullptr;
         A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
+        A.item_scale = half ? (const float *)ctx->f16s.p + 1 : nullptr;
+        A.scale = half ? (const float *)ctx->rscale.p : nullptr;
         float eps_coef = 0.0f, eps3_coef = 0.0f;
         float *thr3 = nullptr, *eps2_3 = nullptr;
         if (rescore) {
             if ((rc = ensure(ctx, ctx->eps2, (size_t)2 * n_rows * sizeof(float)))) return rc;  // 2 eps | 2 eps of the 3-pass retry
-            eps_coef = (float)(ldexp(1.0, -10) + (2.5 * d + 8.0) * ldexp(1.0, -22));
+            eps_coef = (float)(ldexp(1.0, -10) + (2.5 * d + 8.0) * ldexp(1.0, -22));  // fp16 rn: the same 2^-11 per operand as TF32 rna
             eps3_coef = (float)((3.25 * d + 11.0) * ldexp(1.0, -22));
             thr3 = (float *)ctx->thr.p + 3 * n_rows;
             eps2_3 = (float *)ctx->eps2.p + n_rows;
         }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
-        if ((rc = launch_tc(ctx, nkb, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, mhi, mlo, A, P))) return rc;
+        if ((rc = launch_tc(ctx, nkb_1, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, m1, mlo, A, P, half))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
         {
             typedef void (*ThrKernel)(const float *, int64_t, int, float *, const float *, int64_t, int, const float *, float, float *, float *, float *, float,
-                                      float *, float *);
+                                      float *, float *, const float *, float *);
             const ThrKernel thr_k = samp_chunks == 1 ? (ThrKernel)k_sample_thr<1> : samp_chunks == 2 ? (ThrKernel)k_sample_thr<2>
                                     : samp_chunks == 3 ? (ThrKernel)k_sample_thr<3> : (ThrKernel)k_sample_thr<4>;
             SKR_CUDA(ctx, launch_pdl(thr_k, dim3((unsigned)((n_rows + 7) / 8)), dim3(256u), (size_t)0, st, (const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
                                      (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : (float *)nullptr, (float *)A.thr_hi, (float *)A.thr_lo, eps3_coef, eps2_3,
-                                     thr3));
+                                     thr3, A.item_scale, (float *)ctx->rscale.p));
         }
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
@@ -1250,12 +1292,12 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         }
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
         SKR_AFTER(ctx, st, "k_sample_thr");
-        if ((rc = launch_tc(ctx, nkb, passes, TC_MODE_COLLECT, grid_tc, st, mhi, mlo, A, P))) return rc;
+        if ((rc = launch_tc(ctx, nkb_1, passes, TC_MODE_COLLECT, grid_tc, st, m1, mlo, A, P, half))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc COLLECT");
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
         SKR_CUDA(ctx, cudaGetLastError());
-        ctx->last_fused = (passes == 3) ? "tcgen05_3xtf32" : (rescore ? "tcgen05_tf32r" : "tcgen05_1xtf32");
+        ctx->last_fused = (passes == 3) ? "tcgen05_3xtf32" : (half ? "tcgen05_f16r" : (rescore ? "tcgen05_tf32r" : "tcgen05_1xtf32"));
         ctx->last_plan = {n_samp, stride, r, cap, P.S, passes == 3 ? 4 : 8};
         ctx->ev_calls++;
         const ExactArgs E = {user_vecs_dev, ld_u, item_vecs_dev, ld_i, d, bias_dev, (int)n_items, tp, ti};
@@ -1271,9 +1313,15 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
                                                       : (int)std::max(4.0, std::min(1.0e9, sweep_us / exact_row_us));
         // the retry of unsettled rows (tf32r only): lo table on demand, then the three-pass kernel over the same work list
         const std::function<int()> retry_collect = [&]() -> int {
-            SKR_CUDA(ctx, launch_pdl(k_split_lo_if, dim3((unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm)), dim3(256u), (size_t)0, st, (const int *)fail_count, retry_min, item_vecs_dev, ld_i,
-                                     n_items, d, d_pad, (float *)ctx->blo.p));
+            if (half)  // the first attempt built neither TF32 table
+                SKR_CUDA(ctx, launch_pdl(k_split_hilo_if, dim3((unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm)), dim3(256u), (size_t)0, st, (const int *)fail_count, retry_min,
+                                         item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p, (float *)ctx->blo.p));
+            else
+                SKR_CUDA(ctx, launch_pdl(k_split_lo_if, dim3((unsigned)std::min<int64_t>((n_items + 7) / 8, 16 * ctx->n_sm)), dim3(256u), (size_t)0, st, (const int *)fail_count, retry_min, item_vecs_dev, ld_i,
+                                         n_items, d, d_pad, (float *)ctx->blo.p));
             TcArgs A2 = A;
+            A2.item_scale = nullptr;
+            A2.scale = nullptr;
             A2.thr = thr3;
             A2.thr_hi = nullptr;
             A2.thr_lo = nullptr;

@@ -208,8 +208,8 @@ class RankingEvaluator(object):
         grid replaces the thread pool.  `batch_size` is the user batch of the `predict` path.
     Keyword-only additions:
         device: CUDA device index (default: current torch device).
-        precision: "auto" | "3xtf32" | "fp32" | "tf32r" -- arithmetic of the fused scoring
-            ("tf32r": one TF32 pass finds candidates inside a rigorous error band, the survivors are
+        precision: "auto" | "3xtf32" | "fp32" | "tf32r" | "f16r" -- arithmetic of the fused scoring
+            ("tf32r" / "f16r": one TF32 / scaled-FP16 pass finds candidates inside a rigorous error band, the survivors are
             re-scored in exact FP32; same results as "fp32").
         mean: "f64" (float64 sums, rounded once to float32) or "numpy_f32" (the reference's
             float32 row-order accumulation of np.mean, evaluator.py:208, bit for bit;
@@ -269,10 +269,10 @@ class RankingEvaluator(object):
             self.top_show = np.sort(top_k)
 
         import os
-        allowed = ("auto", "3xtf32", "fp32", "tf32r") + (("1xtf32",) if os.environ.get("SKR_ALLOW_1XTF32") == "1" else ())
+        allowed = ("auto", "3xtf32", "fp32", "tf32r", "f16r") + (("1xtf32",) if os.environ.get("SKR_ALLOW_1XTF32") == "1" else ())
         # "1xtf32" (one TF32 pass, no re-scoring) misses the 1e-5 metric contract: measurement only,
         # reachable only with SKR_ALLOW_1XTF32=1
-        assert precision in allowed, "precision must be auto|3xtf32|fp32|tf32r"
+        assert precision in allowed, "precision must be auto|3xtf32|fp32|tf32r|f16r"
         assert mean in ("f64", "numpy_f32"), "mean must be f64|numpy_f32"
         assert shard in ("users", "items"), "shard must be users|items"
         assert upload in ("sharded", "replicated"), "upload must be sharded|replicated"

@@ -682,12 +682,13 @@ def test_from_csr_equals_dict_construction(torch_cuda):
 
 
 # ---- precision "tf32r": one TF32 pass + exact re-scoring == the FP32 path, bit for bit -----------------------
+@pytest.mark.parametrize("prec", ["tf32r", "f16r"])
 @pytest.mark.parametrize("U,I,d,bias,K,max_train", FUSED_SHAPES + [(700, 9000, 64, True, 50, 60)])
-def test_fused_tf32r_equals_fp32_path_bit_for_bit(torch_cuda, ctx, U, I, d, bias, K, max_train):
+def test_fused_tf32r_equals_fp32_path_bit_for_bit(torch_cuda, ctx, U, I, d, bias, K, max_train, prec):
     ue, ie, b, tr, te = _fused_case(U + I + 1, U, I, d, bias, max_train)
     metric = [1, 2, 3, 4, 5]
-    got = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "tf32r")
-    assert ctx.last_fused_kernel == "tcgen05_tf32r"
+    got = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, prec)
+    assert ctx.last_fused_kernel == "tcgen05_" + prec
     ref = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "fp32")
     assert ctx.last_fused_kernel == "simt_fp32"
     assert np.array_equal(got[0], ref[0])      # same items in the same order
@@ -697,16 +698,20 @@ def test_fused_tf32r_equals_fp32_path_bit_for_bit(torch_cuda, ctx, U, I, d, bias
     _check_fused(*got, ue, ie, b, tr, te, metric, K)
 
 
-@pytest.mark.parametrize("d,bias", [(32, True), (64, False), (96, True), (128, True)])
-def test_fused_tf32r_with_working_thresholds_equals_fp32_path(torch_cuda, ctx, d, bias):
+@pytest.mark.parametrize("prec", ["tf32r", "f16r"])
+@pytest.mark.parametrize("d,bias", [(32, True), (64, False), (96, True), (128, True), (128, False), (50, False)])
+def test_fused_tf32r_with_working_thresholds_equals_fp32_path(torch_cuda, ctx, d, bias, prec):
     """Catalogue large enough for the sampled thresholds to settle (nearly) every row in the candidate path -- small
     shapes go through the exact fallback and would not exercise the threshold MMA (d <= 96) or the FADD epilogue (d = 128)."""
     U, I, K = 300, 16384, 50
     ue, ie, b, tr, te = _fused_case(1000 + d, U, I, d, bias, 40)
     metric = [1, 2, 4]
-    got = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "tf32r")
-    assert ctx.last_fused_kernel == "tcgen05_tf32r"
+    got = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, prec)
+    assert ctx.last_fused_kernel == "tcgen05_" + prec
     assert ctx.fused_stats()["exact_rows"] <= U // 20
+    if d % 4 != 0:  # the FP32 tile kernel needs d % 4 == 0: the oracle is the judge
+        _check_fused(*got, ue, ie, b, tr, te, metric, K, tol_score=TOL_SCORE * max(1.0, 0.5 * np.sqrt(d)))
+        return
     ref = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "fp32")
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
     x3 = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "3xtf32")
@@ -734,7 +739,8 @@ def test_tf32_error_stays_inside_the_band_tf32r_assumes(torch_cuda, ctx):
         assert err.max() > 2.0 ** -20 * np.abs(s2).max()  # the single pass really is inexact: the band is needed
 
 
-def test_tf32r_ties_and_degenerate_rows_fall_back_exactly(torch_cuda, ctx):
+@pytest.mark.parametrize("prec", ["tf32r", "f16r"])
+def test_tf32r_ties_and_degenerate_rows_fall_back_exactly(torch_cuda, ctx, prec):
     """Many equal scores (popularity-style integer scores) and rows with fewer unmasked items than K."""
     g = np.random.default_rng(6)
     U, I, d, K = 200, 1500, 64, 20
@@ -744,13 +750,40 @@ def test_tf32r_ties_and_degenerate_rows_fall_back_exactly(torch_cuda, ctx):
     ie[:, 0] = g.integers(0, 12, size=I).astype(np.float32)  # heavy ties
     tr = _rand_csr(g, U, I, 30)
     te = _rand_csr(g, U, I, 10, min_n=1)
-    got = _run_fused(torch_cuda, ctx, ue, ie, None, tr, te, [1, 2, 4], K, "tf32r")
+    got = _run_fused(torch_cuda, ctx, ue, ie, None, tr, te, [1, 2, 4], K, prec)
     ref = _run_fused(torch_cuda, ctx, ue, ie, None, tr, te, [1, 2, 4], K, "fp32")
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2])
     S = oracle.scores(ue, ie, None)
     oracle.mask_rows(S, tr[0], tr[1])
     eper, etop = oracle.eval_scores(S, te[0], te[1], [1, 2, 4], K, return_topk=True)
     assert np.array_equal(got[0], etop) and np.array_equal(got[2], eper)  # lower item id first among equals
+
+
+@pytest.mark.parametrize("d,bias_scale", [(64, 0.0), (128, 0.05), (128, 30.0), (64, 1e4)])
+@pytest.mark.parametrize("su,si", [(1.0, 1.0), (1e-6, 1e-3), (3e3, 2e2), (1e-12, 1e6)])
+def test_f16r_power_of_two_scaling_is_invisible(torch_cuda, ctx, d, bias_scale, su, si):
+    """FP16 operands need the tables scaled into fp16's range (per user row, per catalogue): tiny, huge and mixed
+    magnitudes, user rows 10^4 apart, a bias that dwarfs the dot products (the threshold operand then forces a smaller
+    row scale, or the row is handed to the exact kernel) -- always the FP32 path's items, scores and metrics, bit for bit."""
+    g = np.random.default_rng(int(d + 1000 * bias_scale) + 7)
+    U, I, K = 260, 16384, 50
+    ue = (g.standard_normal((U, d)) * 0.1 * su).astype(np.float32)
+    ue[::3] *= 1e-4                                            # rows of very different magnitude: the scale is per row
+    ue[1, : d // 2] *= 1e-7                                    # elements far below the row's largest: fp16 subnormals
+    ie = (g.standard_normal((I, d)) * 0.1 * si).astype(np.float32)
+    ie[::11] *= 30.0
+    ie[5, :] *= 1e-9
+    b = (g.standard_normal(I) * bias_scale * su * si).astype(np.float32) if bias_scale > 0 else None
+    tr = _rand_csr(g, U, I, 40)
+    te = _rand_csr(g, U, I, 6, min_n=1)
+    metric = [1, 2, 4]
+    got = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "f16r")
+    assert ctx.last_fused_kernel == "tcgen05_f16r"
+    stats = ctx.fused_stats()
+    ref = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "fp32")
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    if bias_scale <= 30.0:  # a bias 10^4 times the dot products may cost rows to the exact kernel; anything milder must not
+        assert stats["exact_rows"] <= U // 10, stats
 
 
 def test_c2_full_size_tf32r_equals_fp32_path(torch_cuda, ctx, c2_data):
@@ -762,6 +795,9 @@ def test_c2_full_size_tf32r_equals_fp32_path(torch_cuda, ctx, c2_data):
     b = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, "fp32")
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert stats["exact_rows"] < 0.01 * d["users"]  # the fast path settles (almost) every row
+    h = _run_fused(torch_cuda, ctx, d["user_emb"], d["item_emb"], None, tr, te, [1, 2, 4], 50, "f16r")  # FP16 operands: the same bits
+    assert ctx.last_fused_kernel == "tcgen05_f16r" and ctx.fused_stats()["exact_rows"] < 0.01 * d["users"]
+    assert np.array_equal(h[0], b[0]) and np.array_equal(h[1], b[1]) and np.array_equal(h[2], b[2])
 
 
 def test_c4_catalogue_size_tf32r_equals_fp32_path_and_oracle_sample(torch_cuda, ctx):
@@ -783,6 +819,9 @@ def test_c4_catalogue_size_tf32r_equals_fp32_path_and_oracle_sample(torch_cuda, 
     b = _run_fused(torch, ctx, d["user_emb"], d["item_emb"], d["bias"], tr, te, metric, K, "fp32")
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert stats["exact_rows"] < 0.01 * U  # the sampled thresholds settle (almost) every row
+    h = _run_fused(torch, ctx, d["user_emb"], d["item_emb"], d["bias"], tr, te, metric, K, "f16r")  # FP16 operands: the same bits
+    assert ctx.last_fused_kernel == "tcgen05_f16r" and ctx.fused_stats()["exact_rows"] < 0.01 * U
+    assert np.array_equal(h[0], b[0]) and np.array_equal(h[1], b[1]) and np.array_equal(h[2], b[2])
     # every list: K distinct, unmasked items in descending (score, -id) order
     assert np.all((a[1][:, :-1] > a[1][:, 1:]) | ((a[1][:, :-1] == a[1][:, 1:]) & (a[0][:, :-1] < a[0][:, 1:])))
     rows = np.repeat(np.arange(U), np.diff(tr[0]))
@@ -831,7 +870,7 @@ def test_fused_precisions_on_awkward_shapes(torch_cuda, ctx, U, I, d, K, bias, m
     tr = _rand_csr(g, U, I, max_train) if max_train > 0 else None
     te = _rand_csr(g, U, I, 8, min_n=0)  # users without test items: all metrics 0, still counted by the caller
     metric = [int(x) for x in g.permutation(5)[: int(g.integers(1, 6))] + 1]
-    precisions = ["3xtf32", "tf32r"] + (["fp32"] if d % 4 == 0 else [])
+    precisions = ["3xtf32", "tf32r", "f16r"] + (["fp32"] if d % 4 == 0 else [])
     outs = {}
     for prec in precisions:
         outs[prec] = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, prec)
@@ -839,6 +878,7 @@ def test_fused_precisions_on_awkward_shapes(torch_cuda, ctx, U, I, d, K, bias, m
         _check_fused(*outs[prec], ue, ie, b, tr, te, metric, K, tol_score=TOL_SCORE * max(1.0, 0.5 * d ** 0.5))
     if "fp32" in outs:
         assert np.array_equal(outs["tf32r"][0], outs["fp32"][0]) and np.array_equal(outs["tf32r"][2], outs["fp32"][2])
+        assert np.array_equal(outs["f16r"][0], outs["fp32"][0]) and np.array_equal(outs["f16r"][2], outs["fp32"][2])
 
 
 def test_fused_special_values_and_limits(torch_cuda, ctx):
@@ -854,7 +894,7 @@ def test_fused_special_values_and_limits(torch_cuda, ctx):
     ie[::7] = -0.0
     tr = _rand_csr(g, U, I, 20)
     te = _rand_csr(g, U, I, 6, min_n=1)
-    for prec in ("3xtf32", "tf32r", "fp32"):
+    for prec in ("3xtf32", "tf32r", "f16r", "fp32"):
         idx, val, per, sums = _run_fused(torch_cuda, ctx, ue, ie, None, tr, te, [1, 2, 3, 4, 5], K, prec)
         S = oracle.scores(ue, ie, None)
         oracle.mask_rows(S, tr[0], tr[1])
@@ -1030,7 +1070,7 @@ def test_tf32r_on_heavy_tailed_tables_equals_fp32_and_retries_instead_of_walking
     metric = [1, 2, 3, 4, 5]
     out = {}
     c.set_option("retry_min", 1)  # always retry (the cost model would hand a handful of rows straight to the exact kernel)
-    for prec in ("tf32r", "fp32", "tf32r_model"):
+    for prec in ("tf32r", "fp32", "f16r", "tf32r_model"):  # f16r: its unsettled rows take the same three-pass TF32 retry
         if prec == "tf32r_model":
             c.set_option("retry_min", -1)
             prec = "tf32r"
@@ -1049,6 +1089,8 @@ def test_tf32r_on_heavy_tailed_tables_equals_fp32_and_retries_instead_of_walking
     a, f, am = out["tf32r"], out["fp32"], out["tf32r_model"]
     assert np.array_equal(a[0], f[0]) and np.array_equal(a[1], f[1]) and np.array_equal(a[2], f[2])
     assert np.array_equal(am[0], f[0]) and np.array_equal(am[1], f[1]) and np.array_equal(am[2], f[2])
+    h = out["f16r"]
+    assert np.array_equal(h[0], f[0]) and np.array_equal(h[1], f[1]) and np.array_equal(h[2], f[2])
     assert np.max(np.abs(a[3] - f[3])) < 1e-9 and np.max(np.abs(am[3] - f[3])) < 1e-9
     _check_fused(*a, dta["user_emb"], dta["item_emb"], dta["bias"], (dta["train_indptr"], dta["train_indices"]),
                  (dta["test_indptr"], dta["test_indices"]), metric, K)

@@ -25,7 +25,7 @@ for name in (sys.argv[1:] or ["c2", "c3b", "big128"]):
     ids = [synth.METRIC_IDS[m] for m in cfg["metric"]]
     K = max(cfg["top_k"])
     res = {}
-    for prec in ("3xtf32", "tf32r"):
+    for prec in os.environ.get("SKR_PRECS", "3xtf32,tf32r,f16r").split(","):
         sums = torch.zeros(len(ids) * K, dtype=torch.float64, device="cuda")
         ts = []
         for it in range(6):
@@ -39,5 +39,6 @@ for name in (sys.argv[1:] or ["c2", "c3b", "big128"]):
         res[prec] = (min(ts[2:]), ctx.fused_kernel_ms(0), ctx.fused_prepass_ms(0), ctx.fused_stats(), (sums / d["users"]).cpu().numpy())
         print("%-7s %-7s evaluate %.3f ms (main kernel %.3f, prepass %.3f) -> %.2f M users/s; %s" % (
             name, prec, res[prec][0], res[prec][1], res[prec][2], d["users"] / res[prec][0] / 1e3, res[prec][3]), flush=True)
-    print("%-7s max |mean metric diff| between the two: %.2e" % (name, float(np.max(np.abs(res["3xtf32"][4] - res["tf32r"][4])))), flush=True)
+    ks = list(res)
+    print("%-7s max |mean metric diff| against %s: %s" % (name, ks[0], ", ".join("%s %.2e" % (k, float(np.max(np.abs(res[ks[0]][4] - res[k][4])))) for k in ks[1:])), flush=True)
     ctx.close()
