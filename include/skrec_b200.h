@@ -58,7 +58,7 @@ extern "C" {
 #define SKR_ERR_STATE (-5)       /* call order (e.g. no test CSR set) */
 
 /* scoring arithmetic of the fused path */
-#define SKR_PREC_AUTO 0   /* tensor cores when the shape allows (3xTF32, or TF32R for large catalogues), else FP32 FMA */
+#define SKR_PREC_AUTO 0   /* tensor cores when the shape allows (3xTF32; for large catalogues TF32R at d <= 64, F16R above), else FP32 FMA */
 #define SKR_PREC_FP32 1   /* FP32 FMA on CUDA cores (exact products, sequential k order) */
 #define SKR_PREC_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split, 3 products, FP32 accumulate */
 #define SKR_PREC_1XTF32 3 /* single TF32 pass; NOT reference-grade, for measurement only */
@@ -197,7 +197,8 @@ int skr_fused_trace(skr_ctx *ctx, int64_t *out, int64_t n_out);
  * (ignored: the ring depth is fixed by the kernel instantiation), "sample_tiles" / "rank" (pre-pass size and threshold rank, 0 =
  * automatic), "event_ring" (see skr_fused_kernel_ms), "trace_cta"
  * (see skr_fused_trace; -1 = off), "dbg" (timing ablations, results invalid), "chunk_rows" (rows per internal chunk of the
- * fused pipeline, 0 = 131,072), "retry_min" (tf32r: unsettled rows from which the three-pass retry runs, -1 = cost model). */
+ * fused pipeline, 0 = 131,072), "retry_min" (tf32r: unsettled rows from which the three-pass retry runs, -1 = cost model),
+ * "no_aug" (f16r: 1 = add the item bias in the epilogue instead of inside the contraction; measurements only). */
 int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
 
 /* ---- negative sampler ----------------------------------------------------------------------------------------------

@@ -277,6 +277,11 @@ struct TcArgs {
     // nothing (no usable threshold); SAMPLE derives s_u from the row itself
     const float *item_scale;
     const float *scale;
+    // FP16 operands with the bias folded into the contraction (AUG): the item table carries one more k-block whose first
+    // columns are (C, C, b_hi, b_lo) 2^m-scaled, the user operand (-T_hi, -T_lo, g, g); bias_shift -> m (k_split_f16),
+    // rowg: per-row g = s_u 2^-m from k_sample_thr (COLLECT; SAMPLE derives it from the row)
+    const int *bias_shift;
+    const float *rowg;
     int cap;                 // entries per (row, chunk, column quarter) sub-list
     uint2 *cand;             // [n_rows, S*4, cap] (score bits, item); PRESUB kernels store score - thr[row]
     uint32_t *cand_cnt;      // [n_rows, S*4] entries offered (> cap means overflow)
@@ -428,14 +433,20 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
 
 // HALF: FP16 operands (tm_bhi describes the scaled fp16 item table; a k-block is 64 elements = the same 128-byte swizzle
 // row, 32 TMEM columns of packed pairs and four K = 16 MMAs, so the pipeline below is unchanged), single pass only.
-template <int NKB, int PASSES, int MODE, bool HALF = false>
+// AUG (with HALF, models with an item bias): the LAST of the NKB k-blocks is the augmentation block -- item side
+// (C, C, beta_hi, beta_lo, 0...) with beta = bias s_i 2^m, user side (-T_hi, -T_lo, g, g, 0...) with g = s_u 2^-m -- and
+// contributes ONE K = 16 MMA per tile that both subtracts the row threshold and adds the item bias inside the tensor core:
+// the epilogue of a biased model becomes the unbiased one (no bias loads, no FMAs: ~40 of its ~155 instructions per tile).
+template <int NKB, int PASSES, int MODE, bool HALF = false, bool AUG = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, TcArgs A, FusedParams P)
 {
     pdl_trigger();  // the wait comes after the prologue, which touches nothing an earlier kernel wrote
     constexpr bool SAMPLE = (MODE == TC_MODE_SAMPLE);
     constexpr int KB_ELEMS = HALF ? 2 * TC_KB : TC_KB;  // operand elements per k-block
+    constexpr int NKB_REAL = AUG ? NKB - 1 : NKB;       // k-blocks of embedding dimensions
     static_assert(!HALF || PASSES == 1, "FP16 operands: single pass");
+    static_assert(!AUG || (HALF && NKB >= 2), "the augmentation block rides on the FP16 pipeline");
     constexpr int STAGES = (PASSES == 3) ? 4 : 8;
     constexpr int STAGE_BYTES = (PASSES == 3) ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
     static_assert(NKB >= 1 && NKB <= 4 && (PASSES == 1 || PASSES == 3), "tile shape");
@@ -446,8 +457,8 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     // instruction issue, not by the tensor pipe.  Needs 16 more TMEM columns; at d = 128 (NKB = 4) that leaves two
     // accumulator buffers instead of three, which still measured 4 % faster than three buffers with the FADDs.
     constexpr bool PRESUB = !SAMPLE && PASSES == 1;
-    constexpr int A_THR_COL = TC_KB * NKB * (PASSES == 3 ? 2 : 1);  // first column of A'
-    constexpr int A_COLS = A_THR_COL + (PRESUB ? 16 : 0);
+    constexpr int A_THR_COL = AUG ? TC_KB * NKB_REAL : TC_KB * NKB * (PASSES == 3 ? 2 : 1);  // first column of A'
+    constexpr int A_COLS = AUG ? TC_KB * NKB : A_THR_COL + (PRESUB ? 16 : 0);
     constexpr int NBUF = (A_COLS <= 512 - 3 * TN) ? 3 : 2;
     constexpr int ACC_COL = 512 - NBUF * TN;  // first accumulator column
 
@@ -497,10 +508,10 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             mbar_init(tile_full + b, 2);
             mbar_init(tile_empty + b, TC_EPI_WARPS);
         }
-        mbar_init(a_ready, 4 * NKB + (PRESUB ? 4 : 0));
+        mbar_init(a_ready, 4 * NKB_REAL + ((PRESUB || AUG) ? 4 : 0));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (PRESUB) {
+    if (PRESUB && !AUG) {
         // B' in the K-major SWIZZLE_128B layout the item tiles use: logical 16-byte chunk c of row r sits at
         // chunk position c ^ (r & 7); chunk 0 holds k = 0..3 = (1, 1, 0, 0), everything else is zero
         uint4 *t4 = reinterpret_cast<uint4 *>(thr_tile);
@@ -586,15 +597,16 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 if (elect_one()) {
                     if (kb == 0) tc_trace(A, i, 3);
                     if (do_mma) {
-                        if (PRESUB && kb == 0) {  // acc = -T0[row]
+                        if (PRESUB && !AUG && kb == 0) {  // acc = -T0[row]
                             if (HALF) tc_mma_ts_f16(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC_F16, 0u);
                             else tc_mma_ts(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC, 0u);
                         }
 #pragma unroll
                         for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 / 16 fp16 = 32 bytes of B, 8 TMEM columns of A
+                            if (AUG && kb == NKB - 1 && k8 > 0) break;  // the augmentation block holds 4 non-zero columns
                             const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
                             const uint64_t dhi = ds + (uint64_t)(k8 * 2);
-                            const uint32_t acc = (PRESUB || (kb | k8)) ? 1u : 0u;
+                            const uint32_t acc = ((PRESUB && !AUG) || (kb | k8)) ? 1u : 0u;
                             if (PASSES == 3) {
                                 const uint64_t dlo = dhi + (uint64_t)(TC_TILE_BYTES >> 4);
                                 tc_mma_ts(d_tmem, a_lo0 + acol, dhi, TC_IDESC, acc);
@@ -745,7 +757,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
 
         // FP16 operands: scale of my row.  su: what the row is multiplied by before the conversion; inv = 1 / (su s_i)
         // brings accumulator values back to true units; dead: the row has no usable threshold and collects nothing.
-        float su = 1.0f, inv = 1.0f;
+        float su = 1.0f, inv = 1.0f, g_aug = 0.0f;
         uint32_t dead = 0u;
         if (HALF) {
             const float si = __ldg(A.item_scale);
@@ -762,19 +774,26 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                         for (int k = 0; k < P.d; ++k) amax = fmaxf(amax, fabsf(__ldg(urow + k)));
                     }
                 }
-                su = exp2i(f16_scale_exp(amax));
+                int eu = f16_scale_exp(amax);
+                if (AUG) {  // g = s_u 2^-m must be an fp16 power of two: rows dwarfed by the bias scale less, giants drop it
+                    const int m = __ldg(A.bias_shift);
+                    eu = min(eu, m + 15);
+                    g_aug = (eu - m < -24) ? 0.0f : exp2i(eu - m);
+                }
+                su = exp2i(eu);
                 inv = 1.0f / (su * si);  // powers of two with exponents within +-60 each: exact
             } else {
                 const float S = my_valid ? __ldg(A.scale + my_row) : 0.0f;
                 if (S > 0.0f) {
                     su = S / si;
                     inv = 1.0f / S;
+                    if (AUG) g_aug = __ldg(A.rowg + my_row);
                 } else {
                     dead = 0xffffffffu;
                 }
             }
         }
-        if (HALF && cq < NKB) {  // A: k-block cq (64 elements) of my user's vector -> scaled fp16 pairs -> 32 TMEM columns
+        if (HALF && cq < NKB_REAL) {  // A: k-block cq (64 elements) of my user's vector -> scaled fp16 pairs -> 32 TMEM columns
             const int kb = cq;
             const float *urow = A.U + (my_valid ? my_row : 0) * A.ld_u;
             const bool vec = ((A.ld_u & 3) == 0) && ((reinterpret_cast<uintptr_t>(A.U) & 15) == 0);
@@ -857,12 +876,13 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
             }
         }
         if (!SAMPLE && my_valid) wbase = A.cand + ((my_row * P.S + c) * 4 + cq) * (int64_t)A.cap;
-        if (PRESUB && cq == 3) {  // A': -T0 as TF32 hi + lo (k_sample_thr), 16 columns reserved, 8 read
+        if ((PRESUB || AUG) && cq == 3) {  // A': -T0 as TF32 hi + lo (k_sample_thr), 16 columns reserved, 8 read
             uint32_t x[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) x[q] = 0u;
             if (HALF) {  // k_sample_thr wrote hi, lo as fp16 values of T0 su s_i / C; a dead row's operand is irrelevant
-                x[0] = dead ? 0u : pack_h2(-thr_hi, -thr_lo);
+                x[0] = (SAMPLE || dead) ? 0u : pack_h2(-thr_hi, -thr_lo);
+                if (AUG) x[1] = pack_h2(g_aug, g_aug);
             } else {
                 x[0] = __float_as_uint(-thr_hi);
                 x[1] = __float_as_uint(-thr_lo);
@@ -958,8 +978,13 @@ __global__ void __launch_bounds__(256)
 k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__restrict__ thr, const float *__restrict__ U, int64_t ld_u,
              int d, const float *__restrict__ stats, float eps_coef, float *__restrict__ eps2_out, float *__restrict__ thr_hi_out,
              float *__restrict__ thr_lo_out, float eps3_coef, float *__restrict__ eps2_3_out, float *__restrict__ thr3_out,
-             const float *__restrict__ item_scale, float *__restrict__ scale_out)
+             const float *__restrict__ item_scale, float *__restrict__ scale_out, const int *__restrict__ bias_shift, float *__restrict__ g_out)
 {
+    // bias_shift != null: the bias rides in the contraction (AUG, k_fused_tc).  beta = bias s_i 2^m is carried as two fp16
+    // values (error <= 2^-22 |b|), g = s_u 2^-m is a power of two and exact; the accumulator's partial sums grow by the
+    // bias, so the accumulation term of the band is taken on ||u|| N_max + B_max.  g must be an fp16 value: rows so small
+    // that s_u 2^-m > 2^15 are scaled less (their scores are all bias anyway), rows so large that it would drop below
+    // 2^-24 lose the bias in the candidate pass and get B_max added to their band.
     // item_scale != null: FP16 operands (precision "f16r").  The band gets one more term -- elements too small for an fp16
     // normal are off by up to 2^-25 in scaled units instead of 2^-11 relative: sum_k |du'_k i'_k| + |u'_k di'_k| <=
     // 2^-25 sqrt(d) (N'_max + ||u'||), i.e. 2^-25 sqrt(d) (N_max / s_u + ||u|| / s_i) in true units (fp16 round-to-nearest
@@ -1016,6 +1041,12 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
             ei = (int)((__float_as_uint(__ldg(item_scale)) >> 23) & 0xffu) - 127;
             const int eu0 = f16_scale_exp(amax);
             eu = eu0;
+            int m_aug = 0;
+            if (bias_shift != nullptr) {
+                m_aug = __ldg(bias_shift);
+                eu = min(eu, m_aug + 15);
+                eps += 1.25f * (((2.5f * (float)d + 8.0f) * 2.384185791015625e-07f + 4.76837158203125e-07f) * __ldg(stats + 1));
+            }
             // |T0 - 2 eps| 2^(eu + ei - 12) < 2^14 (one binade of headroom for the terms added below)
             const float tmag = fabsf(t0) + 2.0f * eps;
             if (tmag < 3.0e38f && tmag > 0.0f) {
@@ -1025,6 +1056,14 @@ k_sample_thr(const float *__restrict__ samp, int64_t n_rows, int r, float *__res
             half_dead = !(tmag < 3.0e38f) || eu < eu0 - 14 || eu + ei < -100 || eu + ei > 100;
             if (!half_dead)
                 eps += 1.25f * 2.98023223876953125e-08f * sqrtf((float)d) * (sqrtf(__ldg(stats)) * exp2i(-eu) + sqrtf(ss) * exp2i(-ei));
+            if (bias_shift != nullptr) {
+                float g = 0.0f;
+                if (!half_dead) {
+                    if (eu - m_aug < -24) eps += 1.25f * __ldg(stats + 1);  // the candidate pass scores this row without the bias
+                    else g = exp2i(eu - m_aug);
+                }
+                if (lane == 0) g_out[row] = g;
+            }
         }
         float e2 = 2.0f * eps;
         const float INF = __int_as_float(0x7f800000);
@@ -1151,22 +1190,28 @@ k_split_tf32(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pa
 
 // ---- FP16 operands: largest item magnitude, then the scaled fp16 item table ---------------------------------------------
 // amax_bits: zeroed by the host before the launch; non-negative floats order like their bit patterns.
+// f16s words: [0] max |item element| bits, [1] s_i (float), [2] max |bias| bits, [3] m (int): beta = bias s_i 2^m
 __global__ void __launch_bounds__(256)
-k_item_absmax(const float *__restrict__ X, int64_t ld, int64_t n, int d, uint32_t *__restrict__ amax_bits)
+k_item_absmax(const float *__restrict__ X, int64_t ld, int64_t n, int d, const float *__restrict__ bias, uint32_t *__restrict__ f16s)
 {
     pdl_wait();
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float best = 0.0f;
+    float best = 0.0f, bb = 0.0f;
     for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 4; row0 < n; row0 += (int64_t)gridDim.x * 32) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
             if (row0 + r < n)
                 for (int k = lane; k < d; k += 32) best = fmaxf(best, fabsf(__ldg(X + (row0 + r) * ld + k)));  // NaNs are skipped
+        if (bias != nullptr && lane < 4 && row0 + lane < n) bb = fmaxf(bb, fabsf(__ldg(bias + row0 + lane)));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane == 0 && best > 0.0f) atomicMax(amax_bits, __float_as_uint(best));
+    for (int o = 16; o > 0; o >>= 1) {
+        best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+        bb = fmaxf(bb, __shfl_xor_sync(0xffffffffu, bb, o));
+    }
+    if (lane == 0 && best > 0.0f) atomicMax(f16s, __float_as_uint(best));
+    if (lane == 0 && bb > 0.0f) atomicMax(f16s + 2, __float_as_uint(bb));
 }
 
 // item table -> fp16 table [n, d_pad] (d_pad = 64 or 128, zero padded in k), every element multiplied by s_i = 2^e with
@@ -1174,18 +1219,30 @@ k_item_absmax(const float *__restrict__ X, int64_t ld, int64_t n, int d, uint32_
 // side jobs as k_split_tf32: max ||item||^2 and max |bias| of the UNscaled table for the error band, counters reset.
 __global__ void __launch_bounds__(256)
 k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, __half *__restrict__ out, const float *__restrict__ bias,
-            int *__restrict__ zero_a, uint32_t *__restrict__ stats_cur, uint32_t *__restrict__ stats_next, const uint32_t *__restrict__ amax_bits,
-            float *__restrict__ si_out)
+            int *__restrict__ zero_a, uint32_t *__restrict__ stats_cur, uint32_t *__restrict__ stats_next, uint32_t *__restrict__ f16s, int aug)
 {
+    // aug: d_pad includes a last block of 64 columns, (C, C, beta_hi, beta_lo, 0 ...) with beta = bias s_i 2^m and m such that
+    // the largest |beta| lies in [2^13, 2^14) (see k_fused_tc AUG); words [1] and [3] of f16s are written here, read by the
+    // kernels that follow ([0], [2] come from k_item_absmax: every block reads them before any later kernel may start)
     pdl_wait();
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float si = exp2i(f16_scale_exp(__uint_as_float(__ldg(amax_bits))));
+    const int ei = f16_scale_exp(__uint_as_float(__ldg(f16s)));
+    const float si = exp2i(ei);
+    int m = 0;
+    {
+        const float bmax = __uint_as_float(__ldg(f16s + 2));
+        if (bmax > 0.0f && bmax < 3.0e38f) m = 13 - ((int)((__float_as_uint(bmax) >> 23) & 0xffu) - 127) - ei;
+        m = max(-100 - min(ei, 0), min(100 - max(ei, 0), m));  // 2^(ei + m) stays a normal float
+    }
+    const float bscale = exp2i(ei + m);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (zero_a != nullptr) { zero_a[0] = 0; zero_a[1] = 0; }
         if (stats_next != nullptr) { stats_next[0] = 0u; stats_next[1] = 0u; }
-        *si_out = si;
+        reinterpret_cast<float *>(f16s)[1] = si;
+        reinterpret_cast<int *>(f16s)[3] = m;
     }
+    const int d_emb = aug ? d_pad - 64 : d_pad;  // columns that hold embedding dimensions
     float best = 0.0f, bb = 0.0f;
     // four rows per warp and step; lane l owns the element pairs (2 l, 2 l + 1) and (64 + 2 l, 65 + 2 l) of a row
     for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 4; row0 < n; row0 += (int64_t)gridDim.x * 32) {
@@ -1204,7 +1261,7 @@ k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad
 #pragma unroll
             for (int q = 0; q < 4; q += 2) {
                 const int k = 2 * lane + 64 * (q >> 1);
-                if (k < d_pad) {
+                if (k < d_emb) {
                     *reinterpret_cast<uint32_t *>(out + (row0 + r) * d_pad + k) = pack_h2(x[r][q] * si, x[r][q + 1] * si);
                     ss = fmaf(x[r][q], x[r][q], ss);
                     ss = fmaf(x[r][q + 1], x[r][q + 1], ss);
@@ -1213,9 +1270,21 @@ k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
             best = fmaxf(best, (ss == ss) ? ss : __int_as_float(0x7f800000));
-            if (bias != nullptr && lane == 0) {
-                const float v = fabsf(__ldg(bias + row0 + r));
-                bb = fmaxf(bb, (v == v) ? v : __int_as_float(0x7f800000));
+            float bv = 0.0f;
+            if (bias != nullptr) {
+                bv = __ldg(bias + row0 + r);
+                const float v = fabsf(bv);
+                if (lane == 0) bb = fmaxf(bb, (v == v) ? v : __int_as_float(0x7f800000));
+            }
+            if (aug) {  // one 128-byte line per row: lane 0 (C, C), lane 1 (beta_hi, beta_lo), zeros
+                uint32_t w = 0u;
+                if (lane == 0) w = 0x6c006c00u;  // C = 2^12 twice
+                if (lane == 1) {
+                    const float beta = bv * bscale;
+                    const float bh = __half2float(__float2half_rn(beta));
+                    w = pack_h2(bh, beta - bh);
+                }
+                *reinterpret_cast<uint32_t *>(out + (row0 + r) * d_pad + d_emb + 2 * lane) = w;
             }
         }
     }

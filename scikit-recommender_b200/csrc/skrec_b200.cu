@@ -84,6 +84,7 @@ struct skr_ctx {
     int64_t opt_chunk_rows = 0;      // rows per chunk of the fused pipeline (0 = default)
     int64_t opt_score_fn = 0;        // 0: u . i + b   1: -||u - i|| + b (FP32 tile kernels only)
     int64_t opt_retry_min = -1;      // tf32r: unsettled rows from which the three-pass retry runs (-1 = cost model)
+    int64_t opt_no_aug = 0;          // f16r: 1 = add the bias in the epilogue instead of inside the contraction (A/B measurements)
     int64_t opt_exact_seg_rows = -1;  // development: how many failed rows are cut in segments (-1 = default)
     bool debug_sync = false;  // SKR_DEBUG_SYNC=1: synchronise and check after every kernel, naming the one that failed
     int64_t opt_trace_cta = -1;  // >= 0: record the tile timeline of that CTA of the main pass (development aid)
@@ -589,15 +590,19 @@ TcKernel tc_kernel_for(int passes, int mode)
     return passes == 3 ? k_fused_tc<NKB, 3, TC_MODE_COLLECT> : k_fused_tc<NKB, 1, TC_MODE_COLLECT>;
 }
 
-// half: FP16 operands (nkb counts 64-element k-blocks: 1 or 2; single pass)
+// half: 0 TF32 operands; 1 FP16 operands (nkb counts 64-element k-blocks: 1 or 2; single pass); 2 FP16 with the bias folded
+// into the contraction (nkb includes the augmentation block: 2 or 3)
 int launch_tc(skr_ctx *ctx, int nkb, int passes, int mode, unsigned grid, cudaStream_t st, const CUtensorMap &mhi, const CUtensorMap &mlo,
-              const TcArgs &A, const FusedParams &P, bool half = false)
+              const TcArgs &A, const FusedParams &P, int half = 0)
 {
     TcKernel k = nkb == 1 ? tc_kernel_for<1>(passes, mode) : nkb == 2 ? tc_kernel_for<2>(passes, mode)
                : nkb == 3 ? tc_kernel_for<3>(passes, mode) : tc_kernel_for<4>(passes, mode);
-    if (half) {
+    if (half == 1) {
         if (mode == TC_MODE_SAMPLE) k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_SAMPLE, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_SAMPLE, true>;
         else k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_COLLECT, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_COLLECT, true>;
+    } else if (half == 2) {
+        if (mode == TC_MODE_SAMPLE) k = nkb == 2 ? (TcKernel)k_fused_tc<2, 1, TC_MODE_SAMPLE, true, true> : (TcKernel)k_fused_tc<3, 1, TC_MODE_SAMPLE, true, true>;
+        else k = nkb == 2 ? (TcKernel)k_fused_tc<2, 1, TC_MODE_COLLECT, true, true> : (TcKernel)k_fused_tc<3, 1, TC_MODE_COLLECT, true, true>;
     }
     const size_t smem = tc_smem_bytes();
     SKR_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -717,6 +722,7 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
         return SKR_OK;
     }
     if (!strcmp(name, "retry_min")) { ctx->opt_retry_min = value; return SKR_OK; }
+    if (!strcmp(name, "no_aug")) { ctx->opt_no_aug = value; return SKR_OK; }
     if (!strcmp(name, "chunk_rows")) { ctx->opt_chunk_rows = value < 0 ? 0 : value; return SKR_OK; }
     if (!strcmp(name, "exact_seg_rows")) { ctx->opt_exact_seg_rows = value; return SKR_OK; }
     if (!strcmp(name, "trace_cta")) { ctx->opt_trace_cta = value; return SKR_OK; }
@@ -1132,21 +1138,29 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         // AUTO: re-scoring costs a fixed ~60 candidate rows per user, the two extra MMA passes of 3xTF32 grow with
         // the catalogue: measured on one B200, tf32r is 5 % faster at c2 (I d = 2.6 M) and 22 % at c3b (5.9 M); below
         // ~1 M the sampled thresholds stop working for either and the choice does not matter
-        if (precision == SKR_PREC_AUTO) precision = ((double)n_items * d >= 2.0e6) ? SKR_PREC_TF32R : SKR_PREC_3XTF32;
+        // d > 64: a tile's TF32 MMAs (13-17 x 64 cycles) outlast its epilogue; with FP16 operands (9 MMAs, half the item-panel
+        // bytes) the epilogue is the limit instead: c4 (d = 128) 453.7 -> 318.6 ms per 10^6 users.  At d <= 64 both are
+        // epilogue-bound and equally fast (c2: 0.660 vs 0.675 ms), so TF32 stays.
+        if (precision == SKR_PREC_AUTO)
+            precision = ((double)n_items * d >= 2.0e6) ? (d > 64 ? SKR_PREC_F16R : SKR_PREC_TF32R) : SKR_PREC_3XTF32;
         const bool half = (precision == SKR_PREC_F16R);  // FP16 operands for the first attempt; the retry stays 3xTF32
         const bool rescore = (precision == SKR_PREC_TF32R) || half;
         const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
         // operand prep: item table -> hi (and, for three passes, lo) TF32 tables, TMA descriptors
         const int d_pad = nkb * TC_KB;
-        const int nkb_h = (d + 2 * TC_KB - 1) / (2 * TC_KB), d_pad_h = nkb_h * 2 * TC_KB;  // FP16: 64-element k-blocks
+        // FP16: 64-element k-blocks; with a bias one more block carries (C, C, beta_hi, beta_lo): threshold and bias are then
+        // applied by one MMA per tile and the epilogue is that of an unbiased model (k_fused_tc AUG)
+        const bool aug = half && bias_dev != nullptr && ctx->opt_no_aug == 0;
+        const int nkb_h = (d + 2 * TC_KB - 1) / (2 * TC_KB) + (aug ? 1 : 0), d_pad_h = nkb_h * 2 * TC_KB;
         const int nkb_1 = half ? nkb_h : nkb;  // k-blocks of the first attempt's kernels
+        const int half_mode = half ? (aug ? 2 : 1) : 0;
         const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
         if ((rc = ensure(ctx, ctx->bhi, tbytes))) return rc;  // f16r: filled on demand by the retry, like blo
         if ((passes == 3 || rescore) && (rc = ensure(ctx, ctx->blo, tbytes))) return rc;  // tf32r: filled on demand by the retry
         if (half) {
             if ((rc = ensure(ctx, ctx->bh16, (size_t)n_items * d_pad_h * 2))) return rc;
-            if ((rc = ensure(ctx, ctx->f16s, 2 * sizeof(uint32_t)))) return rc;
-            if ((rc = ensure(ctx, ctx->rscale, (size_t)n_rows * sizeof(float)))) return rc;
+            if ((rc = ensure(ctx, ctx->f16s, 4 * sizeof(uint32_t)))) return rc;
+            if ((rc = ensure(ctx, ctx->rscale, (size_t)2 * n_rows * sizeof(float)))) return rc;  // s_u s_i | g
         }
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(2 * n_rows + 2) * sizeof(int32_t)))) return rc;
         if (ctx->stats.cap == 0) {  // two slots of {max ||item||^2, max |bias|}, alternating between evaluates
@@ -1160,10 +1174,11 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
             ctx->stats_cur_ptr = stats_cur;
             const dim3 sgrid((unsigned)std::min<int64_t>((n_items + 31) / 32, 16 * ctx->n_sm));
             if (half) {
-                SKR_CUDA(ctx, cudaMemsetAsync(ctx->f16s.p, 0, 2 * sizeof(uint32_t), st));
-                SKR_CUDA(ctx, launch_pdl(k_item_absmax, sgrid, dim3(256u), (size_t)0, st, item_vecs_dev, ld_i, n_items, d, (uint32_t *)ctx->f16s.p));
+                SKR_CUDA(ctx, cudaMemsetAsync(ctx->f16s.p, 0, 4 * sizeof(uint32_t), st));
+                SKR_CUDA(ctx, launch_pdl(k_item_absmax, sgrid, dim3(256u), (size_t)0, st, item_vecs_dev, ld_i, n_items, d, aug ? bias_dev : (const float *)nullptr,
+                                         (uint32_t *)ctx->f16s.p));
                 SKR_CUDA(ctx, launch_pdl(k_split_f16, sgrid, dim3(256u), (size_t)0, st, item_vecs_dev, ld_i, n_items, d, d_pad_h, (__half *)ctx->bh16.p, bias_dev,
-                                         (int *)ctx->fail_list.p, stats_cur, stats_next, (const uint32_t *)ctx->f16s.p, (float *)ctx->f16s.p + 1));
+                                         (int *)ctx->fail_list.p, stats_cur, stats_next, (uint32_t *)ctx->f16s.p, aug ? 1 : 0));
                 ctx->launches++;
             } else {
                 SKR_CUDA(ctx, launch_pdl(k_split_tf32, sgrid, dim3((unsigned)(256)), (size_t)(0), st, item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
@@ -1259,6 +1274,10 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         A.thr_lo = presub ? A.thr + 2 * n_rows : nullptr;
         A.item_scale = half ? (const float *)ctx->f16s.p + 1 : nullptr;
         A.scale = half ? (const float *)ctx->rscale.p : nullptr;
+        A.bias_shift = aug ? (const int *)ctx->f16s.p + 3 : nullptr;
+        A.rowg = aug ? (const float *)ctx->rscale.p + n_rows : nullptr;
+        FusedParams P1 = P;  // what the first attempt's kernels see: no bias to add when it is part of the contraction
+        if (aug) P1.bias = nullptr;
         float eps_coef = 0.0f, eps3_coef = 0.0f;
         float *thr3 = nullptr, *eps2_3 = nullptr;
         if (rescore) {
@@ -1270,16 +1289,16 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
-        if ((rc = launch_tc(ctx, nkb_1, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, m1, mlo, A, P, half))) return rc;
+        if ((rc = launch_tc(ctx, nkb_1, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, m1, mlo, A, P1, half_mode))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
         {
             typedef void (*ThrKernel)(const float *, int64_t, int, float *, const float *, int64_t, int, const float *, float, float *, float *, float *, float,
-                                      float *, float *, const float *, float *);
+                                      float *, float *, const float *, float *, const int *, float *);
             const ThrKernel thr_k = samp_chunks == 1 ? (ThrKernel)k_sample_thr<1> : samp_chunks == 2 ? (ThrKernel)k_sample_thr<2>
                                     : samp_chunks == 3 ? (ThrKernel)k_sample_thr<3> : (ThrKernel)k_sample_thr<4>;
             SKR_CUDA(ctx, launch_pdl(thr_k, dim3((unsigned)((n_rows + 7) / 8)), dim3(256u), (size_t)0, st, (const float *)ctx->samp.p, n_rows, r, (float *)ctx->thr.p, user_vecs_dev, ld_u, d,
                                      (const float *)stats_cur, eps_coef, rescore ? (float *)ctx->eps2.p : (float *)nullptr, (float *)A.thr_hi, (float *)A.thr_lo, eps3_coef, eps2_3,
-                                     thr3, A.item_scale, (float *)ctx->rscale.p));
+                                     thr3, A.item_scale, (float *)ctx->rscale.p, A.bias_shift, (float *)A.rowg));
         }
         // main pass: every item tile, reference-grade scores, survivors to the candidate lists
         if (ctx->opt_trace_cta >= 0) {
@@ -1292,7 +1311,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         }
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
         SKR_AFTER(ctx, st, "k_sample_thr");
-        if ((rc = launch_tc(ctx, nkb_1, passes, TC_MODE_COLLECT, grid_tc, st, m1, mlo, A, P, half))) return rc;
+        if ((rc = launch_tc(ctx, nkb_1, passes, TC_MODE_COLLECT, grid_tc, st, m1, mlo, A, P1, half_mode))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc COLLECT");
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
@@ -1322,6 +1341,8 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
             TcArgs A2 = A;
             A2.item_scale = nullptr;
             A2.scale = nullptr;
+            A2.bias_shift = nullptr;
+            A2.rowg = nullptr;
             A2.thr = thr3;
             A2.thr_hi = nullptr;
             A2.thr_lo = nullptr;

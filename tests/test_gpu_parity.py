@@ -784,6 +784,13 @@ def test_f16r_power_of_two_scaling_is_invisible(torch_cuda, ctx, d, bias_scale, 
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
     if bias_scale <= 30.0:  # a bias 10^4 times the dot products may cost rows to the exact kernel; anything milder must not
         assert stats["exact_rows"] <= U // 10, stats
+    if b is not None:  # the bias inside the contraction (default) and added by the epilogue: the same bits
+        ctx.set_option("no_aug", 1)
+        try:
+            alt = _run_fused(torch_cuda, ctx, ue, ie, b, tr, te, metric, K, "f16r")
+        finally:
+            ctx.set_option("no_aug", 0)
+        assert np.array_equal(alt[0], ref[0]) and np.array_equal(alt[1], ref[1]) and np.array_equal(alt[2], ref[2])
 
 
 def test_c2_full_size_tf32r_equals_fp32_path(torch_cuda, ctx, c2_data):

@@ -36,6 +36,24 @@ sums = torch.zeros(len(ids) * K, dtype=torch.float64, device="cuda")
 ms = []
 import time
 wall = []
+for kv in filter(None, os.environ.get("SKR_OPTS", "").split(",")):  # e.g. SKR_OPTS=no_aug=1,retry_min=1
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+ab = os.environ.get("SKR_AB")  # A/B an option under the same thermal / power state: blocks of n evaluates, value 0 and 1 alternating
+if ab:
+    for blk in range(6):
+        ctx.set_option(ab, blk & 1)
+        ks, ws = [], []
+        for _ in range(n):
+            sums.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.eval_fused(ue, ie, b, 0, ids, K, precision=prec, sums=sums)
+            torch.cuda.synchronize()
+            ws.append((time.perf_counter() - t0) * 1e3)
+            ks.append(ctx.fused_kernel_ms(0))
+        print("%s=%d: evaluate ms %s | kernel ms %s | prepass %.3f" % (ab, blk & 1, " ".join("%.2f" % w for w in ws), " ".join("%.2f" % k for k in ks),
+                                                                     ctx.fused_prepass_ms(0)), flush=True)
+    sys.exit(0)
 for _ in range(n):
     sums.zero_()
     torch.cuda.synchronize()
