@@ -222,6 +222,18 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
+// K-major SWIZZLE_32B (layout 6): rows are 32 bytes (one K = 16 fp16 slice), 8-row atoms 256 bytes apart -- the 4 KB
+// augmentation tiles of the FP16 pipeline (cute: Swizzle<1,4,3> o ((8,n),2):((2,SBO),1) in 16-byte units)
+__device__ __forceinline__ uint64_t make_b_desc_sw32(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
 // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format TF32 (2) [7,10) | b_format TF32 (2)
 // [10,13) | a/b K-major | N>>3 [17,23) | M>>4 [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -433,10 +445,12 @@ __device__ __forceinline__ void tc_process(const uint32_t (&raw)[32], const floa
 
 // HALF: FP16 operands (tm_bhi describes the scaled fp16 item table; a k-block is 64 elements = the same 128-byte swizzle
 // row, 32 TMEM columns of packed pairs and four K = 16 MMAs, so the pipeline below is unchanged), single pass only.
-// AUG (with HALF, models with an item bias): the LAST of the NKB k-blocks is the augmentation block -- item side
-// (C, C, beta_hi, beta_lo, 0...) with beta = bias s_i 2^m, user side (-T_hi, -T_lo, g, g, 0...) with g = s_u 2^-m -- and
-// contributes ONE K = 16 MMA per tile that both subtracts the row threshold and adds the item bias inside the tensor core:
-// the epilogue of a biased model becomes the unbiased one (no bias loads, no FMAs: ~40 of its ~155 instructions per tile).
+// AUG (with HALF, models with an item bias): the B' tile of the threshold MMA is no longer a constant but a 4 KB slice
+// of an augmentation table streamed with the item tiles (tm_blo; SWIZZLE_32B rows of 16 fp16: C, C, beta_hi, beta_lo, 0...,
+// beta = bias s_i 2^m), and the user side holds (-T_hi, -T_lo, g, g, 0...) with g = s_u 2^-m: ONE K = 16 MMA per tile both
+// subtracts the row threshold and adds the item bias inside the tensor core, and the epilogue of a biased model becomes
+// the unbiased one (no bias loads, no FMAs: ~40 of its ~155 instructions per tile).  (A first version carried the four
+// columns in a whole extra 16 KB k-block: 48 KB per tile put the kernel on the L2 -> SM limit, 13 of ~14.5 TB/s.)
 template <int NKB, int PASSES, int MODE, bool HALF = false, bool AUG = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo, TcArgs A, FusedParams P)
@@ -444,21 +458,26 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
     pdl_trigger();  // the wait comes after the prologue, which touches nothing an earlier kernel wrote
     constexpr bool SAMPLE = (MODE == TC_MODE_SAMPLE);
     constexpr int KB_ELEMS = HALF ? 2 * TC_KB : TC_KB;  // operand elements per k-block
-    constexpr int NKB_REAL = AUG ? NKB - 1 : NKB;       // k-blocks of embedding dimensions
+    constexpr int NKB_REAL = NKB;                        // k-blocks of embedding dimensions
+    constexpr int AUG_TILE_BYTES = TN * 32;              // 128 item rows x 16 fp16
+    constexpr int AUG_SLOTS = 4;                         // in the 16 KB the constant threshold tile occupies otherwise
     static_assert(!HALF || PASSES == 1, "FP16 operands: single pass");
-    static_assert(!AUG || (HALF && NKB >= 2), "the augmentation block rides on the FP16 pipeline");
-    constexpr int STAGES = (PASSES == 3) ? 4 : 8;
+    static_assert(!AUG || HALF, "the augmentation tile rides on the FP16 pipeline");
+    // AUG: the producer may run at most AUG_SLOTS tiles ahead of the MMAs (slot i & 3 is reloaded for tile i + 4 once the
+    // stage of tile i's first k-block is free, i.e. after tile i's augmentation MMA, which is issued first)
+    constexpr int STAGES = (PASSES == 3) ? 4 : ((AUG && NKB == 1) ? 4 : 8);
     constexpr int STAGE_BYTES = (PASSES == 3) ? 2 * TC_TILE_BYTES : TC_TILE_BYTES;
     static_assert(NKB >= 1 && NKB <= 4 && (PASSES == 1 || PASSES == 3), "tile shape");
-    static_assert(STAGES * STAGE_BYTES == TC_RING_BYTES, "ring size");
+    static_assert(STAGES * STAGE_BYTES <= TC_RING_BYTES, "ring size");
+    static_assert(!AUG || STAGES / NKB <= AUG_SLOTS, "augmentation slots");
     // Single-pass COLLECT (precision tf32r / 1xtf32): one extra K = 8 MMA per tile starts the accumulator at -T0[row]
     // (A' = [-hi, -lo, 0 x 6] per row in TMEM, B' = [1, 1, 0 x 6] for every column, a constant shared-memory tile),
     // so the epilogue tests sign bits instead of subtracting: the single-pass modes are bound by the epilogue's
     // instruction issue, not by the tensor pipe.  Needs 16 more TMEM columns; at d = 128 (NKB = 4) that leaves two
     // accumulator buffers instead of three, which still measured 4 % faster than three buffers with the FADDs.
     constexpr bool PRESUB = !SAMPLE && PASSES == 1;
-    constexpr int A_THR_COL = AUG ? TC_KB * NKB_REAL : TC_KB * NKB * (PASSES == 3 ? 2 : 1);  // first column of A'
-    constexpr int A_COLS = AUG ? TC_KB * NKB : A_THR_COL + (PRESUB ? 16 : 0);
+    constexpr int A_THR_COL = TC_KB * NKB * (PASSES == 3 ? 2 : 1);  // first column of A'
+    constexpr int A_COLS = A_THR_COL + ((PRESUB || AUG) ? 16 : 0);
     constexpr int NBUF = (A_COLS <= 512 - 3 * TN) ? 3 : 2;
     constexpr int ACC_COL = 512 - NBUF * TN;  // first accumulator column
 
@@ -555,8 +574,9 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                     if (TC_DBG(A.dbg, 8)) {
                         mbar_arrive(full + s);
                     } else {
-                        mbar_expect_tx(full + s, STAGE_BYTES);
+                        mbar_expect_tx(full + s, STAGE_BYTES + ((AUG && kb == 0) ? AUG_TILE_BYTES : 0));
                         unsigned char *dst = b_tiles + (size_t)s * STAGE_BYTES;
+                        if (AUG && kb == 0) tma_load_2d(thr_tile + (i & (AUG_SLOTS - 1)) * AUG_TILE_BYTES, &tm_blo, 0, t * TN, full + s);
                         tma_load_2d(dst, &tm_bhi, kb * KB_ELEMS, t * TN, full + s);
                         if (PASSES == 3) tma_load_2d(dst + TC_TILE_BYTES, &tm_blo, kb * TC_KB, t * TN, full + s);
                     }
@@ -580,6 +600,7 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
         const uint32_t a_lo0 = tmem_base + (uint32_t)(NKB * TC_KB);
         const uint64_t desc0 = make_b_desc(smem_u32(b_tiles));
         const uint64_t desc_thr = make_b_desc(smem_u32(thr_tile));
+        const uint64_t desc_aug = make_b_desc_sw32(smem_u32(thr_tile));
         for (int i = p; i < n_tiles; i += 2) {
             const int b = i % NBUF;
             const uint32_t d_tmem = tmem_base + (uint32_t)(ACC_COL + b * TN);
@@ -597,16 +618,16 @@ k_fused_tc(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ C
                 if (elect_one()) {
                     if (kb == 0) tc_trace(A, i, 3);
                     if (do_mma) {
-                        if (PRESUB && !AUG && kb == 0) {  // acc = -T0[row]
-                            if (HALF) tc_mma_ts_f16(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC_F16, 0u);
+                        if ((PRESUB || AUG) && kb == 0) {  // acc = -T0[row] (AUG: + bias[col])
+                            if (AUG) tc_mma_ts_f16(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_aug + (uint64_t)((i & (AUG_SLOTS - 1)) * (AUG_TILE_BYTES >> 4)), TC_IDESC_F16, 0u);
+                            else if (HALF) tc_mma_ts_f16(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC_F16, 0u);
                             else tc_mma_ts(d_tmem, tmem_base + (uint32_t)A_THR_COL, desc_thr, TC_IDESC, 0u);
                         }
 #pragma unroll
                         for (int k8 = 0; k8 < 4; ++k8) {  // UMMA K = 8 tf32 / 16 fp16 = 32 bytes of B, 8 TMEM columns of A
-                            if (AUG && kb == NKB - 1 && k8 > 0) break;  // the augmentation block holds 4 non-zero columns
                             const uint32_t acol = (uint32_t)(kb * TC_KB + k8 * 8);
                             const uint64_t dhi = ds + (uint64_t)(k8 * 2);
-                            const uint32_t acc = ((PRESUB && !AUG) || (kb | k8)) ? 1u : 0u;
+                            const uint32_t acc = (PRESUB || AUG || (kb | k8)) ? 1u : 0u;
                             if (PASSES == 3) {
                                 const uint64_t dlo = dhi + (uint64_t)(TC_TILE_BYTES >> 4);
                                 tc_mma_ts(d_tmem, a_lo0 + acol, dhi, TC_IDESC, acc);
@@ -1219,9 +1240,10 @@ k_item_absmax(const float *__restrict__ X, int64_t ld, int64_t n, int d, const f
 // side jobs as k_split_tf32: max ||item||^2 and max |bias| of the UNscaled table for the error band, counters reset.
 __global__ void __launch_bounds__(256)
 k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad, __half *__restrict__ out, const float *__restrict__ bias,
-            int *__restrict__ zero_a, uint32_t *__restrict__ stats_cur, uint32_t *__restrict__ stats_next, uint32_t *__restrict__ f16s, int aug)
+            int *__restrict__ zero_a, uint32_t *__restrict__ stats_cur, uint32_t *__restrict__ stats_next, uint32_t *__restrict__ f16s,
+            __half *__restrict__ aug)
 {
-    // aug: d_pad includes a last block of 64 columns, (C, C, beta_hi, beta_lo, 0 ...) with beta = bias s_i 2^m and m such that
+    // aug != null: augmentation table [n, 16] fp16, row = (C, C, beta_hi, beta_lo, 0 ...) with beta = bias s_i 2^m and m such that
     // the largest |beta| lies in [2^13, 2^14) (see k_fused_tc AUG); words [1] and [3] of f16s are written here, read by the
     // kernels that follow ([0], [2] come from k_item_absmax: every block reads them before any later kernel may start)
     pdl_wait();
@@ -1242,7 +1264,7 @@ k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad
         reinterpret_cast<float *>(f16s)[1] = si;
         reinterpret_cast<int *>(f16s)[3] = m;
     }
-    const int d_emb = aug ? d_pad - 64 : d_pad;  // columns that hold embedding dimensions
+    const int d_emb = d_pad;
     float best = 0.0f, bb = 0.0f;
     // four rows per warp and step; lane l owns the element pairs (2 l, 2 l + 1) and (64 + 2 l, 65 + 2 l) of a row
     for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 4; row0 < n; row0 += (int64_t)gridDim.x * 32) {
@@ -1276,7 +1298,7 @@ k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad
                 const float v = fabsf(bv);
                 if (lane == 0) bb = fmaxf(bb, (v == v) ? v : __int_as_float(0x7f800000));
             }
-            if (aug) {  // one 128-byte line per row: lane 0 (C, C), lane 1 (beta_hi, beta_lo), zeros
+            if (aug != nullptr && lane < 8) {  // 32 bytes per row: lane 0 (C, C), lane 1 (beta_hi, beta_lo), zeros
                 uint32_t w = 0u;
                 if (lane == 0) w = 0x6c006c00u;  // C = 2^12 twice
                 if (lane == 1) {
@@ -1284,7 +1306,7 @@ k_split_f16(const float *__restrict__ X, int64_t ld, int64_t n, int d, int d_pad
                     const float bh = __half2float(__float2half_rn(beta));
                     w = pack_h2(bh, beta - bh);
                 }
-                *reinterpret_cast<uint32_t *>(out + (row0 + r) * d_pad + d_emb + 2 * lane) = w;
+                *reinterpret_cast<uint32_t *>(aug + (row0 + r) * 16 + 2 * lane) = w;
             }
         }
     }

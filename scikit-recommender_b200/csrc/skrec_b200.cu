@@ -71,7 +71,7 @@ struct skr_ctx {
     int disc_n = 0;
     // workspace, grow-only
     Buf trace, stats, stage_s, eps2, rs_keys, rs_cnt, keys, per_user, partial, part, thr, bhi, blo, bias, sums, stage_a, stage_b, stage_c, out_idx, samp, cand, cand_cnt, fail_list;
-    Buf bh16, f16s, rscale;  // precision "f16r": scaled fp16 item table; {max |item| bits, s_i}; per-row scale s_u s_i
+    Buf bh16, f16s, rscale, baug;  // precision "f16r": scaled fp16 item table; {max |item| bits, s_i, max |bias| bits, m}; per-row s_u s_i | g; augmentation table
     int *d_err = nullptr;
     double *h_pin = nullptr;  // pinned host staging for the small results ([sums | watchdog flag]), SKR_PIN_DOUBLES doubles
     int64_t launches = 0;
@@ -581,6 +581,20 @@ int make_tmap_f16(skr_ctx *ctx, CUtensorMap *map, const void *base, int64_t n_ro
     return SKR_OK;
 }
 
+// augmentation table [n_rows, 16] fp16 (32-byte rows): boxes of 16 x 128 = 4 KB, SWIZZLE_32B
+int make_tmap_aug(skr_ctx *ctx, CUtensorMap *map, const void *base, int64_t n_rows)
+{
+    cuuint64_t dims[2] = {16, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {32};
+    cuuint32_t box[2] = {16, (cuuint32_t)TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SKR_ERR_CUDA, "cuTensorMapEncodeTiled (augmentation table) failed (%d)", (int)r);
+    return SKR_OK;
+}
+
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, TcArgs, FusedParams);
 
 template <int NKB>
@@ -591,7 +605,7 @@ TcKernel tc_kernel_for(int passes, int mode)
 }
 
 // half: 0 TF32 operands; 1 FP16 operands (nkb counts 64-element k-blocks: 1 or 2; single pass); 2 FP16 with the bias folded
-// into the contraction (nkb includes the augmentation block: 2 or 3)
+// into the contraction (mlo then describes the augmentation table)
 int launch_tc(skr_ctx *ctx, int nkb, int passes, int mode, unsigned grid, cudaStream_t st, const CUtensorMap &mhi, const CUtensorMap &mlo,
               const TcArgs &A, const FusedParams &P, int half = 0)
 {
@@ -601,8 +615,8 @@ int launch_tc(skr_ctx *ctx, int nkb, int passes, int mode, unsigned grid, cudaSt
         if (mode == TC_MODE_SAMPLE) k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_SAMPLE, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_SAMPLE, true>;
         else k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_COLLECT, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_COLLECT, true>;
     } else if (half == 2) {
-        if (mode == TC_MODE_SAMPLE) k = nkb == 2 ? (TcKernel)k_fused_tc<2, 1, TC_MODE_SAMPLE, true, true> : (TcKernel)k_fused_tc<3, 1, TC_MODE_SAMPLE, true, true>;
-        else k = nkb == 2 ? (TcKernel)k_fused_tc<2, 1, TC_MODE_COLLECT, true, true> : (TcKernel)k_fused_tc<3, 1, TC_MODE_COLLECT, true, true>;
+        if (mode == TC_MODE_SAMPLE) k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_SAMPLE, true, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_SAMPLE, true, true>;
+        else k = nkb == 1 ? (TcKernel)k_fused_tc<1, 1, TC_MODE_COLLECT, true, true> : (TcKernel)k_fused_tc<2, 1, TC_MODE_COLLECT, true, true>;
     }
     const size_t smem = tc_smem_bytes();
     SKR_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -696,7 +710,7 @@ int skr_ctx_destroy(skr_ctx *ctx)
     free_dev(ctx->d_tr_indptr); free_dev(ctx->d_tr_idx); free_dev(ctx->d_mask_keys); free_dev(ctx->d_mask_tile_ptr); free_dev(ctx->d_mask_tile_off);
     free_dev(ctx->d_te_indptr); free_dev(ctx->d_te_idx); free_dev(ctx->d_disc); free_dev(ctx->d_idcg); free_dev(ctx->d_err);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
-    Buf *bufs[] = {&ctx->bh16, &ctx->f16s, &ctx->rscale, &ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
+    Buf *bufs[] = {&ctx->bh16, &ctx->f16s, &ctx->rscale, &ctx->baug, &ctx->keys, &ctx->per_user, &ctx->partial, &ctx->part, &ctx->thr, &ctx->bhi, &ctx->blo, &ctx->bias,
                    &ctx->sums, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->out_idx, &ctx->samp, &ctx->cand, &ctx->cand_cnt,
                    &ctx->fail_list, &ctx->trace, &ctx->stats, &ctx->stage_s, &ctx->eps2, &ctx->rs_keys, &ctx->rs_cnt};
     for (Buf *b : bufs) free_dev(b->p);
@@ -1148,10 +1162,10 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         const int passes = (precision == SKR_PREC_1XTF32 || rescore) ? 1 : 3;
         // operand prep: item table -> hi (and, for three passes, lo) TF32 tables, TMA descriptors
         const int d_pad = nkb * TC_KB;
-        // FP16: 64-element k-blocks; with a bias one more block carries (C, C, beta_hi, beta_lo): threshold and bias are then
-        // applied by one MMA per tile and the epilogue is that of an unbiased model (k_fused_tc AUG)
+        // FP16: 64-element k-blocks; with a bias an augmentation table carries (C, C, beta_hi, beta_lo) per item: threshold and
+        // bias are then applied by one MMA per tile and the epilogue is that of an unbiased model (k_fused_tc AUG)
         const bool aug = half && bias_dev != nullptr && ctx->opt_no_aug == 0;
-        const int nkb_h = (d + 2 * TC_KB - 1) / (2 * TC_KB) + (aug ? 1 : 0), d_pad_h = nkb_h * 2 * TC_KB;
+        const int nkb_h = (d + 2 * TC_KB - 1) / (2 * TC_KB), d_pad_h = nkb_h * 2 * TC_KB;
         const int nkb_1 = half ? nkb_h : nkb;  // k-blocks of the first attempt's kernels
         const int half_mode = half ? (aug ? 2 : 1) : 0;
         const size_t tbytes = (size_t)n_items * d_pad * sizeof(float);
@@ -1160,6 +1174,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         if (half) {
             if ((rc = ensure(ctx, ctx->bh16, (size_t)n_items * d_pad_h * 2))) return rc;
             if ((rc = ensure(ctx, ctx->f16s, 4 * sizeof(uint32_t)))) return rc;
+            if (aug && (rc = ensure(ctx, ctx->baug, (size_t)n_items * 32))) return rc;
             if ((rc = ensure(ctx, ctx->rscale, (size_t)2 * n_rows * sizeof(float)))) return rc;  // s_u s_i | g
         }
         if ((rc = ensure(ctx, ctx->fail_list, (size_t)(2 * n_rows + 2) * sizeof(int32_t)))) return rc;
@@ -1178,7 +1193,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
                 SKR_CUDA(ctx, launch_pdl(k_item_absmax, sgrid, dim3(256u), (size_t)0, st, item_vecs_dev, ld_i, n_items, d, aug ? bias_dev : (const float *)nullptr,
                                          (uint32_t *)ctx->f16s.p));
                 SKR_CUDA(ctx, launch_pdl(k_split_f16, sgrid, dim3(256u), (size_t)0, st, item_vecs_dev, ld_i, n_items, d, d_pad_h, (__half *)ctx->bh16.p, bias_dev,
-                                         (int *)ctx->fail_list.p, stats_cur, stats_next, (uint32_t *)ctx->f16s.p, aug ? 1 : 0));
+                                         (int *)ctx->fail_list.p, stats_cur, stats_next, (uint32_t *)ctx->f16s.p, aug ? (__half *)ctx->baug.p : (__half *)nullptr));
                 ctx->launches++;
             } else {
                 SKR_CUDA(ctx, launch_pdl(k_split_tf32, sgrid, dim3((unsigned)(256)), (size_t)(0), st, item_vecs_dev, ld_i, n_items, d, d_pad, (float *)ctx->bhi.p,
@@ -1196,6 +1211,8 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         if (half) { if ((rc = make_tmap_f16(ctx, &mh16, ctx->bh16.p, n_items, d_pad_h))) return rc; }
         else mh16 = mhi;
         const CUtensorMap &m1 = half ? mh16 : mhi;  // what the first attempt's kernels stream
+        CUtensorMap maug = mlo;                     // ... and the second map they get: lo table (3xTF32) or augmentation table (f16r with a bias)
+        if (aug && (rc = make_tmap_aug(ctx, &maug, ctx->baug.p, n_items))) return rc;
 
         // sampling plan (k_fused_tc.cuh header): fraction f ~ 6/K of the item tiles, threshold = r-th largest
         // sampled group maximum with r = K f + 4.5 sqrt(K f) + 8 (a ~4-sigma margin against fewer than K survivors)
@@ -1289,7 +1306,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         }
         // pre-pass: thresholds from a strided sample of the item tiles, single TF32 pass
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev2[slot], st));
-        if ((rc = launch_tc(ctx, nkb_1, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, m1, mlo, A, P1, half_mode))) return rc;
+        if ((rc = launch_tc(ctx, nkb_1, 1, TC_MODE_SAMPLE, (unsigned)(P.n_rt * samp_chunks), st, m1, maug, A, P1, half_mode))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc SAMPLE");
         {
             typedef void (*ThrKernel)(const float *, int64_t, int, float *, const float *, int64_t, int, const float *, float, float *, float *, float *, float,
@@ -1311,7 +1328,7 @@ static int fused_chunk(skr_ctx *ctx, const float *user_vecs_dev, int64_t n_rows,
         }
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev0[slot], st));
         SKR_AFTER(ctx, st, "k_sample_thr");
-        if ((rc = launch_tc(ctx, nkb_1, passes, TC_MODE_COLLECT, grid_tc, st, m1, mlo, A, P1, half_mode))) return rc;
+        if ((rc = launch_tc(ctx, nkb_1, passes, TC_MODE_COLLECT, grid_tc, st, m1, maug, A, P1, half_mode))) return rc;
         SKR_AFTER(ctx, st, "k_fused_tc COLLECT");
         SKR_CUDA(ctx, cudaEventRecord(ctx->ev1[slot], st));
         ctx->launches += 3;
