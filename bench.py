@@ -568,6 +568,9 @@ def run_ours(args):
                     "exact_rows_last_chunk": r["plan"].get("exact_rows"), "retried_rows_last_chunk": r["plan"].get("retried_rows"),
                     "algorithmic_flops_per_step_rank0": flops, "mma_passes": passes,
                     "tensor_pipe_utilisation_est": passes * achieved / peak, "peak_note": peak_note,
+                    # the same kernel against the SUSTAINED cuBLAS figure (what a back-to-back GEMM holds at the power cap): the
+                    # fair denominator for launches inside a long, power-capped step (c4, c5); `frac` keeps the burst peak
+                    "frac_of_sustained_peak": (achieved / (pk["bf16_sustained"] * (peak / pk["bf16"]))) if kern.startswith("tcgen05") else None,
                     "rank0_rows": rows_rank0, "rank0_items": items_rank0}
 
     kern = r.get("kernel", "score blocks")

@@ -53,6 +53,28 @@ struct RowDot {
         }
         int k = 0;
         if (vec_ok) {
+            // two k-steps per trip: eight 16-byte loads in flight per thread (a failed row of a 10^6-item catalogue is
+            // walked by 40 blocks only -- the merge takes 4,096 keys -- and every trip waits one DRAM round trip)
+            for (; k + 8 <= d; k += 8) {
+                float4 x[4], y[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const float4 *>(it[q] + k));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) y[q] = __ldg(reinterpret_cast<const float4 *>(it[q] + k + 4));
+                const float u0 = u[k], u1 = u[k + 1], u2 = u[k + 2], u3 = u[k + 3];
+                const float u4 = u[k + 4], u5 = u[k + 5], u6 = u[k + 6], u7 = u[k + 7];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[q] = fmaf(u0, x[q].x, acc[q]);
+                    acc[q] = fmaf(u1, x[q].y, acc[q]);
+                    acc[q] = fmaf(u2, x[q].z, acc[q]);
+                    acc[q] = fmaf(u3, x[q].w, acc[q]);
+                    acc[q] = fmaf(u4, y[q].x, acc[q]);
+                    acc[q] = fmaf(u5, y[q].y, acc[q]);
+                    acc[q] = fmaf(u6, y[q].z, acc[q]);
+                    acc[q] = fmaf(u7, y[q].w, acc[q]);
+                }
+            }
             for (; k + 4 <= d; k += 4) {
                 float4 x[4];
 #pragma unroll
