@@ -198,7 +198,8 @@ int skr_fused_trace(skr_ctx *ctx, int64_t *out, int64_t n_out);
  * automatic), "event_ring" (see skr_fused_kernel_ms), "trace_cta"
  * (see skr_fused_trace; -1 = off), "dbg" (timing ablations, results invalid), "chunk_rows" (rows per internal chunk of the
  * fused pipeline, 0 = 131,072), "retry_min" (tf32r: unsettled rows from which the three-pass retry runs, -1 = cost model),
- * "no_aug" (f16r: 1 = add the item bias in the epilogue instead of inside the contraction; measurements only). */
+ * "no_aug" (f16r: 1 = add the item bias in the epilogue instead of inside the contraction; measurements only),
+ * "full_rescore" (tf32r / f16r: 1 = exact scores for every survivor even when no top-K list is requested; measurements only). */
 int skr_set_option(skr_ctx *ctx, const char *name, int64_t value);
 
 /* ---- negative sampler ----------------------------------------------------------------------------------------------

@@ -55,10 +55,17 @@ struct RowMetrics {
     __device__ __forceinline__ void chunk(int i0, int lane, int K, int32_t item, const MetricIds &mids, const double *__restrict__ disc,
                                           const float *__restrict__ idcg, float *__restrict__ per_user_row, double *acc)
     {
+        const bool hit = (i0 + lane < K) && (item >= 0) && sorted_contains(truth, nt, item);
+        chunk_hit(i0, lane, K, hit, mids, disc, idcg, per_user_row, acc);
+    }
+
+    // the same when the caller already knows which positions hold test items (hit: position i0 + lane < K is one)
+    __device__ __forceinline__ void chunk_hit(int i0, int lane, int K, bool hit, const MetricIds &mids, const double *__restrict__ disc,
+                                              const float *__restrict__ idcg, float *__restrict__ per_user_row, double *acc)
+    {
         const int i = i0 + lane;
         const bool valid = i < K;
-        const bool hit = valid && (item >= 0) && sorted_contains(truth, nt, item);
-        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        const uint32_t mask = __ballot_sync(0xffffffffu, hit && valid);
         const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // lanes <= mine
         // 0 / x is exactly +0: skipping those divisions keeps every bit and avoids the IEEE division's slow path,
         // which the compiler's fast-path check sends every zero numerator through (most positions have no hit yet)

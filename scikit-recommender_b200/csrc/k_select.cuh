@@ -116,7 +116,16 @@ __device__ __forceinline__ void sel_sort_emit(const u64 *skey, uint32_t cut, uin
     }
 }
 
-template <int PER, bool RESCORE>
+// HITS (with RESCORE, when the caller wants metrics but no top-K lists): the metrics depend on the rank list only through
+// the positions of the row's test items.  A test item h among the survivors has rank 1 + #{survivors j: s_j > s_h}; against
+// a survivor whose approximate score differs from h's by more than 2 eps the comparison of the approximate scores is
+// already the comparison of the exact ones, so only the test items found among the survivors and the survivors within
+// 2 eps of one of them are re-scored exactly (c4: ~25 item rows per test item in the top 100 instead of ~115 per user;
+// a user without one among the survivors needs none), everything else is counted.  Items that did not survive cannot
+// outrank a test item that ends up in the top K (they lie below the K-th exact score).  Ranks come from one pass over
+// the survivors' keys -- exact where re-scored, approximate elsewhere -- per chunk of 32 survivors holding a test item:
+// no sort.  Per-user metric vectors and sums are bit-identical to the full re-scoring path.
+template <int PER, bool RESCORE, bool HITS = false>
 __global__ void __launch_bounds__(SEL_WARPS * 32, 8)
 k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand_cnt, int n_sub, int cap, int sub_stride, int K,
                int64_t n_rows, int64_t row0, u64 *__restrict__ out_keys, int32_t *__restrict__ fail_list, int *__restrict__ fail_count,
@@ -316,15 +325,65 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
             // (Staging the item rows through shared memory with coalesced 128-byte segments was tried and measured
             // 7 % slower than letting every lane walk its own row: the gather is latency, not L1-tag, bound.)
             float *u = s_u[warp];
-            for (int k = lane; k < R.d; k += 32) u[k] = __ldg(R.U + row * R.ld_u + k);
-            __syncwarp();
             const bool vec_ok = ((R.ld_v & 3) == 0) && ((reinterpret_cast<uintptr_t>(R.V) & 15) == 0);
             uint32_t omin = 0xffffffffu, omax = 0u;
-            for (int i0 = 0; i0 < m; i0 += 32) {
+            // HITS: the slots to re-score are listed in `hist` (free after the cut search); else every survivor
+            int n_rs = m;
+            RowMetrics rm;
+            uint32_t hb[PER];  // HITS: ballot of "survivor e * 32 + lane is a test item"
+            if (HITS) {
+                __syncwarp();
+                rm.begin(te_indptr, te_idx, row0 + row);
+                int n_hit = 0;
+#pragma unroll
+                for (int e = 0; e < PER; ++e) {
+                    const int i = e * 32 + lane;
+                    const bool is = (e * 32 < m) && i < m && sorted_contains(rm.truth, rm.nt, (int32_t)key_item(skey[i]));
+                    hb[e] = (e * 32 < m) ? __ballot_sync(0xffffffffu, is) : 0u;
+                    n_hit += __popc(hb[e]);
+                }
+                if (n_hit == 0) {  // no test item can be in this user's top K: every metric of the row is 0
+                    if (per_user != nullptr) {
+                        float *pr = per_user + row * (int64_t)MK;
+                        for (int c = lane; c < MK; c += 32) pr[c] = 0.0f;
+                    }
+                    if (lane == 0) R.rs_cnt[row] = m;
+                    continue;
+                }
+                // survivors within 2 eps of a test item's approximate score (the test items themselves included)
+                const float e2 = __ldg(R.eps2 + row);
+                uint32_t need = 0u;  // bit e: my survivor e * 32 + lane gets an exact score
+#pragma unroll
+                for (int e2i = 0; e2i < PER; ++e2i) {
+                    for (uint32_t mb = hb[e2i]; mb != 0u; mb &= mb - 1u) {  // warp-uniform: the row's test items among the survivors
+                        const float ah = key_score(skey[e2i * 32 + (__ffs(mb) - 1)]);
+                        const float lo = __fsub_rd(ah, e2), hi = __fadd_ru(ah, e2);
+#pragma unroll
+                        for (int e = 0; e < PER; ++e) {
+                            const int i = e * 32 + lane;
+                            if (i < m) {
+                                const float a = key_score(skey[i]);
+                                if (a >= lo && a <= hi) need |= 1u << e;
+                            }
+                        }
+                    }
+                }
+                n_rs = 0;
+#pragma unroll
+                for (int e = 0; e < PER; ++e) {
+                    const bool f = (need >> e) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, f);
+                    if (f) hist[n_rs + __popc(bal & lt_mask)] = (uint32_t)(e * 32 + lane);
+                    n_rs += __popc(bal);
+                }
+            }
+            for (int k = lane; k < R.d; k += 32) u[k] = __ldg(R.U + row * R.ld_u + k);
+            __syncwarp();
+            for (int i0 = 0; i0 < n_rs; i0 += 32) {
                 // one candidate per lane; its row is fetched 8 float4 at a time, all loads issued before the first FMA
                 // (with the loads inside the FMA loop every 4 k-values waited a full L2 round trip: 16 trips per row)
-                const int ia = i0 + lane;
-                const bool va = ia < m;
+                const bool va = i0 + lane < n_rs;
+                const int ia = HITS ? (va ? (int)hist[i0 + lane] : 0) : i0 + lane;
                 const uint32_t item_a = va ? ~(uint32_t)skey[ia] : 0u;
                 const float *pa = R.V + (int64_t)item_a * R.ld_v;
                 float a = 0.0f;
@@ -361,8 +420,31 @@ k_select_cands(const uint2 *__restrict__ cand, const uint32_t *__restrict__ cand
                     omax = max(omax, (uint32_t)(key >> 32));
                 }
             }
-            // hand the exact keys to k_sort_metrics
             __syncwarp();
+            if (HITS) {
+                // rank of every test item among the survivors = number of keys above its own (exact against exact where both
+                // were re-scored, else the approximate one decides: they differ by more than 2 eps) -> bit mask of hit positions
+                uint32_t *pos = reinterpret_cast<uint32_t *>(s_off[warp]);
+                if (lane < 8) pos[lane] = 0u;
+                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < PER; ++e) {
+                    if (hb[e] == 0u) continue;  // warp-uniform
+                    if ((hb[e] >> lane) & 1u) {
+                        const u64 kh = skey[e * 32 + lane];
+                        int above = 0;
+                        for (int j = 0; j < m; ++j) above += (skey[j] > kh) ? 1 : 0;
+                        if (above < K) atomicOr(&pos[above >> 5], 1u << (above & 31));
+                    }
+                    __syncwarp();
+                }
+                float *pr = (per_user != nullptr) ? per_user + row * (int64_t)MK : nullptr;
+                for (int i0 = 0; i0 < K; i0 += 32)
+                    rm.chunk_hit(i0, lane, K, (pos[i0 >> 5] >> lane) & 1u, mids, disc, idcg, pr, acc);
+                if (lane == 0) R.rs_cnt[row] = m;
+                continue;
+            }
+            // hand the exact keys to k_sort_metrics
             u64 *dst = R.rs_keys + row * (int64_t)CAP;
             for (int i = lane; i < m; i += 32) dst[i] = skey[i];
             if (lane == 0) R.rs_cnt[row] = m;

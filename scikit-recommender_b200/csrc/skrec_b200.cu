@@ -85,6 +85,7 @@ struct skr_ctx {
     int64_t opt_score_fn = 0;        // 0: u . i + b   1: -||u - i|| + b (FP32 tile kernels only)
     int64_t opt_retry_min = -1;      // tf32r: unsettled rows from which the three-pass retry runs (-1 = cost model)
     int64_t opt_no_aug = 0;          // f16r: 1 = add the bias in the epilogue instead of inside the contraction (A/B measurements)
+    int64_t opt_full_rescore = 0;    // tf32r / f16r: 1 = re-score every survivor and sort even when only metrics are wanted (A/B measurements)
     int64_t opt_exact_seg_rows = -1;  // development: how many failed rows are cut in segments (-1 = default)
     bool debug_sync = false;  // SKR_DEBUG_SYNC=1: synchronise and check after every kernel, naming the one that failed
     int64_t opt_trace_cta = -1;  // >= 0: record the tile timeline of that CTA of the main pass (development aid)
@@ -346,7 +347,10 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     typedef void (*SortKernel)(const u64 *, const int *, int, int64_t, int64_t, u64 *, const int64_t *, const int32_t *, MetricIds, const double *,
                                const float *, float *, int32_t *, float *, double *);
     const int per = rescore ? (K <= 64 ? 4 : 8) : (K <= 64 ? 2 : 4);
-    SelKernel sel = rescore ? (K <= 64 ? (SelKernel)k_select_cands<4, true> : (SelKernel)k_select_cands<8, true>)
+    // metrics without top-K lists: exact scores only for the test items among the survivors and their near-ties (k_select.cuh HITS)
+    const bool hits = rescore && keys_only == nullptr && topk_idx == nullptr && topk_val == nullptr && ctx->opt_full_rescore == 0;
+    SelKernel sel = hits ? (K <= 64 ? (SelKernel)k_select_cands<4, true, true> : (SelKernel)k_select_cands<8, true, true>)
+                  : rescore ? (K <= 64 ? (SelKernel)k_select_cands<4, true> : (SelKernel)k_select_cands<8, true>)
                             : (K <= 64 ? (SelKernel)k_select_cands<2, false> : (SelKernel)k_select_cands<4, false>);
     SortKernel srt = (K <= 64) ? (SortKernel)k_sort_metrics<4> : (SortKernel)k_sort_metrics<8>;
     int rc;
@@ -397,8 +401,9 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     u64 *keys = (u64 *)ctx->keys.p;
     const int g_fix = (int)std::min<int64_t>((n_rows + K4_WARPS - 1) / K4_WARPS, ctx->n_sm);
     double *acc = nullptr;
+    const int n_sel_parts = (hits && RP.collect != nullptr) ? 2 * g_sel : g_sel;  // HITS: the first selection and the retry's each hold sums
     if (fused_sums) {
-        if ((rc = ensure(ctx, ctx->partial, (size_t)(g_sel + g_fix) * MK * sizeof(double)))) return rc;
+        if ((rc = ensure(ctx, ctx->partial, (size_t)(n_sel_parts + g_fix) * MK * sizeof(double)))) return rc;
         acc = (double *)ctx->partial.p;
         if (acc_k4 > 48 * 1024) SKR_CUDA(ctx, cudaFuncSetAttribute(k_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_k4));
     }
@@ -406,12 +411,27 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     const size_t dyn_sel = fused_sums ? acc_sel : 0;
     if (dyn_sel > 0) {
         cudaFuncAttributes fa;
-        if (rescore) SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, srt)); else SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, sel));
+        if (rescore && !hits) SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, srt)); else SKR_CUDA(ctx, cudaFuncGetAttributes(&fa, sel));
         if (fa.sharedSizeBytes + dyn_sel > ctx->max_smem) return fail(ctx, SKR_ERR_UNSUPPORTED, "n_metrics * top_k = %d does not fit shared memory", MK);
-        if (rescore) SKR_CUDA(ctx, cudaFuncSetAttribute(srt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
+        if (rescore && !hits) SKR_CUDA(ctx, cudaFuncSetAttribute(srt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
         else SKR_CUDA(ctx, cudaFuncSetAttribute(sel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->max_smem - fa.sharedSizeBytes)));
     }
-    if (rescore) {
+    if (hits) {
+        SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(dyn_sel), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, ctx->d_te_indptr,
+                                 ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, nullptr, nullptr, acc, RA, add_back, 0, (const int *)nullptr, 0));
+        if (RP.collect != nullptr) {
+            if ((rc = (*RP.collect)())) return rc;
+            RescoreArgs R2 = RA;
+            R2.eps2 = RP.eps2_3;
+            R2.thr_c = RP.thr3;
+            SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(dyn_sel), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, RP.fail_list2, RP.fail_count2,
+                                     ctx->d_te_indptr, ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, nullptr, nullptr, acc ? acc + (size_t)g_sel * MK : nullptr, R2, nullptr, 1,
+                                     (const int *)fail_count_first, RP.retry_min));
+            ctx->launches += 3;
+            fail_list = RP.fail_list2;
+            fail_count = RP.fail_count2;
+        }
+    } else if (rescore) {
         SKR_CUDA(ctx, launch_pdl(sel, dim3((unsigned)(g_sel)), dim3((unsigned)(SEL_WARPS * 32)), (size_t)(0), st, cand, cand_cnt, n_sub, cap, cap, K, n_rows, row0, nullptr, fail_list, fail_count, nullptr, nullptr, m, nullptr,
                                               nullptr, nullptr, nullptr, nullptr, nullptr, RA, add_back, 0, (const int *)nullptr, 0));
         if (RP.collect != nullptr) {
@@ -436,10 +456,10 @@ int run_select_metrics(skr_ctx *ctx, const uint2 *cand, const uint32_t *cand_cnt
     if ((rc = run_row_exact(ctx, E, fail_list, fail_count, n_rows, row0, K, keys, st))) return rc;
     SKR_CUDA(ctx, launch_pdl(k_metrics, dim3((unsigned)(g_fix)), dim3((unsigned)(K4_WARPS * 32)), (size_t)(fused_sums ? acc_k4 : 0), st, keys, nullptr, K, n_rows, row0, fail_list, fail_count, ctx->d_te_indptr,
                                                                      ctx->d_te_idx, m, ctx->d_disc, ctx->d_idcg, pu, topk_idx, topk_val,
-                                                                     acc ? acc + (size_t)g_sel * MK : nullptr));
+                                                                     acc ? acc + (size_t)n_sel_parts * MK : nullptr));
     ctx->launches += 2;
     if (fused_sums) {
-        SKR_CUDA(ctx, launch_pdl(k_colsum_fold, dim3((unsigned)(MK)), dim3((unsigned)(256)), (size_t)(0), st, acc, g_sel + g_fix, MK, sums));
+        SKR_CUDA(ctx, launch_pdl(k_colsum_fold, dim3((unsigned)(MK)), dim3((unsigned)(256)), (size_t)(0), st, acc, n_sel_parts + g_fix, MK, sums));
         ctx->launches++;
     } else if (sums) {
         const int nblk = (int)std::min<int64_t>(n_rows, 2 * ctx->n_sm);
@@ -737,6 +757,7 @@ int skr_set_option(skr_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "retry_min")) { ctx->opt_retry_min = value; return SKR_OK; }
     if (!strcmp(name, "no_aug")) { ctx->opt_no_aug = value; return SKR_OK; }
+    if (!strcmp(name, "full_rescore")) { ctx->opt_full_rescore = value; return SKR_OK; }
     if (!strcmp(name, "chunk_rows")) { ctx->opt_chunk_rows = value < 0 ? 0 : value; return SKR_OK; }
     if (!strcmp(name, "exact_seg_rows")) { ctx->opt_exact_seg_rows = value; return SKR_OK; }
     if (!strcmp(name, "trace_cta")) { ctx->opt_trace_cta = value; return SKR_OK; }

@@ -214,6 +214,21 @@ def _run_fused(torch, ctx, ue, ie, b, tr, te, metric, K, precision, chunks=0):
     ctx.eval_fused(torch.from_numpy(ue).cuda(), torch.from_numpy(ie).cuda(), None if b is None else torch.from_numpy(b).cuda(),
                    0, metric, K, precision=precision, topk_idx=idx, topk_val=val, per_user=per, sums=sums)
     torch.cuda.synchronize()
+    if precision in ("tf32r", "f16r"):
+        # metrics without lists: exact scores only for the test items among the survivors and their near-ties (k_select.cuh
+        # HITS) -- the per-user block must come out bit for bit as from the full re-scoring above
+        per2 = torch.full((U, MK), -1.0, dtype=torch.float32, device="cuda")
+        sums2 = torch.zeros(MK, dtype=torch.float64, device="cuda")
+        ctx.eval_fused(torch.from_numpy(ue).cuda(), torch.from_numpy(ie).cuda(), None if b is None else torch.from_numpy(b).cuda(),
+                       0, metric, K, precision=precision, per_user=per2, sums=sums2)
+        torch.cuda.synchronize()
+        assert torch.equal(per2, per), "hits-only re-scoring changed a per-user metric"
+        assert float((sums2 - sums).abs().max()) < 1e-9
+        sums3 = torch.zeros(MK, dtype=torch.float64, device="cuda")  # sums only (what evaluate() asks for)
+        ctx.eval_fused(torch.from_numpy(ue).cuda(), torch.from_numpy(ie).cuda(), None if b is None else torch.from_numpy(b).cuda(),
+                       0, metric, K, precision=precision, sums=sums3)
+        torch.cuda.synchronize()
+        assert float((sums3 - sums).abs().max()) < 1e-9
     ctx.set_option("chunks", 0)
     return idx.cpu().numpy(), val.cpu().numpy(), per.cpu().numpy(), sums.cpu().numpy()
 
