@@ -246,7 +246,8 @@ constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((ui
 // chosen so that the largest magnitude lands in [2^9, 2^10).  Elements down to 2^-23 of the largest keep a relative error
 // of 2^-11 (fp16 normals reach down to 2^-14); smaller ones are off by at most 2^-25 in scaled units, which the error
 // band accounts for (k_sample_thr).  Scaled scores stay below d 2^20 <= 2^27.  The threshold operand of the threshold
-// MMA is (hi + lo) x C with C = 2^12 in the constant B' tile, hi and lo fp16 values of magnitude < 2^15.
+// MMA is (hi + lo) x C with C = 2^12 in the B' tile (constant, or the augmentation tile), hi and lo fp16 values of
+// magnitude < 2^15.
 constexpr int TC_F16_TARGET = 9;     // floor(log2(scaled maximum))
 constexpr int TC_F16_THR_SHIFT = 12;  // log2 C
 __host__ __device__ inline int f16_scale_exp(float amax)
@@ -289,9 +290,9 @@ struct TcArgs {
     // nothing (no usable threshold); SAMPLE derives s_u from the row itself
     const float *item_scale;
     const float *scale;
-    // FP16 operands with the bias folded into the contraction (AUG): the item table carries one more k-block whose first
-    // columns are (C, C, b_hi, b_lo) 2^m-scaled, the user operand (-T_hi, -T_lo, g, g); bias_shift -> m (k_split_f16),
-    // rowg: per-row g = s_u 2^-m from k_sample_thr (COLLECT; SAMPLE derives it from the row)
+    // FP16 operands with the bias folded into the contraction (AUG): an augmentation table (second tensor map) carries
+    // (C, C, beta_hi, beta_lo, 0...) per item, beta = bias s_i 2^m, the user operand (-T_hi, -T_lo, g, g); bias_shift -> m
+    // (k_split_f16), rowg: per-row g = s_u 2^-m from k_sample_thr (COLLECT; SAMPLE derives it from the row)
     const int *bias_shift;
     const float *rowg;
     int cap;                 // entries per (row, chunk, column quarter) sub-list
