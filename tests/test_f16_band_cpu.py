@@ -63,6 +63,8 @@ def band(U, I, b, eus, ei):
     eps = (2.0 ** -10 + (2.5 * d + 8) * 2.0 ** -22) * un * nmax + 2.0 ** -22 * bmax
     if b is not None:
         eps = eps + ((2.5 * d + 8) * 2.0 ** -22 + 2.0 ** -21) * bmax
+        m = 13 - int(np.floor(np.log2(bmax))) - ei if bmax > 0 else 0
+        eps = eps + np.where(eus - m < -24, bmax, 0.0)  # rows whose g = s_u 2^-m leaves fp16: the candidate pass drops their bias
     eps = eps + 2.0 ** -25 * np.sqrt(d) * (nmax / 2.0 ** eus + un / 2.0 ** ei)
     return 1.25 * eps
 
@@ -111,3 +113,26 @@ def test_threshold_operand_is_exact_and_never_above_the_threshold():
         s = hi + lo
         assert s <= t and float(np.float32(s)) == s      # collect a superset; exact in FP32
         assert t - s <= max(2.0 ** -24, abs(t) * 2.0 ** -20)
+
+
+def test_rows_dwarfed_by_the_bias_and_rows_that_dwarf_it():
+    """g = s_u 2^-m has to be an fp16 power of two: a row 2^-20 of the bias is scaled less (its largest element then sits far
+    below 2^9 and the absolute 2^-25 term of the band carries it), a row 2^35 times the bias loses the bias in the candidate
+    pass (B_max joins its band).  Both stay inside the band."""
+    g = np.random.default_rng(11)
+    d = 64
+    I = (g.standard_normal((500, d)) * 0.1).astype(np.float32)
+    b = (g.standard_normal(500) * 0.5).astype(np.float32)
+    U = (g.standard_normal((6, d)) * 0.1).astype(np.float32)
+    U[0] *= 2.0 ** -22      # all bias
+    U[1] *= 2.0 ** 38       # no bias to speak of
+    exact = U.astype(np.float64) @ I.astype(np.float64).T + b.astype(np.float64)
+    got, eus, ei = candidate_scores(U, I, b, list(range(d)))
+    bmax = float(np.abs(b).max())
+    m = 13 - int(np.floor(np.log2(bmax))) - ei
+    assert eus[0] == m + 15 and eus[0] < scale_exp(np.abs(U[0]).max())   # scaled less than its own magnitude asks for
+    assert eus[1] - m < -24                                                # g underflows: bias dropped
+    eps = band(U, I, b, eus, ei)
+    err = np.abs(got - exact).max(axis=1)
+    assert np.all(err <= 0.9 * eps), (err / eps).tolist()
+    assert err[1] > 0.5 * bmax                                             # the bias really is missing from row 1's candidate scores
